@@ -1,0 +1,562 @@
+"""CPU ORACLE for the Severo.jl IRLBA-PCA hot path — TEST INFRASTRUCTURE, NOT THE PRODUCT.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module. The product package (``severo.jl_b200``)
+never imports, links or executes anything under ``oracle/``.
+
+It restates, on the CPU and in Float64, the algorithms of the reference's path (paths relative
+to the reference repo root):
+
+* ``src/normalize.jl:17-55``      row_norm / log_norm / normalize_cells
+* ``src/scaling.jl:18-44,119-147`` mean_var / mean_std (sequential Welford, implicit zeros pre-counted)
+* ``src/variablefeatures.jl:19-28`` standardized_var_clipped
+* ``src/scaling.jl:199-217``      scale_data
+* ``src/scaling.jl:219-272,298-314`` CenteredMatrix and its mul! family / convert
+* ``src/irlba.jl:47-99``          irlba!/irlba wrapper defaults (work = nu+7, tol = 1e-5, maxit = 1000)
+* ``src/embedding.jl:46-76``      _pca post-processing
+* ``src/utils.jl:215-228``        svd_flip!
+
+Order-exact loops (Welford, ``sf*x/s``, ``x/std``) run in ``csrc/severo_oracle.c`` compiled with
+``-ffp-contract=off`` (Julia never contracts to FMA); small inputs can also be run through the
+pure-Python twins below (``*_py``), which the CPU tests use to validate the C build.
+
+PARITY STATUS
+-------------
+* Pre-processing + operator: pinned against the reference's own fixed-input tests
+  (``test/test_scaling.jl:22-45,72-112``, ``test/test_input.jl:47-75``) — see tests/golden/.
+* IRLBA: the arithmetic lives in the external, un-vendored and un-pinned binary ``libcell``
+  (package ``Severo_jll``, no version in Project.toml; call site ``src/irlba.jl:66-71``). Neither
+  Julia nor libcell exists in this image, so the *iterates* are **parity unpinned**. The loop
+  below restates the published algorithm libcell derives from (Baglama & Reichel's implicitly
+  restarted Lanczos bidiagonalisation as implemented in B. W. Lewis' ``irlb.c`` of the R package
+  *irlba*: same signature, same defaults). What IS pinned is the converged result, by the
+  reference's own criteria in ``test/test_irlba.jl`` (singular values vs dense LAPACK ``svd`` at
+  rtol sqrt(eps); ``||X'U - V S|| / ||X|| < tol``; rank-k reconstruction error).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+import scipy.sparse as sp
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(_HERE, "csrc", "severo_oracle.c")
+_BUILD = os.path.join(_HERE, "_build")
+_LIB = os.path.join(_BUILD, "libsevero_oracle.so")
+
+_i64p = ctypes.POINTER(ctypes.c_int64)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_f64p = ctypes.POINTER(ctypes.c_double)
+_f32p = ctypes.POINTER(ctypes.c_float)
+
+
+def build(force: bool = False) -> str:
+    """Compile csrc/severo_oracle.c -> _build/libsevero_oracle.so (gcc, no FMA contraction)."""
+    if not force and os.path.exists(_LIB) and os.path.getmtime(_LIB) >= os.path.getmtime(_SRC):
+        return _LIB
+    os.makedirs(_BUILD, exist_ok=True)
+    cmd = ["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-shared", "-fPIC",
+           "-fvisibility=hidden", "-o", _LIB, _SRC, "-lm"]
+    subprocess.run(cmd, check=True)
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        _lib.orc_num_threads.restype = ctypes.c_int
+    return _lib
+
+
+def num_threads() -> int:
+    return int(lib().orc_num_threads())
+
+
+def set_num_threads(n: int) -> None:
+    lib().orc_set_num_threads(ctypes.c_int(int(n)))
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+def _csc(A):
+    """Canonical CSC with int64 indices, sorted rows (what Julia's SparseMatrixCSC guarantees)."""
+    A = sp.csc_matrix(A)
+    if not A.has_sorted_indices:
+        A = A.copy()
+        A.sort_indices()
+    return A
+
+
+def _idx64(A):
+    return (np.ascontiguousarray(A.indptr, dtype=np.int64),
+            np.ascontiguousarray(A.indices, dtype=np.int64))
+
+
+# --------------------------------------------------------------------------------------
+# normalize.jl
+# --------------------------------------------------------------------------------------
+def row_norm(A, scale_factor=1.0, dtype=np.float64):
+    """normalize.jl:17-32. Integer counts in, ``dtype`` values out, same sparsity pattern."""
+    A = _csc(A)
+    colptr, rowval = _idx64(A)
+    if not np.issubdtype(A.dtype, np.integer):
+        raise TypeError("oracle row_norm restates the integer-count path (normalize.jl:24 exact Int sum)")
+    nz = np.ascontiguousarray(A.data, dtype=np.int64)
+    m, n = A.shape
+    s = np.zeros(m, dtype=np.int64)
+    L = lib()
+    L.orc_row_sums_i64(ctypes.c_int64(n), _p(colptr, _i64p), _p(rowval, _i64p), _p(nz, _i64p),
+                       ctypes.c_int64(m), _p(s, _i64p))
+    return _row_norm_apply(A, rowval, nz, s, scale_factor, dtype, do_log=0)
+
+
+def _row_norm_apply(A, rowval, nz, s, scale_factor, dtype, do_log):
+    L = lib()
+    out = np.empty(nz.shape[0], dtype=dtype)
+    if np.dtype(dtype) == np.float64:
+        L.orc_row_norm_f64(ctypes.c_int64(nz.shape[0]), _p(rowval, _i64p), _p(nz, _i64p), _p(s, _i64p),
+                           ctypes.c_double(float(scale_factor)), ctypes.c_int(do_log), _p(out, _f64p))
+    elif np.dtype(dtype) == np.float32:
+        L.orc_row_norm_f32(ctypes.c_int64(nz.shape[0]), _p(rowval, _i64p), _p(nz, _i64p), _p(s, _i64p),
+                           ctypes.c_float(float(np.float32(scale_factor))), ctypes.c_int(do_log),
+                           _p(out, _f32p))
+    else:
+        raise TypeError("dtype must be float32 or float64")
+    return sp.csc_matrix((out, A.indices.copy(), A.indptr.copy()), shape=A.shape)
+
+
+def log_norm(A, scale_factor=1.0, dtype=np.float64):
+    """normalize.jl:34-38 (row_norm then log1p on the stored values)."""
+    A = _csc(A)
+    colptr, rowval = _idx64(A)
+    nz = np.ascontiguousarray(A.data, dtype=np.int64)
+    m, n = A.shape
+    s = np.zeros(m, dtype=np.int64)
+    lib().orc_row_sums_i64(ctypes.c_int64(n), _p(colptr, _i64p), _p(rowval, _i64p), _p(nz, _i64p),
+                           ctypes.c_int64(m), _p(s, _i64p))
+    return _row_norm_apply(A, rowval, nz, s, scale_factor, dtype, do_log=1)
+
+
+def normalize_cells(X, method="lognormalize", scale_factor=1.0, dtype=np.float64):
+    """normalize.jl:40-55 — method Symbol-or-String dispatch, scale_factor converted to dtype."""
+    method = str(method)
+    if method == "lognormalize":
+        f = log_norm
+    elif method == "relativecounts":
+        f = row_norm
+    else:
+        raise ValueError(f"unknown normalization method: {method}")
+    return f(X, np.dtype(dtype).type(scale_factor), dtype)
+
+
+def row_norm_py(A, scale_factor=1.0, do_log=False):
+    """Pure-Python twin of row_norm/log_norm (tiny inputs only) — validates the C build."""
+    import math
+    A = _csc(A)
+    m, n = A.shape
+    s = [0] * m
+    for c in range(n):
+        for j in range(A.indptr[c], A.indptr[c + 1]):
+            s[A.indices[j]] += int(A.data[j])
+    out = np.empty(A.nnz, dtype=np.float64)
+    for j in range(A.nnz):
+        v = (float(scale_factor) * float(A.data[j])) / float(s[A.indices[j]])
+        out[j] = math.log1p(v) if do_log else v
+    return sp.csc_matrix((out, A.indices.copy(), A.indptr.copy()), shape=A.shape)
+
+
+# --------------------------------------------------------------------------------------
+# scaling.jl — moments
+# --------------------------------------------------------------------------------------
+def mean_var_py(values, n, dtype=np.float64):
+    """scaling.jl:18-34 literally, in Python floats (Float64) or numpy float32 scalars."""
+    T = np.dtype(dtype).type
+    count = n - len(values)
+    mu = T(0)
+    s = T(0)
+    for v in values:
+        v = T(v)
+        count += 1
+        delta = v - mu
+        mu = T(mu + T(delta / T(count)))
+        s = T(s + T(delta * T(v - mu)))
+    var = T(s / T(n - 1))
+    return mu, var
+
+
+def mean_var(A, dtype=None):
+    """scaling.jl:132-147 mean_var(A::SparseMatrixCSC): integer data -> Float64; float data -> own type."""
+    A = _csc(A)
+    colptr, _ = _idx64(A)
+    m, n = A.shape
+    L = lib()
+    if np.issubdtype(A.dtype, np.integer):
+        if dtype is not None and np.dtype(dtype) != np.float64:
+            # mean_var(Float32, A) on integer data: run the generic twin
+            return _mean_var_generic(A, dtype)
+        nz = np.ascontiguousarray(A.data, dtype=np.int64)
+        mu = np.empty(n)
+        var = np.empty(n)
+        L.orc_mean_var_csc_i64(ctypes.c_int64(m), ctypes.c_int64(n), _p(colptr, _i64p), _p(nz, _i64p),
+                               _p(mu, _f64p), _p(var, _f64p))
+        return mu, var
+    if A.dtype == np.float32 and (dtype is None or np.dtype(dtype) == np.float32):
+        nz = np.ascontiguousarray(A.data, dtype=np.float32)
+        mu = np.empty(n, dtype=np.float32)
+        var = np.empty(n, dtype=np.float32)
+        L.orc_mean_var_csc_f32(ctypes.c_int64(m), ctypes.c_int64(n), _p(colptr, _i64p), _p(nz, _f32p),
+                               _p(mu, _f32p), _p(var, _f32p))
+        return mu, var
+    nz = np.ascontiguousarray(A.data, dtype=np.float64)
+    mu = np.empty(n)
+    var = np.empty(n)
+    L.orc_mean_var_csc_f64(ctypes.c_int64(m), ctypes.c_int64(n), _p(colptr, _i64p), _p(nz, _f64p),
+                           _p(mu, _f64p), _p(var, _f64p))
+    return mu, var
+
+
+def _mean_var_generic(A, dtype):
+    m, n = A.shape
+    mu = np.empty(n, dtype=dtype)
+    var = np.empty(n, dtype=dtype)
+    for c in range(n):
+        mu[c], var[c] = mean_var_py(A.data[A.indptr[c]:A.indptr[c + 1]], m, dtype)
+    return mu, var
+
+
+def mean_std(A, dtype=None):
+    """scaling.jl:119-130."""
+    mu, var = mean_var(A, dtype)
+    return mu, np.sqrt(var)
+
+
+# --------------------------------------------------------------------------------------
+# variablefeatures.jl — the data sweep after the (host, unpinned) loess fit
+# --------------------------------------------------------------------------------------
+def standardized_var_clipped(A, mu, sd, vmax=None):
+    """variablefeatures.jl:21-28. Returns the per-gene clipped standardised variance."""
+    A = _csc(A)
+    if not np.issubdtype(A.dtype, np.integer):
+        raise TypeError("standardized_var_clipped is defined on integer counts (variablefeatures.jl:21)")
+    colptr, _ = _idx64(A)
+    nz = np.ascontiguousarray(A.data, dtype=np.int64)
+    m, n = A.shape
+    if vmax is None:
+        vmax = np.sqrt(float(m))
+    mu = np.ascontiguousarray(mu, dtype=np.float64)
+    sd = np.ascontiguousarray(sd, dtype=np.float64)
+    out = np.zeros(n)
+    lib().orc_stdvar_clipped_i64(ctypes.c_int64(m), ctypes.c_int64(n), _p(colptr, _i64p), _p(nz, _i64p),
+                                 _p(mu, _f64p), _p(sd, _f64p), ctypes.c_double(float(vmax)), _p(out, _f64p))
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# scaling.jl — scale_data / CenteredMatrix
+# --------------------------------------------------------------------------------------
+def scale_data(A, scale_max=np.inf):
+    """scaling.jl:199-217. Returns (B, mu) with mu = mean/std (trap T3)."""
+    A = _csc(A)
+    colptr, _ = _idx64(A)
+    m, n = A.shape
+    out = np.empty(A.nnz)
+    mu = np.empty(n)
+    L = lib()
+    if np.issubdtype(A.dtype, np.integer):
+        nz = np.ascontiguousarray(A.data, dtype=np.int64)
+        L.orc_scale_data_i64(ctypes.c_int64(m), ctypes.c_int64(n), _p(colptr, _i64p), _p(nz, _i64p),
+                             ctypes.c_double(float(scale_max)), _p(out, _f64p), _p(mu, _f64p))
+    else:
+        nz = np.ascontiguousarray(A.data, dtype=np.float64)
+        L.orc_scale_data_f64(ctypes.c_int64(m), ctypes.c_int64(n), _p(colptr, _i64p), _p(nz, _f64p),
+                             ctypes.c_double(float(scale_max)), _p(out, _f64p), _p(mu, _f64p))
+    return sp.csc_matrix((out, A.indices.copy(), A.indptr.copy()), shape=A.shape), mu
+
+
+def scale_features(X, scale_max=np.inf, features=None):
+    """scaling.jl:335-357 (without the NamedArray labels). Returns a CenteredMatrix."""
+    X = _csc(X)
+    if features is not None:
+        X = _csc(X[:, np.asarray(features)])
+    B, mu = scale_data(X, scale_max)
+    return CenteredMatrix(B, mu)
+
+
+class CenteredMatrix:
+    """scaling.jl:219-272: the implicit operator S = A - 1*mu' ; A is CSC, a lazy adjoint of a CSC
+    (``transposed=True`` keeps the parent, as ``CenteredMatrix(X', mu)`` in test_irlba.jl:111), or dense."""
+
+    def __init__(self, A, mu, transposed=False):
+        self.dense = not sp.issparse(A)
+        self.transposed = bool(transposed)
+        if self.dense:
+            P = np.asarray(A, dtype=np.float64)
+            self.P = P.T if transposed else P
+            self.transposed = False
+        else:
+            P = _csc(A).astype(np.float64)
+            self.P = P
+            self.colptr, self.rowval = _idx64(P)
+            self.nz = np.ascontiguousarray(P.data, dtype=np.float64)
+            self._csr = None
+        pm, pn = self.P.shape
+        self.shape = (pn, pm) if self.transposed else (pm, pn)
+        self.mu = None if mu is None else np.ascontiguousarray(mu, dtype=np.float64)
+        if self.mu is not None:
+            assert self.mu.shape[0] == self.shape[1]  # scaling.jl:226
+
+    # -- raw products with the *parent* CSC P (pm x pn) --------------------------------
+    def _P_mul(self, v, alpha, beta, y, parallel=False):
+        pm, pn = self.P.shape
+        if parallel:
+            if self._csr is None:
+                rowptr = np.empty(pm + 1, dtype=np.int64)
+                colidx = np.empty(self.nz.shape[0], dtype=np.int32)
+                val = np.empty(self.nz.shape[0])
+                lib().orc_csc_to_csr(ctypes.c_int64(pm), ctypes.c_int64(pn), _p(self.colptr, _i64p),
+                                     _p(self.rowval, _i64p), _p(self.nz, _f64p), _p(rowptr, _i64p),
+                                     _p(colidx, _i32p), _p(val, _f64p))
+                self._csr = (rowptr, colidx, val)
+            rowptr, colidx, val = self._csr
+            lib().orc_csr_mul(ctypes.c_int64(pm), _p(rowptr, _i64p), _p(colidx, _i32p), _p(val, _f64p),
+                              _p(v, _f64p), ctypes.c_double(alpha), ctypes.c_double(beta), _p(y, _f64p))
+        else:
+            lib().orc_csc_mul(ctypes.c_int64(pm), ctypes.c_int64(pn), _p(self.colptr, _i64p),
+                              _p(self.rowval, _i64p), _p(self.nz, _f64p), _p(v, _f64p),
+                              ctypes.c_double(alpha), ctypes.c_double(beta), _p(y, _f64p))
+
+    def _Pt_mul(self, v, alpha, beta, y):
+        pm, pn = self.P.shape
+        lib().orc_csc_mul_t(ctypes.c_int64(pm), ctypes.c_int64(pn), _p(self.colptr, _i64p),
+                            _p(self.rowval, _i64p), _p(self.nz, _f64p), _p(v, _f64p),
+                            ctypes.c_double(alpha), ctypes.c_double(beta), _p(y, _f64p))
+
+    # -- mul!(C, S, v, a, b)  scaling.jl:245-250 ;  mul!(C, S', v, a, b)  scaling.jl:252-257 --
+    def mul(self, v, alpha=1.0, beta=0.0, y=None, trans=False, parallel=False):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        m, n = self.shape
+        if v.ndim == 2:
+            return self._mul_mat(v, alpha, beta, y, trans, parallel)
+        out_len = n if trans else m
+        assert v.shape[0] == (m if trans else n)
+        if y is None:
+            y = np.zeros(out_len)
+            beta = 0.0
+        if self.dense:
+            Av = (self.P.T @ v) if trans else (self.P @ v)
+            y[:] = alpha * Av + (beta * y if beta != 0.0 else 0.0)
+        else:
+            use_parent_adjoint = (trans != self.transposed)
+            if use_parent_adjoint:
+                self._Pt_mul(v, alpha, beta, y)
+            else:
+                self._P_mul(v, alpha, beta, y, parallel)
+        if self.mu is not None:
+            if trans:
+                y += (-alpha * np.sum(v)) * self.mu        # axpy!(-a*sum(v), mu, C)  scaling.jl:256
+            else:
+                y -= alpha * np.dot(self.mu, v)             # C .-= a*dot(mu, v)       scaling.jl:248
+        return y
+
+    def _mul_mat(self, V, alpha, beta, Y, trans, parallel):
+        """scaling.jl:259-272 matrix forms, column by column. The adjoint form SUBTRACTS the
+        rank-1 term (mathematically correct); the reference's :271 adds it — untested upstream
+        sign slip, SURVEY trap T4."""
+        k = V.shape[1]
+        m, n = self.shape
+        out_len = n if trans else m
+        if Y is None:
+            Y = np.zeros((out_len, k), order="F")
+            beta = 0.0
+        for c in range(k):
+            yc = np.ascontiguousarray(Y[:, c])
+            Y[:, c] = self.mul(np.ascontiguousarray(V[:, c]), alpha, beta, yc, trans, parallel)
+        return Y
+
+    def to_dense(self):
+        """convert(Matrix, C) scaling.jl:298-303."""
+        X = self.P if self.dense else self.P.toarray()
+        X = np.array(X.T if self.transposed else X, dtype=np.float64)
+        if self.mu is not None:
+            X = X - self.mu[None, :]
+        return X
+
+
+# --------------------------------------------------------------------------------------
+# IRLBA (libcell.irlba restated; see module docstring for parity status)
+# --------------------------------------------------------------------------------------
+@dataclass
+class IrlbaResult:
+    U: np.ndarray
+    S: np.ndarray
+    V: np.ndarray
+    iters: int
+    mprod: int
+    info: int
+
+
+_EPS23 = np.finfo(np.float64).eps ** (2.0 / 3.0)
+
+
+def _orthog(X, y, j):
+    """Classical Gram-Schmidt, one pass: y -= X[:, :j] (X[:, :j]' y)  (irlb.c `orthog`)."""
+    if j > 0:
+        t = X[:, :j].T @ y
+        y -= X[:, :j] @ t
+    return y
+
+
+def irlba(A, nu, init=None, tol=1e-5, svtol=None, maxit=1000, work=None, rng=None, parallel=False,
+          restart_from=None):
+    """Restated ``libcell.irlba`` as wrapped by src/irlba.jl:47-85.
+
+    ``A`` needs ``.shape`` and ``.mul(v, trans=...)`` (CenteredMatrix) or is a numpy / scipy matrix.
+    Defaults follow irlba.jl: work = min(nu+7, min(m,n)) (:50-58), tol = 1e-5, maxit = 1000,
+    init = randn(n) (:62-64). ``svtol`` defaults to ``tol`` (the wrapper computes a svtol at :60 but
+    never passes it to C, trap T5).
+    Returns IrlbaResult with info = 0 (converged) or -2 (maxit) / -4 (init in null space).
+    """
+    if not isinstance(A, CenteredMatrix):
+        A = CenteredMatrix(A, None)
+    m, n = A.shape
+    nu = int(nu)
+    if work is None:
+        work = nu + 7                       # irlba.jl:50
+    if work < nu:
+        work = nu + 1
+    work = min(work, min(m, n))             # irlba.jl:56-58
+    if svtol is None:
+        svtol = tol
+    if rng is None:
+        rng = np.random.default_rng(0)
+    if init is None:
+        init = rng.standard_normal(n)
+    w = work
+    V = np.zeros((n, w), order="F")
+    W = np.zeros((m, w), order="F")
+    B = np.zeros((w, w))
+    F = np.zeros(n)
+    k = 0
+    if restart_from is not None:            # warm restart irlba.jl:87-99 (broken upstream, test_irlba.jl:61)
+        U0, s0, V0 = restart_from
+        k = len(s0)
+        V[:, :k] = V0
+        W[:, :k] = U0
+        B[np.arange(k), np.arange(k)] = s0
+        V[:, k] = init / np.linalg.norm(init)
+    else:
+        V[:, 0] = init / np.linalg.norm(init)
+    sv_prev = np.zeros(w)
+    smax = 0.0
+    it = 0
+    mprod = 0
+    info = -2
+    BU = BS = BVt = None
+    while it < maxit:
+        j = k if (it > 0 or restart_from is not None) else 0
+        W[:, j] = A.mul(np.ascontiguousarray(V[:, j]), trans=False, parallel=parallel)
+        mprod += 1
+        if j > 0:
+            _orthog(W, W[:, j], j)
+        s = np.linalg.norm(W[:, j])
+        if s < _EPS23 and j == 0:
+            info = -4
+            break
+        W[:, j] /= s
+        while j < w:
+            F = A.mul(np.ascontiguousarray(W[:, j]), trans=True, parallel=parallel)
+            mprod += 1
+            F -= s * V[:, j]
+            _orthog(V, F, j + 1)
+            if j + 1 < w:
+                r = np.linalg.norm(F)
+                if r < _EPS23:              # Lanczos breakdown: fresh random direction, B entry 0
+                    F = rng.standard_normal(n)
+                    _orthog(V, F, j + 1)
+                    V[:, j + 1] = F / np.linalg.norm(F)
+                    r = 0.0
+                else:
+                    V[:, j + 1] = F / r
+                B[j, j] = s
+                B[j, j + 1] = r
+                Wn = A.mul(np.ascontiguousarray(V[:, j + 1]), trans=False, parallel=parallel)
+                mprod += 1
+                Wn -= r * W[:, j]
+                _orthog(W, Wn, j + 1)
+                s = np.linalg.norm(Wn)
+                if s < _EPS23:
+                    Wn = rng.standard_normal(m)
+                    _orthog(W, Wn, j + 1)
+                    W[:, j + 1] = Wn / np.linalg.norm(Wn)
+                    s = 0.0
+                else:
+                    W[:, j + 1] = Wn / s
+            else:
+                B[j, j] = s
+            j += 1
+        BU, BS, BVt = np.linalg.svd(B)
+        rF = np.linalg.norm(F)
+        F = F / rF if rF > 0 else F
+        res = rF * BU[w - 1, :]
+        smax = max(smax, BS[0])
+        ratio = np.abs(sv_prev - BS) / BS
+        conv = (np.abs(res) < tol * smax) & (ratio < svtol)
+        nconv = int(np.count_nonzero(conv))
+        it += 1
+        if nconv >= nu or s == 0.0:
+            info = 0
+            break
+        if it >= maxit:
+            break
+        sv_prev = BS.copy()
+        k = max(k, nu + nconv)
+        k = min(k, w - 3)
+        k = max(k, 1)
+        V[:, :k] = V @ BVt[:k, :].T
+        V[:, k] = F
+        W[:, :k] = W @ BU[:, :k]
+        B[:] = 0.0
+        B[np.arange(k), np.arange(k)] = BS[:k]
+        B[:k, k] = res[:k]
+    if BU is None:
+        return IrlbaResult(np.zeros((m, nu)), np.zeros(nu), np.zeros((n, nu)), it, mprod, info)
+    U = W @ BU[:, :nu]
+    Vout = V @ BVt[:nu, :].T
+    return IrlbaResult(np.asfortranarray(U), BS[:nu].copy(), np.asfortranarray(Vout), it, mprod, info)
+
+
+# --------------------------------------------------------------------------------------
+# embedding.jl:46-76 _pca post-processing ; utils.jl:215-228 svd_flip!
+# --------------------------------------------------------------------------------------
+def pca_post(U, S, V, npcs, m):
+    """Z = U[:, :k] * Diagonal(S[:k]); stdev = S[:k] / sqrt(max(1, m-1)); loadings = V[:, :k]."""
+    Z = U[:, :npcs] * S[None, :npcs]
+    stdev = S[:npcs] / np.sqrt(max(1, m - 1))
+    return Z, stdev, V[:, :npcs]
+
+
+def svd_flip(U, V, u_based_decision=True):
+    """utils.jl:215-228: make the max-|.| entry of each U (or V) column positive."""
+    M = U if u_based_decision else V
+    idx = np.argmax(np.abs(M), axis=0)
+    signs = np.sign(M[idx, np.arange(M.shape[1])])
+    return U * signs[None, :], V * signs[None, :]
+
+
+def principal_angle(X, Y):
+    """Largest principal angle (radians) between span(X) and span(Y) (both n x k)."""
+    Qx, _ = np.linalg.qr(X)
+    Qy, _ = np.linalg.qr(Y)
+    # sin of the largest angle = ||(I - Qx Qx') Qy||_2 : accurate for small angles
+    R = Qy - Qx @ (Qx.T @ Qy)
+    return float(np.arcsin(min(1.0, np.linalg.norm(R, 2))))
