@@ -1,0 +1,187 @@
+/*
+ * severo_b200.h — C ABI of libsevero_b200.so: hand-written sm_100a CUDA kernels for the
+ * truncated-PCA hot path of ExaScience/Severo.jl (log-normalise -> per-gene moments ->
+ * centre/scale -> IRLBA on the implicit centred sparse operator).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ / torch types. It replaces
+ *   - the `ccall(("irlba", libcell), ...)` of src/irlba.jl:66-71 together with the two Julia
+ *     callbacks `matmul` (src/irlba.jl:23-38) and `randv` (src/irlba.jl:40-45): the mat-vec
+ *     now runs on the GPU inside svb_irlba, nothing calls back into the host language;
+ *   - the Julia loops of src/normalize.jl:17-38, src/scaling.jl:18-34,119-147,199-217,245-272
+ *     and src/variablefeatures.jl:19-28 (one entry point each, cited below).
+ * The reference-side bindings (Julia `ccall` overlay, Python ctypes) are shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - One process drives ONE GPU (svb_init(device)); N GPUs = N processes, each holding a
+ *     contiguous range of cells, joined by svb_comm_init (NCCL over NVLink).
+ *   - Matrices follow Severo's orientation: rows = cells, columns = genes, CSC (column = gene),
+ *     exactly the layout of `SparseMatrixCSC{T,Int64}` (src/Severo.jl:26-34). Index arrays may be
+ *     Julia's 1-based Int64 (index_base = 1) or 0-based.
+ *   - Dense arrays are column-major Float64 (Julia `Matrix{Float64}`).
+ *   - Every function returns 0 on success or a negative code; svb_last_error() gives the text.
+ *     Codes -1/-2/-3/-4 keep the meaning of the legacy `irlba` return value (src/irlba.jl:73
+ *     treats any non-zero as "convergence failed").
+ *   - Calls are synchronous for the caller; the library owns its CUDA stream (or uses the one
+ *     given to svb_set_stream). Not re-entrant; call from one host thread at a time.
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef SEVERO_B200_H
+#define SEVERO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+typedef struct svb_matrix_s *svb_matrix_t;     /* device-resident sparse matrix, CSC cells x genes */
+typedef struct svb_operator_s *svb_operator_t; /* implicit operator S = A - 1*mu' (scaling.jl:219-232) */
+typedef struct svb_result_s *svb_result_t;     /* device-resident U, s, V of one IRLBA solve */
+
+/* element types of host/device value arrays */
+#define SVB_I32 0
+#define SVB_I64 1
+#define SVB_F32 2
+#define SVB_F64 3
+
+/* return codes */
+#define SVB_OK 0
+#define SVB_EDIM (-1)       /* bad dimensions / arguments */
+#define SVB_ENOCONV (-2)    /* not converged within maxit */
+#define SVB_ENOMEM (-3)     /* out of (device) memory */
+#define SVB_ENULLSPACE (-4) /* starting vector (numerically) in the null space */
+#define SVB_EARG (-5)       /* invalid handle / enum / null pointer */
+#define SVB_ECUDA (-100)    /* CUDA runtime failure (also: no device) */
+#define SVB_ENCCL (-101)    /* NCCL failure / NCCL not loadable */
+
+/* normalisation methods (normalize.jl:41-50) */
+#define SVB_NORM_LOGNORMALIZE 0
+#define SVB_NORM_RELATIVECOUNTS 1
+
+/* ---- library / device -------------------------------------------------------------------- */
+int svb_init(int device);
+int svb_shutdown(void);
+const char *svb_last_error(void);
+const char *svb_version(void);
+int svb_set_stream(void *cuda_stream); /* NULL = library-owned stream */
+int svb_synchronize(void);
+int svb_device_info(int *sm_count, int64_t *total_mem, int *cc_major, int *cc_minor);
+
+/* per-kernel-class device timers (CUDA events on the launching stream). class ids below. */
+#define SVB_K_SPMV_FWD 0   /* S*v   (scaling.jl:245-250) */
+#define SVB_K_SPMV_ADJ 1   /* S'*w  (scaling.jl:252-257), incl. the partial reduce */
+#define SVB_K_REORTH 2     /* tall-skinny CGS passes (libcell `orthog`) */
+#define SVB_K_RESTART 3    /* W*P / V*Q restart + final GEMMs */
+#define SVB_K_VECTOR 4     /* norms / scales / small vector kernels */
+#define SVB_K_COMM 5       /* NCCL allreduce */
+#define SVB_K_NCLASS 6
+int svb_profile_enable(int on);
+int svb_profile_reset(void);
+/* ms[c], launches[c], bytes[c] (algorithmic bytes, SURVEY 8d formulas with this build's storage widths) */
+int svb_profile_get(double *ms, int64_t *launches, double *bytes);
+int64_t svb_launch_count(void); /* kernels launched by this library since init / last reset */
+int svb_launch_count_reset(void);
+
+/* ---- multi-GPU: one process per GPU, cells sharded, NCCL allreduce -------------------------- */
+int svb_comm_unique_id(unsigned char id[128]);
+int svb_comm_init(int nranks, int rank, const unsigned char id[128]);
+int svb_comm_destroy(void);
+int svb_comm_info(int *nranks, int *rank);
+int svb_comm_allreduce_f64(double *host_buf, int64_t n); /* sum over ranks, in place (host buffer) */
+
+/* ---- sparse matrices (CSC, cells x genes) ----------------------------------------------------- */
+/* Upload a SparseMatrixCSC. colptr: int64[ncol+1]. rowval: int32 or int64 (rowval_type), nzval:
+ * vtype in {I32,I64,F32,F64}. index_base 1 for Julia arrays. Int64 values are narrowed to int32 on
+ * the device (counts; overflow is an error), Float32 stays Float32, Float64 stays Float64. */
+int svb_csc_upload(int64_t nrow, int64_t ncol, const int64_t *colptr, const void *rowval,
+                   int rowval_type, const void *nzval, int vtype, int index_base,
+                   svb_matrix_t *out);
+int svb_matrix_free(svb_matrix_t a);
+int svb_matrix_info(svb_matrix_t a, int64_t *nrow, int64_t *ncol, int64_t *nnz, int *vtype);
+/* Download. Any of colptr/rowval/nzval may be NULL. Indices are written as int64 with index_base. */
+int svb_matrix_download(svb_matrix_t a, int64_t *colptr, int64_t *rowval, void *nzval, int vtype,
+                        int index_base);
+/* X[:, idx] (docs/src/pbmc.md:121; scaling.jl:339). idx in any order, duplicates allowed. */
+int svb_column_subset(svb_matrix_t a, const int64_t *idx, int64_t k, int index_base,
+                      svb_matrix_t *out);
+/* rows [row0, row1) of a (0-based, half-open): the cell shard of one rank. */
+int svb_row_slice(svb_matrix_t a, int64_t row0, int64_t row1, svb_matrix_t *out);
+/* copy(X') : stable transpose on the device (every reader of src/input.jl ends with it). */
+int svb_transpose(svb_matrix_t a, svb_matrix_t *out);
+
+/* ---- pre-processing sweeps ---------------------------------------------------------------- */
+/* normalize.jl:17-55  row_norm / log_norm. Integer counts in; dtype = SVB_F32 | SVB_F64 out.
+ * B = scale_factor * x / s_cell (one rounded multiply, one rounded divide), then log1p. */
+int svb_normalize(svb_matrix_t counts, int method, double scale_factor, int dtype,
+                  svb_matrix_t *out);
+/* normalize.jl:24 s = sum(A, dims=2): exact int64 library sizes (length nrow). With a communicator
+ * nothing is exchanged: a cell lives on one rank. */
+int svb_row_sums(svb_matrix_t counts, int64_t *s);
+/* scaling.jl:18-34,132-142 mean_var(A): order-exact sequential Welford per gene. */
+int svb_mean_var(svb_matrix_t a, double *mu, double *var);
+/* variablefeatures.jl:19-28 standardized_var_clipped (vmax <= 0 => sqrt(nrow)). */
+int svb_stdvar_clipped(svb_matrix_t counts, const double *mu, const double *sd, double vmax,
+                       double *out);
+/* scaling.jl:199-217 scale_data: out = min(x/std, scale_max + mu/std); mu_out = mean/std. */
+int svb_scale(svb_matrix_t a, double scale_max, int dtype, svb_matrix_t *out, double *mu_out);
+
+/* ---- the implicit centred operator (scaling.jl:219-272) -------------------------------------- */
+/* S = A - 1*mu' with A = a (transposed = 0) or A = a' (transposed = 1, the lazy Adjoint of
+ * test_irlba.jl:111). mu may be NULL (plain sparse matrix). Builds the two streaming layouts
+ * (row-major for S*v, cell-tiled gene-major for S'*w) on the device; `a` is not retained. */
+int svb_operator_create(svb_matrix_t a, const double *mu, int transposed, svb_operator_t *out);
+/* Dense column-major A (m x n, leading dimension lda >= m) for the StridedMatrix methods. */
+int svb_operator_create_dense(int64_t m, int64_t n, const double *a, int64_t lda, const double *mu,
+                              int transposed, svb_operator_t *out);
+int svb_operator_free(svb_operator_t op);
+int svb_operator_info(svb_operator_t op, int64_t *m, int64_t *n, int64_t *nnz, int *is_dense,
+                      int *value_bytes, int *index_bytes);
+/* mul!(C, S, v, alpha, beta) / mul!(C, S', v, alpha, beta), vector and k-column matrix forms
+ * (scaling.jl:245-272). trans = 'N' or 'T' (84, as the legacy matmul callback). Host buffers,
+ * column-major with leading dimension = vector length. The adjoint matrix form subtracts the
+ * rank-1 term (the reference's :271 adds it — untested sign slip). */
+int svb_mul(svb_operator_t op, char trans, double alpha, const double *x, double beta, double *y,
+            int64_t k);
+/* Device-pointer variant for benchmarking one product (x, y already in HBM). */
+int svb_mul_device(svb_operator_t op, char trans, double alpha, const double *dx, double beta,
+                   double *dy);
+
+/* ---- IRLBA (replaces libcell `irlba`, src/irlba.jl:66-71) -------------------------------------- */
+/* Same buffers and return convention as the legacy call: init[n] in; s[nu], U[m x nu], V[n x nu]
+ * out (column-major, caller-owned). m_b = work size (irlba.jl:50: nu+7, clamped to min(m,n)).
+ * restart > 0: the first `restart` columns/values of U, s, V are inputs (irlba.jl:93-98).
+ * With a communicator, m is the local number of cells and U the local rows; s and V are
+ * identical on all ranks. iter / mprod (optional) return restarts and mat-vec count. */
+int svb_irlba(svb_operator_t op, int64_t nu, int64_t m_b, int64_t maxit, int64_t restart,
+              double tol, double svtol, const double *init, double *s, double *U, double *V,
+              int64_t *iter, int64_t *mprod);
+/* Split form: solve leaving U, s, V on the device; download later (or never, for timing). */
+int svb_irlba_solve(svb_operator_t op, int64_t nu, int64_t m_b, int64_t maxit, int64_t restart,
+                    double tol, double svtol, const double *init, const double *s0,
+                    const double *U0, const double *V0, svb_result_t *out);
+int svb_result_info(svb_result_t r, int64_t *m, int64_t *n, int64_t *nu, int64_t *iter,
+                    int64_t *mprod, int *info);
+/* scale_u != 0 returns Z = U*Diagonal(s) (embedding.jl:67 coordinates) instead of U. */
+int svb_result_download(svb_result_t r, double *s, double *U, double *V, int scale_u);
+int svb_result_free(svb_result_t r);
+
+/* ---- synthetic count matrices (benchmark inputs; counter-based RNG, any shard reproducible) ---- */
+/* Poisson counts x_ij ~ Poisson(L_i * p_j * f_{c(i),j}), L_i log-normal, p_j gamma-shaped,
+ * K planted cell programs with fold-change `fold` on ~5% of genes each. Rows [row0,row1) of the
+ * m_total x genes matrix are generated (a rank's shard). Values int32. */
+int svb_synth_counts(int64_t m_total, int64_t genes, int64_t row0, int64_t row1,
+                     double mean_nnz_per_cell, int64_t programs, double fold, uint64_t seed,
+                     svb_matrix_t *out);
+/* standard-normal vector from the same counter-based generator (IRLBA init). */
+int svb_synth_normal(int64_t n, uint64_t seed, double *host_out);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEVERO_B200_H */

@@ -1,0 +1,239 @@
+// core.cu — library context, error reporting, per-class device timers, device prefix scan.
+#include "svb_internal.h"
+
+#include <cstring>
+#include <mutex>
+
+namespace svb {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string &msg) { g_last_error = msg; }
+
+Context &ctx() {
+    static Context c;
+    return c;
+}
+
+void require_init() {
+    if (!ctx().initialised)
+        throw Error(SVB_ECUDA, "svb_init has not been called (or no CUDA device): there is no CPU fallback");
+}
+
+void count_launch(int n) { ctx().launches += n; }
+
+KTimer::KTimer(int c, double algorithmic_bytes, int nlaunch) : cls(c), bytes(algorithmic_bytes) {
+    Context &C = ctx();
+    C.launches += nlaunch;
+    if (C.profile) {
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, C.stream);
+    }
+    if (c >= 0 && c < SVB_K_NCLASS) {
+        C.prof_launches[c] += nlaunch;
+        C.prof_bytes[c] += algorithmic_bytes;
+    }
+}
+
+KTimer::~KTimer() {
+    Context &C = ctx();
+    if (e0) {
+        cudaEventRecord(e1, C.stream);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (cls >= 0 && cls < SVB_K_NCLASS) C.prof_ms[cls] += ms;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exclusive scan (int64, in place). Three passes: per-block scan + block totals, scan of the
+// totals (recursive), add offsets. 1024 threads x 4 items per block.
+// ---------------------------------------------------------------------------------------------
+constexpr int SCAN_T = 1024;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_BLOCK = SCAN_T * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(SCAN_T) scan_block_kernel(int64_t *data, int64_t n, int64_t *block_sums) {
+    __shared__ int64_t warp_tot[32];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK + (int64_t)threadIdx.x * SCAN_ITEMS;
+    int64_t v[SCAN_ITEMS];
+    int64_t tsum = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        v[i] = (base + i < n) ? data[base + i] : 0;
+        tsum += v[i];
+    }
+    // inclusive scan of tsum across the block
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int64_t x = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        int64_t w = warp_tot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int64_t y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += y;
+        }
+        warp_tot[lane] = w;
+    }
+    __syncthreads();
+    int64_t excl = x - tsum + (wid > 0 ? warp_tot[wid - 1] : 0);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < n) data[base + i] = excl;
+        excl += v[i];
+    }
+    if (threadIdx.x == SCAN_T - 1 && block_sums) block_sums[blockIdx.x] = excl;
+}
+
+__global__ void scan_add_kernel(int64_t *data, int64_t n, const int64_t *block_offs) {
+    const int64_t i = (int64_t)blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    const int64_t off = block_offs[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        int64_t idx = i + (int64_t)k * SCAN_T;
+        if (idx < n) data[idx] += off;
+    }
+}
+
+void exclusive_scan_i64(int64_t *d, int64_t n, cudaStream_t st) {
+    if (n <= 0) return;
+    const int64_t nblk = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    if (nblk == 1) {
+        scan_block_kernel<<<1, SCAN_T, 0, st>>>(d, n, nullptr);
+        count_launch();
+        SVB_CUDA(cudaGetLastError());
+        return;
+    }
+    DevBuf<int64_t> sums((size_t)nblk);
+    scan_block_kernel<<<(unsigned)nblk, SCAN_T, 0, st>>>(d, n, sums.p);
+    count_launch();
+    SVB_CUDA(cudaGetLastError());
+    exclusive_scan_i64(sums.p, nblk, st);
+    scan_add_kernel<<<(unsigned)nblk, SCAN_T, 0, st>>>(d, n, sums.p);
+    count_launch();
+    SVB_CUDA(cudaGetLastError());
+    SVB_CUDA(cudaStreamSynchronize(st));  // sums freed on return
+}
+
+}  // namespace svb
+
+using namespace svb;
+
+extern "C" {
+
+const char *svb_last_error(void) { return g_last_error.c_str(); }
+const char *svb_version(void) { return "severo_b200 0.1 (sm_100a)"; }
+
+int svb_init(int device) {
+    SVB_API_BEGIN
+    Context &C = ctx();
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        throw Error(SVB_ECUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                                   "); libsevero_b200 has no CPU fallback");
+    SVB_CHECK(device >= 0 && device < ndev, SVB_EARG, "svb_init: device index out of range");
+    SVB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp p;
+    SVB_CUDA(cudaGetDeviceProperties(&p, device));
+    C.device = device;
+    C.sm_count = p.multiProcessorCount;
+    C.smem_optin = p.sharedMemPerBlockOptin;
+    if (!C.stream) {
+        SVB_CUDA(cudaStreamCreateWithFlags(&C.stream, cudaStreamNonBlocking));
+        C.own_stream = true;
+    }
+    C.initialised = true;
+    SVB_API_END
+}
+
+int svb_shutdown(void) {
+    SVB_API_BEGIN
+    Context &C = ctx();
+    if (C.initialised) {
+        cudaDeviceSynchronize();
+        if (C.own_stream && C.stream) cudaStreamDestroy(C.stream);
+        C.stream = nullptr;
+        C.own_stream = false;
+        C.initialised = false;
+    }
+    SVB_API_END
+}
+
+int svb_set_stream(void *s) {
+    SVB_API_BEGIN
+    require_init();
+    Context &C = ctx();
+    SVB_CUDA(cudaStreamSynchronize(C.stream));
+    if (C.own_stream && C.stream) cudaStreamDestroy(C.stream);
+    if (s) {
+        C.stream = (cudaStream_t)s;
+        C.own_stream = false;
+    } else {
+        SVB_CUDA(cudaStreamCreateWithFlags(&C.stream, cudaStreamNonBlocking));
+        C.own_stream = true;
+    }
+    SVB_API_END
+}
+
+int svb_synchronize(void) {
+    SVB_API_BEGIN
+    require_init();
+    SVB_CUDA(cudaStreamSynchronize(ctx().stream));
+    SVB_API_END
+}
+
+int svb_device_info(int *sm_count, int64_t *total_mem, int *cc_major, int *cc_minor) {
+    SVB_API_BEGIN
+    require_init();
+    cudaDeviceProp p;
+    SVB_CUDA(cudaGetDeviceProperties(&p, ctx().device));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (total_mem) *total_mem = (int64_t)p.totalGlobalMem;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    SVB_API_END
+}
+
+int svb_profile_enable(int on) {
+    ctx().profile = on != 0;
+    return SVB_OK;
+}
+
+int svb_profile_reset(void) {
+    Context &C = ctx();
+    for (int i = 0; i < SVB_K_NCLASS; ++i) {
+        C.prof_ms[i] = 0;
+        C.prof_launches[i] = 0;
+        C.prof_bytes[i] = 0;
+    }
+    return SVB_OK;
+}
+
+int svb_profile_get(double *ms, int64_t *launches, double *bytes) {
+    Context &C = ctx();
+    for (int i = 0; i < SVB_K_NCLASS; ++i) {
+        if (ms) ms[i] = C.prof_ms[i];
+        if (launches) launches[i] = C.prof_launches[i];
+        if (bytes) bytes[i] = C.prof_bytes[i];
+    }
+    return SVB_OK;
+}
+
+int64_t svb_launch_count(void) { return ctx().launches; }
+int svb_launch_count_reset(void) {
+    ctx().launches = 0;
+    return SVB_OK;
+}
+
+}  // extern "C"

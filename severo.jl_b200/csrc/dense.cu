@@ -1,0 +1,379 @@
+// dense.cu — tall-skinny fp64 kernels of the Lanczos bidiagonalisation (the BLAS-2/3 part of
+// libcell's irlba, call site src/irlba.jl:66-71): classical Gram-Schmidt reorthogonalisation
+// (t = X'y ; y -= X t), norms / normalisation, and the restart / final products W*P, V*Q.
+// All of them are HBM-bound streams over the m x w basis; reductions are two-stage with a
+// last-block pass in a fixed order, so every result is run-to-run deterministic.
+#include "svb_internal.h"
+
+#include <algorithm>
+
+namespace svb {
+
+// ---- persistent scratch for two-stage reductions ----------------------------------------------
+struct Scratch {
+    double *partials = nullptr;
+    size_t cap = 0;
+    unsigned int *counters = nullptr;
+    size_t ncounters = 0;
+};
+static Scratch g_scr;
+
+static void scratch_reserve(size_t ndoubles, size_t ncounters) {
+    cudaStream_t st = ctx().stream;
+    if (ndoubles > g_scr.cap) {
+        SVB_CUDA(cudaStreamSynchronize(st));
+        if (g_scr.partials) cudaFree(g_scr.partials);
+        g_scr.cap = std::max<size_t>(ndoubles, 1u << 16);
+        SVB_CUDA(cudaMalloc((void **)&g_scr.partials, g_scr.cap * sizeof(double)));
+    }
+    if (ncounters > g_scr.ncounters) {
+        SVB_CUDA(cudaStreamSynchronize(st));
+        if (g_scr.counters) cudaFree(g_scr.counters);
+        g_scr.ncounters = std::max<size_t>(ncounters, 4096);
+        SVB_CUDA(cudaMalloc((void **)&g_scr.counters, g_scr.ncounters * sizeof(unsigned int)));
+        SVB_CUDA(cudaMemsetAsync(g_scr.counters, 0, g_scr.ncounters * sizeof(unsigned int), st));
+    }
+}
+
+constexpr int CT = 8;        // columns per CTA in gemv_t
+constexpr int TS_THREADS = 256;
+constexpr int TS_RPT = 4;    // rows per thread per sweep
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// t[c] = sum_i X[i + c*ld] * y[i].  grid (nrb, ceil(j/CT)).
+__global__ void __launch_bounds__(TS_THREADS) ts_gemv_t_kernel(const double *__restrict__ X, int64_t ld, int64_t L, int j,
+                                                               const double *__restrict__ y, double *__restrict__ t,
+                                                               double *__restrict__ partials, unsigned int *counters) {
+    __shared__ double sh[TS_THREADS / 32][CT];
+    __shared__ bool is_last;
+    const int c0 = blockIdx.y * CT;
+    const int nc = min(CT, j - c0);
+    double acc[CT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) acc[c] = 0.0;
+    const int64_t chunk = (int64_t)TS_THREADS * TS_RPT;
+    for (int64_t base = (int64_t)blockIdx.x * chunk; base < L; base += (int64_t)gridDim.x * chunk) {
+#pragma unroll
+        for (int r = 0; r < TS_RPT; ++r) {
+            const int64_t i = base + (int64_t)r * TS_THREADS + threadIdx.x;
+            if (i < L) {
+                const double yv = y[i];
+                const double *xp = X + i + (int64_t)c0 * ld;
+#pragma unroll
+                for (int c = 0; c < CT; ++c)
+                    if (c < nc) acc[c] = fma(__ldg(xp + (int64_t)c * ld), yv, acc[c]);
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+        const double s = warp_sum(acc[c]);
+        if (lane == 0) sh[wid][c] = s;
+    }
+    __syncthreads();
+    double *mypart = partials + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * CT;
+    if (threadIdx.x < CT) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < TS_THREADS / 32; ++w) s += sh[w][threadIdx.x];
+        mypart[threadIdx.x] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int ticket = atomicAdd(&counters[blockIdx.y], 1u);
+        is_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        // warp `wid` sums column `wid` over all row blocks in a fixed order
+        if (wid < nc) {
+            const double *p = partials + (size_t)blockIdx.y * gridDim.x * CT + wid;
+            double s = 0.0;
+            for (unsigned int b = lane; b < gridDim.x; b += 32) s += __ldcg(p + (size_t)b * CT);
+            s = warp_sum(s);
+            if (lane == 0) t[c0 + wid] = s;
+        }
+        if (threadIdx.x == 0) counters[blockIdx.y] = 0u;
+    }
+}
+
+// y[i] = beta*y[i] + alpha * sum_c X[i + c*ld] * t[c] ; optional nrm2_out = sum_i y[i]^2
+__global__ void __launch_bounds__(TS_THREADS) ts_gemv_n_kernel(const double *__restrict__ X, int64_t ld, int64_t L, int j,
+                                                               const double *__restrict__ t, double alpha, double beta,
+                                                               double *__restrict__ y, double *__restrict__ nrm2_out,
+                                                               double *__restrict__ partials, unsigned int *counter) {
+    __shared__ double sh[TS_THREADS / 32];
+    __shared__ bool is_last;
+    double ss = 0.0;
+    const int64_t chunk = (int64_t)TS_THREADS * 2;
+    for (int64_t base = (int64_t)blockIdx.x * chunk; base < L; base += (int64_t)gridDim.x * chunk) {
+        const int64_t i0 = base + threadIdx.x, i1 = i0 + TS_THREADS;
+        const bool v0 = i0 < L, v1 = i1 < L;
+        double a0 = 0.0, a1 = 0.0;
+        int c = 0;
+        for (; c + 4 <= j; c += 4) {
+            const double t0 = __ldg(t + c), t1 = __ldg(t + c + 1), t2 = __ldg(t + c + 2), t3 = __ldg(t + c + 3);
+            const double *xp = X + (int64_t)c * ld;
+            if (v0) {
+                const double x0 = __ldg(xp + i0), x1 = __ldg(xp + ld + i0), x2 = __ldg(xp + 2 * ld + i0), x3 = __ldg(xp + 3 * ld + i0);
+                a0 = fma(x0, t0, a0); a0 = fma(x1, t1, a0); a0 = fma(x2, t2, a0); a0 = fma(x3, t3, a0);
+            }
+            if (v1) {
+                const double x0 = __ldg(xp + i1), x1 = __ldg(xp + ld + i1), x2 = __ldg(xp + 2 * ld + i1), x3 = __ldg(xp + 3 * ld + i1);
+                a1 = fma(x0, t0, a1); a1 = fma(x1, t1, a1); a1 = fma(x2, t2, a1); a1 = fma(x3, t3, a1);
+            }
+        }
+        for (; c < j; ++c) {
+            const double tc = __ldg(t + c);
+            if (v0) a0 = fma(__ldg(X + (int64_t)c * ld + i0), tc, a0);
+            if (v1) a1 = fma(__ldg(X + (int64_t)c * ld + i1), tc, a1);
+        }
+        if (v0) {
+            double r = alpha * a0;
+            if (beta != 0.0) r = fma(beta, y[i0], r);
+            y[i0] = r;
+            ss = fma(r, r, ss);
+        }
+        if (v1) {
+            double r = alpha * a1;
+            if (beta != 0.0) r = fma(beta, y[i1], r);
+            y[i1] = r;
+            ss = fma(r, r, ss);
+        }
+    }
+    if (nrm2_out == nullptr) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    ss = warp_sum(ss);
+    if (lane == 0) sh[wid] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < TS_THREADS / 32; ++w) s += sh[w];
+        partials[blockIdx.x] = s;
+        __threadfence();
+        const unsigned int ticket = atomicAdd(counter, 1u);
+        is_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last && wid == 0) {
+        __threadfence();
+        double s = 0.0;
+        for (unsigned int b = lane; b < gridDim.x; b += 32) s += __ldcg(partials + b);
+        s = warp_sum(s);
+        if (lane == 0) {
+            *nrm2_out = s;
+            *counter = 0u;
+        }
+    }
+}
+
+static int row_blocks(int64_t L, int64_t rows_per_cta, int max_per_sm) {
+    const int64_t need = (L + rows_per_cta - 1) / rows_per_cta;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)ctx().sm_count * max_per_sm));
+}
+
+void ts_gemv_t(const double *X, int64_t ld, int64_t L, int j, const double *y, double *t, int cls) {
+    if (j <= 0) return;
+    const int ctiles = (j + CT - 1) / CT;
+    // keep the total CTA count near 4 waves regardless of the number of column tiles
+    int nrb = row_blocks(L, TS_THREADS * TS_RPT, std::max(1, 8 / std::min(ctiles, 8)) * 2);
+    scratch_reserve((size_t)ctiles * nrb * CT + 4096, (size_t)ctiles + 8);
+    KTimer kt(cls, 8.0 * ((double)L * j + (double)L * ((j + CT - 1) / CT)));
+    dim3 grid((unsigned)nrb, (unsigned)ctiles);
+    ts_gemv_t_kernel<<<grid, TS_THREADS, 0, ctx().stream>>>(X, ld, L, j, y, t, g_scr.partials + 4096, g_scr.counters + 8);
+    SVB_LAUNCH_CHECK();
+}
+
+void ts_gemv_n(const double *X, int64_t ld, int64_t L, int j, const double *t, double alpha, double beta, double *y,
+               double *nrm2_out, int cls) {
+    const int nrb = row_blocks(L, TS_THREADS * 2, 8);
+    scratch_reserve(4096 + 64, 8);
+    KTimer kt(cls, 8.0 * ((double)L * j + 2.0 * L));
+    ts_gemv_n_kernel<<<(unsigned)nrb, TS_THREADS, 0, ctx().stream>>>(X, ld, L, j, t, alpha, beta, y, nrm2_out, g_scr.partials,
+                                                                     g_scr.counters);
+    SVB_LAUNCH_CHECK();
+}
+
+// ---- restart / final products: out[:, 0..k) = X[:, 0..w) * P[0..w, 0..k) (* colscale) --------------
+constexpr int GM_THREADS = 128;
+constexpr int GM_CC = 8;
+
+__global__ void __launch_bounds__(GM_THREADS) ts_gemm_kernel(const double *__restrict__ X, int64_t ld, int64_t L, int w,
+                                                             const double *__restrict__ P, int ldp, int k, int kp,
+                                                             double *__restrict__ out, int64_t ldo,
+                                                             const double *__restrict__ colscale) {
+    extern __shared__ double Ps[];  // [w][kp], zero padded
+    for (int idx = threadIdx.x; idx < w * kp; idx += blockDim.x) {
+        const int l = idx / kp, c = idx - l * kp;
+        double v = (c < k) ? P[l + (int64_t)c * ldp] : 0.0;
+        if (colscale && c < k) v *= colscale[c];
+        Ps[idx] = v;
+    }
+    __syncthreads();
+    const int64_t i0 = (int64_t)blockIdx.x * (GM_THREADS * 2) + threadIdx.x;
+    const int64_t i1 = i0 + GM_THREADS;
+    const bool v0 = i0 < L, v1 = i1 < L;
+    const int64_t j0 = v0 ? i0 : 0, j1 = v1 ? i1 : 0;
+    for (int c0 = 0; c0 < kp; c0 += GM_CC) {
+        double a0[GM_CC], a1[GM_CC];
+#pragma unroll
+        for (int c = 0; c < GM_CC; ++c) { a0[c] = 0.0; a1[c] = 0.0; }
+#pragma unroll 2
+        for (int l = 0; l < w; ++l) {
+            const double x0 = __ldg(X + (int64_t)l * ld + j0);
+            const double x1 = __ldg(X + (int64_t)l * ld + j1);
+            const double2 *pp = reinterpret_cast<const double2 *>(Ps + l * kp + c0);
+#pragma unroll
+            for (int c = 0; c < GM_CC / 2; ++c) {
+                const double2 p = pp[c];
+                a0[2 * c] = fma(x0, p.x, a0[2 * c]);
+                a0[2 * c + 1] = fma(x0, p.y, a0[2 * c + 1]);
+                a1[2 * c] = fma(x1, p.x, a1[2 * c]);
+                a1[2 * c + 1] = fma(x1, p.y, a1[2 * c + 1]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < GM_CC; ++c) {
+            if (c0 + c < k) {
+                if (v0) out[i0 + (int64_t)(c0 + c) * ldo] = a0[c];
+                if (v1) out[i1 + (int64_t)(c0 + c) * ldo] = a1[c];
+            }
+        }
+    }
+}
+
+void ts_gemm(const double *X, int64_t ld, int64_t L, int w, const double *P, int ldp, int k, double *out, int64_t ldo,
+             const double *colscale_dev) {
+    if (k <= 0 || L <= 0) return;
+    const int kp = (k + GM_CC - 1) / GM_CC * GM_CC;
+    const size_t smem = (size_t)w * kp * sizeof(double);
+    SVB_CHECK(smem <= ctx().smem_optin, SVB_EDIM, "restart product: work size too large for shared memory");
+    if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(ts_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t grid = (L + GM_THREADS * 2 - 1) / (GM_THREADS * 2);
+    KTimer kt(SVB_K_RESTART, 8.0 * ((double)L * w + (double)L * k));
+    ts_gemm_kernel<<<(unsigned)grid, GM_THREADS, smem, ctx().stream>>>(X, ld, L, w, P, ldp, k, kp, out, ldo, colscale_dev);
+    SVB_LAUNCH_CHECK();
+}
+
+// ---- vector kernels --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TS_THREADS) sumsq_kernel(const double *__restrict__ x, int64_t L, double *out, double *partials,
+                                                           unsigned int *counter) {
+    __shared__ double sh[TS_THREADS / 32];
+    __shared__ bool is_last;
+    double ss = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = x[i];
+        ss = fma(v, v, ss);
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    ss = warp_sum(ss);
+    if (lane == 0) sh[wid] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < TS_THREADS / 32; ++w) s += sh[w];
+        partials[blockIdx.x] = s;
+        __threadfence();
+        is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last && wid == 0) {
+        __threadfence();
+        double s = 0.0;
+        for (unsigned int b = lane; b < gridDim.x; b += 32) s += __ldcg(partials + b);
+        s = warp_sum(s);
+        if (lane == 0) {
+            *out = s;
+            *counter = 0u;
+        }
+    }
+}
+
+void vec_sumsq(const double *x, int64_t L, double *out) {
+    const int nrb = row_blocks(L, TS_THREADS * 4, 4);
+    scratch_reserve(4096 + 64, 8);
+    KTimer kt(SVB_K_VECTOR, 8.0 * L);
+    sumsq_kernel<<<(unsigned)nrb, TS_THREADS, 0, ctx().stream>>>(x, L, out, g_scr.partials, g_scr.counters + 1);
+    SVB_LAUNCH_CHECK();
+}
+
+__global__ void normalize_kernel(const double *__restrict__ x, int64_t L, const double *__restrict__ nrm2, double *__restrict__ y,
+                                 double *norm_out, int *flag, double eps) {
+    const double nrm = sqrt(*nrm2);
+    const double inv = 1.0 / nrm;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += (int64_t)gridDim.x * blockDim.x) y[i] = x[i] * inv;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (norm_out) *norm_out = nrm;
+        if (flag && !(nrm >= eps)) *flag = 1;
+    }
+}
+
+void vec_normalize(const double *x, int64_t L, const double *nrm2_dev, double *y, double *norm_out, int *flag_dev, double eps) {
+    const int nrb = row_blocks(L, 256 * 4, 8);
+    KTimer kt(SVB_K_VECTOR, 16.0 * L);
+    normalize_kernel<<<(unsigned)nrb, 256, 0, ctx().stream>>>(x, L, nrm2_dev, y, norm_out, flag_dev, eps);
+    SVB_LAUNCH_CHECK();
+}
+
+void vec_copy(const double *x, int64_t L, double *y) {
+    SVB_CUDA(cudaMemcpyAsync(y, x, (size_t)L * sizeof(double), cudaMemcpyDeviceToDevice, ctx().stream));
+}
+
+// ---- counter-based normals (Philox4x32-10 + Box-Muller) ----------------------------------------------
+__device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                           uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        const uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__global__ void fill_normal_kernel(double *x, int64_t L, uint64_t seed, uint64_t offset) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t ctr = (uint64_t)i + offset;
+        uint32_t r[4];
+        philox4x32((uint32_t)ctr, (uint32_t)(ctr >> 32), 0x5eed0001u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+        const double u1 = ((double)(((uint64_t)r[0] << 21) ^ (r[1] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);  // (0,1)
+        const double u2 = ((double)(((uint64_t)r[2] << 21) ^ (r[3] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+        x[i] = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    }
+}
+
+void vec_fill_normal(double *x, int64_t L, uint64_t seed, uint64_t offset) {
+    const int nrb = row_blocks(L, 256, 8);
+    KTimer kt(SVB_K_VECTOR, 8.0 * L);
+    fill_normal_kernel<<<(unsigned)nrb, 256, 0, ctx().stream>>>(x, L, seed, offset);
+    SVB_LAUNCH_CHECK();
+}
+
+}  // namespace svb
+
+extern "C" int svb_synth_normal(int64_t n, uint64_t seed, double *host_out) {
+    SVB_API_BEGIN
+    svb::require_init();
+    SVB_CHECK(host_out && n >= 0, SVB_EARG, "svb_synth_normal: bad argument");
+    svb::DevBuf<double> d((size_t)std::max<int64_t>(n, 1));
+    svb::vec_fill_normal(d.p, n, seed, 0);
+    SVB_CUDA(cudaMemcpyAsync(host_out, d.p, (size_t)n * 8, cudaMemcpyDeviceToHost, svb::ctx().stream));
+    SVB_CUDA(cudaStreamSynchronize(svb::ctx().stream));
+    SVB_API_END
+}

@@ -1,0 +1,345 @@
+// irlba.cu — device-resident implicitly restarted Lanczos bidiagonalisation (IRLBA).
+// Replaces the external `libcell.irlba` reached from src/irlba.jl:66-71 (and with it the Julia
+// callbacks matmul/randv of src/irlba.jl:23-45: the operator products run on the GPU, nothing calls
+// back into the host language). Algorithm: Baglama & Reichel's IRLBA as in B. W. Lewis' irlb.c, from
+// which libcell derives (same signature / defaults: work = nu+7, tol = 1e-5, maxit = 1000); the loop
+// is the one restated in SURVEY.md 8(c). libcell itself is un-vendored and un-pinned, so iterates are
+// "parity unpinned"; converged results are pinned by test/test_irlba.jl's criteria.
+//
+// Execution model: V (n x w, replicated), W (m x w, cell-sharded), F, the bidiagonal entries and all
+// norms stay in HBM. One Lanczos sweep is a host-sync-free sequence of kernels (norms are consumed
+// from device scalars); the host reads the w diagonal / super-diagonal entries once per sweep, does
+// the w x w SVD (small_svd.cpp) and the convergence test, and uploads the rotation for the restart
+// product. A breakdown flag set by any normalisation makes the host redo that sweep in "careful"
+// mode (norm checked on the host after every step, random restart vector from the device RNG).
+#include "svb_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+using namespace svb;
+
+svb_result_s::~svb_result_s() {
+    if (U) cudaFree(U);
+    if (s) cudaFree(s);
+    if (V) cudaFree(V);
+}
+
+namespace svb {
+
+static const double EPS23 = std::pow(2.220446049250313e-16, 2.0 / 3.0);
+
+struct Solver {
+    svb_operator_s *op;
+    int64_t m, n;
+    int w, nu;
+    cudaStream_t st;
+    DevBuf<double> V, V2, W, W2, F, T, Pd, Qd, Bd, Bs, sc;
+    DevBuf<int> flag;
+    bool careful = false;
+    int64_t mprod = 0;
+    uint64_t rng_calls = 0;
+
+    double *Vc(int c) { return V.p + (int64_t)c * n; }
+    double *Wc(int c) { return W.p + (int64_t)c * m; }
+    double *nrm2W() { return sc.p + 0; }
+    double *nrm2F() { return sc.p + 1; }
+
+    double d2h(const double *p) {
+        double v;
+        SVB_CUDA(cudaMemcpyAsync(&v, p, sizeof(double), cudaMemcpyDeviceToHost, st));
+        SVB_CUDA(cudaStreamSynchronize(st));
+        return v;
+    }
+
+    // classical Gram-Schmidt of x (length L) against the first j columns of X; *nrm2 = |x|^2 after.
+    void orthog(const double *X, int64_t L, int j, double *x, double *nrm2, bool sharded) {
+        if (j > 0) {
+            ts_gemv_t(X, L, L, j, x, T.p, SVB_K_REORTH);
+            if (sharded) comm_allreduce_dev(T.p, j);
+            ts_gemv_n(X, L, L, j, T.p, -1.0, 1.0, x, nrm2, SVB_K_REORTH);
+        } else {
+            vec_sumsq(x, L, nrm2);
+        }
+        if (sharded) comm_allreduce_dev(nrm2, 1);
+    }
+
+    // x (|x|^2 in *nrm2) -> out = x/|x| ; |x| -> *slot. Returns false on an unrecoverable state.
+    // careful mode: a tiny norm is replaced by a fresh random direction orthogonal to X[:, :j], slot = 0.
+    void finish(const double *X, int64_t L, int j, double *x, double *nrm2, double *out, double *slot, bool sharded,
+                bool *tiny) {
+        if (tiny) *tiny = false;
+        if (careful) {
+            const double nrm = std::sqrt(d2h(nrm2));
+            if (!(nrm >= EPS23)) {
+                if (tiny) *tiny = true;
+                const uint64_t off = ((uint64_t)(sharded ? ctx().rank : 0) << 40) + ((++rng_calls) << 48);
+                vec_fill_normal(out, L, 0x5e7e70b200ull, off);
+                double *tmpn = sc.p + 2;
+                orthog(X, L, j, out, tmpn, sharded);
+                vec_normalize(out, L, tmpn, out, nullptr, nullptr, 0.0);
+                SVB_CUDA(cudaMemsetAsync(slot, 0, sizeof(double), st));
+                return;
+            }
+        }
+        vec_normalize(x, L, nrm2, out, slot, flag.p, EPS23);
+    }
+};
+
+static void irlba_run(svb_operator_s *op, int64_t nu_, int64_t work_, int64_t maxit, int64_t restart, double tol, double svtol,
+                      const double *init, const double *s0, const double *U0, const double *V0, svb_result_s *res) {
+    Context &C = ctx();
+    Solver S;
+    S.op = op;
+    S.m = op->m;
+    S.n = op->n;
+    S.st = C.stream;
+    const int64_t m = S.m, n = S.n;
+    // global row count decides the work-size clamp (irlba.jl:56-58 uses min(m, n) of the whole matrix)
+    double mglob = (double)m;
+    if (C.nranks > 1) {
+        DevBuf<double> d(1);
+        SVB_CUDA(cudaMemcpyAsync(d.p, &mglob, 8, cudaMemcpyHostToDevice, S.st));
+        comm_allreduce_dev(d.p, 1);
+        SVB_CUDA(cudaMemcpyAsync(&mglob, d.p, 8, cudaMemcpyDeviceToHost, S.st));
+        SVB_CUDA(cudaStreamSynchronize(S.st));
+    }
+    const int64_t minmn = std::min<int64_t>((int64_t)mglob, n);
+    SVB_CHECK(nu_ >= 1 && nu_ <= minmn, SVB_EDIM, "irlba: nu must satisfy 1 <= nu <= min(m, n)");
+    int64_t work = work_ > 0 ? work_ : nu_ + 7;
+    if (work < nu_) work = nu_ + 1;
+    if (work > minmn) work = minmn;
+    SVB_CHECK(work >= nu_, SVB_EDIM, "irlba: work size smaller than nu");
+    SVB_CHECK(restart >= 0 && restart < work, SVB_EDIM, "irlba: restart must be < work");
+    SVB_CHECK(maxit >= 1, SVB_EDIM, "irlba: maxit must be >= 1");
+    const int w = (int)work, nu = (int)nu_;
+    S.w = w;
+    S.nu = nu;
+    S.V.alloc((size_t)n * w);
+    S.V2.alloc((size_t)n * w);
+    S.W.alloc((size_t)m * w);
+    S.W2.alloc((size_t)m * w);
+    S.F.alloc((size_t)n);
+    S.T.alloc((size_t)w + 8);
+    S.Pd.alloc((size_t)w * w);
+    S.Qd.alloc((size_t)w * w);
+    S.Bd.alloc((size_t)w);
+    S.Bs.alloc((size_t)w);
+    S.sc.alloc(8);
+    S.flag.alloc(1);
+    SVB_CUDA(cudaMemsetAsync(S.flag.p, 0, sizeof(int), S.st));
+    SVB_CUDA(cudaMemsetAsync(S.Bd.p, 0, w * sizeof(double), S.st));
+    SVB_CUDA(cudaMemsetAsync(S.Bs.p, 0, w * sizeof(double), S.st));
+
+    std::vector<double> B((size_t)w * w, 0.0), P((size_t)w * w), Q((size_t)w * w), sig(w), sig_prev(w, 0.0), resid(w);
+    std::vector<double> hBd(w), hBs(w);
+    int k = (int)restart;
+    // start vector(s)
+    SVB_CUDA(cudaMemcpyAsync(S.F.p, init, (size_t)n * 8, cudaMemcpyHostToDevice, S.st));
+    vec_sumsq(S.F.p, n, S.nrm2F());
+    if (k > 0) {
+        SVB_CHECK(s0 && U0 && V0, SVB_EARG, "irlba: restart > 0 needs s, U, V inputs");
+        SVB_CUDA(cudaMemcpyAsync(S.V.p, V0, (size_t)n * k * 8, cudaMemcpyHostToDevice, S.st));
+        SVB_CUDA(cudaMemcpyAsync(S.W.p, U0, (size_t)m * k * 8, cudaMemcpyHostToDevice, S.st));
+        for (int i = 0; i < k; ++i) B[(size_t)i * w + i] = s0[i];
+    }
+    vec_normalize(S.F.p, n, S.nrm2F(), S.Vc(k), nullptr, nullptr, 0.0);
+
+    double smax = 0.0;
+    int64_t iter = 0;
+    int info = SVB_ENOCONV;
+    bool have_svd = false;
+    while (iter < maxit) {
+        int j = (iter > 0 || restart > 0) ? k : 0;
+        const int j0 = j;
+        bool tiny = false;
+        // W_j = S*V_j ; orthogonalise against the kept W ; normalise
+        op_apply(op, false, 1.0, S.Vc(j), 0.0, S.Wc(j));
+        S.mprod++;
+        S.orthog(S.W.p, m, j, S.Wc(j), S.nrm2W(), true);
+        S.finish(S.W.p, m, j, S.Wc(j), S.nrm2W(), S.Wc(j), S.Bd.p + j, true, &tiny);
+        if (tiny && iter == 0 && j == 0) {
+            info = SVB_ENULLSPACE;
+            break;
+        }
+        while (j < w) {
+            // F = S'*W_j - s*V_j ; orthogonalise against V[:, :j+1]
+            op_apply(op, true, 1.0, S.Wc(j), 0.0, S.F.p, S.Bd.p + j, -1.0, S.Vc(j));
+            S.mprod++;
+            S.orthog(S.V.p, n, j + 1, S.F.p, S.nrm2F(), false);
+            if (j + 1 < w) {
+                S.finish(S.V.p, n, j + 1, S.F.p, S.nrm2F(), S.Vc(j + 1), S.Bs.p + j, false, nullptr);
+                // W_{j+1} = S*V_{j+1} - r*W_j ; orthogonalise against W[:, :j+1]
+                op_apply(op, false, 1.0, S.Vc(j + 1), 0.0, S.Wc(j + 1), S.Bs.p + j, -1.0, S.Wc(j));
+                S.mprod++;
+                S.orthog(S.W.p, m, j + 1, S.Wc(j + 1), S.nrm2W(), true);
+                S.finish(S.W.p, m, j + 1, S.Wc(j + 1), S.nrm2W(), S.Wc(j + 1), S.Bd.p + j + 1, true, nullptr);
+            }
+            ++j;
+        }
+        // one host round trip per sweep
+        int hflag = 0;
+        double nF2 = 0.0;
+        SVB_CUDA(cudaMemcpyAsync(hBd.data(), S.Bd.p, w * 8, cudaMemcpyDeviceToHost, S.st));
+        SVB_CUDA(cudaMemcpyAsync(hBs.data(), S.Bs.p, w * 8, cudaMemcpyDeviceToHost, S.st));
+        SVB_CUDA(cudaMemcpyAsync(&nF2, S.nrm2F(), 8, cudaMemcpyDeviceToHost, S.st));
+        SVB_CUDA(cudaMemcpyAsync(&hflag, S.flag.p, sizeof(int), cudaMemcpyDeviceToHost, S.st));
+        SVB_CUDA(cudaStreamSynchronize(S.st));
+        if (hflag && !S.careful) {
+            // a (near) breakdown happened somewhere in this sweep: redo it with host-checked norms
+            S.careful = true;
+            SVB_CUDA(cudaMemsetAsync(S.flag.p, 0, sizeof(int), S.st));
+            continue;
+        }
+        for (int c = j0; c < w; ++c) {
+            B[(size_t)c * w + c] = hBd[c];
+            if (c + 1 < w) B[(size_t)(c + 1) * w + c] = hBs[c];
+        }
+        small_svd(w, B.data(), P.data(), sig.data(), Q.data());
+        have_svd = true;
+        const double RF = std::sqrt(nF2);
+        for (int i = 0; i < w; ++i) resid[i] = RF * P[(size_t)i * w + (w - 1)];
+        smax = std::max(smax, sig[0]);
+        int nconv = 0;
+        for (int i = 0; i < w; ++i) {
+            const double ratio = std::fabs(sig_prev[i] - sig[i]) / sig[i];
+            if (std::fabs(resid[i]) < tol * smax && ratio < svtol) ++nconv;
+        }
+        ++iter;
+        if (nconv >= nu || hBd[w - 1] == 0.0) {
+            info = SVB_OK;
+            break;
+        }
+        if (iter >= maxit) break;
+        sig_prev = sig;
+        k = std::max(k, nu + nconv);
+        k = std::min(k, w - 3);
+        k = std::max(k, 1);
+        // restart: V[:, :k] = V*Q[:, :k] ; V[:, k] = F/|F| ; W[:, :k] = W*P[:, :k] ; B = [diag(sig) | resid]
+        SVB_CUDA(cudaMemcpyAsync(S.Pd.p, P.data(), (size_t)w * w * 8, cudaMemcpyHostToDevice, S.st));
+        SVB_CUDA(cudaMemcpyAsync(S.Qd.p, Q.data(), (size_t)w * w * 8, cudaMemcpyHostToDevice, S.st));
+        ts_gemm(S.V.p, n, n, w, S.Qd.p, w, k, S.V2.p, n, nullptr);
+        vec_normalize(S.F.p, n, S.nrm2F(), S.V2.p + (int64_t)k * n, nullptr, nullptr, 0.0);
+        ts_gemm(S.W.p, m, m, w, S.Pd.p, w, k, S.W2.p, m, nullptr);
+        std::swap(S.V, S.V2);
+        std::swap(S.W, S.W2);
+        std::fill(B.begin(), B.end(), 0.0);
+        for (int i = 0; i < k; ++i) {
+            B[(size_t)i * w + i] = sig[i];
+            B[(size_t)k * w + i] = resid[i];
+        }
+    }
+    res->m = m;
+    res->n = n;
+    res->nu = nu;
+    res->iter = iter;
+    res->mprod = S.mprod;
+    res->info = info;
+    SVB_CUDA(cudaMalloc((void **)&res->U, (size_t)m * nu * 8));
+    SVB_CUDA(cudaMalloc((void **)&res->V, (size_t)n * nu * 8));
+    SVB_CUDA(cudaMalloc((void **)&res->s, (size_t)nu * 8));
+    if (have_svd) {
+        SVB_CUDA(cudaMemcpyAsync(S.Pd.p, P.data(), (size_t)w * w * 8, cudaMemcpyHostToDevice, S.st));
+        SVB_CUDA(cudaMemcpyAsync(S.Qd.p, Q.data(), (size_t)w * w * 8, cudaMemcpyHostToDevice, S.st));
+        SVB_CUDA(cudaMemcpyAsync(res->s, sig.data(), (size_t)nu * 8, cudaMemcpyHostToDevice, S.st));
+        ts_gemm(S.W.p, m, m, w, S.Pd.p, w, nu, res->U, m, nullptr);
+        ts_gemm(S.V.p, n, n, w, S.Qd.p, w, nu, res->V, n, nullptr);
+    } else {
+        SVB_CUDA(cudaMemsetAsync(res->U, 0, (size_t)m * nu * 8, S.st));
+        SVB_CUDA(cudaMemsetAsync(res->V, 0, (size_t)n * nu * 8, S.st));
+        SVB_CUDA(cudaMemsetAsync(res->s, 0, (size_t)nu * 8, S.st));
+    }
+    SVB_CUDA(cudaStreamSynchronize(S.st));
+}
+
+__global__ void colscale_kernel(const double *__restrict__ U, const double *__restrict__ s, int64_t m, int64_t nu,
+                                double *__restrict__ out) {
+    const int64_t total = m * nu;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = U[i] * s[i / m];
+}
+
+}  // namespace svb
+
+extern "C" {
+
+int svb_irlba_solve(svb_operator_t op, int64_t nu, int64_t m_b, int64_t maxit, int64_t restart, double tol, double svtol,
+                    const double *init, const double *s0, const double *U0, const double *V0, svb_result_t *out) {
+    SVB_API_BEGIN
+    require_init();
+    SVB_CHECK(op && init && out, SVB_EARG, "svb_irlba_solve: null argument");
+    if (!(svtol > 0.0)) svtol = tol;
+    auto *r = new svb_result_s();
+    try {
+        irlba_run(op, nu, m_b, maxit, restart, tol, svtol, init, s0, U0, V0, r);
+    } catch (...) {
+        delete r;
+        throw;
+    }
+    *out = r;
+    SVB_API_END
+}
+
+int svb_result_info(svb_result_t r, int64_t *m, int64_t *n, int64_t *nu, int64_t *iter, int64_t *mprod, int *info) {
+    SVB_API_BEGIN
+    SVB_CHECK(r, SVB_EARG, "null result handle");
+    if (m) *m = r->m;
+    if (n) *n = r->n;
+    if (nu) *nu = r->nu;
+    if (iter) *iter = r->iter;
+    if (mprod) *mprod = r->mprod;
+    if (info) *info = r->info;
+    SVB_API_END
+}
+
+int svb_result_download(svb_result_t r, double *s, double *U, double *V, int scale_u) {
+    SVB_API_BEGIN
+    require_init();
+    SVB_CHECK(r, SVB_EARG, "null result handle");
+    cudaStream_t st = ctx().stream;
+    if (s) SVB_CUDA(cudaMemcpyAsync(s, r->s, (size_t)r->nu * 8, cudaMemcpyDeviceToHost, st));
+    if (V) SVB_CUDA(cudaMemcpyAsync(V, r->V, (size_t)r->n * r->nu * 8, cudaMemcpyDeviceToHost, st));
+    if (U) {
+        if (scale_u) {
+            // coordinates Z = U * Diagonal(s)  (embedding.jl:67)
+            DevBuf<double> z((size_t)r->m * r->nu);
+            colscale_kernel<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>((r->m * r->nu + 255) / 256, 148 * 8)), 256, 0, st>>>(
+                r->U, r->s, r->m, r->nu, z.p);
+            count_launch();
+            SVB_LAUNCH_CHECK();
+            SVB_CUDA(cudaMemcpyAsync(U, z.p, (size_t)r->m * r->nu * 8, cudaMemcpyDeviceToHost, st));
+            SVB_CUDA(cudaStreamSynchronize(st));
+        } else {
+            SVB_CUDA(cudaMemcpyAsync(U, r->U, (size_t)r->m * r->nu * 8, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    SVB_CUDA(cudaStreamSynchronize(st));
+    SVB_API_END
+}
+
+int svb_result_free(svb_result_t r) {
+    SVB_API_BEGIN
+    if (r) {
+        if (ctx().initialised) cudaStreamSynchronize(ctx().stream);
+        delete r;
+    }
+    SVB_API_END
+}
+
+int svb_irlba(svb_operator_t op, int64_t nu, int64_t m_b, int64_t maxit, int64_t restart, double tol, double svtol,
+              const double *init, double *s, double *U, double *V, int64_t *iter, int64_t *mprod) {
+    svb_result_t r = nullptr;
+    int rc = svb_irlba_solve(op, nu, m_b, maxit, restart, tol, svtol, init, s, U, V, &r);
+    if (rc != SVB_OK) return rc;
+    if (iter) *iter = r->iter;
+    if (mprod) *mprod = r->mprod;
+    const int info = r->info;
+    rc = svb_result_download(r, s, U, V, 0);
+    svb_result_free(r);
+    if (rc != SVB_OK) return rc;
+    if (info != SVB_OK) svb::set_last_error(info == SVB_ENOCONV ? "irlba: not converged within maxit" : "irlba: starting vector in the null space");
+    return info;
+}
+
+}  // extern "C"

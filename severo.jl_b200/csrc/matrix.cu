@@ -1,0 +1,646 @@
+// matrix.cu — device-resident CSC matrices (cells x genes, the SparseMatrixCSC layout of
+// src/Severo.jl:26-34): upload / download, column subset (docs/src/pbmc.md:121), cell-range
+// slice (a rank's shard), and the stable device transposes that feed the operator layouts.
+#include "svb_internal.h"
+#include "layout.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+using namespace svb;
+
+svb_matrix_s::~svb_matrix_s() {
+    if (colptr) cudaFree(colptr);
+    if (rowidx) cudaFree(rowidx);
+    if (val) cudaFree(val);
+}
+
+namespace svb {
+
+size_t vtype_size(int vtype) {
+    switch (vtype) {
+        case SVB_I32: return 4;
+        case SVB_I64: return 8;
+        case SVB_F32: return 4;
+        case SVB_F64: return 8;
+    }
+    throw Error(SVB_EARG, "unknown value type");
+}
+
+svb_matrix_s *matrix_alloc(int64_t nrow, int64_t ncol, int64_t nnz, int vtype) {
+    SVB_CHECK(vtype == SVB_I32 || vtype == SVB_F32 || vtype == SVB_F64, SVB_EARG, "device value type must be I32/F32/F64");
+    auto *a = new svb_matrix_s();
+    try {
+        a->nrow = nrow;
+        a->ncol = ncol;
+        a->nnz = nnz;
+        a->vtype = vtype;
+        SVB_CUDA(cudaMalloc((void **)&a->colptr, (size_t)(ncol + 1) * sizeof(int64_t)));
+        if (nnz > 0) {
+            SVB_CUDA(cudaMalloc((void **)&a->rowidx, (size_t)nnz * sizeof(int32_t)));
+            SVB_CUDA(cudaMalloc(&a->val, (size_t)nnz * vtype_size(vtype)));
+        }
+    } catch (...) {
+        delete a;
+        throw;
+    }
+    return a;
+}
+
+// ---- element-wise conversion kernels ------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void convert_offset_kernel(const TI *in, TO *out, int64_t n, int64_t offset, int *overflow) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        int64_t v = (int64_t)in[i] + offset;
+        if (sizeof(TO) < 8 && (v > 2147483647LL || v < -2147483648LL) && overflow) *overflow = 1;
+        out[i] = (TO)v;
+    }
+}
+
+template <typename TI, typename TO>
+__global__ void convert_value_kernel(const TI *in, TO *out, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = (TO)in[i];
+}
+
+static inline unsigned grid_for(int64_t n, int threads = 256, int max_blocks = 148 * 16) {
+    int64_t b = (n + threads - 1) / threads;
+    if (b < 1) b = 1;
+    if (b > max_blocks) b = max_blocks;
+    return (unsigned)b;
+}
+
+constexpr int64_t STAGE_ELEMS = 32ll << 20;  // staging chunk: 32 Mi elements (256 MiB as int64)
+
+// host int (32/64, any base) -> device int32 0-based, through a staging buffer, chunked
+template <typename TH>
+static void upload_index(const TH *host, int64_t n, int64_t base, int32_t *dev, int *d_overflow) {
+    cudaStream_t st = ctx().stream;
+    const int64_t chunk = std::min<int64_t>(n, STAGE_ELEMS);
+    if (n == 0) return;
+    DevBuf<TH> stage((size_t)chunk);
+    for (int64_t o = 0; o < n; o += chunk) {
+        const int64_t c = std::min(chunk, n - o);
+        SVB_CUDA(cudaMemcpyAsync(stage.p, host + o, (size_t)c * sizeof(TH), cudaMemcpyHostToDevice, st));
+        convert_offset_kernel<TH, int32_t><<<grid_for(c), 256, 0, st>>>(stage.p, dev + o, c, -base, d_overflow);
+        count_launch();
+        SVB_LAUNCH_CHECK();
+    }
+    SVB_CUDA(cudaStreamSynchronize(st));
+}
+
+}  // namespace svb
+
+// =================================================================================================
+// layout builders (declared in layout.cuh)
+// =================================================================================================
+namespace svb {
+
+// startpos[t*ncol + j] = first position in column j whose row >= t*R   (t = 0..ntiles, inclusive)
+__global__ void tile_bounds_kernel(const int64_t *colptr, const int32_t *rowidx, int64_t ncol, int64_t ntiles,
+                                   int log2R, int64_t *startpos) {
+    const int64_t total = (ntiles + 1) * ncol;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        const int64_t t = i / ncol, j = i - t * ncol;
+        const int64_t target = t << log2R;
+        int64_t lo = colptr[j], hi = colptr[j + 1];
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if ((int64_t)rowidx[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        startpos[i] = lo;
+    }
+}
+
+__global__ void tile_counts_kernel(const int64_t *startpos, int64_t ncol, int64_t ntiles, int64_t *cnt) {
+    const int64_t total = ntiles * ncol;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) cnt[i] = startpos[i + ncol] - startpos[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) cnt[total] = 0;
+}
+
+// grid (ncol, YCH): copy column j's entries to their (tile, gene) segments
+template <typename VI, typename VO>
+__global__ void tile_fill_kernel(const int64_t *colptr, const int32_t *rowidx, const VI *val, int64_t ncol,
+                                 int log2R, const int64_t *startpos, const int64_t *gptr, uint16_t *rloc, VO *aval) {
+    const int64_t j = blockIdx.x;
+    const int64_t beg = colptr[j], end = colptr[j + 1];
+    for (int64_t k = beg + (int64_t)blockIdx.y * blockDim.x + threadIdx.x; k < end; k += (int64_t)gridDim.y * blockDim.x) {
+        const int64_t r = rowidx[k];
+        const int64_t t = r >> log2R;
+        const int64_t seg = t * ncol + j;
+        const int64_t dest = gptr[seg] + (k - startpos[seg]);
+        rloc[dest] = (uint16_t)(r - (t << log2R));
+        aval[dest] = (VO)val[k];
+    }
+}
+
+template <typename VI, typename VO>
+void build_tilecsc(const svb_matrix_s *a, int log2R, TileCSC<VO> &out) {
+    cudaStream_t st = ctx().stream;
+    const int64_t R = 1ll << log2R;
+    const int64_t ntiles = std::max<int64_t>(1, (a->nrow + R - 1) / R);
+    out.R = R;
+    out.log2R = log2R;
+    out.ntiles = ntiles;
+    out.gptr.alloc((size_t)(ntiles * a->ncol + 1));
+    out.rloc.alloc((size_t)std::max<int64_t>(a->nnz, 1));
+    out.aval.alloc((size_t)std::max<int64_t>(a->nnz, 1));
+    DevBuf<int64_t> startpos((size_t)((ntiles + 1) * a->ncol + 1));
+    tile_bounds_kernel<<<grid_for((ntiles + 1) * a->ncol), 256, 0, st>>>(a->colptr, a->rowidx, a->ncol, ntiles, log2R, startpos.p);
+    tile_counts_kernel<<<grid_for(ntiles * a->ncol), 256, 0, st>>>(startpos.p, a->ncol, ntiles, out.gptr.p);
+    count_launch(2);
+    SVB_LAUNCH_CHECK();
+    exclusive_scan_i64(out.gptr.p, ntiles * a->ncol + 1, st);
+    if (a->nnz > 0 && a->ncol > 0) {
+        dim3 grid((unsigned)a->ncol, 8);
+        tile_fill_kernel<VI, VO><<<grid, 256, 0, st>>>(a->colptr, a->rowidx, (const VI *)a->val, a->ncol, log2R,
+                                                       startpos.p, out.gptr.p, out.rloc.p, out.aval.p);
+        count_launch();
+        SVB_LAUNCH_CHECK();
+    }
+    SVB_CUDA(cudaStreamSynchronize(st));
+}
+
+__global__ void row_count_kernel(const int32_t *rowidx, int64_t nnz, unsigned long long *cnt) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < nnz; i += stride) atomicAdd(&cnt[rowidx[i]], 1ull);
+}
+
+// One CTA per row tile. Genes (columns) are visited in ascending order; inside one gene segment
+// the rows are distinct, so the per-row cursors need no atomics; the barrier between genes makes
+// the placement stable (ascending gene index inside every row).
+template <typename V, typename IdxT>
+__global__ void __launch_bounds__(512) tile_to_csr_kernel(const int64_t *gptr, const uint16_t *rloc, const V *aval,
+                                                          int64_t ncol, int64_t nrow, int log2R, const int64_t *rowptr,
+                                                          IdxT *fidx, V *fval) {
+    extern __shared__ int32_t cursor[];
+    const int64_t t = blockIdx.x;
+    const int64_t R = 1ll << log2R;
+    const int64_t row0 = t << log2R;
+    const int64_t rows = min(R, nrow - row0);
+    const int64_t base = rowptr[row0];
+    for (int64_t r = threadIdx.x; r < rows; r += blockDim.x) cursor[r] = (int32_t)(rowptr[row0 + r] - base);
+    __syncthreads();
+    const int64_t *gp = gptr + t * ncol;
+    int64_t beg = gp[0];
+    for (int64_t j = 0; j < ncol; ++j) {
+        const int64_t end = gp[j + 1];
+        for (int64_t e = beg + threadIdx.x; e < end; e += blockDim.x) {
+            const int r = rloc[e];
+            const int32_t p = cursor[r];
+            cursor[r] = p + 1;
+            fidx[base + p] = (IdxT)j;
+            fval[base + p] = aval[e];
+        }
+        beg = end;
+        __syncthreads();
+    }
+}
+
+template <typename V, typename IdxT>
+void csr_from_tilecsc(const TileCSC<V> &tc, const svb_matrix_s *a, DevBuf<int64_t> &rowptr, DevBuf<IdxT> &fidx,
+                      DevBuf<V> &fval) {
+    cudaStream_t st = ctx().stream;
+    rowptr.alloc((size_t)(a->nrow + 1));
+    fidx.alloc((size_t)std::max<int64_t>(a->nnz, 1));
+    fval.alloc((size_t)std::max<int64_t>(a->nnz, 1));
+    SVB_CUDA(cudaMemsetAsync(rowptr.p, 0, (size_t)(a->nrow + 1) * sizeof(int64_t), st));
+    if (a->nnz > 0) {
+        row_count_kernel<<<grid_for(a->nnz), 256, 0, st>>>(a->rowidx, a->nnz, (unsigned long long *)rowptr.p);
+        count_launch();
+        SVB_LAUNCH_CHECK();
+    }
+    exclusive_scan_i64(rowptr.p, a->nrow + 1, st);
+    if (a->nnz > 0) {
+        const size_t smem = (size_t)tc.R * sizeof(int32_t);
+        auto kern = tile_to_csr_kernel<V, IdxT>;
+        if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)tc.ntiles, 512, smem, st>>>(tc.gptr.p, tc.rloc.p, tc.aval.p, a->ncol, a->nrow, tc.log2R, rowptr.p,
+                                                     fidx.p, fval.p);
+        count_launch();
+        SVB_LAUNCH_CHECK();
+    }
+    SVB_CUDA(cudaStreamSynchronize(st));
+}
+
+// ---- column-tile path: used when the input has many columns (cells as columns) -----------------------
+// cnt[key] += 1 with key = minor * nct + coltile  (rowmajor_tiles = true, full transpose)
+//            or key = coltile * nrow + minor       (rowmajor_tiles = false, tile-CSC of the transpose)
+__global__ void coltile_count_kernel(const int64_t *colptr, const int32_t *rowidx, int64_t ncol, int64_t nrow,
+                                     int log2R, int64_t nct, bool rowmajor_tiles, unsigned long long *cnt) {
+    // one warp per column
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t c = warp; c < ncol; c += nwarps) {
+        const int64_t t = c >> log2R;
+        for (int64_t k = colptr[c] + lane; k < colptr[c + 1]; k += 32) {
+            const int64_t r = rowidx[k];
+            const int64_t key = rowmajor_tiles ? (r * nct + t) : (t * nrow + r);
+            atomicAdd(&cnt[key], 1ull);
+        }
+    }
+}
+
+// One CTA per column tile; columns visited in ascending order, rows distinct inside a column.
+template <typename VI, typename VO, typename IdxT>
+__global__ void __launch_bounds__(256) coltile_place_kernel(const int64_t *colptr, const int32_t *rowidx, const VI *val,
+                                                            int64_t ncol, int64_t nrow, int log2R, int64_t nct,
+                                                            bool rowmajor_tiles, const int64_t *off, int32_t *cursor,
+                                                            IdxT *oidx, VO *oval, bool local_index) {
+    const int64_t t = blockIdx.x;
+    const int64_t c0 = t << log2R;
+    const int64_t c1 = min(ncol, c0 + ((int64_t)1 << log2R));
+    for (int64_t c = c0; c < c1; ++c) {
+        const int64_t beg = colptr[c], end = colptr[c + 1];
+        for (int64_t k = beg + threadIdx.x; k < end; k += blockDim.x) {
+            const int64_t r = rowidx[k];
+            const int64_t key = rowmajor_tiles ? (r * nct + t) : (t * nrow + r);
+            const int32_t p = __ldcg(&cursor[key]);
+            __stcg(&cursor[key], p + 1);
+            const int64_t dest = off[key] + p;
+            oidx[dest] = (IdxT)(local_index ? (c - c0) : c);
+            oval[dest] = (VO)val[k];
+        }
+        __syncthreads();
+    }
+}
+
+// full stable transpose through column tiles: out = a' as CSC (out.ncol = a.nrow)
+template <typename V>
+static svb_matrix_s *transpose_coltiles(const svb_matrix_s *a) {
+    cudaStream_t st = ctx().stream;
+    const int log2R = 10;
+    const int64_t nct = std::max<int64_t>(1, (a->ncol + (1ll << log2R) - 1) >> log2R);
+    const int64_t nkeys = a->nrow * nct;
+    DevBuf<int64_t> off((size_t)(nkeys + 1));
+    DevBuf<int32_t> cursor((size_t)std::max<int64_t>(nkeys, 1));
+    SVB_CUDA(cudaMemsetAsync(off.p, 0, (size_t)(nkeys + 1) * sizeof(int64_t), st));
+    SVB_CUDA(cudaMemsetAsync(cursor.p, 0, (size_t)std::max<int64_t>(nkeys, 1) * sizeof(int32_t), st));
+    svb_matrix_s *out = matrix_alloc(a->ncol, a->nrow, a->nnz, a->vtype);
+    try {
+        if (a->nnz > 0) {
+            coltile_count_kernel<<<grid_for(a->ncol * 32), 256, 0, st>>>(a->colptr, a->rowidx, a->ncol, a->nrow, log2R, nct,
+                                                                         true, (unsigned long long *)off.p);
+            count_launch();
+            SVB_LAUNCH_CHECK();
+        }
+        exclusive_scan_i64(off.p, nkeys + 1, st);
+        // out.colptr[r] = off[r * nct]
+        launch_strided_copy(off.p, nct, a->nrow, out->colptr, st);
+        SVB_CUDA(cudaMemcpyAsync(out->colptr + a->nrow, off.p + nkeys, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+        if (a->nnz > 0) {
+            coltile_place_kernel<V, V, int32_t><<<(unsigned)nct, 256, 0, st>>>(
+                a->colptr, a->rowidx, (const V *)a->val, a->ncol, a->nrow, log2R, nct, true, off.p, cursor.p, out->rowidx,
+                (V *)out->val, false);
+            count_launch();
+            SVB_LAUNCH_CHECK();
+        }
+        SVB_CUDA(cudaStreamSynchronize(st));
+    } catch (...) {
+        delete out;
+        throw;
+    }
+    return out;
+}
+
+__global__ void strided_copy_kernel(const int64_t *src, int64_t stride, int64_t n, int64_t *dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t s = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += s) dst[i] = src[i * stride];
+}
+void launch_strided_copy(const int64_t *src, int64_t stride, int64_t n, int64_t *dst, cudaStream_t st) {
+    if (n <= 0) return;
+    strided_copy_kernel<<<grid_for(n), 256, 0, st>>>(src, stride, n, dst);
+    count_launch();
+    SVB_LAUNCH_CHECK();
+}
+
+// full stable transpose through row tiles (good when a has few columns)
+template <typename V>
+static svb_matrix_s *transpose_rowtiles(const svb_matrix_s *a) {
+    TileCSC<V> tc;
+    build_tilecsc<V, V>(a, 13, tc);
+    DevBuf<int64_t> rowptr;
+    DevBuf<int32_t> fidx;
+    DevBuf<V> fval;
+    csr_from_tilecsc<V, int32_t>(tc, a, rowptr, fidx, fval);
+    auto *out = new svb_matrix_s();
+    out->nrow = a->ncol;
+    out->ncol = a->nrow;
+    out->nnz = a->nnz;
+    out->vtype = a->vtype;
+    out->colptr = rowptr.take();
+    out->rowidx = fidx.take();
+    out->val = fval.take();
+    return out;
+}
+
+svb_matrix_s *matrix_transpose(const svb_matrix_s *a) {
+    const bool use_rowtiles = a->ncol <= 65536;
+    switch (a->vtype) {
+        case SVB_I32: return use_rowtiles ? transpose_rowtiles<int32_t>(a) : transpose_coltiles<int32_t>(a);
+        case SVB_F32: return use_rowtiles ? transpose_rowtiles<float>(a) : transpose_coltiles<float>(a);
+        case SVB_F64: return use_rowtiles ? transpose_rowtiles<double>(a) : transpose_coltiles<double>(a);
+    }
+    throw Error(SVB_EARG, "bad vtype");
+}
+
+// tile-CSC of a' where a is (genes x cells) CSC: cells tiled by R, gene-major inside a tile.
+template <typename VI, typename VO>
+void build_tilecsc_from_transposed(const svb_matrix_s *a, int log2R, TileCSC<VO> &out) {
+    cudaStream_t st = ctx().stream;
+    const int64_t R = 1ll << log2R;
+    const int64_t ncells = a->ncol, ngenes = a->nrow;
+    const int64_t ntiles = std::max<int64_t>(1, (ncells + R - 1) / R);
+    const int64_t nkeys = ntiles * ngenes;
+    out.R = R;
+    out.log2R = log2R;
+    out.ntiles = ntiles;
+    out.gptr.alloc((size_t)(nkeys + 1));
+    out.rloc.alloc((size_t)std::max<int64_t>(a->nnz, 1));
+    out.aval.alloc((size_t)std::max<int64_t>(a->nnz, 1));
+    DevBuf<int32_t> cursor((size_t)std::max<int64_t>(nkeys, 1));
+    SVB_CUDA(cudaMemsetAsync(out.gptr.p, 0, (size_t)(nkeys + 1) * sizeof(int64_t), st));
+    SVB_CUDA(cudaMemsetAsync(cursor.p, 0, (size_t)std::max<int64_t>(nkeys, 1) * sizeof(int32_t), st));
+    if (a->nnz > 0) {
+        coltile_count_kernel<<<grid_for(ncells * 32), 256, 0, st>>>(a->colptr, a->rowidx, ncells, ngenes, log2R, ntiles, false,
+                                                                    (unsigned long long *)out.gptr.p);
+        count_launch();
+        SVB_LAUNCH_CHECK();
+    }
+    exclusive_scan_i64(out.gptr.p, nkeys + 1, st);
+    if (a->nnz > 0) {
+        coltile_place_kernel<VI, VO, uint16_t><<<(unsigned)ntiles, 256, 0, st>>>(
+            a->colptr, a->rowidx, (const VI *)a->val, ncells, ngenes, log2R, ntiles, false, out.gptr.p, cursor.p, out.rloc.p,
+            out.aval.p, true);
+        count_launch();
+        SVB_LAUNCH_CHECK();
+    }
+    SVB_CUDA(cudaStreamSynchronize(st));
+}
+
+// explicit instantiations used by operator.cu
+template void build_tilecsc<double, double>(const svb_matrix_s *, int, TileCSC<double> &);
+template void build_tilecsc<float, float>(const svb_matrix_s *, int, TileCSC<float> &);
+template void build_tilecsc<int32_t, double>(const svb_matrix_s *, int, TileCSC<double> &);
+template void build_tilecsc<float, double>(const svb_matrix_s *, int, TileCSC<double> &);
+template void build_tilecsc_from_transposed<double, double>(const svb_matrix_s *, int, TileCSC<double> &);
+template void build_tilecsc_from_transposed<float, float>(const svb_matrix_s *, int, TileCSC<float> &);
+template void build_tilecsc_from_transposed<int32_t, double>(const svb_matrix_s *, int, TileCSC<double> &);
+template void csr_from_tilecsc<double, uint16_t>(const TileCSC<double> &, const svb_matrix_s *, DevBuf<int64_t> &, DevBuf<uint16_t> &, DevBuf<double> &);
+template void csr_from_tilecsc<double, int32_t>(const TileCSC<double> &, const svb_matrix_s *, DevBuf<int64_t> &, DevBuf<int32_t> &, DevBuf<double> &);
+template void csr_from_tilecsc<float, uint16_t>(const TileCSC<float> &, const svb_matrix_s *, DevBuf<int64_t> &, DevBuf<uint16_t> &, DevBuf<float> &);
+template void csr_from_tilecsc<float, int32_t>(const TileCSC<float> &, const svb_matrix_s *, DevBuf<int64_t> &, DevBuf<int32_t> &, DevBuf<float> &);
+
+// ---- subset / slice ---------------------------------------------------------------------------------
+__global__ void subset_len_kernel(const int64_t *colptr, const int64_t *idx, int64_t k, int64_t *out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < k) out[i] = colptr[idx[i] + 1] - colptr[idx[i]];
+    if (i == k) out[i] = 0;
+}
+
+template <typename V>
+__global__ void subset_copy_kernel(const int64_t *colptr, const int32_t *rowidx, const V *val, const int64_t *idx,
+                                   const int64_t *ocolptr, int32_t *orow, V *oval, int32_t rowshift, const int64_t *srcbeg) {
+    const int64_t j = blockIdx.x;
+    const int64_t src = srcbeg ? srcbeg[j] : colptr[idx[j]];
+    const int64_t dst = ocolptr[j];
+    const int64_t len = ocolptr[j + 1] - dst;
+    for (int64_t e = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; e < len; e += (int64_t)gridDim.y * blockDim.x) {
+        orow[dst + e] = rowidx[src + e] - rowshift;
+        oval[dst + e] = val[src + e];
+    }
+}
+
+__global__ void slice_bounds_kernel(const int64_t *colptr, const int32_t *rowidx, int64_t ncol, int64_t r0, int64_t r1,
+                                    int64_t *srcbeg, int64_t *len) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j == ncol) len[j] = 0;
+    if (j >= ncol) return;
+    int64_t lo = colptr[j], hi = colptr[j + 1];
+    const int64_t end = hi;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (rowidx[mid] < r0) lo = mid + 1; else hi = mid;
+    }
+    const int64_t b = lo;
+    hi = end;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (rowidx[mid] < r1) lo = mid + 1; else hi = mid;
+    }
+    srcbeg[j] = b;
+    len[j] = lo - b;
+}
+
+template <typename V>
+static void launch_subset_copy(const svb_matrix_s *a, const int64_t *d_idx, svb_matrix_s *out, int32_t rowshift,
+                               const int64_t *srcbeg) {
+    if (out->nnz == 0 || out->ncol == 0) return;
+    dim3 grid((unsigned)out->ncol, 8);
+    subset_copy_kernel<V><<<grid, 256, 0, ctx().stream>>>(a->colptr, a->rowidx, (const V *)a->val, d_idx, out->colptr,
+                                                          out->rowidx, (V *)out->val, rowshift, srcbeg);
+    count_launch();
+    SVB_LAUNCH_CHECK();
+}
+
+static svb_matrix_s *finish_subset(const svb_matrix_s *a, DevBuf<int64_t> &lens, int64_t k, int64_t nrow_out,
+                                   const int64_t *d_idx, int32_t rowshift, const int64_t *srcbeg) {
+    cudaStream_t st = ctx().stream;
+    exclusive_scan_i64(lens.p, k + 1, st);
+    int64_t nnz = 0;
+    SVB_CUDA(cudaMemcpyAsync(&nnz, lens.p + k, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    SVB_CUDA(cudaStreamSynchronize(st));
+    svb_matrix_s *out = matrix_alloc(nrow_out, k, nnz, a->vtype);
+    try {
+        SVB_CUDA(cudaMemcpyAsync(out->colptr, lens.p, (size_t)(k + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+        switch (a->vtype) {
+            case SVB_I32: launch_subset_copy<int32_t>(a, d_idx, out, rowshift, srcbeg); break;
+            case SVB_F32: launch_subset_copy<float>(a, d_idx, out, rowshift, srcbeg); break;
+            case SVB_F64: launch_subset_copy<double>(a, d_idx, out, rowshift, srcbeg); break;
+        }
+        SVB_CUDA(cudaStreamSynchronize(st));
+    } catch (...) {
+        delete out;
+        throw;
+    }
+    return out;
+}
+
+}  // namespace svb
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int svb_csc_upload(int64_t nrow, int64_t ncol, const int64_t *colptr, const void *rowval, int rowval_type,
+                   const void *nzval, int vtype, int index_base, svb_matrix_t *out) {
+    SVB_API_BEGIN
+    require_init();
+    SVB_CHECK(out != nullptr && colptr != nullptr, SVB_EARG, "svb_csc_upload: null pointer");
+    SVB_CHECK(nrow >= 0 && ncol >= 0 && nrow < 2147483647LL, SVB_EDIM, "svb_csc_upload: bad dimensions (nrow must fit int32)");
+    SVB_CHECK(index_base == 0 || index_base == 1, SVB_EARG, "index_base must be 0 or 1");
+    SVB_CHECK(rowval_type == SVB_I32 || rowval_type == SVB_I64, SVB_EARG, "rowval_type must be I32 or I64");
+    const int64_t nnz = colptr[ncol] - index_base;
+    SVB_CHECK(nnz >= 0 && colptr[0] == index_base, SVB_EDIM, "svb_csc_upload: malformed colptr");
+    SVB_CHECK(nnz == 0 || (rowval && nzval), SVB_EARG, "svb_csc_upload: null rowval/nzval");
+    const int dev_vtype = (vtype == SVB_I64) ? SVB_I32 : vtype;
+    cudaStream_t st = ctx().stream;
+    svb_matrix_s *a = matrix_alloc(nrow, ncol, nnz, dev_vtype);
+    try {
+        DevBuf<int> d_over(1);
+        SVB_CUDA(cudaMemsetAsync(d_over.p, 0, sizeof(int), st));
+        // colptr
+        SVB_CUDA(cudaMemcpyAsync(a->colptr, colptr, (size_t)(ncol + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        if (index_base)
+            convert_offset_kernel<int64_t, int64_t><<<grid_for(ncol + 1), 256, 0, st>>>(a->colptr, a->colptr, ncol + 1, -index_base, nullptr);
+        count_launch();
+        if (nnz > 0) {
+            if (rowval_type == SVB_I64)
+                upload_index<int64_t>((const int64_t *)rowval, nnz, index_base, a->rowidx, d_over.p);
+            else if (index_base == 0)
+                SVB_CUDA(cudaMemcpyAsync(a->rowidx, rowval, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+            else
+                upload_index<int32_t>((const int32_t *)rowval, nnz, index_base, a->rowidx, d_over.p);
+            if (vtype == SVB_I64)
+                upload_index<int64_t>((const int64_t *)nzval, nnz, 0, (int32_t *)a->val, d_over.p);
+            else
+                SVB_CUDA(cudaMemcpyAsync(a->val, nzval, (size_t)nnz * vtype_size(vtype), cudaMemcpyHostToDevice, st));
+        }
+        int over = 0;
+        SVB_CUDA(cudaMemcpyAsync(&over, d_over.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SVB_CUDA(cudaStreamSynchronize(st));
+        SVB_CHECK(!over, SVB_EDIM, "svb_csc_upload: an index or count does not fit in int32");
+    } catch (...) {
+        delete a;
+        throw;
+    }
+    *out = a;
+    SVB_API_END
+}
+
+int svb_matrix_free(svb_matrix_t a) {
+    SVB_API_BEGIN
+    if (a) {
+        if (ctx().initialised) cudaStreamSynchronize(ctx().stream);
+        delete a;
+    }
+    SVB_API_END
+}
+
+int svb_matrix_info(svb_matrix_t a, int64_t *nrow, int64_t *ncol, int64_t *nnz, int *vtype) {
+    SVB_API_BEGIN
+    SVB_CHECK(a, SVB_EARG, "null matrix handle");
+    if (nrow) *nrow = a->nrow;
+    if (ncol) *ncol = a->ncol;
+    if (nnz) *nnz = a->nnz;
+    if (vtype) *vtype = a->vtype;
+    SVB_API_END
+}
+
+int svb_matrix_download(svb_matrix_t a, int64_t *colptr, int64_t *rowval, void *nzval, int vtype, int index_base) {
+    SVB_API_BEGIN
+    require_init();
+    SVB_CHECK(a, SVB_EARG, "null matrix handle");
+    cudaStream_t st = ctx().stream;
+    if (colptr) {
+        SVB_CUDA(cudaMemcpyAsync(colptr, a->colptr, (size_t)(a->ncol + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        SVB_CUDA(cudaStreamSynchronize(st));
+        if (index_base)
+            for (int64_t i = 0; i <= a->ncol; ++i) colptr[i] += index_base;
+    }
+    const int64_t chunk = std::min<int64_t>(std::max<int64_t>(a->nnz, 1), STAGE_ELEMS);
+    if (rowval && a->nnz > 0) {
+        DevBuf<int64_t> stage((size_t)chunk);
+        for (int64_t o = 0; o < a->nnz; o += chunk) {
+            const int64_t c = std::min(chunk, a->nnz - o);
+            convert_offset_kernel<int32_t, int64_t><<<grid_for(c), 256, 0, st>>>(a->rowidx + o, stage.p, c, index_base, nullptr);
+            count_launch();
+            SVB_CUDA(cudaMemcpyAsync(rowval + o, stage.p, (size_t)c * 8, cudaMemcpyDeviceToHost, st));
+        }
+        SVB_CUDA(cudaStreamSynchronize(st));
+    }
+    if (nzval && a->nnz > 0) {
+        if (vtype == a->vtype) {
+            SVB_CUDA(cudaMemcpyAsync(nzval, a->val, (size_t)a->nnz * vtype_size(vtype), cudaMemcpyDeviceToHost, st));
+        } else {
+            DevBuf<char> stage((size_t)chunk * vtype_size(vtype));
+            for (int64_t o = 0; o < a->nnz; o += chunk) {
+                const int64_t c = std::min(chunk, a->nnz - o);
+                const unsigned g = grid_for(c);
+                if (a->vtype == SVB_I32 && vtype == SVB_I64)
+                    convert_value_kernel<int32_t, int64_t><<<g, 256, 0, st>>>((const int32_t *)a->val + o, (int64_t *)stage.p, c);
+                else if (a->vtype == SVB_I32 && vtype == SVB_F64)
+                    convert_value_kernel<int32_t, double><<<g, 256, 0, st>>>((const int32_t *)a->val + o, (double *)stage.p, c);
+                else if (a->vtype == SVB_F32 && vtype == SVB_F64)
+                    convert_value_kernel<float, double><<<g, 256, 0, st>>>((const float *)a->val + o, (double *)stage.p, c);
+                else if (a->vtype == SVB_F64 && vtype == SVB_F32)
+                    convert_value_kernel<double, float><<<g, 256, 0, st>>>((const double *)a->val + o, (float *)stage.p, c);
+                else
+                    throw Error(SVB_EARG, "svb_matrix_download: unsupported value conversion");
+                count_launch();
+                SVB_CUDA(cudaMemcpyAsync((char *)nzval + (size_t)o * vtype_size(vtype), stage.p, (size_t)c * vtype_size(vtype),
+                                         cudaMemcpyDeviceToHost, st));
+            }
+        }
+        SVB_CUDA(cudaStreamSynchronize(st));
+    }
+    SVB_API_END
+}
+
+int svb_column_subset(svb_matrix_t a, const int64_t *idx, int64_t k, int index_base, svb_matrix_t *out) {
+    SVB_API_BEGIN
+    require_init();
+    SVB_CHECK(a && out && (idx || k == 0), SVB_EARG, "svb_column_subset: null argument");
+    SVB_CHECK(k >= 0, SVB_EDIM, "svb_column_subset: negative k");
+    std::vector<int64_t> h((size_t)k);
+    for (int64_t i = 0; i < k; ++i) {
+        h[i] = idx[i] - index_base;
+        SVB_CHECK(h[i] >= 0 && h[i] < a->ncol, SVB_EDIM, "svb_column_subset: column index out of range");
+    }
+    cudaStream_t st = ctx().stream;
+    DevBuf<int64_t> d_idx((size_t)std::max<int64_t>(k, 1));
+    DevBuf<int64_t> lens((size_t)(k + 1));
+    if (k) SVB_CUDA(cudaMemcpyAsync(d_idx.p, h.data(), (size_t)k * 8, cudaMemcpyHostToDevice, st));
+    subset_len_kernel<<<(unsigned)((k + 256) / 256), 256, 0, st>>>(a->colptr, d_idx.p, k, lens.p);
+    count_launch();
+    SVB_LAUNCH_CHECK();
+    *out = finish_subset(a, lens, k, a->nrow, d_idx.p, 0, nullptr);
+    SVB_API_END
+}
+
+int svb_row_slice(svb_matrix_t a, int64_t row0, int64_t row1, svb_matrix_t *out) {
+    SVB_API_BEGIN
+    require_init();
+    SVB_CHECK(a && out, SVB_EARG, "svb_row_slice: null argument");
+    SVB_CHECK(0 <= row0 && row0 <= row1 && row1 <= a->nrow, SVB_EDIM, "svb_row_slice: bad row range");
+    cudaStream_t st = ctx().stream;
+    DevBuf<int64_t> srcbeg((size_t)std::max<int64_t>(a->ncol, 1));
+    DevBuf<int64_t> lens((size_t)(a->ncol + 1));
+    slice_bounds_kernel<<<(unsigned)((a->ncol + 256) / 256), 256, 0, st>>>(a->colptr, a->rowidx, a->ncol, row0, row1, srcbeg.p, lens.p);
+    count_launch();
+    SVB_LAUNCH_CHECK();
+    *out = finish_subset(a, lens, a->ncol, row1 - row0, nullptr, (int32_t)row0, srcbeg.p);
+    SVB_API_END
+}
+
+int svb_transpose(svb_matrix_t a, svb_matrix_t *out) {
+    SVB_API_BEGIN
+    require_init();
+    SVB_CHECK(a && out, SVB_EARG, "svb_transpose: null argument");
+    SVB_CHECK(a->ncol < 2147483647LL, SVB_EDIM, "svb_transpose: ncol must fit int32");
+    *out = matrix_transpose(a);
+    SVB_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,366 @@
+// preprocess.cu — the pre-processing sweeps of the path, on the reference's own CSC layout:
+//   svb_row_sums / svb_normalize : normalize.jl:17-38  (library size, sf*x/s, log1p)
+//   svb_mean_var                 : scaling.jl:18-34,132-142 (sequential Welford per gene, order-exact)
+//   svb_stdvar_clipped           : variablefeatures.jl:19-28
+//   svb_scale                    : scaling.jl:199-217 (mean/std, x/std, upper clip at scale_max + mean/std)
+// Arithmetic that must be bit-identical to Julia uses the _rn intrinsics so nvcc cannot contract
+// a*b+c into an FMA (Julia does not).
+#include "svb_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+using namespace svb;
+
+namespace svb {
+
+static inline unsigned grid1(int64_t n, int threads = 256) {
+    int64_t b = (n + threads - 1) / threads;
+    return (unsigned)std::max<int64_t>(1, std::min<int64_t>(b, 148 * 16));
+}
+
+// ---- library sizes ----------------------------------------------------------------------------
+__global__ void row_sums_kernel(const int32_t *__restrict__ rowidx, const int32_t *__restrict__ val, int64_t nnz,
+                                unsigned long long *__restrict__ s) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&s[rowidx[i]], (unsigned long long)(long long)val[i]);  // exact integer sum, order-free
+}
+
+// normalize.jl:27  nzB[j] = scale_factor * nzA[j] / s[rv[j]]  (left to right), :36 log1p
+template <typename T>
+__global__ void libnorm_kernel(const int32_t *__restrict__ rowidx, const int32_t *__restrict__ val, int64_t nnz,
+                                 const long long *__restrict__ s, T sf, int do_log, T *__restrict__ out);
+
+template <>
+__global__ void libnorm_kernel<double>(const int32_t *__restrict__ rowidx, const int32_t *__restrict__ val, int64_t nnz,
+                                         const long long *__restrict__ s, double sf, int do_log, double *__restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+        const double t = __dmul_rn(sf, (double)val[i]);
+        const double v = __ddiv_rn(t, (double)s[rowidx[i]]);
+        out[i] = do_log ? log1p(v) : v;
+    }
+}
+
+template <>
+__global__ void libnorm_kernel<float>(const int32_t *__restrict__ rowidx, const int32_t *__restrict__ val, int64_t nnz,
+                                        const long long *__restrict__ s, float sf, int do_log, float *__restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+        const float t = __fmul_rn(sf, (float)val[i]);
+        const float v = __fdiv_rn(t, (float)s[rowidx[i]]);
+        out[i] = do_log ? log1pf(v) : v;
+    }
+}
+
+// ---- order-exact Welford: one thread walks one gene; genes are handed out longest-first so the
+// lanes of a warp carry chains of similar length. Loads run four elements ahead of the chain. -------
+template <typename T> __device__ __forceinline__ T sub_rn(T a, T b);
+template <> __device__ __forceinline__ double sub_rn<double>(double a, double b) { return __dsub_rn(a, b); }
+template <> __device__ __forceinline__ float sub_rn<float>(float a, float b) { return __fsub_rn(a, b); }
+template <typename T> __device__ __forceinline__ T add_rn(T a, T b);
+template <> __device__ __forceinline__ double add_rn<double>(double a, double b) { return __dadd_rn(a, b); }
+template <> __device__ __forceinline__ float add_rn<float>(float a, float b) { return __fadd_rn(a, b); }
+template <typename T> __device__ __forceinline__ T mul_rn(T a, T b);
+template <> __device__ __forceinline__ double mul_rn<double>(double a, double b) { return __dmul_rn(a, b); }
+template <> __device__ __forceinline__ float mul_rn<float>(float a, float b) { return __fmul_rn(a, b); }
+template <typename T> __device__ __forceinline__ T div_rn(T a, T b);
+template <> __device__ __forceinline__ double div_rn<double>(double a, double b) { return __ddiv_rn(a, b); }
+template <> __device__ __forceinline__ float div_rn<float>(float a, float b) { return __fdiv_rn(a, b); }
+
+template <typename VI, typename T>
+__global__ void __launch_bounds__(64) welford_kernel(const int64_t *__restrict__ colptr, const VI *__restrict__ val,
+                                                     const int32_t *__restrict__ order, int64_t ncol, int64_t nrow,
+                                                     double *__restrict__ mu_out, double *__restrict__ var_out) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ncol) return;
+    const int64_t c = order[g];
+    const int64_t beg = colptr[c], end = colptr[c + 1];
+    long long count = nrow - (end - beg);  // scaling.jl:21 implicit zeros first
+    T mu = (T)0, s = (T)0;
+    int64_t k = beg;
+    VI nxt[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) nxt[u] = (k + u < end) ? val[k + u] : (VI)0;
+    while (k < end) {
+        VI cur[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) nxt[u] = (k + 4 + u < end) ? val[k + 4 + u] : (VI)0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (k + u < end) {
+                count += 1;
+                const T v = (T)cur[u];
+                const T delta = sub_rn<T>(v, mu);
+                mu = add_rn<T>(mu, div_rn<T>(delta, (T)count));
+                s = add_rn<T>(s, mul_rn<T>(delta, sub_rn<T>(v, mu)));
+            }
+        }
+        k += 4;
+    }
+    mu_out[c] = (double)mu;
+    var_out[c] = (double)div_rn<T>(s, (T)(nrow - 1));
+}
+
+// ---- standardized_var_clipped: one warp per gene, double-double accumulation -----------------------
+__device__ __forceinline__ void two_sum(double a, double b, double &s, double &e) {
+    s = __dadd_rn(a, b);
+    const double bb = __dsub_rn(s, a);
+    e = __dadd_rn(__dsub_rn(a, __dsub_rn(s, bb)), __dsub_rn(b, bb));
+}
+__device__ __forceinline__ void dd_add(double &hi, double &lo, double x) {
+    double s, e;
+    two_sum(hi, x, s, e);
+    lo = __dadd_rn(lo, e);
+    hi = s;
+}
+
+__global__ void __launch_bounds__(256) stdvar_kernel(const int64_t *__restrict__ colptr, const int32_t *__restrict__ val,
+                                                     const int32_t *__restrict__ order, int64_t ncol, int64_t nrow,
+                                                     const double *__restrict__ mu, const double *__restrict__ sd, double vmax,
+                                                     double *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= ncol) return;
+    const int64_t c = order[warp];
+    const double m_c = mu[c], s_c = sd[c];
+    if (s_c == 0.0) {  // variablefeatures.jl:24
+        if (lane == 0) out[c] = 0.0;
+        return;
+    }
+    const int64_t beg = colptr[c], end = colptr[c + 1];
+    double hi = 0.0, lo = 0.0;
+    for (int64_t k = beg + lane; k < end; k += 32) {
+        double z = __ddiv_rn(__dsub_rn((double)val[k], m_c), s_c);
+        z = fmin(z, vmax);
+        dd_add(hi, lo, __dmul_rn(z, z));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ohi = __shfl_xor_sync(0xffffffffu, hi, o);
+        const double olo = __shfl_xor_sync(0xffffffffu, lo, o);
+        double s, e;
+        two_sum(hi, ohi, s, e);
+        lo = __dadd_rn(__dadd_rn(lo, olo), e);
+        hi = s;
+    }
+    if (lane == 0) {
+        const double acc = __dadd_rn(hi, lo);
+        double z0 = __ddiv_rn(__dsub_rn(0.0, m_c), s_c);
+        z0 = fmin(z0, vmax);
+        const double zterm = __dmul_rn((double)(nrow - (end - beg)), __dmul_rn(z0, z0));
+        out[c] = __ddiv_rn(__dadd_rn(acc, zterm), (double)(nrow - 1));
+    }
+}
+
+// ---- scale_data --------------------------------------------------------------------------------------
+// per gene: sd = sqrt(var); mu_s = mean/sd (stored mu, trap T3); smax = scale_max + mu_s
+template <typename TO>
+__global__ void scale_prepare_kernel(const double *__restrict__ mean, const double *__restrict__ var, int64_t ncol,
+                                     double scale_max, double *__restrict__ sd, double *__restrict__ mu_s, double *__restrict__ smax) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncol) return;
+    const double s = sqrt(var[c]);
+    sd[c] = s;
+    // mu = zeros(R, d); mu[i] = mean (rounded to R); mu[i] /= std (scaling.jl:205-207)
+    const TO m0 = (TO)mean[c];
+    const TO m1 = (TO)__ddiv_rn((double)m0, s);
+    mu_s[c] = (double)m1;
+    smax[c] = (double)((TO)scale_max + m1);
+}
+
+template <typename VI, typename TO>
+__global__ void scale_apply_kernel(const int64_t *__restrict__ colptr, const VI *__restrict__ val, const double *__restrict__ sd,
+                                   const double *__restrict__ smax, TO *__restrict__ out) {
+    const int64_t c = blockIdx.x;
+    const int64_t beg = colptr[c], end = colptr[c + 1];
+    const double s = sd[c], cap = smax[c];
+    for (int64_t k = beg + (int64_t)blockIdx.y * blockDim.x + threadIdx.x; k < end; k += (int64_t)gridDim.y * blockDim.x) {
+        const double v = __ddiv_rn((double)val[k], s);  // scaling.jl:211
+        out[k] = (TO)((v > cap) ? cap : v);              // scaling.jl:212 (upper clip only)
+    }
+}
+
+// float input: statistics and the division run in Float32 (scaling.jl:43-44, :211 with T = Float32)
+__global__ void scale_apply_f32_kernel(const int64_t *__restrict__ colptr, const float *__restrict__ val,
+                                       const double *__restrict__ sd, const double *__restrict__ smax, float *__restrict__ out) {
+    const int64_t c = blockIdx.x;
+    const int64_t beg = colptr[c], end = colptr[c + 1];
+    const float s = (float)sd[c], cap = (float)smax[c];
+    for (int64_t k = beg + (int64_t)blockIdx.y * blockDim.x + threadIdx.x; k < end; k += (int64_t)gridDim.y * blockDim.x) {
+        const float v = __fdiv_rn(val[k], s);
+        out[k] = (v > cap) ? cap : v;
+    }
+}
+
+// columns ordered by decreasing length (host; ncol is the number of genes)
+static void column_order(const svb_matrix_s *a, DevBuf<int32_t> &order) {
+    cudaStream_t st = ctx().stream;
+    std::vector<int64_t> cp((size_t)a->ncol + 1);
+    SVB_CUDA(cudaMemcpyAsync(cp.data(), a->colptr, cp.size() * 8, cudaMemcpyDeviceToHost, st));
+    SVB_CUDA(cudaStreamSynchronize(st));
+    std::vector<int32_t> ord((size_t)a->ncol);
+    std::iota(ord.begin(), ord.end(), 0);
+    std::stable_sort(ord.begin(), ord.end(), [&](int32_t x, int32_t y) { return cp[x + 1] - cp[x] > cp[y + 1] - cp[y]; });
+    order.alloc(std::max<size_t>(ord.size(), 1));
+    if (!ord.empty()) SVB_CUDA(cudaMemcpyAsync(order.p, ord.data(), ord.size() * 4, cudaMemcpyHostToDevice, st));
+    SVB_CUDA(cudaStreamSynchronize(st));
+}
+
+static void mean_var_device(const svb_matrix_s *a, double *d_mu, double *d_var) {
+    if (a->ncol == 0) return;
+    DevBuf<int32_t> order;
+    column_order(a, order);
+    const unsigned grid = (unsigned)((a->ncol + 63) / 64);
+    cudaStream_t st = ctx().stream;
+    switch (a->vtype) {
+        case SVB_I32: welford_kernel<int32_t, double><<<grid, 64, 0, st>>>(a->colptr, (const int32_t *)a->val, order.p, a->ncol, a->nrow, d_mu, d_var); break;
+        case SVB_F64: welford_kernel<double, double><<<grid, 64, 0, st>>>(a->colptr, (const double *)a->val, order.p, a->ncol, a->nrow, d_mu, d_var); break;
+        case SVB_F32: welford_kernel<float, float><<<grid, 64, 0, st>>>(a->colptr, (const float *)a->val, order.p, a->ncol, a->nrow, d_mu, d_var); break;
+        default: throw Error(SVB_EARG, "bad vtype");
+    }
+    count_launch();
+    SVB_LAUNCH_CHECK();
+    SVB_CUDA(cudaStreamSynchronize(st));
+}
+
+}  // namespace svb
+
+extern "C" {
+
+int svb_row_sums(svb_matrix_t a, int64_t *s) {
+    SVB_API_BEGIN
+    require_init();
+    SVB_CHECK(a && s, SVB_EARG, "svb_row_sums: null argument");
+    SVB_CHECK(a->vtype == SVB_I32, SVB_EARG, "svb_row_sums: integer counts required (normalize.jl:24)");
+    cudaStream_t st = ctx().stream;
+    DevBuf<long long> d((size_t)std::max<int64_t>(a->nrow, 1));
+    SVB_CUDA(cudaMemsetAsync(d.p, 0, (size_t)a->nrow * 8, st));
+    if (a->nnz > 0) {
+        row_sums_kernel<<<grid1(a->nnz), 256, 0, st>>>(a->rowidx, (const int32_t *)a->val, a->nnz, (unsigned long long *)d.p);
+        count_launch();
+        SVB_LAUNCH_CHECK();
+    }
+    SVB_CUDA(cudaMemcpyAsync(s, d.p, (size_t)a->nrow * 8, cudaMemcpyDeviceToHost, st));
+    SVB_CUDA(cudaStreamSynchronize(st));
+    SVB_API_END
+}
+
+int svb_normalize(svb_matrix_t a, int method, double scale_factor, int dtype, svb_matrix_t *out) {
+    SVB_API_BEGIN
+    require_init();
+    SVB_CHECK(a && out, SVB_EARG, "svb_normalize: null argument");
+    SVB_CHECK(a->vtype == SVB_I32, SVB_EARG, "svb_normalize: integer counts required");
+    SVB_CHECK(method == SVB_NORM_LOGNORMALIZE || method == SVB_NORM_RELATIVECOUNTS, SVB_EARG, "unknown normalization method");
+    SVB_CHECK(dtype == SVB_F32 || dtype == SVB_F64, SVB_EARG, "svb_normalize: dtype must be F32 or F64");
+    cudaStream_t st = ctx().stream;
+    svb_matrix_s *b = matrix_alloc(a->nrow, a->ncol, a->nnz, dtype);
+    try {
+        SVB_CUDA(cudaMemcpyAsync(b->colptr, a->colptr, (size_t)(a->ncol + 1) * 8, cudaMemcpyDeviceToDevice, st));
+        if (a->nnz > 0) {
+            SVB_CUDA(cudaMemcpyAsync(b->rowidx, a->rowidx, (size_t)a->nnz * 4, cudaMemcpyDeviceToDevice, st));
+            DevBuf<long long> s((size_t)std::max<int64_t>(a->nrow, 1));
+            SVB_CUDA(cudaMemsetAsync(s.p, 0, (size_t)a->nrow * 8, st));
+            row_sums_kernel<<<grid1(a->nnz), 256, 0, st>>>(a->rowidx, (const int32_t *)a->val, a->nnz, (unsigned long long *)s.p);
+            const int do_log = method == SVB_NORM_LOGNORMALIZE;
+            if (dtype == SVB_F64)
+                libnorm_kernel<double><<<grid1(a->nnz), 256, 0, st>>>(a->rowidx, (const int32_t *)a->val, a->nnz, s.p, scale_factor, do_log, (double *)b->val);
+            else
+                libnorm_kernel<float><<<grid1(a->nnz), 256, 0, st>>>(a->rowidx, (const int32_t *)a->val, a->nnz, s.p, (float)scale_factor, do_log, (float *)b->val);
+            count_launch(2);
+            SVB_LAUNCH_CHECK();
+            SVB_CUDA(cudaStreamSynchronize(st));
+        }
+        SVB_CUDA(cudaStreamSynchronize(st));
+    } catch (...) {
+        delete b;
+        throw;
+    }
+    *out = b;
+    SVB_API_END
+}
+
+int svb_mean_var(svb_matrix_t a, double *mu, double *var) {
+    SVB_API_BEGIN
+    require_init();
+    SVB_CHECK(a && mu && var, SVB_EARG, "svb_mean_var: null argument");
+    DevBuf<double> d_mu((size_t)std::max<int64_t>(a->ncol, 1)), d_var((size_t)std::max<int64_t>(a->ncol, 1));
+    mean_var_device(a, d_mu.p, d_var.p);
+    cudaStream_t st = ctx().stream;
+    SVB_CUDA(cudaMemcpyAsync(mu, d_mu.p, (size_t)a->ncol * 8, cudaMemcpyDeviceToHost, st));
+    SVB_CUDA(cudaMemcpyAsync(var, d_var.p, (size_t)a->ncol * 8, cudaMemcpyDeviceToHost, st));
+    SVB_CUDA(cudaStreamSynchronize(st));
+    SVB_API_END
+}
+
+int svb_stdvar_clipped(svb_matrix_t a, const double *mu, const double *sd, double vmax, double *out) {
+    SVB_API_BEGIN
+    require_init();
+    SVB_CHECK(a && mu && sd && out, SVB_EARG, "svb_stdvar_clipped: null argument");
+    SVB_CHECK(a->vtype == SVB_I32, SVB_EARG, "svb_stdvar_clipped: integer counts required (variablefeatures.jl:21)");
+    if (!(vmax > 0.0)) vmax = std::sqrt((double)a->nrow);
+    cudaStream_t st = ctx().stream;
+    const size_t nc = (size_t)std::max<int64_t>(a->ncol, 1);
+    DevBuf<double> d_mu(nc), d_sd(nc), d_out(nc);
+    SVB_CUDA(cudaMemcpyAsync(d_mu.p, mu, (size_t)a->ncol * 8, cudaMemcpyHostToDevice, st));
+    SVB_CUDA(cudaMemcpyAsync(d_sd.p, sd, (size_t)a->ncol * 8, cudaMemcpyHostToDevice, st));
+    if (a->ncol > 0) {
+        DevBuf<int32_t> order;
+        column_order(a, order);
+        const unsigned grid = (unsigned)((a->ncol * 32 + 255) / 256);
+        stdvar_kernel<<<grid, 256, 0, st>>>(a->colptr, (const int32_t *)a->val, order.p, a->ncol, a->nrow, d_mu.p, d_sd.p, vmax, d_out.p);
+        count_launch();
+        SVB_LAUNCH_CHECK();
+        SVB_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)a->ncol * 8, cudaMemcpyDeviceToHost, st));
+        SVB_CUDA(cudaStreamSynchronize(st));
+    }
+    SVB_API_END
+}
+
+int svb_scale(svb_matrix_t a, double scale_max, int dtype, svb_matrix_t *out, double *mu_out) {
+    SVB_API_BEGIN
+    require_init();
+    SVB_CHECK(a && out && mu_out, SVB_EARG, "svb_scale: null argument");
+    SVB_CHECK(dtype == SVB_F32 || dtype == SVB_F64, SVB_EARG, "svb_scale: dtype must be F32 or F64");
+    SVB_CHECK(!(a->vtype == SVB_F32 && dtype == SVB_F64), SVB_EARG, "svb_scale: Float32 data scales to Float32");
+    cudaStream_t st = ctx().stream;
+    const size_t nc = (size_t)std::max<int64_t>(a->ncol, 1);
+    DevBuf<double> d_mean(nc), d_var(nc), d_sd(nc), d_mus(nc), d_smax(nc);
+    mean_var_device(a, d_mean.p, d_var.p);
+    svb_matrix_s *b = matrix_alloc(a->nrow, a->ncol, a->nnz, dtype);
+    try {
+        SVB_CUDA(cudaMemcpyAsync(b->colptr, a->colptr, (size_t)(a->ncol + 1) * 8, cudaMemcpyDeviceToDevice, st));
+        if (a->ncol > 0) {
+            const unsigned g = (unsigned)((a->ncol + 255) / 256);
+            if (dtype == SVB_F64) scale_prepare_kernel<double><<<g, 256, 0, st>>>(d_mean.p, d_var.p, a->ncol, scale_max, d_sd.p, d_mus.p, d_smax.p);
+            else scale_prepare_kernel<float><<<g, 256, 0, st>>>(d_mean.p, d_var.p, a->ncol, scale_max, d_sd.p, d_mus.p, d_smax.p);
+            count_launch();
+        }
+        if (a->nnz > 0) {
+            SVB_CUDA(cudaMemcpyAsync(b->rowidx, a->rowidx, (size_t)a->nnz * 4, cudaMemcpyDeviceToDevice, st));
+            dim3 grid((unsigned)a->ncol, 8);
+            if (a->vtype == SVB_F64 && dtype == SVB_F64)
+                scale_apply_kernel<double, double><<<grid, 256, 0, st>>>(a->colptr, (const double *)a->val, d_sd.p, d_smax.p, (double *)b->val);
+            else if (a->vtype == SVB_F64 && dtype == SVB_F32)
+                scale_apply_kernel<double, float><<<grid, 256, 0, st>>>(a->colptr, (const double *)a->val, d_sd.p, d_smax.p, (float *)b->val);
+            else if (a->vtype == SVB_I32 && dtype == SVB_F64)
+                scale_apply_kernel<int32_t, double><<<grid, 256, 0, st>>>(a->colptr, (const int32_t *)a->val, d_sd.p, d_smax.p, (double *)b->val);
+            else if (a->vtype == SVB_I32 && dtype == SVB_F32)
+                scale_apply_kernel<int32_t, float><<<grid, 256, 0, st>>>(a->colptr, (const int32_t *)a->val, d_sd.p, d_smax.p, (float *)b->val);
+            else
+                scale_apply_f32_kernel<<<grid, 256, 0, st>>>(a->colptr, (const float *)a->val, d_sd.p, d_smax.p, (float *)b->val);
+            count_launch();
+            SVB_LAUNCH_CHECK();
+        }
+        SVB_CUDA(cudaMemcpyAsync(mu_out, d_mus.p, (size_t)a->ncol * 8, cudaMemcpyDeviceToHost, st));
+        SVB_CUDA(cudaStreamSynchronize(st));
+    } catch (...) {
+        delete b;
+        throw;
+    }
+    *out = b;
+    SVB_API_END
+}
+
+}  // extern "C"

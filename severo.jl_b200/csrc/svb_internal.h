@@ -1,0 +1,194 @@
+// svb_internal.h — shared internals of libsevero_b200 (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/severo_b200.h"
+
+namespace svb {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+void set_last_error(const std::string &msg);
+
+#define SVB_CUDA(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            char _b[512];                                                                    \
+            snprintf(_b, sizeof(_b), "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e),     \
+                     __FILE__, __LINE__, cudaGetErrorString(_e));                            \
+            throw svb::Error(_e == cudaErrorMemoryAllocation ? SVB_ENOMEM : SVB_ECUDA, _b);  \
+        }                                                                                    \
+    } while (0)
+
+#define SVB_CHECK(cond, code, msg)                                                           \
+    do {                                                                                     \
+        if (!(cond)) throw svb::Error((code), std::string(msg));                             \
+    } while (0)
+
+
+#define SVB_API_BEGIN try {
+#define SVB_API_END                                   \
+    }                                                 \
+    catch (const svb::Error &e) {                     \
+        svb::set_last_error(e.what());                \
+        return e.code;                                \
+    }                                                 \
+    catch (const std::bad_alloc &) {                  \
+        svb::set_last_error("host out of memory");    \
+        return SVB_ENOMEM;                            \
+    }                                                 \
+    catch (const std::exception &e) {                 \
+        svb::set_last_error(e.what());                \
+        return SVB_EARG;                              \
+    }                                                 \
+    return SVB_OK;
+
+#define SVB_LAUNCH_CHECK() SVB_CUDA(cudaGetLastError())
+
+// ---- global context ---------------------------------------------------------------------------
+struct Context {
+    bool initialised = false;
+    int device = -1;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // profiling
+    bool profile = false;
+    double prof_ms[SVB_K_NCLASS] = {0};
+    int64_t prof_launches[SVB_K_NCLASS] = {0};
+    double prof_bytes[SVB_K_NCLASS] = {0};
+    int64_t launches = 0;
+    // comm
+    int nranks = 1;
+    int rank = 0;
+    void *nccl_comm = nullptr;
+};
+Context &ctx();
+void require_init();
+
+// RAII device buffer
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) SVB_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    T *take() { T *r = p; p = nullptr; n = 0; return r; }
+};
+
+// scoped timer for one kernel class: records events only when profiling is on.
+struct KTimer {
+    int cls;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    double bytes;
+    KTimer(int c, double algorithmic_bytes, int nlaunch = 1);
+    ~KTimer();
+};
+void count_launch(int n = 1);
+
+// ---- matrix / operator objects ------------------------------------------------------------------
+}  // namespace svb
+
+struct svb_matrix_s {
+    int64_t nrow = 0, ncol = 0, nnz = 0;
+    int vtype = SVB_F64;         // SVB_I32 | SVB_F32 | SVB_F64 on device
+    int64_t *colptr = nullptr;   // [ncol+1], 0-based
+    int32_t *rowidx = nullptr;   // [nnz], 0-based, ascending inside a column
+    void *val = nullptr;         // [nnz]
+    ~svb_matrix_s();
+};
+
+struct svb_operator_s {
+    int64_t m = 0, n = 0, nnz = 0;  // S is m x n (cells x genes)
+    bool dense = false;
+    int vbytes = 8;                 // value storage width (8 = f64, 4 = f32)
+    int ibytes = 2;                 // forward index width (2 = u16, 4 = i32)
+    double *mu = nullptr;           // [n] or null
+    // forward layout: CSR by cell
+    int64_t *rowptr = nullptr;      // [m+1]
+    void *fidx = nullptr;           // [nnz] u16 or i32 gene index
+    void *fval = nullptr;           // [nnz]
+    // adjoint layout: cells tiled by R, gene-major inside a tile
+    int64_t R = 0, ntiles = 0;
+    int log2R = 0;
+    int fwd_lps = 0, adj_lps = 0, adj_gs = 1;  // launch shape knobs (0 = choose from the average segment length)
+    int64_t *gptr = nullptr;        // [ntiles*n + 1] segment (tile, gene) -> offset
+    uint16_t *rloc = nullptr;       // [nnz] cell index inside the tile
+    void *aval = nullptr;           // [nnz]
+    double *partial = nullptr;      // [ntiles * (n+1)] per-tile partial S'w (+ tile sum of w)
+    // dense variant (column-major, ld = rows of the stored array)
+    double *dA = nullptr;
+    int64_t lda = 0;
+    bool dense_transposed = false;
+    // scratch
+    double *xdev = nullptr, *ydev = nullptr;  // for svb_mul host staging
+    double *tmp = nullptr;                    // [max(m,n)] product before the epilogue / allreduce
+    double *scal = nullptr;                   // [8] device scalars
+    ~svb_operator_s();
+};
+
+struct svb_result_s {
+    int64_t m = 0, n = 0, nu = 0, iter = 0, mprod = 0;
+    int info = 0;
+    double *U = nullptr, *s = nullptr, *V = nullptr;  // device
+    ~svb_result_s();
+};
+
+namespace svb {
+// ---- scan.cu
+void exclusive_scan_i64(int64_t *d_inout, int64_t n, cudaStream_t st);  // in place, n elements; returns nothing
+// ---- matrix.cu
+svb_matrix_s *matrix_alloc(int64_t nrow, int64_t ncol, int64_t nnz, int vtype);
+size_t vtype_size(int vtype);
+// ---- operator / spmv
+void op_apply(svb_operator_s *op, bool trans, double alpha, const double *dx, double beta, double *dy,
+              const double *axpy_coef_dev = nullptr, double axpy_sign = 0.0, const double *axpy_vec = nullptr);
+// ---- dense.cu (tall-skinny kernels; all pointers device)
+// t[0..j) = X[:, 0..j)' * y      (X col-major L x j, leading dim ld)
+void ts_gemv_t(const double *X, int64_t ld, int64_t L, int j, const double *y, double *t, int cls);
+// y = beta*y + alpha * X[:, 0..j) * t ; nrm2_out (optional) receives sum(y.^2) of the result
+void ts_gemv_n(const double *X, int64_t ld, int64_t L, int j, const double *t, double alpha, double beta,
+               double *y, double *nrm2_out, int cls);
+// out[:, 0..k) = X[:, 0..w) * P[0..w, 0..k)  (P device, col-major ldp), optional per-column scale
+void ts_gemm(const double *X, int64_t ld, int64_t L, int w, const double *P, int ldp, int k, double *out,
+             int64_t ldo, const double *colscale_dev);
+void vec_sumsq(const double *x, int64_t L, double *out);            // out = sum x^2 (device scalar)
+// y = x * (1/sqrt(*nrm2)) ; also writes sqrt(*nrm2) to *norm_out (device) and flags breakdown
+void vec_normalize(const double *x, int64_t L, const double *nrm2_dev, double *y, double *norm_out,
+                   int *flag_dev, double eps);
+void vec_copy(const double *x, int64_t L, double *y);
+void vec_fill_normal(double *x, int64_t L, uint64_t seed, uint64_t offset);
+// ---- comm.cpp
+void comm_allreduce_dev(double *dbuf, int64_t n);  // no-op when nranks == 1
+// ---- jacobi_svd.cpp : A (w x w, col-major) = P diag(s) Q', s descending
+void small_svd(int w, const double *A, double *P, double *s, double *Q);
+}  // namespace svb

@@ -1,0 +1,227 @@
+// synth.cu — synthetic single-cell count matrices for the benchmark configurations:
+// Poisson counts x_ij ~ Poisson(scale * L_i * p_j * f_{c(i),j}) with log-normal library sizes L_i,
+// heavy-tailed gene propensities p_j and K planted cell programs (fold-change on ~5% of the genes
+// each) so that sigma_nu / sigma_{nu+1} has a gap (SURVEY trap T1). Counter-based Philox keyed on the
+// GLOBAL (cell, gene) pair: any rank regenerates exactly its own rows, independent of the sharding.
+// Output: CSC cells x genes, int32 counts, rows ascending inside every gene.
+#include "svb_internal.h"
+#include "layout.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+using namespace svb;
+
+namespace svb {
+
+__device__ __forceinline__ void philox4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        const uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// per-cell parameters: lib[i] = scale * L_i (float), prog[i] = program id
+__global__ void cell_params_kernel(int64_t row0, int64_t rows, uint64_t seed, float sigma_l, int programs, float scale,
+                                   float *__restrict__ lib, uint8_t *__restrict__ prog) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = (uint64_t)(row0 + r);
+        uint32_t u[4];
+        philox4((uint32_t)i, (uint32_t)(i >> 32), 0xC0FFEEu, 1u, (uint32_t)seed, (uint32_t)(seed >> 32), u);
+        const float u1 = ((float)(u[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        const float u2 = ((float)(u[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        const float z = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+        lib[r] = scale * expf(sigma_l * z - 0.5f * sigma_l * sigma_l);
+        prog[r] = (uint8_t)(u[2] % (uint32_t)programs);
+    }
+}
+
+__device__ __forceinline__ int poisson_from_uniform(float lambda, uint32_t bits) {
+    // inverse-CDF walk on a 32-bit uniform; lambda is small for almost every (cell, gene) pair
+    const double u = ((double)bits + 0.5) * (1.0 / 4294967296.0);
+    double p = exp(-(double)lambda);
+    if (u < p) return 0;
+    double cdf = p;
+    int k = 0;
+    while (u >= cdf && k < 4096) {
+        ++k;
+        p *= (double)lambda / (double)k;
+        cdf += p;
+        if (p < 1e-300) break;
+    }
+    return k;
+}
+
+// grid (nchunks, genes); block 256 threads, thread t owns cells 4t..4t+3 of the 1024-cell chunk.
+// PASS 0: cnt[g * nchunks + chunk] = #nonzeros ; PASS 1: write them at off[g * nchunks + chunk] + rank.
+template <int PASS>
+__global__ void __launch_bounds__(256) synth_kernel(int64_t row0, int64_t rows, int64_t genes, uint64_t seed,
+                                                    const float *__restrict__ lib, const uint8_t *__restrict__ prog,
+                                                    const float *__restrict__ pgene, const float *__restrict__ fold, int programs,
+                                                    int64_t nchunks, int64_t *__restrict__ cnt, int32_t *__restrict__ rowidx,
+                                                    int32_t *__restrict__ val) {
+    __shared__ int warp_cnt[8];
+    const int64_t chunk = blockIdx.x, g = blockIdx.y;
+    const int64_t r0 = chunk * 1024 + (int64_t)threadIdx.x * 4;
+    const float pg = pgene[g];
+    const float *fg = fold + g * programs;
+    int x[4] = {0, 0, 0, 0};
+    if (r0 < rows) {
+        const uint64_t q = (uint64_t)(row0 + r0) >> 2;  // cell quad (row0 is a multiple of 4 by construction)
+        uint32_t u[4];
+        philox4((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)g, 2u, (uint32_t)seed, (uint32_t)(seed >> 32), u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (r0 + e < rows) {
+                const float lam = lib[r0 + e] * pg * fg[prog[r0 + e]];
+                // fast reject: P(X = 0) = exp(-lam)
+                const float uf = ((float)(u[e] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+                if (uf >= __expf(-lam) - 1e-6f) x[e] = poisson_from_uniform(lam, u[e]);
+            }
+        }
+    }
+    const int mine = (x[0] != 0) + (x[1] != 0) + (x[2] != 0) + (x[3] != 0);
+    // block exclusive scan of `mine`
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) warp_cnt[wid] = incl;
+    __syncthreads();
+    int wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        if (w < wid) wbase += warp_cnt[w];
+        total += warp_cnt[w];
+    }
+    if (PASS == 0) {
+        if (threadIdx.x == 0) cnt[g * nchunks + chunk] = total;
+    } else {
+        int64_t pos = cnt[g * nchunks + chunk] + wbase + incl - mine;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (x[e] != 0) {
+                rowidx[pos] = (int32_t)(r0 + e);
+                val[pos] = x[e];
+                ++pos;
+            }
+        }
+    }
+}
+
+static inline uint64_t splitmix64(uint64_t &s) {
+    uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static inline double u01(uint64_t &s) { return ((double)(splitmix64(s) >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
+static inline double gauss(uint64_t &s) {
+    const double u1 = u01(s), u2 = u01(s);
+    return std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586 * u2);
+}
+
+}  // namespace svb
+
+extern "C" int svb_synth_counts(int64_t m_total, int64_t genes, int64_t row0, int64_t row1, double mean_nnz_per_cell,
+                                int64_t programs, double fold, uint64_t seed, svb_matrix_t *out) {
+    SVB_API_BEGIN
+    require_init();
+    SVB_CHECK(out, SVB_EARG, "svb_synth_counts: null argument");
+    SVB_CHECK(m_total >= 1 && genes >= 1 && 0 <= row0 && row0 <= row1 && row1 <= m_total, SVB_EDIM, "svb_synth_counts: bad shape");
+    SVB_CHECK(row0 % 4 == 0, SVB_EDIM, "svb_synth_counts: shard start must be a multiple of 4");
+    SVB_CHECK(programs >= 1 && programs <= 255, SVB_EARG, "svb_synth_counts: 1 <= programs <= 255");
+    SVB_CHECK(genes <= 65535, SVB_EDIM, "svb_synth_counts: genes must be <= 65535 (grid.y)");
+    SVB_CHECK(mean_nnz_per_cell > 0 && mean_nnz_per_cell < 0.9 * genes, SVB_EARG, "svb_synth_counts: bad density");
+    cudaStream_t st = ctx().stream;
+    const int64_t rows = row1 - row0;
+    const int K = (int)programs;
+    // gene-level parameters on the host (same on every rank: keyed by the seed only)
+    uint64_t s = seed * 0x9E3779B97F4A7C15ull + 12345;
+    std::vector<double> p((size_t)genes);
+    double psum = 0.0;
+    for (int64_t j = 0; j < genes; ++j) {
+        p[j] = std::exp(1.8 * gauss(s));
+        psum += p[j];
+    }
+    for (auto &v : p) v /= psum;
+    std::vector<float> f((size_t)genes * K, 1.0f);
+    for (int64_t j = 0; j < genes; ++j)
+        for (int c = 0; c < K; ++c)
+            if (u01(s) < 0.05) f[(size_t)j * K + c] = (float)fold;
+    // calibrate the global intensity so that E[#nonzeros per cell] = mean_nnz_per_cell (L = 1, averaged over programs)
+    const double sigma_l = 0.35;
+    auto expected_nnz = [&](double scale) {
+        double tot = 0.0;
+        for (int64_t j = 0; j < genes; ++j) {
+            double nz = 0.0;
+            const double base = scale * p[j];
+            // fraction of programs with the fold on this gene
+            int up = 0;
+            for (int c = 0; c < K; ++c) up += f[(size_t)j * K + c] != 1.0f;
+            nz += (K - up) * (1.0 - std::exp(-base)) + up * (1.0 - std::exp(-base * fold));
+            tot += nz / K;
+        }
+        return tot;
+    };
+    double lo = 1.0, hi = 1e9;
+    for (int it = 0; it < 200; ++it) {
+        const double mid = std::sqrt(lo * hi);
+        if (expected_nnz(mid) < mean_nnz_per_cell) lo = mid; else hi = mid;
+    }
+    const double scale = std::sqrt(lo * hi);
+    std::vector<float> pf((size_t)genes);
+    for (int64_t j = 0; j < genes; ++j) pf[j] = (float)p[j];
+
+    DevBuf<float> d_lib((size_t)std::max<int64_t>(rows, 1)), d_p((size_t)genes), d_f((size_t)genes * K);
+    DevBuf<uint8_t> d_prog((size_t)std::max<int64_t>(rows, 1));
+    SVB_CUDA(cudaMemcpyAsync(d_p.p, pf.data(), pf.size() * 4, cudaMemcpyHostToDevice, st));
+    SVB_CUDA(cudaMemcpyAsync(d_f.p, f.data(), f.size() * 4, cudaMemcpyHostToDevice, st));
+    const int64_t nchunks = std::max<int64_t>(1, (rows + 1023) / 1024);
+    DevBuf<int64_t> cnt((size_t)(genes * nchunks + 1));
+    SVB_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)(genes * nchunks + 1) * 8, st));
+    svb_matrix_s *a = nullptr;
+    if (rows > 0) {
+        cell_params_kernel<<<(unsigned)std::min<int64_t>((rows + 255) / 256, 148 * 8), 256, 0, st>>>(
+            row0, rows, seed, (float)sigma_l, K, (float)scale, d_lib.p, d_prog.p);
+        dim3 grid((unsigned)nchunks, (unsigned)genes);
+        synth_kernel<0><<<grid, 256, 0, st>>>(row0, rows, genes, seed, d_lib.p, d_prog.p, d_p.p, d_f.p, K, nchunks, cnt.p, nullptr, nullptr);
+        count_launch(2);
+        SVB_LAUNCH_CHECK();
+    }
+    exclusive_scan_i64(cnt.p, genes * nchunks + 1, st);
+    int64_t nnz = 0;
+    SVB_CUDA(cudaMemcpyAsync(&nnz, cnt.p + genes * nchunks, 8, cudaMemcpyDeviceToHost, st));
+    SVB_CUDA(cudaStreamSynchronize(st));
+    a = matrix_alloc(rows, genes, nnz, SVB_I32);
+    try {
+        launch_strided_copy(cnt.p, nchunks, genes, a->colptr, st);
+        SVB_CUDA(cudaMemcpyAsync(a->colptr + genes, cnt.p + genes * nchunks, 8, cudaMemcpyDeviceToDevice, st));
+        if (rows > 0 && nnz > 0) {
+            dim3 grid((unsigned)nchunks, (unsigned)genes);
+            synth_kernel<1><<<grid, 256, 0, st>>>(row0, rows, genes, seed, d_lib.p, d_prog.p, d_p.p, d_f.p, K, nchunks, cnt.p, a->rowidx,
+                                                  (int32_t *)a->val);
+            count_launch();
+            SVB_LAUNCH_CHECK();
+        }
+        SVB_CUDA(cudaStreamSynchronize(st));
+    } catch (...) {
+        delete a;
+        throw;
+    }
+    *out = a;
+    SVB_API_END
+}

@@ -1,0 +1,117 @@
+"""CPU: the C-ABI library loads and exports every symbol the header declares; host-side logic."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "severo_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(svb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    import severo_jl_b200 as sv
+    lib = sv.load()
+    syms = _header_symbols()
+    assert len(syms) >= 40
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/severo_b200.h but not exported"
+    assert sorted(sv.SIGNATURES) == syms, "python binding table out of sync with the header"
+
+
+def test_no_cpu_fallback_without_device():
+    import severo_jl_b200 as sv
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(sv.SeveroB200Error):
+        sv.init()
+    with pytest.raises(sv.SeveroB200Error):
+        sv.normalize_cells(__import__("scipy.sparse").sparse.csc_matrix(np.eye(3, dtype=np.int64)))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "severo.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_shard_bounds():
+    from severo_jl_b200 import sharding
+    b = sharding.shard_bounds(1306127, 8)
+    assert b[0][0] == 0 and b[-1][1] == 1306127
+    assert all(lo % 4 == 0 for lo, _ in b) and all(b[i][1] == b[i + 1][0] for i in range(7))
+    nnz = np.r_[np.full(500, 10), np.full(500, 1)]
+    b2 = sharding.shard_bounds(1000, 2, row_nnz=nnz)
+    assert b2[0][1] < 500 and b2[0][1] % 4 == 0
+    assert sharding.shard_bounds(10, 1) == [(0, 10)]
+
+
+def test_loess_recovers_smooth_trend():
+    from severo_jl_b200.loess import loess_fit_predict
+    rng = np.random.default_rng(0)
+    x = np.sort(rng.uniform(-3, 1, 3000))
+    y = 0.5 * x + 0.1 * x ** 2 + 0.01 * rng.standard_normal(3000)
+    f = loess_fit_predict(x, y, span=0.5)
+    assert np.max(np.abs(f - (0.5 * x + 0.1 * x ** 2))) < 0.02
+
+
+def test_svd_flip_matches_reference_rule():
+    import severo_jl_b200 as sv
+    U = np.array([[0.1, -0.9], [-0.8, 0.2]])
+    Vt = np.array([[1.0, 2.0], [3.0, -4.0]])
+    S = sv.svd_flip(sv.SVD(U.copy(), np.ones(2), Vt.copy()))
+    assert S.U[1, 0] > 0 and S.U[0, 1] > 0
+    np.testing.assert_array_equal(S.Vt, -Vt)
+
+
+_GLOO = r"""
+import os, sys
+import numpy as np, scipy.sparse as sp
+import torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from oracle import severo_oracle as orc
+from severo_jl_b200 import sharding
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+rng = np.random.default_rng(0)
+X = sp.random(403, 60, 0.2, random_state=1, format="csc")
+mu = rng.standard_normal(60)
+bounds = sharding.shard_bounds(403, world)
+lo, hi = bounds[rank]
+full = orc.CenteredMatrix(X, mu)
+local = orc.CenteredMatrix(X[lo:hi], mu)
+v = rng.standard_normal(60); w = rng.standard_normal(403)
+# S*v is shard-local; S'*w needs the sum over ranks (SURVEY 8e)
+yl = local.mul(v)
+assert np.allclose(yl, full.mul(v)[lo:hi], rtol=1e-13, atol=1e-13)
+t = torch.from_numpy(local.mul(w[lo:hi], trans=True).copy())
+dist.all_reduce(t)
+assert np.allclose(t.numpy(), full.mul(w, trans=True), rtol=1e-12, atol=1e-12)
+U = sharding.gather_rows(np.asfortranarray(yl[:, None]), bounds, rank)
+assert np.allclose(U[:, 0], full.mul(v), rtol=1e-13, atol=1e-13)
+dist.destroy_process_group()
+print("OK", rank)
+"""
+
+
+def test_cell_sharding_two_ranks_gloo(tmp_path):
+    script = tmp_path / "gloo_shard.py"
+    script.write_text(_GLOO)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", str(script), ROOT],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("OK") == 2

@@ -1,0 +1,137 @@
+"""CPU: pin the oracle against the reference's fixed-input tests (tests/golden) and its solver criteria."""
+import numpy as np
+import scipy.sparse as sp
+
+
+def test_welford_bits_match_literal_transcription(orc, golden):
+    X = sp.csc_matrix(np.array(golden["X"], dtype=np.int64))
+    mu, var = orc.mean_var(X)
+    assert [float(v).hex() for v in mu] == golden["welford_mu_hex"]
+    assert [float(v).hex() for v in var] == golden["welford_var_hex"]
+    # pure-python twin of the same loop
+    for j in range(X.shape[1]):
+        m2, v2 = orc.mean_var_py(X.data[X.indptr[j]:X.indptr[j + 1]], X.shape[0])
+        assert float(m2).hex() == golden["welford_mu_hex"][j] and float(v2).hex() == golden["welford_var_hex"][j]
+
+
+def test_scale_features_fixed_matrix(orc, golden):
+    # test/test_scaling.jl:22-45
+    X = sp.csc_matrix(np.array(golden["X"], dtype=np.int64))
+    S = orc.scale_features(X)
+    np.testing.assert_allclose(S.mu, golden["mu_over_std"], rtol=1.5e-8)
+    np.testing.assert_allclose(S.to_dense(), np.array(golden["scaled_dense"]), rtol=1.5e-8, atol=1e-15)
+    assert [float(v).hex() for v in S.mu] == golden["welford_mu_over_sd_hex"]
+
+
+def test_scale_max_clip_rule(orc):
+    # scaling.jl:209-212: upper clip at scale_max + mu/std on stored entries only
+    X = sp.csc_matrix(np.array([[100, 1], [0, 1], [0, 2], [0, 0], [1, 0], [0, 0]], dtype=np.int64))
+    S = orc.scale_features(X, scale_max=1.0)
+    D = S.P.toarray()
+    mu, sd = orc.mean_std(X)
+    assert D[0, 0] == 1.0 + mu[0] / sd[0]
+    assert D[4, 0] == 1.0 / sd[0]
+
+
+def test_centered_operator_fixed_vectors(orc, golden):
+    # test/test_scaling.jl:72-112
+    op = golden["op"]
+    for A in (sp.csc_matrix(np.array(op["A"])), np.array(op["A"])):
+        C = orc.CenteredMatrix(A, op["mu"])
+        assert C.shape == (4, 3)
+        r = np.array(op["r"])
+        np.testing.assert_allclose(C.mul(r), op["Qr"], rtol=1.5e-8, atol=1e-15)
+        y = C.mul(r, 2.0, 1.0, np.array(op["y0"]))
+        np.testing.assert_allclose(y, op["y"], rtol=1.5e-8)
+        np.testing.assert_allclose(C.mul(y, trans=True), op["Qty"], rtol=1.5e-8)
+        np.testing.assert_allclose(C.mul(y, 2.0, 1.0, r.copy(), trans=True), op["r2"], rtol=1.5e-8)
+
+
+def test_normalize_cells_fixed_matrix(orc, golden):
+    # test/test_input.jl:47-75
+    X = np.array(golden["X"], dtype=np.int64)[np.ix_(golden["filter_cells"], golden["filter_genes"])]
+    A = sp.csc_matrix(X)
+    Q = orc.normalize_cells(A, method="relativecounts")
+    assert Q.dtype == np.float64
+    np.testing.assert_allclose(np.asarray(Q.sum(axis=1)).ravel(), 1.0, rtol=1.5e-8)
+    np.testing.assert_allclose(Q.toarray(), np.array(golden["relcounts_dense"]), rtol=1e-15)
+    Q2 = orc.normalize_cells(A, method="lognormalize")
+    np.testing.assert_array_equal(Q2.data, np.log1p(Q.data))
+    Q10 = orc.normalize_cells(A, method="relativecounts", scale_factor=10.0)
+    np.testing.assert_allclose(np.asarray(Q10.sum(axis=1)).ravel(), 10.0, rtol=1.5e-8)
+    assert orc.normalize_cells(A, method="lognormalize", dtype=np.float32).dtype == np.float32
+    # C build == pure-python twin, bit for bit
+    np.testing.assert_array_equal(orc.row_norm_py(A, 1e4, True).data, orc.normalize_cells(A, "lognormalize", 1e4).data)
+
+
+def test_stdvar_clipped_against_dense_formula(orc):
+    rng = np.random.default_rng(3)
+    X = sp.csc_matrix(rng.poisson(0.3, (500, 40)).astype(np.int64))
+    mu, sd = orc.mean_std(X)
+    sd[5] = 0.0
+    out = orc.standardized_var_clipped(X, mu, sd)
+    D = X.toarray().astype(float)
+    vmax = np.sqrt(500)
+    for j in range(40):
+        if sd[j] == 0:
+            assert out[j] == 0.0
+            continue
+        z = np.minimum((D[:, j] - mu[j]) / sd[j], vmax)
+        np.testing.assert_allclose(out[j], np.sum(z * z) / 499, rtol=1e-13)
+
+
+def _rel_err(X, U, s, V):
+    return np.linalg.norm(X - (U * s) @ V.T)
+
+
+def test_irlba_reference_scenarios(orc):
+    # the eight scenarios of test/test_irlba.jl:25-115 with seeded inputs, same acceptance criteria
+    rng = np.random.default_rng(7)
+    for shape in ((50, 50), (100, 50)):
+        X = rng.standard_normal(shape)
+        R = orc.irlba(X, 20, tol=1e-5, rng=rng)
+        sv = np.linalg.svd(X, compute_uv=False)
+        assert R.info == 0
+        np.testing.assert_allclose(R.S, sv[:20], rtol=1.5e-8)
+        assert np.linalg.norm(X.T @ R.U - R.V * R.S) / np.linalg.norm(X) < 1e-5
+        Ud, sd_, Vtd = np.linalg.svd(X, full_matrices=False)
+        np.testing.assert_allclose(_rel_err(X, R.U, R.S, R.V), _rel_err(X, Ud[:, :20], sd_[:20], Vtd[:20].T), rtol=1.5e-8)
+    Xs = sp.random(2000, 400, 0.1, random_state=11, format="csc")
+    R = orc.irlba(Xs, 2, tol=1e-9, rng=rng)
+    sv = np.linalg.svd(Xs.toarray(), compute_uv=False)
+    np.testing.assert_allclose(R.S, sv[:2], rtol=1.5e-8)
+    assert np.linalg.norm(Xs.T @ R.U - R.V * R.S) / np.linalg.norm(Xs.toarray()) < 1e-9
+    # centred dense / sparse
+    Xd = rng.standard_normal((20, 10))
+    C = orc.CenteredMatrix(Xd, Xd.mean(axis=0))
+    Q = C.to_dense()
+    R = orc.irlba(C, 3, rng=rng)
+    np.testing.assert_allclose(R.S, np.linalg.svd(Q, compute_uv=False)[:3], rtol=1.5e-8)
+    assert np.linalg.norm(Q.T @ R.U - R.V * R.S) / np.linalg.norm(Q) < 1e-9
+    C = orc.CenteredMatrix(Xs, np.asarray(Xs.mean(axis=0)).ravel())
+    Q = C.to_dense()
+    R = orc.irlba(C, 2, tol=1e-9, rng=rng)
+    np.testing.assert_allclose(R.S, np.linalg.svd(Q, compute_uv=False)[:2], rtol=1.5e-8)
+    assert np.linalg.norm(Q.T @ R.U - R.V * R.S) / np.linalg.norm(Q) < 1e-9
+    # tall-skinny and its transpose with svd_flip
+    Xt = rng.standard_normal((10000, 10))
+    R1 = orc.irlba(Xt, 2, tol=1e-9, rng=rng)
+    R2 = orc.irlba(np.ascontiguousarray(Xt.T), 2, tol=1e-9, rng=rng)
+    U1, V1 = orc.svd_flip(R1.U, R1.V, True)
+    U2, V2 = orc.svd_flip(R2.U, R2.V, False)
+    np.testing.assert_allclose(R1.S, R2.S, rtol=1.5e-8)
+    np.testing.assert_allclose(U1, V2, atol=1e-7)
+    np.testing.assert_allclose(V1, U2, atol=1e-7)
+    # count matrix through the lazy adjoint (test_irlba.jl:107-115)
+    Xc = sp.random(300, 1000, 0.05, random_state=5, format="csc", data_rvs=lambda k: rng.poisson(10, k).astype(float))
+    C = orc.CenteredMatrix(Xc, np.asarray(Xc.mean(axis=1)).ravel(), transposed=True)
+    R = orc.irlba(C, 10, rng=rng)
+    np.testing.assert_allclose(R.S, np.linalg.svd(C.to_dense(), compute_uv=False)[:10], rtol=1.5e-8)
+
+
+def test_parallel_forward_product_is_bit_identical(orc):
+    rng = np.random.default_rng(2)
+    Xs = sp.random(3000, 200, 0.05, random_state=1, format="csc")
+    C = orc.CenteredMatrix(Xs, rng.standard_normal(200))
+    v = rng.standard_normal(200)
+    np.testing.assert_array_equal(C.mul(v), C.mul(v, parallel=True))
