@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py — IRLBA 50-PC wall time on the 1.3M-cell configuration (BASELINE.json metric), 1/2/4/8 B200.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores (oracle port)
+
+A "step" is one full IRLBA solve (nu PCs, tol 1e-5, fixed start vector) of the implicit centred operator of
+the configuration, operator resident in HBM (`value`), or through the C ABI with HOST buffers — upload of the
+scaled CSC matrix, layout build, solve, download of U, s, V — inside the timed region (`e2e`).
+Strong scaling: the matrix is fixed, its cells are sharded over the N ranks (one process per GPU).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # cells, genes, nnz per cell, HVGs, PCs, planted programs. programs = nu: K programs give K-1 cluster
+    # directions + 1 library-size direction = nu signal directions, so sigma_nu/sigma_{nu+1} ~ 1.2 (K = 64 leaves no gap at 50)
+    "C1": dict(m=2_700, g=32_738, nnz=852.0, n=2000, nu=50, programs=50, desc="PBMC-3k-shaped"),
+    "C2": dict(m=68_579, g=32_738, nnz=671.0, n=2000, nu=50, programs=50, desc="PBMC-68k-shaped"),
+    "C3": dict(m=1_306_127, g=27_998, nnz=1914.0, n=2000, nu=50, programs=50, desc="1.3M-cell mouse-brain-shaped"),
+    "C4": dict(m=1_306_127, g=27_998, nnz=1914.0, n=5000, nu=100, programs=100, desc="1.3M-cell, reorthogonalisation-heavy"),
+}
+SEED = 20260103
+TOL = 1e-5
+SCALE_MAX = 10.0
+METRIC = "irlba_50pc_wall_time_1.3M_cells"
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def build_workload(sv, cfg, rank, world, rows_total=None):
+    """Generate this rank's cells on the device and run the path's pre-processing:
+    log-normalise -> :vst HVG metric -> top-n -> scale_features(scale_max=10). Returns (B, mu, info)."""
+    from severo_jl_b200 import sharding
+    m = cfg["m"] if rows_total is None else rows_total
+    bounds = sharding.shard_bounds(m, world)
+    lo, hi = bounds[rank]
+    t = {}
+    t0 = time.perf_counter()
+    counts = sv.synthetic_counts(cfg["m"], cfg["g"], cfg["nnz"], programs=cfg["programs"], fold=6.0, seed=SEED, rows=(lo, hi))
+    sv.lib().svb_synchronize()
+    t["generate_s"] = time.perf_counter() - t0
+    Z = counts.nnz
+    t0 = time.perf_counter()
+    Y = sv.normalize_cells(counts, method="lognormalize", scale_factor=1e4)
+    sv.lib().svb_synchronize()
+    t["normalize_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    metric = sharding.sharded_vst_metric(counts)
+    t["hvg_metric_s"] = time.perf_counter() - t0
+    hvf = np.argsort(-metric, kind="stable")[:cfg["n"]]
+    counts.free()
+    t0 = time.perf_counter()
+    B, mu = sharding.sharded_scale_features(Y, scale_max=SCALE_MAX, features=hvf)
+    sv.lib().svb_synchronize()
+    t["scale_s"] = time.perf_counter() - t0
+    Y.free()
+    info = dict(rows=(lo, hi), bounds=bounds, Z_local=int(Z), z_local=int(B.nnz), setup=t)
+    return B, mu, info
+
+
+def make_operator(sv, B, mu):
+    h = ctypes.c_void_p()
+    sv._lib.check(sv.lib().svb_operator_create(B._h, sv._lib.ptr(np.ascontiguousarray(mu)), 0, ctypes.byref(h)))
+    return h
+
+
+def solve_device(sv, op, nu, init):
+    """One solve with the operator resident; U, s, V stay on the device. Returns (iter, mprod, info)."""
+    L = sv._lib
+    r = ctypes.c_void_p()
+    L.check(sv.lib().svb_irlba_solve(op, nu, 0, 1000, 0, TOL, TOL, L.ptr(init), None, None, None, ctypes.byref(r)))
+    it, mp, info = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int()
+    sv.lib().svb_result_info(r, None, None, None, ctypes.byref(it), ctypes.byref(mp), ctypes.byref(info))
+    return r, it.value, mp.value, info.value
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import severo_jl_b200 as sv
+    from severo_jl_b200 import sharding
+    L = sv._lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg = CONFIGS[args.config]
+    stream = torch.cuda.Stream()
+    lib = sv.init(local)
+    with torch.cuda.stream(stream):
+        L.check(lib.svb_set_stream(ctypes.c_void_p(stream.cuda_stream)))
+        if world > 1:
+            sharding.init_comm_from_torch()
+        B, mu, winfo = build_workload(sv, cfg, rank, world)
+        n, nu = cfg["n"], cfg["nu"]
+        m_local = B.shape[0]
+        init = np.random.default_rng(SEED).standard_normal(n)
+        op = make_operator(sv, B, mu)
+
+        def barrier():
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        # ---- device-resident timing --------------------------------------------------------------
+        last = None
+        for _ in range(args.warmup):
+            r, it, mp, info = solve_device(sv, op, nu, init)
+            lib.svb_result_free(r)
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        lib.svb_launch_count_reset()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            r, it, mp, info = solve_device(sv, op, nu, init)
+            if last is not None:
+                lib.svb_result_free(last)
+            last = r
+        e1.record(stream)
+        barrier()
+        launches = int(lib.svb_launch_count())
+        clocks = sampler.stop() if sampler else None
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms_per_step = float(ms.item()) / args.steps
+        s_host = np.zeros(nu)
+        L.check(lib.svb_result_download(last, L.ptr(s_host), None, None, 0))
+        lib.svb_result_free(last)
+
+        # ---- per-kernel-class device timers (one extra, untimed solve) -------------------------------
+        lib.svb_profile_enable(1)
+        lib.svb_profile_reset()
+        r, _, _, _ = solve_device(sv, op, nu, init)
+        lib.svb_result_free(r)
+        lib.svb_profile_enable(0)
+        pms = (ctypes.c_double * 6)()
+        pl = (ctypes.c_int64 * 6)()
+        pb = (ctypes.c_double * 6)()
+        lib.svb_profile_get(pms, pl, pb)
+        classes = {}
+        for i, name in enumerate(L.K_CLASSES):
+            if pl[i]:
+                classes[name] = {"ms": round(pms[i], 4), "launches": int(pl[i]), "algorithmic_GB": round(pb[i] / 1e9, 4),
+                                 "GBps": round(pb[i] / 1e9 / (pms[i] / 1e3), 1) if pms[i] > 0 else None}
+        peak, peak_src = measured_peak_gbs()
+        # dominant kernel = the SpMV class with the larger share of the step
+        dom = max(("spmv_fwd", "spmv_adj"), key=lambda k: classes.get(k, {}).get("ms", 0.0))
+        dc = classes[dom]
+        nlaunch_dom = dc["launches"] / (2 if dom == "spmv_adj" else 1)  # the adjoint is two launches per product
+        achieved = dc["GBps"]
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "bytes_per_launch": round(dc["algorithmic_GB"] * 1e9 / nlaunch_dom),
+                    "avg_launch_ms": round(dc["ms"] / nlaunch_dom, 5),
+                    "share_of_step": round(dc["ms"] / sum(c["ms"] for c in classes.values()), 4),
+                    "other": {k: {"GBps": v["GBps"], "frac": round(v["GBps"] / peak, 4) if v["GBps"] else None, "ms": v["ms"]}
+                              for k, v in classes.items() if k != dom}}
+
+        # ---- end to end through the C ABI with HOST buffers --------------------------------------------
+        e2e = None
+        if not args.no_e2e:
+            z = B.nnz
+            t_colptr = torch.empty(n + 1, dtype=torch.int64, pin_memory=True)
+            t_rowval = torch.empty(max(z, 1), dtype=torch.int64, pin_memory=True)
+            t_nzval = torch.empty(max(z, 1), dtype=torch.float64, pin_memory=True)
+            colptr, rowval, nzval = t_colptr.numpy(), t_rowval.numpy(), t_nzval.numpy()
+            # the caller's SparseMatrixCSC{Float64,Int64}: 1-based Int64 indices, as Julia holds it
+            L.check(lib.svb_matrix_download(B._h, L.ptr(colptr), L.ptr(rowval), L.ptr(nzval), L.SVB_F64, 1))
+            t_U = torch.empty((nu, m_local), dtype=torch.float64, pin_memory=True)
+            t_V = torch.empty((nu, n), dtype=torch.float64, pin_memory=True)
+            U, V, s = t_U.numpy().T, t_V.numpy().T, np.zeros(nu)
+            mu_c = np.ascontiguousarray(mu)
+
+            def e2e_step():
+                h = ctypes.c_void_p()
+                L.check(lib.svb_csc_upload(m_local, n, L.ptr(colptr), L.ptr(rowval), L.SVB_I64, L.ptr(nzval), L.SVB_F64, 1,
+                                           ctypes.byref(h)))
+                o = ctypes.c_void_p()
+                L.check(lib.svb_operator_create(h, L.ptr(mu_c), 0, ctypes.byref(o)))
+                lib.svb_matrix_free(h)
+                it_, mp_ = ctypes.c_int64(), ctypes.c_int64()
+                L.check(lib.svb_irlba(o, nu, 0, 1000, 0, TOL, TOL, L.ptr(init), L.ptr(s), L.ptr(U), L.ptr(V),
+                                      ctypes.byref(it_), ctypes.byref(mp_)))
+                lib.svb_operator_free(o)
+
+            B.free()  # the e2e call owns its own device copy
+            lib.svb_operator_free(op)
+            op = None
+            e2e_step()  # warm-up
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                e2e_step()
+            barrier()
+            dt = torch.tensor([(time.perf_counter() - t0) / args.steps], device="cuda")
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            h2d = 8 * (n + 1) + 16 * z + 8 * n + 8 * n  # colptr + rowval + nzval + mu + init
+            d2h = 8 * (m_local * nu + n * nu + nu)
+            e2e = {"value": round(float(dt.item()), 6), "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "includes": "pinned-host CSC{Float64,Int64} upload, device layout build, solve, U/s/V download"}
+            assert np.allclose(s, s_host, rtol=1e-6), "e2e and device-resident solves disagree"
+
+        # ---- totals over ranks --------------------------------------------------------------------------
+        tot = torch.tensor([float(winfo["z_local"]), float(winfo["Z_local"])], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tot)
+        z_total, Z_total = int(tot[0].item()), int(tot[1].item())
+
+    out = None
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": round(ms_per_step / 1e3, 6), "unit": "s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.config}: synthetic {cfg['desc']} Poisson counts, {cfg['m']} cells x {cfg['g']} genes, "
+                                   f"Z={Z_total} nnz -> lognormalize -> {cfg['n']} HVGs (vst) -> scale_features(scale_max=10) -> "
+                                   f"irlba nu={cfg['nu']} work={cfg['nu'] + 7} tol={TOL}",
+                       "cells": cfg["m"], "genes": cfg["g"], "hvgs": cfg["n"], "nu": cfg["nu"], "hvg_nnz": z_total,
+                       "parallelism": f"cells sharded over {world} GPU(s), NCCL allreduce of S'w / reorth coefficients",
+                       "l2_policy": "inputs larger than L2 (operator layouts 2 x %.2f GB, basis %.2f GB; L2 126 MB)" % (
+                           z_total * 10 / 1e9 / world, cfg["m"] * (cfg["nu"] + 7) * 8 / 1e9 / world)},
+            "solve": {"restarts": it, "matvecs": mp, "info": info, "sigma_1": float(s_host[0]), "sigma_nu": float(s_host[-1])},
+            "roofline": roofline, "kernel_classes": classes, "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
+            "setup_s": {k: round(v, 4) for k, v in winfo["setup"].items()},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(sv, cfg, steps=1, warmup=0)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        lib.svb_comm_destroy()
+        dist.destroy_process_group()
+    return out
+
+
+def cpu_sample_problem(sv, cfg, cells):
+    """The first `cells` cells of the configuration through the same pre-processing, downloaded to the host."""
+    import scipy.sparse as sp  # noqa: F401
+    cells = min(cfg["m"], (cells // 4) * 4)
+    sub = dict(cfg)
+    B, mu, info = build_workload(sv, sub, 0, 1, rows_total=cells)
+    Bh = B.to_host()
+    B.free()
+    return Bh, mu, cells
+
+
+def cpu_baseline(sv, cfg, steps=1, warmup=0, cells=163_840):
+    """The reference algorithm (oracle port: stdlib-order sparse products, CGS reorth, restart GEMMs, LAPACK SVD of B)
+    on the host cores, on a bounded sample of the workload, extrapolated linearly in the number of cells."""
+    from oracle import severo_oracle as orc
+    Bh, mu, cells = cpu_sample_problem(sv, cfg, cells)
+    C = orc.CenteredMatrix(Bh, mu)
+    init = np.random.default_rng(SEED).standard_normal(cfg["n"])
+    threads = orc.num_threads()
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        R = orc.irlba(C, cfg["nu"], init=init, tol=TOL, parallel=True)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    t = float(np.mean(times))
+    scale = cfg["m"] / cells
+    return {"value": round(t * scale, 4), "unit": "s", "cores": threads, "kind": "port",
+            "sample": f"first {cells} of {cfg['m']} cells (same generator/pre-processing, {Bh.nnz} nnz), full IRLBA solve "
+                      f"({R.iters} restarts, {R.mprod} mat-vecs) took {t:.3f} s on {threads} threads; value = x{scale:.2f} "
+                      f"(cost is linear in cells)",
+            "sample_seconds": round(t, 4)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    import severo_jl_b200 as sv
+    cfg = CONFIGS[args.config]
+    sv.init(int(os.environ.get("LOCAL_RANK", "0")))  # input generation / pre-processing only; the timed solve is pure CPU
+    base = cpu_baseline(sv, cfg, steps=args.steps, warmup=min(args.warmup, 1))
+    out = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "s", "n_gpus": world, "steps": args.steps,
+           "warmup": min(args.warmup, 1), "ms_per_step": round(base["value"] * 1e3, 2), "higher_is_better": False,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"{args.config}: same synthetic workload as the b200 arm (bounded sample, extrapolated)",
+                      "cells": cfg["m"], "genes": cfg["g"], "hvgs": cfg["n"], "nu": cfg["nu"]},
+           "cpu_baseline": base,
+           "e2e": {"value": base["value"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "note": "Julia and libcell are absent from the image; this arm times the oracle port of the reference algorithm "
+                   "on all host threads (sparse products in C/OpenMP, dense algebra in numpy/OpenBLAS)"}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="C3", choices=sorted(CONFIGS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -127,6 +127,10 @@ int svb_stdvar_clipped(svb_matrix_t counts, const double *mu, const double *sd, 
                        double *out);
 /* scaling.jl:199-217 scale_data: out = min(x/std, scale_max + mu/std); mu_out = mean/std. */
 int svb_scale(svb_matrix_t a, double scale_max, int dtype, svb_matrix_t *out, double *mu_out);
+/* Same sweep with caller-supplied per-gene mean / unbiased variance: the cell-sharded form, where the
+ * moments of the whole matrix come from merging the per-rank moments (SURVEY 8e "fast mode"). */
+int svb_scale_with_moments(svb_matrix_t a, const double *mean, const double *var, double scale_max,
+                           int dtype, svb_matrix_t *out, double *mu_out);
 
 /* ---- the implicit centred operator (scaling.jl:219-272) -------------------------------------- */
 /* S = A - 1*mu' with A = a (transposed = 0) or A = a' (transposed = 1, the lazy Adjoint of

@@ -202,7 +202,7 @@ static void irlba_run(svb_operator_s *op, int64_t nu_, int64_t work_, int64_t ma
         for (int i = 0; i < w; ++i) resid[i] = RF * P[(size_t)i * w + (w - 1)];
         smax = std::max(smax, sig[0]);
         int nconv = 0;
-        for (int i = 0; i < w; ++i) {
+        for (int i = 0; i < nu; ++i) {  // the nu wanted Ritz values only (convergence test)
             const double ratio = std::fabs(sig_prev[i] - sig[i]) / sig[i];
             if (std::fabs(resid[i]) < tol * smax && ratio < svtol) ++nconv;
         }

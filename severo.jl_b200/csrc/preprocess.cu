@@ -318,7 +318,8 @@ int svb_stdvar_clipped(svb_matrix_t a, const double *mu, const double *sd, doubl
     SVB_API_END
 }
 
-int svb_scale(svb_matrix_t a, double scale_max, int dtype, svb_matrix_t *out, double *mu_out) {
+static int scale_impl(svb_matrix_t a, const double *h_mean, const double *h_var, double scale_max, int dtype,
+                      svb_matrix_t *out, double *mu_out) {
     SVB_API_BEGIN
     require_init();
     SVB_CHECK(a && out && mu_out, SVB_EARG, "svb_scale: null argument");
@@ -327,7 +328,12 @@ int svb_scale(svb_matrix_t a, double scale_max, int dtype, svb_matrix_t *out, do
     cudaStream_t st = ctx().stream;
     const size_t nc = (size_t)std::max<int64_t>(a->ncol, 1);
     DevBuf<double> d_mean(nc), d_var(nc), d_sd(nc), d_mus(nc), d_smax(nc);
-    mean_var_device(a, d_mean.p, d_var.p);
+    if (h_mean) {
+        SVB_CUDA(cudaMemcpyAsync(d_mean.p, h_mean, (size_t)a->ncol * 8, cudaMemcpyHostToDevice, st));
+        SVB_CUDA(cudaMemcpyAsync(d_var.p, h_var, (size_t)a->ncol * 8, cudaMemcpyHostToDevice, st));
+    } else {
+        mean_var_device(a, d_mean.p, d_var.p);
+    }
     svb_matrix_s *b = matrix_alloc(a->nrow, a->ncol, a->nnz, dtype);
     try {
         SVB_CUDA(cudaMemcpyAsync(b->colptr, a->colptr, (size_t)(a->ncol + 1) * 8, cudaMemcpyDeviceToDevice, st));
@@ -361,6 +367,19 @@ int svb_scale(svb_matrix_t a, double scale_max, int dtype, svb_matrix_t *out, do
     }
     *out = b;
     SVB_API_END
+}
+
+int svb_scale(svb_matrix_t a, double scale_max, int dtype, svb_matrix_t *out, double *mu_out) {
+    return scale_impl(a, nullptr, nullptr, scale_max, dtype, out, mu_out);
+}
+
+int svb_scale_with_moments(svb_matrix_t a, const double *mean, const double *var, double scale_max, int dtype,
+                           svb_matrix_t *out, double *mu_out) {
+    if (!mean || !var) {
+        svb::set_last_error("svb_scale_with_moments: null moments");
+        return SVB_EARG;
+    }
+    return scale_impl(a, mean, var, scale_max, dtype, out, mu_out);
 }
 
 }  // extern "C"

@@ -72,3 +72,78 @@ def gather_rows(local: np.ndarray, bounds, rank: int, group=None):
         dist.broadcast(t, src=r, group=group)
         out[lo:hi] = t.cpu().numpy()
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# cell-sharded pre-processing (SURVEY 8e): per-rank sweeps + a merge of per-gene statistics.
+# "fast mode": the merged moments are mathematically the moments of the whole matrix but are not the
+# bits of one sequential Welford over all cells (that needs a rank-ordered carry; single-GPU runs use
+# the order-exact kernel). Every rank performs the same merge in rank order -> identical results.
+# ------------------------------------------------------------------------------------------------
+def allgather_f64(local: np.ndarray) -> np.ndarray:
+    """[nranks, len(local)] via the library's own allreduce (zero-padded slots)."""
+    lib = L.lib()
+    nr, rk = ctypes.c_int(), ctypes.c_int()
+    lib.svb_comm_info(ctypes.byref(nr), ctypes.byref(rk))
+    local = np.ascontiguousarray(local, dtype=np.float64).ravel()
+    buf = np.zeros((nr.value, local.shape[0]))
+    buf[rk.value] = local
+    L.check(lib.svb_comm_allreduce_f64(L.ptr(buf), buf.size))
+    return buf
+
+
+def merged_mean_var(dA):
+    """Per-gene mean / unbiased variance of the whole (row-sharded) matrix from per-rank Welford moments,
+    merged with Chan's pairwise formula in rank order."""
+    from .api import mean_var
+    mu_r, var_r = mean_var(dA)
+    n_r = float(dA.shape[0])
+    g = mu_r.shape[0]
+    packed = allgather_f64(np.concatenate([[n_r], np.asarray(mu_r, dtype=np.float64), np.asarray(var_r, dtype=np.float64)]))
+    n = 0.0
+    mean = np.zeros(g)
+    m2 = np.zeros(g)
+    for row in packed:
+        nb, mb, vb = row[0], row[1:1 + g], row[1 + g:]
+        if nb == 0:
+            continue
+        m2b = vb * (nb - 1.0) if nb > 1 else np.zeros(g)
+        delta = mb - mean
+        tot = n + nb
+        mean = mean + delta * (nb / tot)
+        m2 = m2 + m2b + delta * delta * (n * nb / tot)
+        n = tot
+    return mean, m2 / (n - 1.0), int(n)
+
+
+def sharded_vst_metric(counts, loess_span=0.5, expected_std_fn=None):
+    """variance_stabilizing_transformation (variablefeatures.jl:34-50) over a row-sharded count matrix."""
+    from .api import standardized_var_clipped
+    from .loess import loess_fit_predict
+    mu, var, m_total = merged_mean_var(counts)
+    sd = np.sqrt(var)
+    non_const = sd > 0
+    expected = sd.copy()
+    if expected_std_fn is not None:
+        expected[non_const] = expected_std_fn(mu[non_const])
+    else:
+        expected[non_const] = 10.0 ** loess_fit_predict(np.log10(mu[non_const]), np.log10(sd[non_const]), span=loess_span)
+    expected = np.where(np.isnan(expected), 0.0, expected)
+    # per-rank numerator sum_nz clip(.)^2 + (#zeros) clip(0)^2 is additive over cells; vmax uses the global m
+    part = standardized_var_clipped(counts, mu, expected, vmax=np.sqrt(float(m_total))) * (counts.shape[0] - 1.0)
+    total = allgather_f64(part).sum(axis=0)
+    return total / (m_total - 1.0)
+
+
+def sharded_scale_features(Y, scale_max=np.inf, features=None):
+    """scale_features (scaling.jl:335-357) over a row-sharded matrix: returns (DeviceMatrix B_local, mu)."""
+    from .api import DeviceMatrix, _DT
+    if features is not None:
+        Y = Y.columns(np.asarray(features, dtype=np.int64))
+    mean, var, _ = merged_mean_var(Y)
+    mu = np.empty(Y.shape[1])
+    h = ctypes.c_void_p()
+    dtype = np.float32 if Y.vtype == L.SVB_F32 else np.float64
+    L.check(L.lib().svb_scale_with_moments(Y._h, L.ptr(np.ascontiguousarray(mean)), L.ptr(np.ascontiguousarray(var)),
+                                            float(scale_max), _DT[np.dtype(dtype)], ctypes.byref(h), L.ptr(mu)))
+    return DeviceMatrix(h), mu

@@ -340,7 +340,7 @@ def test_irlba_errors(sv):
 # ---------------------------------------------------------------------------------------------
 def test_pipeline_config1_against_oracle(sv, orc):
     nu = 50
-    counts = sv.synthetic_counts(2700, 32738, 852.0, programs=64, seed=20260101)
+    counts = sv.synthetic_counts(2700, 32738, 852.0, programs=50, seed=20260101)
     X = counts.to_host()
     assert X.shape == (2700, 32738) and 0.8 * 852 < X.nnz / 2700 < 1.2 * 852
     Y = sv.normalize_cells(counts, method="lognormalize", scale_factor=1e4)
