@@ -48,7 +48,7 @@ __device__ __forceinline__ double block_sum(double v, double *red /* >= 32 doubl
 
 template <typename V, typename IdxT, int LPS>
 __device__ __forceinline__ double seg_dot(const V *__restrict__ val, const IdxT *__restrict__ idx, int64_t beg,
-                                          int64_t end, const double *__restrict__ xs, int sub_lane) {
+                                          int64_t end, const double *__restrict__ xs, int sub_lane, unsigned submask) {
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     int64_t k = beg + sub_lane;
     for (; k + 3 * LPS < end; k += 4 * LPS) {
@@ -62,21 +62,43 @@ __device__ __forceinline__ double seg_dot(const V *__restrict__ val, const IdxT 
     for (; k < end; k += LPS) a0 = fma((double)__ldg(val + k), xs[__ldg(idx + k)], a0);
     double acc = (a0 + a1) + (a2 + a3);
 #pragma unroll
-    for (int o = LPS >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    for (int o = LPS >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(submask, acc, o);
     return acc;
+}
+
+// first index s in [0, len] with ptr[s] >= target (ptr ascending)
+__device__ __forceinline__ int64_t lower_bound_i64(const int64_t *__restrict__ ptr, int64_t len, int64_t target) {
+    int64_t lo = 0, hi = len;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(ptr + mid) < target) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// CTA b of G owns the segments whose first nonzero lies in its 1/G share of the nonzero stream: equal
+// bytes per CTA whatever the segment lengths are. Every segment id belongs to exactly one CTA.
+__device__ __forceinline__ void cta_segment_range(const int64_t *__restrict__ ptr, int64_t nseg, int64_t nnz, int64_t &s0,
+                                                  int64_t &s1) {
+    const int64_t G = gridDim.x, b = blockIdx.x;
+    const int64_t lo = (int64_t)(((__int128)nnz * b) / G), hi = (int64_t)(((__int128)nnz * (b + 1)) / G);
+    s0 = (b == 0) ? 0 : lower_bound_i64(ptr, nseg, lo);
+    s1 = (b == G - 1) ? nseg : lower_bound_i64(ptr, nseg, hi);
 }
 
 // ---------------------------------------------------------------------------------------------
 // forward: y_i = alpha*(sum_j a_ij x_j - mu.x) + beta*y_i + csign*(*coef)*cvec_i
+// persistent grid (one resident wave); sub-warps of LPS lanes grab cells dynamically inside the CTA's range
 // ---------------------------------------------------------------------------------------------
 template <typename V, typename IdxT, int LPS, bool XSMEM>
-__global__ void __launch_bounds__(256) spmv_fwd_kernel(const int64_t *__restrict__ rowptr, const IdxT *__restrict__ fidx,
-                                                       const V *__restrict__ fval, int64_t m, int64_t n,
-                                                       const double *__restrict__ x, const double *__restrict__ mu,
-                                                       double alpha, double beta, double *__restrict__ y,
-                                                       const double *__restrict__ coef, double csign,
-                                                       const double *__restrict__ cvec) {
+__global__ void __launch_bounds__(256, 6) spmv_fwd_kernel(const int64_t *__restrict__ rowptr, const IdxT *__restrict__ fidx,
+                                                          const V *__restrict__ fval, int64_t m, int64_t n, int64_t nnz,
+                                                          const double *__restrict__ x, const double *__restrict__ mu,
+                                                          double alpha, double beta, double *__restrict__ y,
+                                                          const double *__restrict__ coef, double csign,
+                                                          const double *__restrict__ cvec) {
     extern __shared__ double smem[];
+    __shared__ unsigned long long next_row;
     double *red = smem;       // 32 doubles
     double *xs = smem + 32;   // n doubles when XSMEM
     double part = 0.0;
@@ -89,72 +111,77 @@ __global__ void __launch_bounds__(256) spmv_fwd_kernel(const int64_t *__restrict
     } else if (mu) {
         for (int64_t j = threadIdx.x; j < n; j += blockDim.x) part = fma(mu[j], x[j], part);
     }
-    const double mudot = mu ? block_sum(part, red) : 0.0;  // contains the __syncthreads that publish xs
+    int64_t r0, r1;
+    cta_segment_range(rowptr, m, nnz, r0, r1);
+    constexpr int NSUB = 256 / LPS;
+    if (threadIdx.x == 0) next_row = (unsigned long long)(r0 + NSUB);
+    const double mudot = mu ? block_sum(part, red) : 0.0;  // contains the __syncthreads that publish xs / next_row
     if (!mu) __syncthreads();
     const double *xg = XSMEM ? xs : x;
     const double c = (coef != nullptr) ? csign * (*coef) : 0.0;
 
-    const int sub_lane = threadIdx.x & (LPS - 1);
-    const int64_t subs_per_cta = blockDim.x / LPS;
-    const int64_t sub = (int64_t)blockIdx.x * subs_per_cta + threadIdx.x / LPS;
-    const int64_t nsub = (int64_t)gridDim.x * subs_per_cta;
-    // every lane of a warp runs the same number of iterations (shuffles need the full warp)
-    const int64_t iters = (m + nsub - 1) / nsub;
-    for (int64_t it = 0; it < iters; ++it) {
-        const int64_t row = it * nsub + sub;
-        double acc = 0.0;
-        if (row < m) acc = seg_dot<V, IdxT, LPS>(fval, fidx, rowptr[row], rowptr[row + 1], xg, sub_lane);
-        else {
-#pragma unroll
-            for (int o = LPS >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        }
-        if (row < m && sub_lane == 0) {
+    const int lane = threadIdx.x & 31;
+    const int sub_lane = lane & (LPS - 1);
+    const unsigned submask = (LPS == 32) ? 0xffffffffu : (((1u << LPS) - 1u) << (lane & ~(LPS - 1)));
+    int64_t row = r0 + threadIdx.x / LPS;
+    while (row < r1) {
+        const double acc = seg_dot<V, IdxT, LPS>(fval, fidx, __ldg(rowptr + row), __ldg(rowptr + row + 1), xg, sub_lane, submask);
+        unsigned long long nxt = 0;
+        if (sub_lane == 0) {
             double r = alpha * (acc - mudot);
             if (beta != 0.0) r = fma(beta, y[row], r);
             if (coef != nullptr) r = fma(c, cvec[row], r);
             y[row] = r;
+            nxt = atomicAdd(&next_row, 1ull);
         }
+        row = (int64_t)__shfl_sync(submask, nxt, lane & ~(LPS - 1));
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // adjoint, stage 1: partial[t][g] = sum_{cells i in tile t} a_ig * w_i ; partial[t][n] = sum_i w_i
-// grid (ntiles, GS); CTA (t, q) owns every GS-th group of genes of tile t.
+// persistent grid; a CTA walks its equal-nnz range of (tile, gene) segments, reloading the w tile
+// (R doubles, shared memory) when the range crosses a tile boundary.
 // ---------------------------------------------------------------------------------------------
 template <typename V, int LPS>
-__global__ void __launch_bounds__(256) spmv_adj_kernel(const int64_t *__restrict__ gptr, const uint16_t *__restrict__ rloc,
-                                                       const V *__restrict__ aval, int64_t m, int64_t n, int log2R,
-                                                       const double *__restrict__ w, double *__restrict__ partial) {
+__global__ void __launch_bounds__(256, 5) spmv_adj_kernel(const int64_t *__restrict__ gptr, const uint16_t *__restrict__ rloc,
+                                                          const V *__restrict__ aval, int64_t m, int64_t n, int log2R,
+                                                          int64_t ntiles, int64_t nnz, const double *__restrict__ w,
+                                                          double *__restrict__ partial) {
     extern __shared__ double smem[];
+    __shared__ unsigned long long next_seg;
     double *red = smem;      // 32
     double *ws = smem + 32;  // R
-    const int64_t t = blockIdx.x;
-    const int64_t R = 1ll << log2R;
-    const int64_t row0 = t << log2R;
-    double part = 0.0;
-    for (int64_t r = threadIdx.x; r < R; r += blockDim.x) {
-        const double wv = (row0 + r < m) ? w[row0 + r] : 0.0;
-        ws[r] = wv;
-        part += wv;
-    }
-    const double wsum = block_sum(part, red);
-    if (blockIdx.y == 0 && threadIdx.x == 0) partial[t * (n + 1) + n] = wsum;
-
-    const int sub_lane = threadIdx.x & (LPS - 1);
-    const int64_t subs_per_cta = blockDim.x / LPS;
-    const int64_t sub = (int64_t)blockIdx.y * subs_per_cta + threadIdx.x / LPS;
-    const int64_t nsub = (int64_t)gridDim.y * subs_per_cta;
-    const int64_t iters = (n + nsub - 1) / nsub;
-    const int64_t *gp = gptr + t * n;
-    for (int64_t it = 0; it < iters; ++it) {
-        const int64_t g = it * nsub + sub;
-        double acc = 0.0;
-        if (g < n) acc = seg_dot<V, uint16_t, LPS>(aval, rloc, gp[g], gp[g + 1], ws, sub_lane);
-        else {
-#pragma unroll
-            for (int o = LPS >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    const int64_t R = (int64_t)1 << log2R;
+    int64_t s0, s1;
+    cta_segment_range(gptr, ntiles * n, nnz, s0, s1);
+    constexpr int NSUB = 256 / LPS;
+    const int lane = threadIdx.x & 31;
+    const int sub_lane = lane & (LPS - 1);
+    const unsigned submask = (LPS == 32) ? 0xffffffffu : (((1u << LPS) - 1u) << (lane & ~(LPS - 1)));
+    for (int64_t t = s0 / n; t < ntiles && t * n < s1; ++t) {
+        const int64_t a = max(s0, t * n), b = min(s1, (t + 1) * n);
+        const int64_t row0 = t << log2R;
+        __syncthreads();  // everybody is done with the previous tile
+        double part = 0.0;
+        for (int64_t r = threadIdx.x; r < R; r += blockDim.x) {
+            const double wv = (row0 + r < m) ? w[row0 + r] : 0.0;
+            ws[r] = wv;
+            part += wv;
         }
-        if (g < n && sub_lane == 0) partial[t * (n + 1) + g] = acc;
+        if (threadIdx.x == 0) next_seg = (unsigned long long)(a + NSUB);
+        const double wsum = block_sum(part, red);  // also publishes ws / next_seg
+        if (a == t * n && threadIdx.x == 0) partial[t * (n + 1) + n] = wsum;
+        int64_t s = a + threadIdx.x / LPS;
+        while (s < b) {
+            const double acc = seg_dot<V, uint16_t, LPS>(aval, rloc, __ldg(gptr + s), __ldg(gptr + s + 1), ws, sub_lane, submask);
+            unsigned long long nxt = 0;
+            if (sub_lane == 0) {
+                partial[t * (n + 1) + (s - t * n)] = acc;
+                nxt = atomicAdd(&next_seg, 1ull);
+            }
+            s = (int64_t)__shfl_sync(submask, nxt, lane & ~(LPS - 1));
+        }
     }
 }
 
@@ -225,6 +252,14 @@ __global__ void __launch_bounds__(1024) dot_small_kernel(const double *__restric
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
+// one resident wave: SMs x (CTAs that fit per SM for this kernel and shared-memory size)
+template <typename K>
+static int resident_grid(K kernel, size_t smem) {
+    int per_sm = 0;
+    SVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem));
+    return std::max(1, per_sm) * ctx().sm_count;
+}
+
 template <typename V, typename IdxT, int LPS>
 static void launch_fwd_lps(svb_operator_s *op, double alpha, const double *dx, double beta, double *dy, const double *coef,
                            double csign, const double *cvec) {
@@ -232,20 +267,17 @@ static void launch_fwd_lps(svb_operator_s *op, double alpha, const double *dx, d
     const size_t xs_bytes = (size_t)op->n * sizeof(double);
     const bool xsmem = xs_bytes + 256 + 1024 <= C.smem_optin;
     const size_t smem = 32 * sizeof(double) + (xsmem ? xs_bytes : 0);
-    int ctas_per_sm = 8;
-    if (xsmem) ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (C.smem_optin + 1024) / (smem + 1024)));
-    const int64_t subs_per_cta = 256 / LPS;
-    int64_t grid = std::min<int64_t>((op->m + subs_per_cta - 1) / subs_per_cta, (int64_t)C.sm_count * ctas_per_sm);
-    grid = std::max<int64_t>(grid, 1);
     if (xsmem) {
         auto k = spmv_fwd_kernel<V, IdxT, LPS, true>;
         if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<(unsigned)grid, 256, smem, C.stream>>>(op->rowptr, (const IdxT *)op->fidx, (const V *)op->fval, op->m, op->n, dx,
-                                                   op->mu, alpha, beta, dy, coef, csign, cvec);
+        if (op->fwd_grid == 0) op->fwd_grid = (int)std::min<int64_t>(resident_grid(k, smem), std::max<int64_t>(1, op->m / 8));
+        k<<<(unsigned)op->fwd_grid, 256, smem, C.stream>>>(op->rowptr, (const IdxT *)op->fidx, (const V *)op->fval, op->m, op->n,
+                                                           op->nnz, dx, op->mu, alpha, beta, dy, coef, csign, cvec);
     } else {
         auto k = spmv_fwd_kernel<V, IdxT, LPS, false>;
-        k<<<(unsigned)grid, 256, smem, C.stream>>>(op->rowptr, (const IdxT *)op->fidx, (const V *)op->fval, op->m, op->n, dx,
-                                                   op->mu, alpha, beta, dy, coef, csign, cvec);
+        if (op->fwd_grid == 0) op->fwd_grid = (int)std::min<int64_t>(resident_grid(k, smem), std::max<int64_t>(1, op->m / 8));
+        k<<<(unsigned)op->fwd_grid, 256, smem, C.stream>>>(op->rowptr, (const IdxT *)op->fidx, (const V *)op->fval, op->m, op->n,
+                                                           op->nnz, dx, op->mu, alpha, beta, dy, coef, csign, cvec);
     }
     SVB_LAUNCH_CHECK();
 }
@@ -270,8 +302,12 @@ static void launch_adj_lps(svb_operator_s *op, const double *dx) {
     const size_t smem = (32 + (size_t)op->R) * sizeof(double);
     auto k = spmv_adj_kernel<V, LPS>;
     if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)op->ntiles, (unsigned)op->adj_gs);
-    k<<<grid, 256, smem, C.stream>>>(op->gptr, op->rloc, (const V *)op->aval, op->m, op->n, (int)op->log2R, dx, op->partial);
+    if (op->adj_grid == 0) {
+        const int64_t nseg = op->ntiles * op->n;
+        op->adj_grid = (int)std::max<int64_t>(1, std::min<int64_t>(resident_grid(k, smem), nseg / 8 + 1));
+    }
+    k<<<(unsigned)op->adj_grid, 256, smem, C.stream>>>(op->gptr, op->rloc, (const V *)op->aval, op->m, op->n, (int)op->log2R,
+                                                       op->ntiles, op->nnz, dx, op->partial);
     SVB_LAUNCH_CHECK();
 }
 

@@ -140,7 +140,8 @@ struct svb_operator_s {
     // adjoint layout: cells tiled by R, gene-major inside a tile
     int64_t R = 0, ntiles = 0;
     int log2R = 0;
-    int fwd_lps = 0, adj_lps = 0, adj_gs = 1;  // launch shape knobs (0 = choose from the average segment length)
+    int fwd_lps = 0, adj_lps = 0, adj_gs = 1;
+    int fwd_grid = 0, adj_grid = 0;          // persistent grid sizes (one resident wave), set at first launch  // launch shape knobs (0 = choose from the average segment length)
     int64_t *gptr = nullptr;        // [ntiles*n + 1] segment (tile, gene) -> offset
     uint16_t *rloc = nullptr;       // [nnz] cell index inside the tile
     void *aval = nullptr;           // [nnz]
