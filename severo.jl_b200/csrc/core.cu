@@ -1,4 +1,5 @@
 // core.cu — library context, error reporting, per-class device timers, device prefix scan.
+#define SVB_NO_ALLOC_MACROS
 #include "svb_internal.h"
 
 #include <cstring>
@@ -20,6 +21,20 @@ void require_init() {
 }
 
 void count_launch(int n) { ctx().launches += n; }
+
+cudaError_t dev_malloc(void **p, size_t bytes) {
+    Context &C = ctx();
+    if (bytes == 0) bytes = 8;
+    if (C.initialised && C.stream && C.pool_ok) return cudaMallocAsync(p, bytes, C.stream);
+    return cudaMalloc(p, bytes);
+}
+
+cudaError_t dev_free(void *p) {
+    Context &C = ctx();
+    if (!p) return cudaSuccess;
+    if (C.initialised && C.stream && C.pool_ok) return cudaFreeAsync(p, C.stream);
+    return cudaFree(p);  // valid for pool memory too (synchronises)
+}
 
 KTimer::KTimer(int c, double algorithmic_bytes, int nlaunch) : cls(c), bytes(algorithmic_bytes) {
     Context &C = ctx();
@@ -152,6 +167,16 @@ int svb_init(int device) {
     if (!C.stream) {
         SVB_CUDA(cudaStreamCreateWithFlags(&C.stream, cudaStreamNonBlocking));
         C.own_stream = true;
+    }
+    {
+        int pools = 0;
+        cudaDeviceGetAttribute(&pools, cudaDevAttrMemoryPoolsSupported, device);
+        cudaMemPool_t pool;
+        if (pools && cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t thr = UINT64_MAX;
+            C.pool_ok = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr) == cudaSuccess;
+        }
+        cudaGetLastError();
     }
     C.initialised = true;
     SVB_API_END

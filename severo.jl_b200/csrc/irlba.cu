@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstring>
 
 using namespace svb;
@@ -96,6 +97,9 @@ static void irlba_run(svb_operator_s *op, int64_t nu_, int64_t work_, int64_t ma
     S.n = op->n;
     S.st = C.stream;
     const int64_t m = S.m, n = S.n;
+    const bool dbg = getenv("SVB_DEBUG_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_alloc = 0, t_svd = 0, t_wait = 0, t_issue = 0, t_start = now(), t_mark = 0;
     // global row count decides the work-size clamp (irlba.jl:56-58 uses min(m, n) of the whole matrix)
     double mglob = (double)m;
     if (C.nranks > 1) {
@@ -116,6 +120,7 @@ static void irlba_run(svb_operator_s *op, int64_t nu_, int64_t work_, int64_t ma
     const int w = (int)work, nu = (int)nu_;
     S.w = w;
     S.nu = nu;
+    t_mark = now();
     S.V.alloc((size_t)n * w);
     S.V2.alloc((size_t)n * w);
     S.W.alloc((size_t)m * w);
@@ -128,6 +133,7 @@ static void irlba_run(svb_operator_s *op, int64_t nu_, int64_t work_, int64_t ma
     S.Bs.alloc((size_t)w);
     S.sc.alloc(8);
     S.flag.alloc(1);
+    t_alloc += now() - t_mark;
     SVB_CUDA(cudaMemsetAsync(S.flag.p, 0, sizeof(int), S.st));
     SVB_CUDA(cudaMemsetAsync(S.Bd.p, 0, w * sizeof(double), S.st));
     SVB_CUDA(cudaMemsetAsync(S.Bs.p, 0, w * sizeof(double), S.st));
@@ -153,6 +159,7 @@ static void irlba_run(svb_operator_s *op, int64_t nu_, int64_t work_, int64_t ma
     while (iter < maxit) {
         int j = (iter > 0 || restart > 0) ? k : 0;
         const int j0 = j;
+        t_mark = now();
         bool tiny = false;
         // W_j = S*V_j ; orthogonalise against the kept W ; normalise
         op_apply(op, false, 1.0, S.Vc(j), 0.0, S.Wc(j));
@@ -185,7 +192,10 @@ static void irlba_run(svb_operator_s *op, int64_t nu_, int64_t work_, int64_t ma
         SVB_CUDA(cudaMemcpyAsync(hBs.data(), S.Bs.p, w * 8, cudaMemcpyDeviceToHost, S.st));
         SVB_CUDA(cudaMemcpyAsync(&nF2, S.nrm2F(), 8, cudaMemcpyDeviceToHost, S.st));
         SVB_CUDA(cudaMemcpyAsync(&hflag, S.flag.p, sizeof(int), cudaMemcpyDeviceToHost, S.st));
+        t_issue += now() - t_mark;
+        t_mark = now();
         SVB_CUDA(cudaStreamSynchronize(S.st));
+        t_wait += now() - t_mark;
         if (hflag && !S.careful) {
             // a (near) breakdown happened somewhere in this sweep: redo it with host-checked norms
             S.careful = true;
@@ -196,7 +206,9 @@ static void irlba_run(svb_operator_s *op, int64_t nu_, int64_t work_, int64_t ma
             B[(size_t)c * w + c] = hBd[c];
             if (c + 1 < w) B[(size_t)(c + 1) * w + c] = hBs[c];
         }
+        t_mark = now();
         small_svd(w, B.data(), P.data(), sig.data(), Q.data());
+        t_svd += now() - t_mark;
         have_svd = true;
         const double RF = std::sqrt(nF2);
         for (int i = 0; i < w; ++i) resid[i] = RF * P[(size_t)i * w + (w - 1)];
@@ -236,9 +248,11 @@ static void irlba_run(svb_operator_s *op, int64_t nu_, int64_t work_, int64_t ma
     res->iter = iter;
     res->mprod = S.mprod;
     res->info = info;
+    t_mark = now();
     SVB_CUDA(cudaMalloc((void **)&res->U, (size_t)m * nu * 8));
     SVB_CUDA(cudaMalloc((void **)&res->V, (size_t)n * nu * 8));
     SVB_CUDA(cudaMalloc((void **)&res->s, (size_t)nu * 8));
+    t_alloc += now() - t_mark;
     if (have_svd) {
         SVB_CUDA(cudaMemcpyAsync(S.Pd.p, P.data(), (size_t)w * w * 8, cudaMemcpyHostToDevice, S.st));
         SVB_CUDA(cudaMemcpyAsync(S.Qd.p, Q.data(), (size_t)w * w * 8, cudaMemcpyHostToDevice, S.st));
@@ -251,6 +265,9 @@ static void irlba_run(svb_operator_s *op, int64_t nu_, int64_t work_, int64_t ma
         SVB_CUDA(cudaMemsetAsync(res->s, 0, (size_t)nu * 8, S.st));
     }
     SVB_CUDA(cudaStreamSynchronize(S.st));
+    if (dbg)
+        fprintf(stderr, "[svb irlba] total %.2f ms: alloc %.2f, issue %.2f, wait %.2f, svd %.2f (iters %lld, mprod %lld)\n",
+                (now() - t_start) * 1e3, t_alloc * 1e3, t_issue * 1e3, t_wait * 1e3, t_svd * 1e3, (long long)iter, (long long)S.mprod);
 }
 
 __global__ void colscale_kernel(const double *__restrict__ U, const double *__restrict__ s, int64_t m, int64_t nu,

@@ -19,6 +19,17 @@ struct Error : std::runtime_error {
 
 void set_last_error(const std::string &msg);
 
+// Every device allocation of the library goes through the stream-ordered pool (cudaMallocAsync /
+// cudaFreeAsync on the library stream, release threshold = unlimited): a plain cudaFree of the
+// multi-GB Lanczos workspace costs ~100 ms per solve on a B200, the pool makes it free.
+cudaError_t dev_malloc(void **p, size_t bytes);
+cudaError_t dev_free(void *p);
+
+#ifndef SVB_NO_ALLOC_MACROS
+#define cudaMalloc(pp, bytes) svb::dev_malloc((void **)(pp), (bytes))
+#define cudaFree(p) svb::dev_free((void *)(p))
+#endif
+
 #define SVB_CUDA(expr)                                                                       \
     do {                                                                                     \
         cudaError_t _e = (expr);                                                             \
@@ -63,6 +74,7 @@ struct Context {
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    bool pool_ok = false;  // stream-ordered allocator available
     // profiling
     bool profile = false;
     double prof_ms[SVB_K_NCLASS] = {0};
