@@ -1,0 +1,152 @@
+# SeveroB200.jl — Julia overlay that routes Severo.jl's IRLBA-PCA hot path through libsevero_b200.so.
+# Same function names, keyword arguments and return types as the reference (src/normalize.jl:40-79,
+# src/scaling.jl:335-357, src/irlba.jl:47-99, src/embedding.jl:46-94); only the bodies change: every loop /
+# the `ccall(("irlba", libcell), ...)` becomes a `ccall` into the C ABI of include/severo_b200.h.
+# NOTE: Julia is not installed in the build image, so this file is the binding a maintainer would add; it is
+# exercised through the identical C ABI by the Python ctypes harness (severo.jl_b200/api.py).
+module SeveroB200
+
+using SparseArrays, LinearAlgebra, NamedArrays
+import Severo
+import Severo: CenteredMatrix, NamedCenteredMatrix, NamedCountMatrix, LinearEmbedding
+
+const libsvb = get(ENV, "SEVERO_B200_LIB", joinpath(@__DIR__, "..", "severo.jl_b200", "libsevero_b200.so"))
+const SVB_I32, SVB_I64, SVB_F32, SVB_F64 = Cint(0), Cint(1), Cint(2), Cint(3)
+svbtype(::Type{Int32}) = SVB_I32; svbtype(::Type{Int64}) = SVB_I64
+svbtype(::Type{Float32}) = SVB_F32; svbtype(::Type{Float64}) = SVB_F64
+
+function check(rc::Cint)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:svb_last_error, libsvb), Cstring, ()))
+    error("severo_b200 [$rc]: $msg")
+end
+
+__init__() = check(ccall((:svb_init, libsvb), Cint, (Cint,), parse(Cint, get(ENV, "LOCAL_RANK", "0"))))
+
+# ---- device handles -------------------------------------------------------------------------------
+mutable struct DeviceMatrix
+    h::Ptr{Cvoid}
+    function DeviceMatrix(h)
+        x = new(h)
+        finalizer(d -> ccall((:svb_matrix_free, libsvb), Cint, (Ptr{Cvoid},), d.h), x)
+    end
+end
+
+# SparseMatrixCSC{T,Int64}: colptr / rowval are 1-based Int64 — passed as they are (index_base = 1)
+function upload(A::SparseMatrixCSC{T,Int64}) where {T<:Union{Int32,Int64,Float32,Float64}}
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:svb_csc_upload, libsvb), Cint,
+        (Int64, Int64, Ptr{Int64}, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint, Cint, Ref{Ptr{Cvoid}}),
+        size(A, 1), size(A, 2), A.colptr, A.rowval, SVB_I64, A.nzval, svbtype(T), 1, h))
+    DeviceMatrix(h[])
+end
+
+function download_values(d::DeviceMatrix, ::Type{R}, nnz::Integer) where {R}
+    nz = Vector{R}(undef, nnz)
+    check(ccall((:svb_matrix_download, libsvb), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Cvoid}, Cint, Cint),
+        d.h, C_NULL, C_NULL, nz, svbtype(R), 1))
+    nz
+end
+
+# ---- normalize.jl:40-79 ------------------------------------------------------------------------------
+function normalize_cells(X::SparseMatrixCSC{<:Integer,Int64}; method=:lognormalize, scale_factor::Real=1., dtype::Type{T}=Float64) where {T<:AbstractFloat}
+    method = Symbol(method)
+    code = method == :lognormalize ? Cint(0) : method == :relativecounts ? Cint(1) : error("unknown normalization method: $method")
+    d = upload(X)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:svb_normalize, libsvb), Cint, (Ptr{Cvoid}, Cint, Float64, Cint, Ref{Ptr{Cvoid}}),
+        d.h, code, Float64(convert(dtype, scale_factor)), svbtype(dtype), h))
+    out = DeviceMatrix(h[])
+    SparseMatrixCSC(size(X, 1), size(X, 2), copy(X.colptr), copy(X.rowval), download_values(out, dtype, nnz(X)))
+end
+
+function normalize_cells(X::NamedCountMatrix; kw...)
+    S = normalize_cells(X.array; kw...)
+    NamedArray(S, X.dicts, X.dimnames)                       # normalize.jl:77-78
+end
+
+# ---- scaling.jl:119-147, 199-217, 335-357 ------------------------------------------------------------
+function mean_var(A::SparseMatrixCSC)
+    d = upload(A); mu = zeros(size(A, 2)); var = zeros(size(A, 2))
+    check(ccall((:svb_mean_var, libsvb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), d.h, mu, var))
+    mu, var
+end
+
+function scale_data(A::SparseMatrixCSC, scale_max::R=Inf) where {R<:AbstractFloat}
+    d = upload(A); mu = zeros(Float64, size(A, 2)); h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:svb_scale, libsvb), Cint, (Ptr{Cvoid}, Float64, Cint, Ref{Ptr{Cvoid}}, Ptr{Float64}),
+        d.h, Float64(scale_max), svbtype(R), h, mu))
+    out = DeviceMatrix(h[])
+    B = SparseMatrixCSC(size(A, 1), size(A, 2), copy(A.colptr), copy(A.rowval), download_values(out, R, nnz(A)))
+    B, convert(Vector{R}, mu)
+end
+
+function scale_features(X::NamedArray{T,2,SparseMatrixCSC{T,Int64}}; scale_max::Real=Inf,
+        dtype::Type{<:AbstractFloat}=(T <: AbstractFloat ? T : Float64), features=nothing) where {T}
+    features !== nothing && (X = X[:, features])
+    B, mu = scale_data(X.array, convert(dtype, scale_max))
+    CenteredMatrix(NamedArray(B, X.dicts, X.dimnames), NamedArray(mu, (X.dicts[2],), (X.dimnames[2],)))   # scaling.jl:344
+end
+
+# ---- the operator + irlba.jl:47-99 -----------------------------------------------------------------------
+mutable struct DeviceOperator
+    h::Ptr{Cvoid}
+    function DeviceOperator(h)
+        x = new(h)
+        finalizer(o -> ccall((:svb_operator_free, libsvb), Cint, (Ptr{Cvoid},), o.h), x)
+    end
+end
+
+_mu_ptr(mu::Nothing) = Ptr{Float64}(C_NULL)
+_mu_ptr(mu::AbstractVector) = convert(Vector{Float64}, mu)
+
+function operator(A::SparseMatrixCSC, mu=nothing; transposed::Bool=false)
+    d = upload(A isa SparseMatrixCSC{<:AbstractFloat} ? A : convert(SparseMatrixCSC{Float64,Int64}, A))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:svb_operator_create, libsvb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Ref{Ptr{Cvoid}}),
+        d.h, _mu_ptr(mu), Cint(transposed), h))
+    DeviceOperator(h[])
+end
+operator(A::Adjoint{<:Any,<:SparseMatrixCSC}, mu=nothing) = operator(parent(A), mu; transposed=true)   # test_irlba.jl:111
+function operator(A::StridedMatrix{Float64}, mu=nothing)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:svb_operator_create_dense, libsvb), Cint,
+        (Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Cint, Ref{Ptr{Cvoid}}),
+        size(A, 1), size(A, 2), A, stride(A, 2), _mu_ptr(mu), Cint(0), h))
+    DeviceOperator(h[])
+end
+operator(S::CenteredMatrix) = operator(Severo._A_mu(S)...)
+operator(S::NamedCenteredMatrix) = operator(S.A.array, S.mu.array)
+
+# Same signature, buffers, defaults and error as Severo.irlba! (irlba.jl:47-76); `rng` only seeds `init`
+# (the breakdown vector comes from the device generator: no callback into Julia, see T6).
+function irlba!(rng, A, U::Matrix{Float64}, s::Vector{Float64}, V::Matrix{Float64}; init=nothing, tol=1e-5, svtol=tol, maxit=1000, restart=0)
+    m, n = size(A)
+    nu = length(s)
+    m_b = min(nu + 7, min(m, n))                               # irlba.jl:50-58
+    init === nothing && (init = randn(rng, n))                  # irlba.jl:62-64
+    op = operator(A)
+    iter = Ref{Int64}(0); mprod = Ref{Int64}(0)
+    info = ccall((:svb_irlba, libsvb), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Int64}, Ref{Int64}),
+        op.h, nu, m_b, maxit, restart, tol, svtol, init, s, U, V, iter, mprod)
+    info == 0 || error("convergence failed")                  # irlba.jl:73
+    SVD(U, s, V')                                              # irlba.jl:75
+end
+
+function irlba(A, nu::Integer; kw...)
+    m, n = size(A)
+    irlba!(Random.default_rng(), A, zeros(m, nu), zeros(nu), zeros(n, nu); kw...)
+end
+
+# embedding.jl:46-94 with algorithm = :irlba
+function _pca(X, npcs::Int64; kw...)
+    m, n = size(X)
+    npcs = min(min(m, n), npcs)
+    S = irlba(X, npcs; kw...)
+    Z = view(S.U, :, 1:npcs) * Diagonal(view(S.S, 1:npcs))
+    stdev = view(S.S, 1:npcs) ./ sqrt(max(1, m - 1))
+    Z, stdev, S.V
+end
+
+end # module
