@@ -1,0 +1,182 @@
+// bsvd.cu — the per-restart bookkeeping of IRLBA on the device, in ONE single-CTA kernel:
+//   1. SVD of the w x w projected matrix B (one-sided Jacobi, parallel round-robin ordering, G and the
+//      accumulated right rotations in shared memory, one warp per column pair);
+//   2. Ritz residuals  res_i = |F| * P[w-1, i], S_max, convergence count over the nu wanted values;
+//   3. the restart size k and the next B = [diag(sigma_1..k) | res column] written back in place.
+// The host reads one small status struct per sweep (it needs k and `converged` to launch the restart
+// products); P and Q never leave the device. libcell does this on the host with LAPACK dgesdd (call site
+// src/irlba.jl:66-71); with the cells sharded over 8 GPUs a 2 ms host SVD + uploads per sweep is >15 % of
+// the solve, the kernel takes well under 0.1 ms. All ranks run it redundantly on identical inputs.
+#include "svb_internal.h"
+
+#include <algorithm>
+
+namespace svb {
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(1024) bsvd_kernel(int w, int nu, double *__restrict__ B, double *__restrict__ P,
+                                                    double *__restrict__ Q, double *__restrict__ sig,
+                                                    double *__restrict__ sig_prev, const double *__restrict__ nrm2F,
+                                                    double *__restrict__ smax_io, double tol, double svtol, int k_in,
+                                                    const int *__restrict__ flag, BsvdStatus *__restrict__ status) {
+    extern __shared__ double sm[];
+    if (*flag) {  // a normalisation in this sweep hit a (near) breakdown: the host redoes the sweep, B untouched
+        if (threadIdx.x == 0) status->converged = -1;
+        return;
+    }
+    const int ld = w | 1;
+    double *G = sm;                      // [w][ld] column-major: column c at G + c*ld
+    double *V = G + (size_t)w * ld;      // accumulated right rotations
+    double *nrm = V + (size_t)w * ld;    // [w]
+    double *res = nrm + w;               // [w]
+    __shared__ int rotated;
+    __shared__ int rank_of[256];
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+    for (int idx = tid; idx < w * w; idx += nthreads) {
+        const int c = idx / w, i = idx - c * w;
+        G[c * ld + i] = B[idx];
+        V[c * ld + i] = (i == c) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    const double eps = 2.220446049250313e-16;
+    const int n = (w + 1) & ~1;  // even number of players (index w is a bye when w is odd)
+    int sweeps = 0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        if (tid == 0) rotated = 0;
+        __syncthreads();
+        for (int r = 0; r < n - 1; ++r) {
+            for (int pi = warp; pi < n / 2; pi += nwarps) {
+                int p, q;
+                if (pi == 0) {
+                    p = n - 1;
+                    q = r;
+                } else {
+                    p = (r + pi) % (n - 1);
+                    q = (r - pi + (n - 1)) % (n - 1);
+                }
+                if (p > q) { const int t = p; p = q; q = t; }
+                if (q >= w) continue;
+                double *gp = G + p * ld, *gq = G + q * ld;
+                double a = 0.0, b = 0.0, g = 0.0;
+                for (int i = lane; i < w; i += 32) {
+                    const double x = gp[i], y = gq[i];
+                    a = fma(x, x, a);
+                    b = fma(y, y, b);
+                    g = fma(x, y, g);
+                }
+                a = warp_sum_d(a);
+                b = warp_sum_d(b);
+                g = warp_sum_d(g);
+                if (g == 0.0 || fabs(g) <= eps * sqrt(a * b)) continue;
+                const double zeta = (b - a) / (2.0 * g);
+                const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                double *vp = V + p * ld, *vq = V + q * ld;
+                for (int i = lane; i < w; i += 32) {
+                    const double x = gp[i], y = gq[i];
+                    gp[i] = c * x - s * y;
+                    gq[i] = s * x + c * y;
+                    const double vx = vp[i], vy = vq[i];
+                    vp[i] = c * vx - s * vy;
+                    vq[i] = s * vx + c * vy;
+                }
+                if (lane == 0) rotated = 1;
+            }
+            __syncthreads();
+        }
+        ++sweeps;
+        const int any = rotated;
+        __syncthreads();
+        if (!any) break;
+    }
+    // singular values = column norms; rank them (descending, ties by column index)
+    for (int c = warp; c < w; c += nwarps) {
+        double a = 0.0;
+        for (int i = lane; i < w; i += 32) a = fma(G[c * ld + i], G[c * ld + i], a);
+        a = warp_sum_d(a);
+        if (lane == 0) nrm[c] = sqrt(a);
+    }
+    __syncthreads();
+    for (int c = tid; c < w; c += nthreads) {
+        int rk = 0;
+        const double mine = nrm[c];
+        for (int o = 0; o < w; ++o) rk += (nrm[o] > mine) || (nrm[o] == mine && o < c);
+        rank_of[c] = rk;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < w * w; idx += nthreads) {
+        const int c = idx / w, i = idx - c * w;
+        const int k = rank_of[c];
+        const double inv = nrm[c] > 0.0 ? 1.0 / nrm[c] : 0.0;
+        P[(size_t)k * w + i] = G[c * ld + i] * inv;
+        Q[(size_t)k * w + i] = V[c * ld + i];
+    }
+    const double last_diag = B[(size_t)(w - 1) * w + (w - 1)];  // S of the last Lanczos step (0 => invariant subspace)
+    const double RF = sqrt(*nrm2F);
+    for (int c = tid; c < w; c += nthreads) {
+        const int k = rank_of[c];
+        const double inv = nrm[c] > 0.0 ? 1.0 / nrm[c] : 0.0;
+        sig[k] = nrm[c];
+        res[k] = RF * (G[c * ld + (w - 1)] * inv);  // RF * P[w-1, k]
+    }
+    __syncthreads();
+    __shared__ int sh_k, sh_conv;
+    if (tid == 0) {
+        const double smax = fmax(*smax_io, sig[0]);
+        *smax_io = smax;
+        int nconv = 0;
+        for (int i = 0; i < nu; ++i) {
+            const double ratio = fabs(sig_prev[i] - sig[i]) / sig[i];
+            if (fabs(res[i]) < tol * smax && ratio < svtol) ++nconv;
+        }
+        const int converged = (nconv >= nu) || (last_diag == 0.0);
+        int k = k_in;
+        if (k < nu + nconv) k = nu + nconv;
+        if (k > w - 3) k = w - 3;
+        if (k < 1) k = 1;
+        sh_k = k;
+        sh_conv = converged;
+        status->converged = converged;
+        status->nconv = nconv;
+        status->k = k;
+        status->sweeps = sweeps;
+        status->sigma0 = sig[0];
+        status->RF = RF;
+    }
+    __syncthreads();
+    const int k = sh_k;
+    if (!sh_conv) {
+        // next projected matrix: B = 0 ; B_ii = sigma_i ; B_{i,k} = res_i (i < k)
+        for (int idx = tid; idx < w * w; idx += nthreads) {
+            const int c = idx / w, i = idx - c * w;
+            double v = 0.0;
+            if (i < k && c == i) v = sig[i];
+            if (i < k && c == k) v = res[i];
+            B[idx] = v;
+        }
+        for (int i = tid; i < w; i += nthreads) sig_prev[i] = sig[i];
+    }
+}
+
+size_t bsvd_smem_bytes(int w) { return ((size_t)2 * w * (w | 1) + 2 * (size_t)w) * sizeof(double); }
+
+bool bsvd_supported(int w) { return w <= 256 && bsvd_smem_bytes(w) + 2048 <= ctx().smem_optin; }
+
+void bsvd_launch(int w, int nu, double *B, double *P, double *Q, double *sig, double *sig_prev, const double *nrm2F,
+                 double *smax_io, double tol, double svtol, int k_in, const int *flag_dev, BsvdStatus *status_dev) {
+    const size_t smem = bsvd_smem_bytes(w);
+    if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(bsvd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // one warp per column pair: ceil(w/2) warps, at most 32
+    int warps = std::min(32, std::max(4, (w + 1) / 2));
+    KTimer kt(SVB_K_VECTOR, 8.0 * 3 * w * w);
+    bsvd_kernel<<<1, warps * 32, smem, ctx().stream>>>(w, nu, B, P, Q, sig, sig_prev, nrm2F, smax_io, tol, svtol, k_in, flag_dev, status_dev);
+    SVB_LAUNCH_CHECK();
+}
+
+}  // namespace svb

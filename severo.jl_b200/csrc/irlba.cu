@@ -36,7 +36,7 @@ struct Solver {
     int64_t m, n;
     int w, nu;
     cudaStream_t st;
-    DevBuf<double> V, V2, W, W2, F, T, Pd, Qd, Bd, Bs, sc;
+    DevBuf<double> V, V2, W, W2, F, T, Pd, Qd, sc;
     DevBuf<int> flag;
     bool careful = false;
     int64_t mprod = 0;
@@ -129,17 +129,22 @@ static void irlba_run(svb_operator_s *op, int64_t nu_, int64_t work_, int64_t ma
     S.T.alloc((size_t)w + 8);
     S.Pd.alloc((size_t)w * w);
     S.Qd.alloc((size_t)w * w);
-    S.Bd.alloc((size_t)w);
-    S.Bs.alloc((size_t)w);
     S.sc.alloc(8);
     S.flag.alloc(1);
     t_alloc += now() - t_mark;
     SVB_CUDA(cudaMemsetAsync(S.flag.p, 0, sizeof(int), S.st));
-    SVB_CUDA(cudaMemsetAsync(S.Bd.p, 0, w * sizeof(double), S.st));
-    SVB_CUDA(cudaMemsetAsync(S.Bs.p, 0, w * sizeof(double), S.st));
 
-    std::vector<double> B((size_t)w * w, 0.0), P((size_t)w * w), Q((size_t)w * w), sig(w), sig_prev(w, 0.0), resid(w);
-    std::vector<double> hBd(w), hBs(w);
+    // B (w x w, column-major) lives on the device: the normalisation kernels write the diagonal / super-diagonal
+    // entries straight into it, the fused SpMV epilogues read them back (s, r), bsvd_kernel decomposes it.
+    DevBuf<double> Bm((size_t)w * w), sigd((size_t)w), sigprev((size_t)w), smaxd(1);
+    DevBuf<BsvdStatus> statd(1);
+    SVB_CUDA(cudaMemsetAsync(Bm.p, 0, (size_t)w * w * 8, S.st));
+    SVB_CUDA(cudaMemsetAsync(sigprev.p, 0, (size_t)w * 8, S.st));
+    SVB_CUDA(cudaMemsetAsync(smaxd.p, 0, 8, S.st));
+    auto Bdiag = [&](int j) { return Bm.p + (size_t)j * w + j; };        // B[j, j]   = s_j
+    auto Bsup = [&](int j) { return Bm.p + (size_t)(j + 1) * w + j; };   // B[j, j+1] = r_j
+    const bool dev_svd = bsvd_supported(w) && getenv("SVB_HOST_SVD") == nullptr;
+    std::vector<double> hB((size_t)w * w), P((size_t)w * w), Q((size_t)w * w), sig(w), sig_prev(w, 0.0), resid(w);
     int k = (int)restart;
     // start vector(s)
     SVB_CUDA(cudaMemcpyAsync(S.F.p, init, (size_t)n * 8, cudaMemcpyHostToDevice, S.st));
@@ -148,7 +153,10 @@ static void irlba_run(svb_operator_s *op, int64_t nu_, int64_t work_, int64_t ma
         SVB_CHECK(s0 && U0 && V0, SVB_EARG, "irlba: restart > 0 needs s, U, V inputs");
         SVB_CUDA(cudaMemcpyAsync(S.V.p, V0, (size_t)n * k * 8, cudaMemcpyHostToDevice, S.st));
         SVB_CUDA(cudaMemcpyAsync(S.W.p, U0, (size_t)m * k * 8, cudaMemcpyHostToDevice, S.st));
-        for (int i = 0; i < k; ++i) B[(size_t)i * w + i] = s0[i];
+        std::fill(hB.begin(), hB.end(), 0.0);
+        for (int i = 0; i < k; ++i) hB[(size_t)i * w + i] = s0[i];
+        SVB_CUDA(cudaMemcpyAsync(Bm.p, hB.data(), (size_t)w * w * 8, cudaMemcpyHostToDevice, S.st));
+        SVB_CUDA(cudaStreamSynchronize(S.st));
     }
     vec_normalize(S.F.p, n, S.nrm2F(), S.Vc(k), nullptr, nullptr, 0.0);
 
@@ -158,89 +166,114 @@ static void irlba_run(svb_operator_s *op, int64_t nu_, int64_t work_, int64_t ma
     bool have_svd = false;
     while (iter < maxit) {
         int j = (iter > 0 || restart > 0) ? k : 0;
-        const int j0 = j;
         t_mark = now();
         bool tiny = false;
         // W_j = S*V_j ; orthogonalise against the kept W ; normalise
         op_apply(op, false, 1.0, S.Vc(j), 0.0, S.Wc(j));
         S.mprod++;
         S.orthog(S.W.p, m, j, S.Wc(j), S.nrm2W(), true);
-        S.finish(S.W.p, m, j, S.Wc(j), S.nrm2W(), S.Wc(j), S.Bd.p + j, true, &tiny);
+        S.finish(S.W.p, m, j, S.Wc(j), S.nrm2W(), S.Wc(j), Bdiag(j), true, &tiny);
         if (tiny && iter == 0 && j == 0) {
             info = SVB_ENULLSPACE;
             break;
         }
         while (j < w) {
             // F = S'*W_j - s*V_j ; orthogonalise against V[:, :j+1]
-            op_apply(op, true, 1.0, S.Wc(j), 0.0, S.F.p, S.Bd.p + j, -1.0, S.Vc(j));
+            op_apply(op, true, 1.0, S.Wc(j), 0.0, S.F.p, Bdiag(j), -1.0, S.Vc(j));
             S.mprod++;
             S.orthog(S.V.p, n, j + 1, S.F.p, S.nrm2F(), false);
             if (j + 1 < w) {
-                S.finish(S.V.p, n, j + 1, S.F.p, S.nrm2F(), S.Vc(j + 1), S.Bs.p + j, false, nullptr);
+                S.finish(S.V.p, n, j + 1, S.F.p, S.nrm2F(), S.Vc(j + 1), Bsup(j), false, nullptr);
                 // W_{j+1} = S*V_{j+1} - r*W_j ; orthogonalise against W[:, :j+1]
-                op_apply(op, false, 1.0, S.Vc(j + 1), 0.0, S.Wc(j + 1), S.Bs.p + j, -1.0, S.Wc(j));
+                op_apply(op, false, 1.0, S.Vc(j + 1), 0.0, S.Wc(j + 1), Bsup(j), -1.0, S.Wc(j));
                 S.mprod++;
                 S.orthog(S.W.p, m, j + 1, S.Wc(j + 1), S.nrm2W(), true);
-                S.finish(S.W.p, m, j + 1, S.Wc(j + 1), S.nrm2W(), S.Wc(j + 1), S.Bd.p + j + 1, true, nullptr);
+                S.finish(S.W.p, m, j + 1, S.Wc(j + 1), S.nrm2W(), S.Wc(j + 1), Bdiag(j + 1), true, nullptr);
             }
             ++j;
         }
-        // one host round trip per sweep
+        // ---- end of sweep: SVD of B, convergence test, restart size (device), one small host read ----
         int hflag = 0;
-        double nF2 = 0.0;
-        SVB_CUDA(cudaMemcpyAsync(hBd.data(), S.Bd.p, w * 8, cudaMemcpyDeviceToHost, S.st));
-        SVB_CUDA(cudaMemcpyAsync(hBs.data(), S.Bs.p, w * 8, cudaMemcpyDeviceToHost, S.st));
-        SVB_CUDA(cudaMemcpyAsync(&nF2, S.nrm2F(), 8, cudaMemcpyDeviceToHost, S.st));
-        SVB_CUDA(cudaMemcpyAsync(&hflag, S.flag.p, sizeof(int), cudaMemcpyDeviceToHost, S.st));
-        t_issue += now() - t_mark;
-        t_mark = now();
-        SVB_CUDA(cudaStreamSynchronize(S.st));
-        t_wait += now() - t_mark;
+        BsvdStatus hs{};
+        bool converged = false;
+        if (dev_svd) {
+            bsvd_launch(w, nu, Bm.p, S.Pd.p, S.Qd.p, sigd.p, sigprev.p, S.nrm2F(), smaxd.p, tol, svtol, k, S.flag.p, statd.p);
+            SVB_CUDA(cudaMemcpyAsync(&hs, statd.p, sizeof(BsvdStatus), cudaMemcpyDeviceToHost, S.st));
+            t_issue += now() - t_mark;
+            t_mark = now();
+            SVB_CUDA(cudaStreamSynchronize(S.st));
+            t_wait += now() - t_mark;
+            hflag = hs.converged < 0;
+        } else {
+            double nF2 = 0.0;
+            SVB_CUDA(cudaMemcpyAsync(hB.data(), Bm.p, (size_t)w * w * 8, cudaMemcpyDeviceToHost, S.st));
+            SVB_CUDA(cudaMemcpyAsync(&nF2, S.nrm2F(), 8, cudaMemcpyDeviceToHost, S.st));
+            SVB_CUDA(cudaMemcpyAsync(&hflag, S.flag.p, sizeof(int), cudaMemcpyDeviceToHost, S.st));
+            t_issue += now() - t_mark;
+            t_mark = now();
+            SVB_CUDA(cudaStreamSynchronize(S.st));
+            t_wait += now() - t_mark;
+            if (!hflag || S.careful) {
+                t_mark = now();
+                small_svd(w, hB.data(), P.data(), sig.data(), Q.data());
+                t_svd += now() - t_mark;
+                const double RF = std::sqrt(nF2);
+                for (int i = 0; i < w; ++i) resid[i] = RF * P[(size_t)i * w + (w - 1)];
+                smax = std::max(smax, sig[0]);
+                int nconv = 0;
+                for (int i = 0; i < nu; ++i) {  // the nu wanted Ritz values only (convergence test)
+                    const double ratio = std::fabs(sig_prev[i] - sig[i]) / sig[i];
+                    if (std::fabs(resid[i]) < tol * smax && ratio < svtol) ++nconv;
+                }
+                hs.converged = (nconv >= nu || hB[(size_t)(w - 1) * w + (w - 1)] == 0.0) ? 1 : 0;
+                hs.nconv = nconv;
+                int kk = std::max(k, nu + nconv);
+                kk = std::min(kk, w - 3);
+                hs.k = std::max(kk, 1);
+                SVB_CUDA(cudaMemcpyAsync(S.Pd.p, P.data(), (size_t)w * w * 8, cudaMemcpyHostToDevice, S.st));
+                SVB_CUDA(cudaMemcpyAsync(S.Qd.p, Q.data(), (size_t)w * w * 8, cudaMemcpyHostToDevice, S.st));
+                SVB_CUDA(cudaMemcpyAsync(sigd.p, sig.data(), (size_t)w * 8, cudaMemcpyHostToDevice, S.st));
+                if (!hs.converged) {
+                    sig_prev = sig;
+                    std::fill(hB.begin(), hB.end(), 0.0);
+                    for (int i = 0; i < hs.k; ++i) {
+                        hB[(size_t)i * w + i] = sig[i];
+                        hB[(size_t)hs.k * w + i] = resid[i];
+                    }
+                    SVB_CUDA(cudaMemcpyAsync(Bm.p, hB.data(), (size_t)w * w * 8, cudaMemcpyHostToDevice, S.st));
+                }
+                SVB_CUDA(cudaStreamSynchronize(S.st));
+            }
+        }
         if (hflag && !S.careful) {
             // a (near) breakdown happened somewhere in this sweep: redo it with host-checked norms
             S.careful = true;
             SVB_CUDA(cudaMemsetAsync(S.flag.p, 0, sizeof(int), S.st));
             continue;
         }
-        for (int c = j0; c < w; ++c) {
-            B[(size_t)c * w + c] = hBd[c];
-            if (c + 1 < w) B[(size_t)(c + 1) * w + c] = hBs[c];
+        if (hflag) SVB_CUDA(cudaMemsetAsync(S.flag.p, 0, sizeof(int), S.st));
+        if (hflag && dev_svd) {
+            // careful mode already replaced every tiny vector; the flag is stale (set by the fast normalise of a
+            // legitimately tiny-but-accepted norm): run the decomposition with the flag cleared
+            bsvd_launch(w, nu, Bm.p, S.Pd.p, S.Qd.p, sigd.p, sigprev.p, S.nrm2F(), smaxd.p, tol, svtol, k, S.flag.p, statd.p);
+            SVB_CUDA(cudaMemcpyAsync(&hs, statd.p, sizeof(BsvdStatus), cudaMemcpyDeviceToHost, S.st));
+            SVB_CUDA(cudaStreamSynchronize(S.st));
         }
-        t_mark = now();
-        small_svd(w, B.data(), P.data(), sig.data(), Q.data());
-        t_svd += now() - t_mark;
         have_svd = true;
-        const double RF = std::sqrt(nF2);
-        for (int i = 0; i < w; ++i) resid[i] = RF * P[(size_t)i * w + (w - 1)];
-        smax = std::max(smax, sig[0]);
-        int nconv = 0;
-        for (int i = 0; i < nu; ++i) {  // the nu wanted Ritz values only (convergence test)
-            const double ratio = std::fabs(sig_prev[i] - sig[i]) / sig[i];
-            if (std::fabs(resid[i]) < tol * smax && ratio < svtol) ++nconv;
-        }
+        converged = hs.converged == 1;
         ++iter;
-        if (nconv >= nu || hBd[w - 1] == 0.0) {
+        if (converged) {
             info = SVB_OK;
             break;
         }
         if (iter >= maxit) break;
-        sig_prev = sig;
-        k = std::max(k, nu + nconv);
-        k = std::min(k, w - 3);
-        k = std::max(k, 1);
-        // restart: V[:, :k] = V*Q[:, :k] ; V[:, k] = F/|F| ; W[:, :k] = W*P[:, :k] ; B = [diag(sig) | resid]
-        SVB_CUDA(cudaMemcpyAsync(S.Pd.p, P.data(), (size_t)w * w * 8, cudaMemcpyHostToDevice, S.st));
-        SVB_CUDA(cudaMemcpyAsync(S.Qd.p, Q.data(), (size_t)w * w * 8, cudaMemcpyHostToDevice, S.st));
+        k = hs.k;
+        // restart: V[:, :k] = V*Q[:, :k] ; V[:, k] = F/|F| ; W[:, :k] = W*P[:, :k] ; B = [diag(sig) | resid] (already written)
         ts_gemm(S.V.p, n, n, w, S.Qd.p, w, k, S.V2.p, n, nullptr);
         vec_normalize(S.F.p, n, S.nrm2F(), S.V2.p + (int64_t)k * n, nullptr, nullptr, 0.0);
         ts_gemm(S.W.p, m, m, w, S.Pd.p, w, k, S.W2.p, m, nullptr);
         std::swap(S.V, S.V2);
         std::swap(S.W, S.W2);
-        std::fill(B.begin(), B.end(), 0.0);
-        for (int i = 0; i < k; ++i) {
-            B[(size_t)i * w + i] = sig[i];
-            B[(size_t)k * w + i] = resid[i];
-        }
     }
     res->m = m;
     res->n = n;
@@ -254,9 +287,7 @@ static void irlba_run(svb_operator_s *op, int64_t nu_, int64_t work_, int64_t ma
     SVB_CUDA(cudaMalloc((void **)&res->s, (size_t)nu * 8));
     t_alloc += now() - t_mark;
     if (have_svd) {
-        SVB_CUDA(cudaMemcpyAsync(S.Pd.p, P.data(), (size_t)w * w * 8, cudaMemcpyHostToDevice, S.st));
-        SVB_CUDA(cudaMemcpyAsync(S.Qd.p, Q.data(), (size_t)w * w * 8, cudaMemcpyHostToDevice, S.st));
-        SVB_CUDA(cudaMemcpyAsync(res->s, sig.data(), (size_t)nu * 8, cudaMemcpyHostToDevice, S.st));
+        SVB_CUDA(cudaMemcpyAsync(res->s, sigd.p, (size_t)nu * 8, cudaMemcpyDeviceToDevice, S.st));
         ts_gemm(S.W.p, m, m, w, S.Pd.p, w, nu, res->U, m, nullptr);
         ts_gemm(S.V.p, n, n, w, S.Qd.p, w, nu, res->V, n, nullptr);
     } else {

@@ -202,6 +202,18 @@ void vec_copy(const double *x, int64_t L, double *y);
 void vec_fill_normal(double *x, int64_t L, uint64_t seed, uint64_t offset);
 // ---- comm.cpp
 void comm_allreduce_dev(double *dbuf, int64_t n);  // no-op when nranks == 1
+// ---- bsvd.cu : device-side SVD of B + convergence test + restart bookkeeping (single CTA)
+struct BsvdStatus {
+    int converged;  // 1 converged, 0 not, -1 skipped because the breakdown flag was set
+    int nconv;
+    int k;
+    int sweeps;
+    double sigma0;
+    double RF;
+};
+bool bsvd_supported(int w);
+void bsvd_launch(int w, int nu, double *B, double *P, double *Q, double *sig, double *sig_prev, const double *nrm2F,
+                 double *smax_io, double tol, double svtol, int k_in, const int *flag_dev, BsvdStatus *status_dev);
 // ---- jacobi_svd.cpp : A (w x w, col-major) = P diag(s) Q', s descending
 void small_svd(int w, const double *A, double *P, double *s, double *Q);
 }  // namespace svb
