@@ -137,6 +137,11 @@ int svb_scale_with_moments(svb_matrix_t a, const double *mean, const double *var
  * test_irlba.jl:111). mu may be NULL (plain sparse matrix). Builds the two streaming layouts
  * (row-major for S*v, cell-tiled gene-major for S'*w) on the device; `a` is not retained. */
 int svb_operator_create(svb_matrix_t a, const double *mu, int transposed, svb_operator_t *out);
+/* Same, choosing the storage width of the values in the two streaming layouts: 0 = as the input,
+ * SVB_F32 = Float32 storage with Float64 accumulation (the optional 1e-4 mode: 6 instead of 10 bytes
+ * per nonzero), SVB_F64. */
+int svb_operator_create_ex(svb_matrix_t a, const double *mu, int transposed, int value_storage,
+                           svb_operator_t *out);
 /* Dense column-major A (m x n, leading dimension lda >= m) for the StridedMatrix methods. */
 int svb_operator_create_dense(int64_t m, int64_t n, const double *a, int64_t lda, const double *mu,
                               int transposed, svb_operator_t *out);

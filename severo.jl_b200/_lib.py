@@ -65,6 +65,7 @@ SIGNATURES = {
     "svb_scale": (c_int, [_h, c_double, c_int, _ph, c_void_p]),
     "svb_scale_with_moments": (c_int, [_h, c_void_p, c_void_p, c_double, c_int, _ph, c_void_p]),
     "svb_operator_create": (c_int, [_h, c_void_p, c_int, _ph]),
+    "svb_operator_create_ex": (c_int, [_h, c_void_p, c_int, c_int, _ph]),
     "svb_operator_create_dense": (c_int, [c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int, _ph]),
     "svb_operator_free": (c_int, [_h]),
     "svb_operator_info": (c_int, [_h, _p64, _p64, _p64, _pint, _pint, _pint]),

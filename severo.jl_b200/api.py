@@ -321,8 +321,9 @@ class CenteredMatrix:
     ``X.T`` of a CSC (the lazy ``Adjoint`` of test_irlba.jl:111), a DeviceMatrix, a dense ndarray, or a
     NamedArray of those. Products run on the GPU through svb_mul / svb_irlba."""
 
-    def __init__(self, A, mu, transposed=False):
+    def __init__(self, A, mu, transposed=False, storage=None):
         self.A = A
+        self._storage = {None: 0, "f32": L.SVB_F32, "f64": L.SVB_F64}[storage]  # value width of the device layouts
         self.mu = mu
         payload, _, _ = _unwrap(A)
         self._transposed = bool(transposed)
@@ -370,7 +371,7 @@ class CenteredMatrix:
                     if Ph.dtype.kind != "f":
                         Ph = Ph.astype(np.float64)
                     dev = DeviceMatrix.from_host(Ph)
-                L.check(lib.svb_operator_create(dev._h, L.ptr(mu), int(self._transposed), ctypes.byref(h)))
+                L.check(lib.svb_operator_create_ex(dev._h, L.ptr(mu), int(self._transposed), self._storage, ctypes.byref(h)))
                 if temp:
                     dev.free()
             self._op = h

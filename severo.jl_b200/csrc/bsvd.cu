@@ -73,10 +73,12 @@ __global__ void __launch_bounds__(1024) bsvd_kernel(int w, int nu, double *__res
                 a = warp_sum_d(a);
                 b = warp_sum_d(b);
                 g = warp_sum_d(g);
-                if (g == 0.0 || fabs(g) <= eps * sqrt(a * b)) continue;
-                const double zeta = (b - a) / (2.0 * g);
-                const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                if (g * g <= (eps * eps) * (a * b)) continue;  // |g| <= eps*sqrt(a*b) without the sqrt
+                // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (b-a)/(2g)  ==  2g*sign(d) / (|d| + hypot(d, 2g))
+                const double d = b - a, g2 = 2.0 * g;
+                const double h = sqrt(fma(d, d, g2 * g2));
+                const double t = (d >= 0.0 ? g2 : -g2) / (fabs(d) + h);
+                const double c = rsqrt(fma(t, t, 1.0)), s = c * t;
                 double *vp = V + p * ld, *vq = V + q * ld;
                 for (int i = lane; i < w; i += 32) {
                     const double x = gp[i], y = gq[i];

@@ -53,6 +53,7 @@ static NcclApi &nccl() {
 void comm_allreduce_dev(double *dbuf, int64_t n) {
     Context &C = ctx();
     if (C.nranks <= 1 || n <= 0) return;
+    if (p2p_allreduce(dbuf, n)) return;  // small message: one-shot kernel over NVLink peer memory
     KTimer kt(SVB_K_COMM, 8.0 * n, 1);
     SVB_NCCL(nccl().AllReduce(dbuf, dbuf, (size_t)n, ncclFloat64, ncclSum, (ncclComm_t)C.nccl_comm, C.stream));
 }
@@ -92,12 +93,14 @@ int svb_comm_init(int nranks, int rank, const unsigned char id[128]) {
     C.nccl_comm = comm;
     C.nranks = nranks;
     C.rank = rank;
+    p2p_setup(nranks, rank);
     SVB_API_END
 }
 
 int svb_comm_destroy(void) {
     SVB_API_BEGIN
     Context &C = ctx();
+    p2p_teardown();
     if (C.nccl_comm) {
         cudaStreamSynchronize(C.stream);
         nccl().CommDestroy((ncclComm_t)C.nccl_comm);

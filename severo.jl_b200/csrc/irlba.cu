@@ -99,6 +99,7 @@ static void irlba_run(svb_operator_s *op, int64_t nu_, int64_t work_, int64_t ma
     const int64_t m = S.m, n = S.n;
     const bool dbg = getenv("SVB_DEBUG_TIMING") != nullptr;
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    long long jacobi_sweeps = 0;
     double t_alloc = 0, t_svd = 0, t_wait = 0, t_issue = 0, t_start = now(), t_mark = 0;
     // global row count decides the work-size clamp (irlba.jl:56-58 uses min(m, n) of the whole matrix)
     double mglob = (double)m;
@@ -245,6 +246,7 @@ static void irlba_run(svb_operator_s *op, int64_t nu_, int64_t work_, int64_t ma
                 SVB_CUDA(cudaStreamSynchronize(S.st));
             }
         }
+        if (C.nranks > 1 && p2p_error()) throw Error(SVB_ENCCL, "peer-memory allreduce timed out (a rank is missing)");
         if (hflag && !S.careful) {
             // a (near) breakdown happened somewhere in this sweep: redo it with host-checked norms
             S.careful = true;
@@ -260,6 +262,7 @@ static void irlba_run(svb_operator_s *op, int64_t nu_, int64_t work_, int64_t ma
             SVB_CUDA(cudaStreamSynchronize(S.st));
         }
         have_svd = true;
+        jacobi_sweeps += hs.sweeps;
         converged = hs.converged == 1;
         ++iter;
         if (converged) {
@@ -297,8 +300,8 @@ static void irlba_run(svb_operator_s *op, int64_t nu_, int64_t work_, int64_t ma
     }
     SVB_CUDA(cudaStreamSynchronize(S.st));
     if (dbg)
-        fprintf(stderr, "[svb irlba] total %.2f ms: alloc %.2f, issue %.2f, wait %.2f, svd %.2f (iters %lld, mprod %lld)\n",
-                (now() - t_start) * 1e3, t_alloc * 1e3, t_issue * 1e3, t_wait * 1e3, t_svd * 1e3, (long long)iter, (long long)S.mprod);
+        fprintf(stderr, "[svb irlba] total %.2f ms: alloc %.2f, issue %.2f, wait %.2f, svd %.2f (iters %lld, mprod %lld, jacobi sweeps %lld)\n",
+                (now() - t_start) * 1e3, t_alloc * 1e3, t_issue * 1e3, t_wait * 1e3, t_svd * 1e3, (long long)iter, (long long)S.mprod, jacobi_sweeps);
 }
 
 __global__ void colscale_kernel(const double *__restrict__ U, const double *__restrict__ s, int64_t m, int64_t nu,

@@ -393,6 +393,8 @@ template void build_tilecsc<double, double>(const svb_matrix_s *, int, TileCSC<d
 template void build_tilecsc<float, float>(const svb_matrix_s *, int, TileCSC<float> &);
 template void build_tilecsc<int32_t, double>(const svb_matrix_s *, int, TileCSC<double> &);
 template void build_tilecsc<float, double>(const svb_matrix_s *, int, TileCSC<double> &);
+template void build_tilecsc<double, float>(const svb_matrix_s *, int, TileCSC<float> &);
+template void build_tilecsc_from_transposed<double, float>(const svb_matrix_s *, int, TileCSC<float> &);
 template void build_tilecsc_from_transposed<double, double>(const svb_matrix_s *, int, TileCSC<double> &);
 template void build_tilecsc_from_transposed<float, float>(const svb_matrix_s *, int, TileCSC<float> &);
 template void build_tilecsc_from_transposed<int32_t, double>(const svb_matrix_s *, int, TileCSC<double> &);

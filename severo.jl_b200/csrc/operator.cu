@@ -470,7 +470,7 @@ static void build_sparse(svb_operator_s *op, const svb_matrix_s *a, bool transpo
 
 extern "C" {
 
-int svb_operator_create(svb_matrix_t a, const double *mu, int transposed, svb_operator_t *out) {
+static int operator_create_impl(svb_matrix_t a, const double *mu, int transposed, int value_storage, svb_operator_t *out) {
     SVB_API_BEGIN
     require_init();
     SVB_CHECK(a && out, SVB_EARG, "svb_operator_create: null argument");
@@ -485,8 +485,14 @@ int svb_operator_create(svb_matrix_t a, const double *mu, int transposed, svb_op
         int log2R = env_int("SVB_ADJ_LOG2R", 12);
         log2R = std::max(8, std::min(log2R, 14));
         while (log2R > 8 && (1ll << (log2R - 1)) >= op->m) --log2R;  // small inputs: one small tile
+        SVB_CHECK(value_storage == 0 || value_storage == SVB_F32 || value_storage == SVB_F64, SVB_EARG,
+                  "svb_operator_create_ex: value_storage must be 0, SVB_F32 or SVB_F64");
+        const bool to_f32 = value_storage == SVB_F32;
         switch (a->vtype) {
-            case SVB_F64: build_sparse<double, double>(op, a, transposed != 0, log2R); break;
+            case SVB_F64:
+                if (to_f32) build_sparse<double, float>(op, a, transposed != 0, log2R);
+                else build_sparse<double, double>(op, a, transposed != 0, log2R);
+                break;
             case SVB_F32: build_sparse<float, float>(op, a, transposed != 0, log2R); break;
             case SVB_I32: build_sparse<int32_t, double>(op, a, transposed != 0, log2R); break;
             default: throw Error(SVB_EARG, "bad vtype");
@@ -516,6 +522,14 @@ int svb_operator_create(svb_matrix_t a, const double *mu, int transposed, svb_op
     }
     *out = op;
     SVB_API_END
+}
+
+int svb_operator_create(svb_matrix_t a, const double *mu, int transposed, svb_operator_t *out) {
+    return operator_create_impl(a, mu, transposed, 0, out);
+}
+
+int svb_operator_create_ex(svb_matrix_t a, const double *mu, int transposed, int value_storage, svb_operator_t *out) {
+    return operator_create_impl(a, mu, transposed, value_storage, out);
 }
 
 int svb_operator_create_dense(int64_t m, int64_t n, const double *a, int64_t lda, const double *mu, int transposed,

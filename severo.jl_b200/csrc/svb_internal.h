@@ -202,6 +202,12 @@ void vec_copy(const double *x, int64_t L, double *y);
 void vec_fill_normal(double *x, int64_t L, uint64_t seed, uint64_t offset);
 // ---- comm.cpp
 void comm_allreduce_dev(double *dbuf, int64_t n);  // no-op when nranks == 1
+// ---- p2p.cu : one-shot allreduce through IPC-mapped peer mailboxes (small messages)
+void p2p_setup(int nranks, int rank);
+void p2p_teardown();
+bool p2p_ready();
+bool p2p_allreduce(double *dbuf, int64_t n);  // false => not handled (use NCCL)
+int p2p_error();
 // ---- bsvd.cu : device-side SVD of B + convergence test + restart bookkeeping (single CTA)
 struct BsvdStatus {
     int converged;  // 1 converged, 0 not, -1 skipped because the breakdown flag was set

@@ -413,3 +413,87 @@ def test_pipeline_planted_gap_subspace(sv, orc):
     Gs = sv.svd_flip(G)
     Uo, Vo = orc.svd_flip(O.U, O.V)
     np.testing.assert_allclose(Gs.V, Vo, atol=1e-6)
+
+
+def test_fp32_storage_mode(sv, orc):
+    # optional Float32-storage / Float64-accumulate operator (north_star: singular values to rel 1e-4)
+    import ctypes
+    X = planted_counts(6000, 1200, 10, seed=9, mean_nnz=120)
+    Y = orc.normalize_cells(X, "lognormalize", 1e4)
+    So = orc.scale_features(Y, scale_max=10.0)
+    C64 = sv.CenteredMatrix(So.P, So.mu)
+    C32 = sv.CenteredMatrix(So.P, So.mu, storage="f32")
+    vb, ib = ctypes.c_int(), ctypes.c_int()
+    sv.lib().svb_operator_info(C32._operator(), None, None, None, None, ctypes.byref(vb), ctypes.byref(ib))
+    assert (vb.value, ib.value) == (4, 2)
+    rng = np.random.default_rng(2)
+    v = rng.standard_normal(1200)
+    ref = So.mul(v)
+    assert np.linalg.norm(C32 @ v - ref) <= 1e-6 * np.linalg.norm(ref)      # fp32 rounding of the stored values
+    assert np.linalg.norm(C64 @ v - ref) <= 1e-13 * np.linalg.norm(ref)
+    init = rng.standard_normal(1200)
+    S64 = sv.irlba(C64, 10, init=init, tol=1e-7)
+    S32 = sv.irlba(C32, 10, init=init, tol=1e-7)
+    np.testing.assert_allclose(S32.S, S64.S, rtol=1e-4)
+
+
+_TWO_RANK = r"""
+import os, sys, ctypes
+import numpy as np, scipy.sparse as sp
+import torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+import severo_jl_b200 as sv
+from severo_jl_b200 import sharding
+from oracle import severo_oracle as orc
+mode = sys.argv[2]
+os.environ["SVB_P2P"] = "1" if mode == "p2p" else "0"
+local = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+rank, world = dist.get_rank(), dist.get_world_size()
+sv.init(local)
+sharding.init_comm_from_torch()
+rng = np.random.default_rng(0)
+m, n, nu = 30011, 500, 8
+X = sp.random(m, n, 0.05, random_state=3, format="csc")
+u, v = rng.standard_normal((m, nu)), rng.standard_normal((n, nu))
+X = sp.csc_matrix(X + sp.csc_matrix((u * np.linspace(3, 1, nu)) @ v.T * (rng.random((m, n)) < 0.02)))
+mu = np.asarray(X.mean(axis=0)).ravel()
+bounds = sharding.shard_bounds(m, world)
+lo, hi = bounds[rank]
+C = sv.CenteredMatrix(sp.csc_matrix(X[lo:hi]), mu)
+init = rng.standard_normal(n)
+S = sv.irlba(C, nu, init=init, tol=1e-9)
+O = orc.irlba(orc.CenteredMatrix(X, mu), nu, init=init, tol=1e-9)
+assert np.allclose(S.S, O.S, rtol=1e-6), (S.S, O.S)
+U = sharding.gather_rows(S.U, bounds, rank)
+assert orc.principal_angle(U, O.U) < 1e-4 and orc.principal_angle(S.V, O.V) < 1e-4
+# sharded pre-processing: merged moments == moments of the whole matrix
+cnt = sp.csc_matrix(rng.poisson(0.3, (4000, 60)).astype(np.int64))
+b2 = sharding.shard_bounds(4000, world)
+d = sv.DeviceMatrix.from_host(cnt[b2[rank][0]:b2[rank][1]])
+mean, var, tot = sharding.merged_mean_var(d)
+mo, vo = orc.mean_var(cnt)
+assert tot == 4000 and np.allclose(mean, mo, rtol=1e-13) and np.allclose(var, vo, rtol=1e-12)
+sv.lib().svb_comm_destroy()
+dist.destroy_process_group()
+print("OK", rank, mode)
+"""
+
+
+@pytest.mark.parametrize("mode", ["nccl", "p2p"])
+def test_two_gpu_sharded_irlba(tmp_path, mode):
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "two_rank.py"
+    script.write_text(_TWO_RANK)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29644" if mode == "nccl" else "29645", str(script), root, mode],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("OK") == 2
