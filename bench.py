@@ -221,8 +221,16 @@ def run_b200(args):
         dc = classes[dom]
         nlaunch_dom = dc["launches"] / (2 if dom == "spmv_adj" else 1)  # the adjoint is two launches per product
         achieved = dc["GBps"]
+        traffic = None  # dram bytes per launch from the committed ncu --set full capture of this exact configuration
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                tj = json.load(f)
+            if tj.get("config") == args.config and tj.get("n_gpus") == world:
+                traffic = tj.get(dom)
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                     "bytes_per_launch": round(dc["algorithmic_GB"] * 1e9 / nlaunch_dom),
                     "avg_launch_ms": round(dc["ms"] / nlaunch_dom, 5),
                     "share_of_step": round(dc["ms"] / sum(c["ms"] for c in classes.values()), 4),
@@ -244,17 +252,26 @@ def run_b200(args):
             U, V, s = t_U.numpy().T, t_V.numpy().T, np.zeros(nu)
             mu_c = np.ascontiguousarray(mu)
 
+            phases = {"upload_s": 0.0, "layout_build_s": 0.0, "solve_and_download_s": 0.0}
+
             def e2e_step():
+                t0 = time.perf_counter()
                 h = ctypes.c_void_p()
                 L.check(lib.svb_csc_upload(m_local, n, L.ptr(colptr), L.ptr(rowval), L.SVB_I64, L.ptr(nzval), L.SVB_F64, 1,
                                            ctypes.byref(h)))
+                t1 = time.perf_counter()
                 o = ctypes.c_void_p()
                 L.check(lib.svb_operator_create(h, L.ptr(mu_c), 0, ctypes.byref(o)))
                 lib.svb_matrix_free(h)
+                t2 = time.perf_counter()
                 it_, mp_ = ctypes.c_int64(), ctypes.c_int64()
                 L.check(lib.svb_irlba(o, nu, 0, 1000, 0, TOL, TOL, L.ptr(init), L.ptr(s), L.ptr(U), L.ptr(V),
                                       ctypes.byref(it_), ctypes.byref(mp_)))
                 lib.svb_operator_free(o)
+                t3 = time.perf_counter()
+                phases["upload_s"] += t1 - t0
+                phases["layout_build_s"] += t2 - t1
+                phases["solve_and_download_s"] += t3 - t2
 
             B.free()  # the e2e call owns its own device copy
             lib.svb_operator_free(op)

@@ -181,11 +181,23 @@ static int row_blocks(int64_t L, int64_t rows_per_cta, int max_per_sm) {
     return (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)ctx().sm_count * max_per_sm));
 }
 
+// CTAs of `kernel` that are resident at once on the whole chip (one full wave); the streaming kernels use
+// grid-stride loops, so a grid of exactly this size avoids the partial second wave ncu showed (1.33-1.67 waves).
+template <typename K>
+static int wave_slots(K kernel, int threads) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    return per_sm * ctx().sm_count;
+}
+
 void ts_gemv_t(const double *X, int64_t ld, int64_t L, int j, const double *y, double *t, int cls) {
     if (j <= 0) return;
     const int ctiles = (j + CT - 1) / CT;
     // keep the total CTA count near 4 waves regardless of the number of column tiles
-    int nrb = row_blocks(L, TS_THREADS * TS_RPT, std::max(1, 8 / std::min(ctiles, 8)) * 2);
+    static int slots_t = 0;
+    if (!slots_t) slots_t = wave_slots(ts_gemv_t_kernel, TS_THREADS);
+    const int64_t need_t = (L + TS_THREADS * TS_RPT - 1) / (TS_THREADS * TS_RPT);
+    int nrb = (int)std::max<int64_t>(1, std::min<int64_t>(need_t, std::max(1, slots_t / ctiles)));
     scratch_reserve((size_t)ctiles * nrb * CT + 4096, (size_t)ctiles + 8);
     KTimer kt(cls, 8.0 * ((double)L * j + (double)L * ((j + CT - 1) / CT)));
     dim3 grid((unsigned)nrb, (unsigned)ctiles);
@@ -195,7 +207,9 @@ void ts_gemv_t(const double *X, int64_t ld, int64_t L, int j, const double *y, d
 
 void ts_gemv_n(const double *X, int64_t ld, int64_t L, int j, const double *t, double alpha, double beta, double *y,
                double *nrm2_out, int cls) {
-    const int nrb = row_blocks(L, TS_THREADS * 2, 8);
+    static int slots_n = 0;
+    if (!slots_n) slots_n = wave_slots(ts_gemv_n_kernel, TS_THREADS);
+    const int nrb = (int)std::max<int64_t>(1, std::min<int64_t>((L + TS_THREADS * 2 - 1) / (TS_THREADS * 2), slots_n));
     scratch_reserve(4096 + 64, 8);
     KTimer kt(cls, 8.0 * ((double)L * j + 2.0 * L));
     ts_gemv_n_kernel<<<(unsigned)nrb, TS_THREADS, 0, ctx().stream>>>(X, ld, L, j, t, alpha, beta, y, nrm2_out, g_scr.partials,
