@@ -277,6 +277,8 @@ def run_b200(args):
             lib.svb_operator_free(op)
             op = None
             e2e_step()  # warm-up
+            for k_ in phases:
+                phases[k_] = 0.0
             barrier()
             t0 = time.perf_counter()
             for _ in range(args.steps):
@@ -288,7 +290,8 @@ def run_b200(args):
             h2d = 8 * (n + 1) + 16 * z + 8 * n + 8 * n  # colptr + rowval + nzval + mu + init
             d2h = 8 * (m_local * nu + n * nu + nu)
             e2e = {"value": round(float(dt.item()), 6), "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                   "includes": "pinned-host CSC{Float64,Int64} upload, device layout build, solve, U/s/V download"}
+                   "includes": "pinned-host CSC{Float64,Int64} upload, device layout build, solve, U/s/V download",
+                   "phases_rank0_s": {k_: round(v_ / args.steps, 5) for k_, v_ in phases.items()}}
             assert np.allclose(s, s_host, rtol=1e-6), "e2e and device-resident solves disagree"
 
         # ---- totals over ranks --------------------------------------------------------------------------
