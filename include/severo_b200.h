@@ -122,6 +122,11 @@ int svb_normalize(svb_matrix_t counts, int method, double scale_factor, int dtyp
 int svb_row_sums(svb_matrix_t counts, int64_t *s);
 /* scaling.jl:18-34,132-142 mean_var(A): order-exact sequential Welford per gene. */
 int svb_mean_var(svb_matrix_t a, double *mu, double *var);
+/* The same Welford chain continued across cell shards: count/mu/s (length ncol) hold the state after all
+ * cells of the previous ranks (first rank: count = total cells - total nonzeros of the gene, mu = s = 0,
+ * scaling.jl:21) and receive the state after this shard; var = s/(cells-1) after the last rank. Bit-identical
+ * to one sequential pass over the unsharded matrix. */
+int svb_welford_carry(svb_matrix_t a, int64_t *count, double *mu, double *s);
 /* variablefeatures.jl:19-28 standardized_var_clipped (vmax <= 0 => sqrt(nrow)). */
 int svb_stdvar_clipped(svb_matrix_t counts, const double *mu, const double *sd, double vmax,
                        double *out);

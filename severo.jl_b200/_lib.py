@@ -61,6 +61,7 @@ SIGNATURES = {
     "svb_normalize": (c_int, [_h, c_int, c_double, c_int, _ph]),
     "svb_row_sums": (c_int, [_h, c_void_p]),
     "svb_mean_var": (c_int, [_h, c_void_p, c_void_p]),
+    "svb_welford_carry": (c_int, [_h, c_void_p, c_void_p, c_void_p]),
     "svb_stdvar_clipped": (c_int, [_h, c_void_p, c_void_p, c_double, c_void_p]),
     "svb_scale": (c_int, [_h, c_double, c_int, _ph, c_void_p]),
     "svb_scale_with_moments": (c_int, [_h, c_void_p, c_void_p, c_double, c_int, _ph, c_void_p]),

@@ -103,6 +103,46 @@ __global__ void __launch_bounds__(64) welford_kernel(const int64_t *__restrict__
     var_out[c] = (double)div_rn<T>(s, (T)(nrow - 1));
 }
 
+// Same chain, continued across cell shards: the state (count, mu, s) of every gene enters from the previous
+// rank and leaves for the next one, so the bits equal those of ONE sequential pass over all cells.
+template <typename VI>
+__global__ void __launch_bounds__(64) welford_carry_kernel(const int64_t *__restrict__ colptr, const VI *__restrict__ val,
+                                                           const int32_t *__restrict__ order, int64_t ncol,
+                                                           long long *__restrict__ count_io, double *__restrict__ mu_io,
+                                                           double *__restrict__ s_io) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ncol) return;
+    const int64_t c = order[g];
+    const int64_t beg = colptr[c], end = colptr[c + 1];
+    long long count = count_io[c];
+    double mu = mu_io[c], s = s_io[c];
+    int64_t k = beg;
+    VI nxt[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) nxt[u] = (k + u < end) ? val[k + u] : (VI)0;
+    while (k < end) {
+        VI cur[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) nxt[u] = (k + 4 + u < end) ? val[k + 4 + u] : (VI)0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (k + u < end) {
+                count += 1;
+                const double v = (double)cur[u];
+                const double delta = __dsub_rn(v, mu);
+                mu = __dadd_rn(mu, __ddiv_rn(delta, (double)count));
+                s = __dadd_rn(s, __dmul_rn(delta, __dsub_rn(v, mu)));
+            }
+        }
+        k += 4;
+    }
+    count_io[c] = count;
+    mu_io[c] = mu;
+    s_io[c] = s;
+}
+
 // ---- standardized_var_clipped: one warp per gene, double-double accumulation -----------------------
 __device__ __forceinline__ void two_sum(double a, double b, double &s, double &e) {
     s = __dadd_rn(a, b);
@@ -290,6 +330,35 @@ int svb_mean_var(svb_matrix_t a, double *mu, double *var) {
     cudaStream_t st = ctx().stream;
     SVB_CUDA(cudaMemcpyAsync(mu, d_mu.p, (size_t)a->ncol * 8, cudaMemcpyDeviceToHost, st));
     SVB_CUDA(cudaMemcpyAsync(var, d_var.p, (size_t)a->ncol * 8, cudaMemcpyDeviceToHost, st));
+    SVB_CUDA(cudaStreamSynchronize(st));
+    SVB_API_END
+}
+
+int svb_welford_carry(svb_matrix_t a, int64_t *count, double *mu, double *s) {
+    SVB_API_BEGIN
+    require_init();
+    SVB_CHECK(a && count && mu && s, SVB_EARG, "svb_welford_carry: null argument");
+    SVB_CHECK(a->vtype == SVB_I32 || a->vtype == SVB_F64, SVB_EARG, "svb_welford_carry: Int or Float64 data (Float64 chain)");
+    if (a->ncol == 0) return SVB_OK;
+    cudaStream_t st = ctx().stream;
+    const size_t nc = (size_t)a->ncol;
+    DevBuf<long long> d_c(nc);
+    DevBuf<double> d_mu(nc), d_s(nc);
+    SVB_CUDA(cudaMemcpyAsync(d_c.p, count, nc * 8, cudaMemcpyHostToDevice, st));
+    SVB_CUDA(cudaMemcpyAsync(d_mu.p, mu, nc * 8, cudaMemcpyHostToDevice, st));
+    SVB_CUDA(cudaMemcpyAsync(d_s.p, s, nc * 8, cudaMemcpyHostToDevice, st));
+    DevBuf<int32_t> order;
+    column_order(a, order);
+    const unsigned grid = (unsigned)((a->ncol + 63) / 64);
+    if (a->vtype == SVB_I32)
+        welford_carry_kernel<int32_t><<<grid, 64, 0, st>>>(a->colptr, (const int32_t *)a->val, order.p, a->ncol, d_c.p, d_mu.p, d_s.p);
+    else
+        welford_carry_kernel<double><<<grid, 64, 0, st>>>(a->colptr, (const double *)a->val, order.p, a->ncol, d_c.p, d_mu.p, d_s.p);
+    count_launch();
+    SVB_LAUNCH_CHECK();
+    SVB_CUDA(cudaMemcpyAsync(count, d_c.p, nc * 8, cudaMemcpyDeviceToHost, st));
+    SVB_CUDA(cudaMemcpyAsync(mu, d_mu.p, nc * 8, cudaMemcpyDeviceToHost, st));
+    SVB_CUDA(cudaMemcpyAsync(s, d_s.p, nc * 8, cudaMemcpyDeviceToHost, st));
     SVB_CUDA(cudaStreamSynchronize(st));
     SVB_API_END
 }

@@ -147,3 +147,29 @@ def sharded_scale_features(Y, scale_max=np.inf, features=None):
     L.check(L.lib().svb_scale_with_moments(Y._h, L.ptr(np.ascontiguousarray(mean)), L.ptr(np.ascontiguousarray(var)),
                                             float(scale_max), _DT[np.dtype(dtype)], ctypes.byref(h), L.ptr(mu)))
     return DeviceMatrix(h), mu
+
+
+def exact_mean_var(dA):
+    """Order-exact per-gene mean / variance of a row-sharded matrix: the sequential Welford state of every gene
+    is carried from rank to rank in rank order, so the result has the bits of one pass over all cells
+    (scaling.jl:18-34). Serial over ranks by construction — use ``merged_mean_var`` when speed matters more."""
+    lib = L.lib()
+    nr, rk = ctypes.c_int(), ctypes.c_int()
+    lib.svb_comm_info(ctypes.byref(nr), ctypes.byref(rk))
+    nranks, rank = nr.value, rk.value
+    g = dA.shape[1]
+    nnz_local = np.diff(dA.colptr()).astype(np.float64)
+    tot = allgather_f64(np.concatenate([[float(dA.shape[0])], nnz_local])).sum(axis=0)
+    m_total, nnz_total = int(tot[0]), tot[1:]
+    count = (m_total - nnz_total).astype(np.int64)   # implicit zeros first (scaling.jl:21)
+    mu = np.zeros(g)
+    s = np.zeros(g)
+    for r in range(nranks):
+        if rank == r:
+            L.check(lib.svb_welford_carry(dA._h, L.ptr(count), L.ptr(mu), L.ptr(s)))
+            packed = np.concatenate([count.astype(np.float64), mu, s])
+        else:
+            packed = np.zeros(3 * g)
+        state = allgather_f64(packed)[r] if nranks > 1 else packed
+        count, mu, s = state[:g].astype(np.int64), state[g:2 * g].copy(), state[2 * g:].copy()
+    return mu, s / (m_total - 1.0), m_total

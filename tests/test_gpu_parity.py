@@ -475,6 +475,9 @@ d = sv.DeviceMatrix.from_host(cnt[b2[rank][0]:b2[rank][1]])
 mean, var, tot = sharding.merged_mean_var(d)
 mo, vo = orc.mean_var(cnt)
 assert tot == 4000 and np.allclose(mean, mo, rtol=1e-13) and np.allclose(var, vo, rtol=1e-12)
+# order-exact mode: the Welford state is carried from rank to rank -> the bits of one sequential pass
+me, ve, tot = sharding.exact_mean_var(d)
+assert tot == 4000 and np.array_equal(me, mo) and np.array_equal(ve, vo)
 sv.lib().svb_comm_destroy()
 dist.destroy_process_group()
 print("OK", rank, mode)
@@ -497,3 +500,22 @@ def test_two_gpu_sharded_irlba(tmp_path, mode):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("OK") == 2
+
+
+def test_welford_carry_across_row_slices(sv, orc):
+    # single GPU: chaining svb_welford_carry over three cell ranges reproduces the one-pass Welford bit for bit
+    import ctypes
+    X = planted_counts(3000, 500, 5, seed=12)
+    Y = orc.normalize_cells(X, "lognormalize", 1e4)
+    for M in (X, Y):
+        d = sv.DeviceMatrix.from_host(M)
+        g = M.shape[1]
+        count = (M.shape[0] - np.diff(sp.csc_matrix(M).indptr)).astype(np.int64)
+        mu, s = np.zeros(g), np.zeros(g)
+        for lo, hi in ((0, 1000), (1000, 1004), (1004, 3000)):
+            part = d.rows(lo, hi)
+            sv._lib.check(sv.lib().svb_welford_carry(part._h, sv._lib.ptr(count), sv._lib.ptr(mu), sv._lib.ptr(s)))
+        mo, vo = orc.mean_var(M)
+        assert np.all(count == M.shape[0])
+        np.testing.assert_array_equal(mu, mo)
+        np.testing.assert_array_equal(s / (M.shape[0] - 1.0), vo)
