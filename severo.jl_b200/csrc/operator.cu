@@ -607,7 +607,17 @@ int svb_mul(svb_operator_t op, char trans, double alpha, const double *x, double
         SVB_CUDA(cudaMalloc((void **)&op->xdev, (size_t)std::max(op->m, op->n) * sizeof(double)));
         SVB_CUDA(cudaMalloc((void **)&op->ydev, (size_t)std::max(op->m, op->n) * sizeof(double)));
     }
-    // k right-hand sides, one column at a time (scaling.jl:259-272; full SpMM is a "next" row)
+    if (k > 1 && !op->dense) {
+        // matrix forms (scaling.jl:259-272): SpMM kernels, 4 right-hand sides per pass over the nonzeros
+        DevBuf<double> dX((size_t)inL * k), dY((size_t)outL * k);
+        SVB_CUDA(cudaMemcpyAsync(dX.p, x, (size_t)inL * k * 8, cudaMemcpyHostToDevice, st));
+        if (beta != 0.0) SVB_CUDA(cudaMemcpyAsync(dY.p, y, (size_t)outL * k * 8, cudaMemcpyHostToDevice, st));
+        op_apply_mm(op, t, alpha, dX.p, inL, beta, dY.p, outL, k);
+        SVB_CUDA(cudaMemcpyAsync(y, dY.p, (size_t)outL * k * 8, cudaMemcpyDeviceToHost, st));
+        SVB_CUDA(cudaStreamSynchronize(st));
+        return SVB_OK;
+    }
+    // vector form, or dense operator: one column at a time
     for (int64_t c = 0; c < k; ++c) {
         SVB_CUDA(cudaMemcpyAsync(op->xdev, x + c * inL, (size_t)inL * 8, cudaMemcpyHostToDevice, st));
         if (beta != 0.0) SVB_CUDA(cudaMemcpyAsync(op->ydev, y + c * outL, (size_t)outL * 8, cudaMemcpyHostToDevice, st));

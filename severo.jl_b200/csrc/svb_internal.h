@@ -185,6 +185,9 @@ size_t vtype_size(int vtype);
 // ---- operator / spmv
 void op_apply(svb_operator_s *op, bool trans, double alpha, const double *dx, double beta, double *dy,
               const double *axpy_coef_dev = nullptr, double axpy_sign = 0.0, const double *axpy_vec = nullptr);
+// ---- spmm.cu : k right-hand sides (scaling.jl:259-272), device pointers, column-major with leading dims
+void op_apply_mm(svb_operator_s *op, bool trans, double alpha, const double *dX, int64_t ldx, double beta, double *dY, int64_t ldy,
+                 int64_t k);
 // ---- dense.cu (tall-skinny kernels; all pointers device)
 // t[0..j) = X[:, 0..j)' * y      (X col-major L x j, leading dim ld)
 void ts_gemv_t(const double *X, int64_t ld, int64_t L, int j, const double *y, double *t, int cls);

@@ -188,6 +188,13 @@ def test_centered_matrix_random_vs_oracle(sv, orc):
         assert np.linalg.norm(G.mul(v, -0.5, 2.0, y0.copy()) - O.mul(v, -0.5, 2.0, y0.copy())) <= 1e-13 * (scale + np.linalg.norm(y0))
         # matrix forms (scaling.jl:259-272), adjoint form with the mathematically correct sign (T4)
         Vm, Wm = np.asfortranarray(rng.standard_normal((n, 3))), np.asfortranarray(rng.standard_normal((m, 3)))
+        # SpMM kernels: 9 right-hand sides (3 passes of 4), alpha/beta epilogue, against the oracle's column loop
+        V9, W9 = np.asfortranarray(rng.standard_normal((n, 9))), np.asfortranarray(rng.standard_normal((m, 9)))
+        Y9, Z9 = np.asfortranarray(rng.standard_normal((m, 9))), np.asfortranarray(rng.standard_normal((n, 9)))
+        ref = O.mul(V9, 1.5, -0.5, Y9.copy(order="F"))
+        assert np.linalg.norm(G.mul(V9, 1.5, -0.5, Y9.copy(order="F")) - ref) <= 1e-12 * np.linalg.norm(ref)
+        ref = O.mul(W9, 1.5, -0.5, Z9.copy(order="F"), trans=True)
+        assert np.linalg.norm(G.mul(W9, 1.5, -0.5, Z9.copy(order="F"), trans=True) - ref) <= 1e-12 * np.linalg.norm(ref)
         D = O.to_dense() if m * n < 5e6 else None
         if D is not None:
             np.testing.assert_allclose(G @ Vm, D @ Vm, rtol=1e-10, atol=1e-10)
