@@ -31,6 +31,7 @@ CONFIGS = {
     "C2": dict(m=68_579, g=32_738, nnz=671.0, n=2000, nu=50, programs=50, desc="PBMC-68k-shaped"),
     "C3": dict(m=1_306_127, g=27_998, nnz=1914.0, n=2000, nu=50, programs=50, desc="1.3M-cell mouse-brain-shaped"),
     "C4": dict(m=1_306_127, g=27_998, nnz=1914.0, n=5000, nu=100, programs=100, desc="1.3M-cell, reorthogonalisation-heavy"),
+    "C5": dict(m=4_000_000, g=30_000, nnz=2000.0, n=2000, nu=50, programs=50, desc="4M-cell scaling stress (8 GPUs)"),
 }
 SEED = 20260103
 TOL = 1e-5

@@ -18,7 +18,7 @@
 using namespace svb;
 
 svb_operator_s::~svb_operator_s() {
-    void *ptrs[] = {mu, rowptr, fidx, fval, gptr, rloc, aval, partial, dA, xdev, ydev, tmp};
+    void *ptrs[] = {mu, rowptr, fidx, fval, gptr, rloc, aval, partial, dA, xdev, ydev, tmp, scal, fwd_ranges, adj_ranges};
     for (void *p : ptrs)
         if (p) cudaFree(p);
 }
@@ -77,13 +77,15 @@ __device__ __forceinline__ int64_t lower_bound_i64(const int64_t *__restrict__ p
 }
 
 // CTA b of G owns the segments whose first nonzero lies in its 1/G share of the nonzero stream: equal
-// bytes per CTA whatever the segment lengths are. Every segment id belongs to exactly one CTA.
-__device__ __forceinline__ void cta_segment_range(const int64_t *__restrict__ ptr, int64_t nseg, int64_t nnz, int64_t &s0,
-                                                  int64_t &s1) {
-    const int64_t G = gridDim.x, b = blockIdx.x;
-    const int64_t lo = (int64_t)(((__int128)nnz * b) / G), hi = (int64_t)(((__int128)nnz * (b + 1)) / G);
-    s0 = (b == 0) ? 0 : lower_bound_i64(ptr, nseg, lo);
-    s1 = (b == G - 1) ? nseg : lower_bound_i64(ptr, nseg, hi);
+// bytes per CTA whatever the segment lengths are. Every segment id belongs to exactly one CTA. The G+1
+// boundaries are computed once per operator (two dependent 20-step binary searches per CTA cost ~25 us per
+// launch, 13 % of a product once the cells are sharded over 8 GPUs).
+__global__ void cta_ranges_kernel(const int64_t *__restrict__ ptr, int64_t nseg, int64_t nnz, int G, int64_t *__restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > G) return;
+    if (b == 0) out[0] = 0;
+    else if (b == G) out[G] = nseg;
+    else out[b] = lower_bound_i64(ptr, nseg, (int64_t)(((__int128)nnz * b) / G));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(256, 6) spmv_fwd_kernel(const int64_t *__restr
                                                           const double *__restrict__ x, const double *__restrict__ mu,
                                                           double alpha, double beta, double *__restrict__ y,
                                                           const double *__restrict__ coef, double csign,
-                                                          const double *__restrict__ cvec) {
+                                                          const double *__restrict__ cvec, const int64_t *__restrict__ ranges) {
     extern __shared__ double smem[];
     __shared__ unsigned long long next_row;
     double *red = smem;       // 32 doubles
@@ -111,8 +113,7 @@ __global__ void __launch_bounds__(256, 6) spmv_fwd_kernel(const int64_t *__restr
     } else if (mu) {
         for (int64_t j = threadIdx.x; j < n; j += blockDim.x) part = fma(mu[j], x[j], part);
     }
-    int64_t r0, r1;
-    cta_segment_range(rowptr, m, nnz, r0, r1);
+    const int64_t r0 = __ldg(ranges + blockIdx.x), r1 = __ldg(ranges + blockIdx.x + 1);
     constexpr int NSUB = 256 / LPS;
     if (threadIdx.x == 0) next_row = (unsigned long long)(r0 + NSUB);
     const double mudot = mu ? block_sum(part, red) : 0.0;  // contains the __syncthreads that publish xs / next_row
@@ -147,14 +148,13 @@ template <typename V, int LPS>
 __global__ void __launch_bounds__(256, 5) spmv_adj_kernel(const int64_t *__restrict__ gptr, const uint16_t *__restrict__ rloc,
                                                           const V *__restrict__ aval, int64_t m, int64_t n, int log2R,
                                                           int64_t ntiles, int64_t nnz, const double *__restrict__ w,
-                                                          double *__restrict__ partial) {
+                                                          double *__restrict__ partial, const int64_t *__restrict__ ranges) {
     extern __shared__ double smem[];
     __shared__ unsigned long long next_seg;
     double *red = smem;      // 32
     double *ws = smem + 32;  // R
     const int64_t R = (int64_t)1 << log2R;
-    int64_t s0, s1;
-    cta_segment_range(gptr, ntiles * n, nnz, s0, s1);
+    const int64_t s0 = __ldg(ranges + blockIdx.x), s1 = __ldg(ranges + blockIdx.x + 1);
     constexpr int NSUB = 256 / LPS;
     const int lane = threadIdx.x & 31;
     const int sub_lane = lane & (LPS - 1);
@@ -260,6 +260,15 @@ static int resident_grid(K kernel, size_t smem) {
     return std::max(1, per_sm) * ctx().sm_count;
 }
 
+static int64_t *make_ranges(const int64_t *ptr, int64_t nseg, int64_t nnz, int G) {
+    int64_t *out = nullptr;
+    SVB_CUDA(cudaMalloc((void **)&out, (size_t)(G + 1) * sizeof(int64_t)));
+    cta_ranges_kernel<<<(G + 256) / 256, 256, 0, ctx().stream>>>(ptr, nseg, nnz, G, out);
+    count_launch();
+    SVB_LAUNCH_CHECK();
+    return out;
+}
+
 template <typename V, typename IdxT, int LPS>
 static void launch_fwd_lps(svb_operator_s *op, double alpha, const double *dx, double beta, double *dy, const double *coef,
                            double csign, const double *cvec) {
@@ -270,14 +279,20 @@ static void launch_fwd_lps(svb_operator_s *op, double alpha, const double *dx, d
     if (xsmem) {
         auto k = spmv_fwd_kernel<V, IdxT, LPS, true>;
         if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (op->fwd_grid == 0) op->fwd_grid = (int)std::min<int64_t>(resident_grid(k, smem), std::max<int64_t>(1, op->m / 8));
+        if (op->fwd_grid == 0) {
+            op->fwd_grid = (int)std::min<int64_t>(resident_grid(k, smem), std::max<int64_t>(1, op->m / 8));
+            op->fwd_ranges = make_ranges(op->rowptr, op->m, op->nnz, op->fwd_grid);
+        }
         k<<<(unsigned)op->fwd_grid, 256, smem, C.stream>>>(op->rowptr, (const IdxT *)op->fidx, (const V *)op->fval, op->m, op->n,
-                                                           op->nnz, dx, op->mu, alpha, beta, dy, coef, csign, cvec);
+                                                           op->nnz, dx, op->mu, alpha, beta, dy, coef, csign, cvec, op->fwd_ranges);
     } else {
         auto k = spmv_fwd_kernel<V, IdxT, LPS, false>;
-        if (op->fwd_grid == 0) op->fwd_grid = (int)std::min<int64_t>(resident_grid(k, smem), std::max<int64_t>(1, op->m / 8));
+        if (op->fwd_grid == 0) {
+            op->fwd_grid = (int)std::min<int64_t>(resident_grid(k, smem), std::max<int64_t>(1, op->m / 8));
+            op->fwd_ranges = make_ranges(op->rowptr, op->m, op->nnz, op->fwd_grid);
+        }
         k<<<(unsigned)op->fwd_grid, 256, smem, C.stream>>>(op->rowptr, (const IdxT *)op->fidx, (const V *)op->fval, op->m, op->n,
-                                                           op->nnz, dx, op->mu, alpha, beta, dy, coef, csign, cvec);
+                                                           op->nnz, dx, op->mu, alpha, beta, dy, coef, csign, cvec, op->fwd_ranges);
     }
     SVB_LAUNCH_CHECK();
 }
@@ -305,9 +320,10 @@ static void launch_adj_lps(svb_operator_s *op, const double *dx) {
     if (op->adj_grid == 0) {
         const int64_t nseg = op->ntiles * op->n;
         op->adj_grid = (int)std::max<int64_t>(1, std::min<int64_t>(resident_grid(k, smem), nseg / 8 + 1));
+        op->adj_ranges = make_ranges(op->gptr, nseg, op->nnz, op->adj_grid);
     }
     k<<<(unsigned)op->adj_grid, 256, smem, C.stream>>>(op->gptr, op->rloc, (const V *)op->aval, op->m, op->n, (int)op->log2R,
-                                                       op->ntiles, op->nnz, dx, op->partial);
+                                                       op->ntiles, op->nnz, dx, op->partial, op->adj_ranges);
     SVB_LAUNCH_CHECK();
 }
 

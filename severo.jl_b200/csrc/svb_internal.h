@@ -153,6 +153,7 @@ struct svb_operator_s {
     int64_t R = 0, ntiles = 0;
     int log2R = 0;
     int fwd_lps = 0, adj_lps = 0, adj_gs = 1;
+    int64_t *fwd_ranges = nullptr, *adj_ranges = nullptr;  // [grid+1] equal-nnz CTA boundaries
     int fwd_grid = 0, adj_grid = 0;          // persistent grid sizes (one resident wave), set at first launch  // launch shape knobs (0 = choose from the average segment length)
     int64_t *gptr = nullptr;        // [ntiles*n + 1] segment (tile, gene) -> offset
     uint16_t *rloc = nullptr;       // [nnz] cell index inside the tile
