@@ -265,9 +265,94 @@ __global__ void __launch_bounds__(GM_THREADS) ts_gemm_kernel(const double *__res
     }
 }
 
+// fp64 tensor-core version (mma.sync.m8n8k4 DMMA; tcgen05 has no fp64): one warp owns 32 rows (4 m-tiles),
+// walks the padded K = w in steps of 4 and carries DM_NT = 4 n-tiles (32 output columns) of accumulators per
+// pass. A fragments come straight from the column-major basis (8 consecutive rows of 4 columns per load),
+// B fragments from the zero-padded P staged in shared memory. Fragment layout (PTX ISA, m8n8k4 .f64):
+// a0 = A[lane>>2][lane&3], b0 = B[lane&3][lane>>2], c0/c1 = C[lane>>2][2*(lane&3) + {0,1}].
+constexpr int DM_THREADS = 128;
+constexpr int DM_NT = 4;
+
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(DM_THREADS) ts_gemm_dmma_kernel(const double *__restrict__ X, int64_t ld, int64_t L, int w,
+                                                                  const double *__restrict__ P, int ldp, int k, int kp8, int wp4,
+                                                                  double *__restrict__ out, int64_t ldo,
+                                                                  const double *__restrict__ colscale) {
+    extern __shared__ double Ps[];  // [wp4][kp8], zero padded
+    for (int idx = threadIdx.x; idx < wp4 * kp8; idx += blockDim.x) {
+        const int l = idx / kp8, c = idx - l * kp8;
+        double v = (l < w && c < k) ? P[l + (int64_t)c * ldp] : 0.0;
+        if (colscale && c < k) v *= colscale[c];
+        Ps[idx] = v;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t r0 = ((int64_t)blockIdx.x * (DM_THREADS / 32) + warp) * 32;
+    if (r0 >= L) return;
+    for (int n0 = 0; n0 < kp8; n0 += 8 * DM_NT) {
+        double acc[4][DM_NT][2];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < DM_NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+        for (int l0 = 0; l0 < wp4; l0 += 4) {
+            const int l = l0 + t;
+            double a[4], b[DM_NT];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) {
+                const int64_t row = r0 + mt * 8 + g;
+                a[mt] = (l < w && row < L) ? __ldg(X + (int64_t)l * ld + row) : 0.0;
+            }
+#pragma unroll
+            for (int nt = 0; nt < DM_NT; ++nt) {
+                const int col = n0 + nt * 8 + g;
+                b[nt] = (col < kp8) ? Ps[l * kp8 + col] : 0.0;
+            }
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < DM_NT; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+        }
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            const int64_t row = r0 + mt * 8 + g;
+            if (row < L) {
+#pragma unroll
+                for (int nt = 0; nt < DM_NT; ++nt) {
+                    const int col = n0 + nt * 8 + 2 * t;
+                    if (col < k) out[row + (int64_t)col * ldo] = acc[mt][nt][0];
+                    if (col + 1 < k) out[row + (int64_t)(col + 1) * ldo] = acc[mt][nt][1];
+                }
+            }
+        }
+    }
+}
+
 void ts_gemm(const double *X, int64_t ld, int64_t L, int w, const double *P, int ldp, int k, double *out, int64_t ldo,
              const double *colscale_dev) {
     if (k <= 0 || L <= 0) return;
+    static const bool use_dmma = getenv("SVB_NO_DMMA") == nullptr;
+    if (use_dmma) {
+        const int kp8 = (k + 7) / 8 * 8, wp4 = (w + 3) / 4 * 4;
+        const size_t smem = (size_t)wp4 * kp8 * sizeof(double);
+        if (smem <= ctx().smem_optin) {
+            if (smem > 48 * 1024)
+                SVB_CUDA(cudaFuncSetAttribute(ts_gemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int64_t rows_per_cta = (DM_THREADS / 32) * 32;
+            const int64_t grid = (L + rows_per_cta - 1) / rows_per_cta;
+            KTimer kt(SVB_K_RESTART, 8.0 * ((double)L * w + (double)L * k));
+            ts_gemm_dmma_kernel<<<(unsigned)grid, DM_THREADS, smem, ctx().stream>>>(X, ld, L, w, P, ldp, k, kp8, wp4, out, ldo,
+                                                                                    colscale_dev);
+            SVB_LAUNCH_CHECK();
+            return;
+        }
+    }
     const int kp = (k + GM_CC - 1) / GM_CC * GM_CC;
     const size_t smem = (size_t)w * kp * sizeof(double);
     SVB_CHECK(smem <= ctx().smem_optin, SVB_EDIM, "restart product: work size too large for shared memory");
