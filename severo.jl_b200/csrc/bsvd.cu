@@ -49,6 +49,12 @@ __global__ void __launch_bounds__(1024) bsvd_kernel(int w, int nu, double *__res
     int sweeps = 0;
     for (int sweep = 0; sweep < 60; ++sweep) {
         if (tid == 0) rotated = 0;
+        for (int c = warp; c < w; c += nwarps) {
+            double a = 0.0;
+            for (int i = lane; i < w; i += 32) a = fma(G[c * ld + i], G[c * ld + i], a);
+            a = warp_sum_d(a);
+            if (lane == 0) nrm[c] = a;
+        }
         __syncthreads();
         for (int r = 0; r < n - 1; ++r) {
             for (int pi = warp; pi < n / 2; pi += nwarps) {
@@ -63,22 +69,42 @@ __global__ void __launch_bounds__(1024) bsvd_kernel(int w, int nu, double *__res
                 if (p > q) { const int t = p; p = q; q = t; }
                 if (q >= w) continue;
                 double *gp = G + p * ld, *gq = G + q * ld;
-                double a = 0.0, b = 0.0, g = 0.0;
-                for (int i = lane; i < w; i += 32) {
-                    const double x = gp[i], y = gq[i];
-                    a = fma(x, x, a);
-                    b = fma(y, y, b);
-                    g = fma(x, y, g);
-                }
-                a = warp_sum_d(a);
-                b = warp_sum_d(b);
+                double g = 0.0;
+                for (int i = lane; i < w; i += 32) g = fma(gp[i], gq[i], g);
                 g = warp_sum_d(g);
+                // squared column norms are cached (exact at the start of every sweep, updated by the rotation
+                // formulas in between): one reduction per pair instead of three
+                const double a = nrm[p], b = nrm[q];
                 if (g * g <= (eps * eps) * (a * b)) continue;  // |g| <= eps*sqrt(a*b) without the sqrt
-                // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (b-a)/(2g)  ==  2g*sign(d) / (|d| + hypot(d, 2g))
+                // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (b-a)/(2g)  ==  2g*sign(d) / (|d| + hypot(d, 2g)).
+                // The fp64 sqrt / divide are ~500-cycle software sequences on the critical path of a round; seed
+                // with the fp32 SFU and polish with Newton steps in fp64 (c, s come from the same t, so c^2+s^2 = 1
+                // to rounding whatever the last bits of t are).
                 const double d = b - a, g2 = 2.0 * g;
-                const double h = sqrt(fma(d, d, g2 * g2));
-                const double t = (d >= 0.0 ? g2 : -g2) / (fabs(d) + h);
-                const double c = rsqrt(fma(t, t, 1.0)), s = c * t;
+                const double q2 = fma(d, d, g2 * g2);
+                double t, c;
+                if (q2 > 1e-30 && q2 < 1e30) {
+                    double y = (double)rsqrtf((float)q2);
+                    y = y * fma(-0.5 * q2, y * y, 1.5);
+                    y = y * fma(-0.5 * q2, y * y, 1.5);
+                    const double x = fabs(d) + q2 * y;         // |d| + sqrt(q2)
+                    double r = (double)__frcp_rn((float)x);
+                    r = r * fma(-x, r, 2.0);
+                    r = r * fma(-x, r, 2.0);                   // 1/x
+                    t = (d >= 0.0 ? g2 : -g2) * r;
+                    const double u = fma(t, t, 1.0);
+                    c = (double)rsqrtf((float)u);
+                    c = c * fma(-0.5 * u, c * c, 1.5);
+                    c = c * fma(-0.5 * u, c * c, 1.5);
+                } else {  // outside the fp32 seed range: plain fp64 sqrt / divide
+                    t = (d >= 0.0 ? g2 : -g2) / (fabs(d) + sqrt(q2));
+                    c = rsqrt(fma(t, t, 1.0));
+                }
+                const double s = c * t;
+                if (lane == 0) {
+                    nrm[p] = fmax(0.0, a - t * g);
+                    nrm[q] = fmax(0.0, b + t * g);
+                }
                 double *vp = V + p * ld, *vq = V + q * ld;
                 for (int i = lane; i < w; i += 32) {
                     const double x = gp[i], y = gq[i];
