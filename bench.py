@@ -346,6 +346,14 @@ def cpu_baseline(sv, cfg, steps=1, warmup=0, cells=163_840):
     Bh, mu, cells = cpu_sample_problem(sv, cfg, cells)
     C = orc.CenteredMatrix(Bh, mu)
     init = np.random.default_rng(SEED).standard_normal(cfg["n"])
+    # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1): OpenMP sparse products + BLAS
+    ncores = os.cpu_count() or 1
+    orc.set_num_threads(ncores)
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=ncores)
+    except Exception:
+        pass
     threads = orc.num_threads()
     times = []
     for i in range(warmup + steps):

@@ -1,0 +1,80 @@
+"""GPU edge cases: empty / ragged inputs, zero-variance genes (NaN propagation as upstream, trap T3), shapes
+that do not align with the 32-cell blocks and 4096-cell tiles of the device layouts, tiny operators."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+
+def test_empty_rows_columns_and_odd_shapes(sv, orc):
+    rng = np.random.default_rng(0)
+    for (m, n) in ((1, 1), (3, 2), (33, 7), (4097, 5), (8193, 31), (130, 300)):
+        X = sp.random(m, n, 0.3, random_state=m + n, format="lil")
+        if m > 2:
+            X[1, :] = 0          # an empty cell
+        if n > 2:
+            X[:, 1] = 0          # an empty gene
+        X = sp.csc_matrix(X)
+        X.eliminate_zeros()
+        mu = rng.standard_normal(n)
+        G, O = sv.CenteredMatrix(X, mu), orc.CenteredMatrix(X, mu)
+        v, w = rng.standard_normal(n), rng.standard_normal(m)
+        np.testing.assert_allclose(G @ v, O.mul(v), rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(G.T @ w, O.mul(w, trans=True), rtol=1e-12, atol=1e-12)
+        d = sv.DeviceMatrix.from_host(X)
+        assert (d.transpose().to_host() != sp.csc_matrix(X.T)).nnz == 0
+        G.free()
+
+
+def test_all_zero_matrix_and_single_entry(sv):
+    Z = sp.csc_matrix((50, 8), dtype=np.float64)
+    C = sv.CenteredMatrix(Z, np.arange(8.0))
+    v = np.ones(8)
+    np.testing.assert_allclose(C @ v, -np.full(50, 28.0))
+    np.testing.assert_allclose(C.T @ np.ones(50), -50.0 * np.arange(8.0))
+    E = sp.csc_matrix(([2.5], ([49], [7])), shape=(50, 8))
+    C = sv.CenteredMatrix(E, None)
+    y = C @ np.arange(8.0)
+    assert y[49] == 17.5 and np.count_nonzero(y) == 1
+
+
+def test_zero_variance_gene_propagates_nan_like_upstream(sv, orc):
+    # scaling.jl:206-207: std == 0 -> mu/std = NaN (constant zero gene) or Inf; the reference does not guard it (T3)
+    X = sp.csc_matrix(np.array([[1, 0, 2], [3, 0, 2], [0, 0, 2], [2, 0, 2]], dtype=np.int64))
+    G = sv.scale_features(X)
+    O = orc.scale_features(X)
+    assert np.isnan(np.asarray(G.mu)[1]) and np.isnan(O.mu[1])
+    np.testing.assert_array_equal(np.asarray(G.mu), O.mu)           # NaN == NaN positionally, Inf equal
+    np.testing.assert_array_equal(G.A.data, O.P.data)
+    mu, var = sv.mean_var(X)
+    assert var[1] == 0.0 and var[2] == 0.0
+
+
+def test_irlba_small_and_clamped_work(sv):
+    rng = np.random.default_rng(3)
+    # work = min(nu + 7, min(m, n)) clamps to the full dimension (irlba.jl:56-58): exact in one sweep
+    X = rng.standard_normal((12, 6))
+    S = sv.irlba(X, 4, rng=rng)
+    np.testing.assert_allclose(S.S, np.linalg.svd(X, compute_uv=False)[:4], rtol=1.5e-8)
+    X = sp.random(300, 9, 0.5, random_state=1, format="csc")
+    S = sv.irlba(X, 9, rng=rng, tol=1e-9)
+    np.testing.assert_allclose(S.S, np.linalg.svd(X.toarray(), compute_uv=False), rtol=1e-8)
+    U, s, V = S
+    np.testing.assert_allclose(U.T @ U, np.eye(9), atol=1e-8)
+    # nu = 1
+    S = sv.irlba(sp.random(500, 40, 0.2, random_state=2, format="csc"), 1, rng=rng, tol=1e-9)
+    assert S.S.shape == (1,)
+
+
+def test_reproducible_bits_run_to_run(sv):
+    # all reductions are fixed-order: the same call returns the same bits
+    rng = np.random.default_rng(4)
+    X = sp.random(20000, 300, 0.05, random_state=5, format="csc")
+    C = sv.CenteredMatrix(X, np.asarray(X.mean(axis=0)).ravel())
+    init = rng.standard_normal(300)
+    A = sv.irlba(C, 6, init=init, tol=1e-8)
+    B = sv.irlba(C, 6, init=init, tol=1e-8)
+    np.testing.assert_array_equal(A.S, B.S)
+    np.testing.assert_array_equal(A.U, B.U)
+    np.testing.assert_array_equal(A.Vt, B.Vt)
