@@ -515,7 +515,8 @@ def irlba(A, nu, init=None, tol=1e-5, svtol=None, maxit=1000, work=None, rng=Non
         # nu-th value unconverged and then misses the reference's own `S.S ≈ svd(X).S` test (1.8e-7 vs sqrt(eps))
         nconv = int(np.count_nonzero(conv[:nu]))
         it += 1
-        if nconv >= nu or s == 0.0:
+        # invariant subspace (|F| at rounding level): every Ritz value is exact; restarting would seed on noise
+        if nconv >= nu or s == 0.0 or rF <= 1000.0 * np.finfo(np.float64).eps * smax:
             info = 0
             break
         if it >= maxit:

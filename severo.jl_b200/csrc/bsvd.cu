@@ -163,7 +163,9 @@ __global__ void __launch_bounds__(1024) bsvd_kernel(int w, int nu, double *__res
             const double ratio = fabs(sig_prev[i] - sig[i]) / sig[i];
             if (fabs(res[i]) < tol * smax && ratio < svtol) ++nconv;
         }
-        const int converged = (nconv >= nu) || (last_diag == 0.0);
+        // invariant subspace: |F| at rounding level => every Ritz value is exact, nothing left to iterate on
+        // (work clamped to min(m, n) spans the whole space in the first sweep; the lineage code would restart on noise)
+        const int converged = (nconv >= nu) || (last_diag == 0.0) || (RF <= 1000.0 * 2.220446049250313e-16 * smax);
         int k = k_in;
         if (k < nu + nconv) k = nu + nconv;
         if (k > w - 3) k = w - 3;

@@ -226,7 +226,7 @@ static void irlba_run(svb_operator_s *op, int64_t nu_, int64_t work_, int64_t ma
                     const double ratio = std::fabs(sig_prev[i] - sig[i]) / sig[i];
                     if (std::fabs(resid[i]) < tol * smax && ratio < svtol) ++nconv;
                 }
-                hs.converged = (nconv >= nu || hB[(size_t)(w - 1) * w + (w - 1)] == 0.0) ? 1 : 0;
+                hs.converged = (nconv >= nu || hB[(size_t)(w - 1) * w + (w - 1)] == 0.0 || RF <= 1000.0 * 2.220446049250313e-16 * smax) ? 1 : 0;
                 hs.nconv = nconv;
                 int kk = std::max(k, nu + nconv);
                 kk = std::min(kk, w - 3);
