@@ -453,7 +453,8 @@ def irlba(A, nu, init=None, tol=1e-5, svtol=None, maxit=1000, work=None, rng=Non
         V[:, :k] = V0
         W[:, :k] = U0
         B[np.arange(k), np.arange(k)] = s0
-        V[:, k] = init / np.linalg.norm(init)
+        f0 = _orthog(V, np.array(init, dtype=np.float64), k)   # start vector orthogonal to the supplied V (fixes upstream)
+        V[:, k] = f0 / np.linalg.norm(f0)
     else:
         V[:, 0] = init / np.linalg.norm(init)
     sv_prev = np.zeros(w)

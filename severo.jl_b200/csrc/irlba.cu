@@ -159,6 +159,9 @@ static void irlba_run(svb_operator_s *op, int64_t nu_, int64_t work_, int64_t ma
         SVB_CUDA(cudaMemcpyAsync(Bm.p, hB.data(), (size_t)w * w * 8, cudaMemcpyHostToDevice, S.st));
         SVB_CUDA(cudaStreamSynchronize(S.st));
     }
+    // warm restart (irlba.jl:87-99): the new start vector must be orthogonal to the supplied right vectors; the
+    // reference passes the raw random `init` (its own test of this path is @test_broken, test_irlba.jl:60-62)
+    if (k > 0) S.orthog(S.V.p, n, k, S.F.p, S.nrm2F(), false);
     vec_normalize(S.F.p, n, S.nrm2F(), S.Vc(k), nullptr, nullptr, 0.0);
 
     double smax = 0.0;

@@ -78,3 +78,18 @@ def test_reproducible_bits_run_to_run(sv):
     np.testing.assert_array_equal(A.S, B.S)
     np.testing.assert_array_equal(A.U, B.U)
     np.testing.assert_array_equal(A.Vt, B.Vt)
+
+
+def test_warm_restart_is_correct_and_cheaper(sv):
+    # irlba(A, nu, S::SVD) (irlba.jl:87-99): broken upstream (test_irlba.jl:60-62); here the supplied triplets are
+    # kept and the new start vector is orthogonalised against them, so more PCs can be added incrementally
+    rng = np.random.default_rng(21)
+    X = rng.standard_normal((300, 120))
+    s = np.linalg.svd(X, compute_uv=False)
+    init = rng.standard_normal(120)
+    S5 = sv.irlba(X, 5, init=init, tol=1e-8)
+    S8 = sv.irlba(X, 8, S5, init=rng.standard_normal(120), tol=1e-8)
+    cold = sv.irlba(X, 8, init=init, tol=1e-8)
+    np.testing.assert_allclose(S8.S, s[:8], rtol=1.5e-8)
+    assert np.linalg.norm(X.T @ S8.U - S8.V * S8.S) / np.linalg.norm(X) < 1e-8
+    assert S8.mprod < cold.mprod

@@ -302,6 +302,10 @@ def test_irlba_restart_signature(sv):
     np.testing.assert_allclose(S.S, s[:2], rtol=SQRT_EPS)
     S3 = sv.irlba(X, 3, S, tol=1e-5, rng=rng)
     assert S3.U.shape == (20, 3) and S3.S.shape == (3,)
+    # upstream marks these two @test_broken; with the start vector orthogonalised against the supplied V they hold
+    np.testing.assert_allclose(S3.S, s[:3], rtol=SQRT_EPS)
+    U, sd, Vt = np.linalg.svd(X, full_matrices=False)
+    np.testing.assert_allclose(_relative_error(X, S3), np.linalg.norm(X - (U[:, :3] * sd[:3]) @ Vt[:3]), rtol=1e-6)
 
 
 def test_irlba_tall_skinny_and_transpose(sv):
