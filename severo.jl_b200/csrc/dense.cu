@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(GM_THREADS) ts_gemm_kernel(const double *__res
 // B fragments from the zero-padded P staged in shared memory. Fragment layout (PTX ISA, m8n8k4 .f64):
 // a0 = A[lane>>2][lane&3], b0 = B[lane&3][lane>>2], c0/c1 = C[lane>>2][2*(lane&3) + {0,1}].
 constexpr int DM_THREADS = 128;
-constexpr int DM_NT = 4;
+constexpr int DM_NT = 4;  // n-tiles per pass (7 = one pass for nu = 50 was slower: 160 registers)
 
 __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"

@@ -92,8 +92,8 @@ __global__ void cta_ranges_kernel(const int64_t *__restrict__ ptr, int64_t nseg,
 // forward: y_i = alpha*(sum_j a_ij x_j - mu.x) + beta*y_i + csign*(*coef)*cvec_i
 // persistent grid (one resident wave); sub-warps of LPS lanes grab cells dynamically inside the CTA's range
 // ---------------------------------------------------------------------------------------------
-template <typename V, typename IdxT, int LPS, bool XSMEM>
-__global__ void __launch_bounds__(256, 6) spmv_fwd_kernel(const int64_t *__restrict__ rowptr, const IdxT *__restrict__ fidx,
+template <typename V, typename IdxT, int LPS, bool XSMEM, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, (BLOCK == 256 ? 6 : 3)) spmv_fwd_kernel(const int64_t *__restrict__ rowptr, const IdxT *__restrict__ fidx,
                                                           const V *__restrict__ fval, int64_t m, int64_t n, int64_t nnz,
                                                           const double *__restrict__ x, const double *__restrict__ mu,
                                                           double alpha, double beta, double *__restrict__ y,
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256, 6) spmv_fwd_kernel(const int64_t *__restr
         for (int64_t j = threadIdx.x; j < n; j += blockDim.x) part = fma(mu[j], x[j], part);
     }
     const int64_t r0 = __ldg(ranges + blockIdx.x), r1 = __ldg(ranges + blockIdx.x + 1);
-    constexpr int NSUB = 256 / LPS;
+    constexpr int NSUB = BLOCK / LPS;
     if (threadIdx.x == 0) next_row = (unsigned long long)(r0 + NSUB);
     const double mudot = mu ? block_sum(part, red) : 0.0;  // contains the __syncthreads that publish xs / next_row
     if (!mu) __syncthreads();
@@ -254,9 +254,9 @@ __global__ void __launch_bounds__(1024) dot_small_kernel(const double *__restric
 // ---------------------------------------------------------------------------------------------
 // one resident wave: SMs x (CTAs that fit per SM for this kernel and shared-memory size)
 template <typename K>
-static int resident_grid(K kernel, size_t smem) {
+static int resident_grid(K kernel, size_t smem, int threads = 256) {
     int per_sm = 0;
-    SVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem));
+    SVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
     return std::max(1, per_sm) * ctx().sm_count;
 }
 
@@ -269,6 +269,20 @@ static int64_t *make_ranges(const int64_t *ptr, int64_t nseg, int64_t nnz, int G
     return out;
 }
 
+template <typename V, typename IdxT, int LPS, bool XSMEM, int BLOCK>
+static void launch_fwd_block(svb_operator_s *op, size_t smem, double alpha, const double *dx, double beta, double *dy,
+                             const double *coef, double csign, const double *cvec) {
+    auto k = spmv_fwd_kernel<V, IdxT, LPS, XSMEM, BLOCK>;
+    if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (op->fwd_grid == 0) {
+        op->fwd_grid = (int)std::min<int64_t>(resident_grid(k, smem, BLOCK), std::max<int64_t>(1, op->m / 8));
+        op->fwd_ranges = make_ranges(op->rowptr, op->m, op->nnz, op->fwd_grid);
+    }
+    k<<<(unsigned)op->fwd_grid, BLOCK, smem, ctx().stream>>>(op->rowptr, (const IdxT *)op->fidx, (const V *)op->fval, op->m, op->n,
+                                                             op->nnz, dx, op->mu, alpha, beta, dy, coef, csign, cvec, op->fwd_ranges);
+    SVB_LAUNCH_CHECK();
+}
+
 template <typename V, typename IdxT, int LPS>
 static void launch_fwd_lps(svb_operator_s *op, double alpha, const double *dx, double beta, double *dy, const double *coef,
                            double csign, const double *cvec) {
@@ -276,25 +290,11 @@ static void launch_fwd_lps(svb_operator_s *op, double alpha, const double *dx, d
     const size_t xs_bytes = (size_t)op->n * sizeof(double);
     const bool xsmem = xs_bytes + 256 + 1024 <= C.smem_optin;
     const size_t smem = 32 * sizeof(double) + (xsmem ? xs_bytes : 0);
-    if (xsmem) {
-        auto k = spmv_fwd_kernel<V, IdxT, LPS, true>;
-        if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (op->fwd_grid == 0) {
-            op->fwd_grid = (int)std::min<int64_t>(resident_grid(k, smem), std::max<int64_t>(1, op->m / 8));
-            op->fwd_ranges = make_ranges(op->rowptr, op->m, op->nnz, op->fwd_grid);
-        }
-        k<<<(unsigned)op->fwd_grid, 256, smem, C.stream>>>(op->rowptr, (const IdxT *)op->fidx, (const V *)op->fval, op->m, op->n,
-                                                           op->nnz, dx, op->mu, alpha, beta, dy, coef, csign, cvec, op->fwd_ranges);
-    } else {
-        auto k = spmv_fwd_kernel<V, IdxT, LPS, false>;
-        if (op->fwd_grid == 0) {
-            op->fwd_grid = (int)std::min<int64_t>(resident_grid(k, smem), std::max<int64_t>(1, op->m / 8));
-            op->fwd_ranges = make_ranges(op->rowptr, op->m, op->nnz, op->fwd_grid);
-        }
-        k<<<(unsigned)op->fwd_grid, 256, smem, C.stream>>>(op->rowptr, (const IdxT *)op->fidx, (const V *)op->fval, op->m, op->n,
-                                                           op->nnz, dx, op->mu, alpha, beta, dy, coef, csign, cvec, op->fwd_ranges);
-    }
-    SVB_LAUNCH_CHECK();
+    // a large gene vector leaves little of the 228 KB for L1 when six 256-thread CTAs each hold a copy: share one
+    // copy among 512 threads instead (three CTAs per SM keep the same number of warps)
+    if (!xsmem) launch_fwd_block<V, IdxT, LPS, false, 256>(op, smem, alpha, dx, beta, dy, coef, csign, cvec);
+    else if (smem > 24 * 1024) launch_fwd_block<V, IdxT, LPS, true, 512>(op, smem, alpha, dx, beta, dy, coef, csign, cvec);
+    else launch_fwd_block<V, IdxT, LPS, true, 256>(op, smem, alpha, dx, beta, dy, coef, csign, cvec);
 }
 
 template <typename V, typename IdxT>
