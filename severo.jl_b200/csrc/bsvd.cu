@@ -57,7 +57,9 @@ __global__ void __launch_bounds__(1024) bsvd_kernel(int w, int nu, double *__res
         }
         __syncthreads();
         for (int r = 0; r < n - 1; ++r) {
-            for (int pi = warp; pi < n / 2; pi += nwarps) {
+            // one column pair per 16-lane half-warp: all n/2 <= 64 pairs of a round run concurrently
+            for (int pi = 2 * warp + (lane >> 4); pi - (lane >> 4) < n / 2; pi += 2 * nwarps) {
+                const int hl = lane & 15;
                 int p, q;
                 if (pi == 0) {
                     p = n - 1;
@@ -67,54 +69,57 @@ __global__ void __launch_bounds__(1024) bsvd_kernel(int w, int nu, double *__res
                     q = (r - pi + (n - 1)) % (n - 1);
                 }
                 if (p > q) { const int t = p; p = q; q = t; }
-                if (q >= w) continue;
-                double *gp = G + p * ld, *gq = G + q * ld;
+                const bool live = (pi < n / 2) && (q < w);
+                double *gp = G + (live ? p : 0) * ld, *gq = G + (live ? q : 0) * ld;
                 double g = 0.0;
-                for (int i = lane; i < w; i += 32) g = fma(gp[i], gq[i], g);
-                g = warp_sum_d(g);
+                if (live)
+                    for (int i = hl; i < w; i += 16) g = fma(gp[i], gq[i], g);
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);  // stays inside the half-warp
                 // squared column norms are cached (exact at the start of every sweep, updated by the rotation
                 // formulas in between): one reduction per pair instead of three
-                const double a = nrm[p], b = nrm[q];
-                if (g * g <= (eps * eps) * (a * b)) continue;  // |g| <= eps*sqrt(a*b) without the sqrt
-                // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (b-a)/(2g)  ==  2g*sign(d) / (|d| + hypot(d, 2g)).
-                // The fp64 sqrt / divide are ~500-cycle software sequences on the critical path of a round; seed
-                // with the fp32 SFU and polish with Newton steps in fp64 (c, s come from the same t, so c^2+s^2 = 1
-                // to rounding whatever the last bits of t are).
-                const double d = b - a, g2 = 2.0 * g;
-                const double q2 = fma(d, d, g2 * g2);
-                double t, c;
-                if (q2 > 1e-30 && q2 < 1e30) {
-                    double y = (double)rsqrtf((float)q2);
-                    y = y * fma(-0.5 * q2, y * y, 1.5);
-                    y = y * fma(-0.5 * q2, y * y, 1.5);
-                    const double x = fabs(d) + q2 * y;         // |d| + sqrt(q2)
-                    double r = (double)__frcp_rn((float)x);
-                    r = r * fma(-x, r, 2.0);
-                    r = r * fma(-x, r, 2.0);                   // 1/x
-                    t = (d >= 0.0 ? g2 : -g2) * r;
-                    const double u = fma(t, t, 1.0);
-                    c = (double)rsqrtf((float)u);
-                    c = c * fma(-0.5 * u, c * c, 1.5);
-                    c = c * fma(-0.5 * u, c * c, 1.5);
-                } else {  // outside the fp32 seed range: plain fp64 sqrt / divide
-                    t = (d >= 0.0 ? g2 : -g2) / (fabs(d) + sqrt(q2));
-                    c = rsqrt(fma(t, t, 1.0));
+                const double a = live ? nrm[p] : 0.0, b = live ? nrm[q] : 0.0;
+                if (live && g * g > (eps * eps) * (a * b)) {  // |g| > eps*sqrt(a*b) without the sqrt
+                    // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (b-a)/(2g) == 2g*sign(d) / (|d| + hypot(d, 2g)).
+                    // fp64 sqrt / divide are ~500-cycle software sequences on the critical path of a round: seed with
+                    // the fp32 SFU and polish with Newton steps in fp64 (c, s come from the same t, so c^2 + s^2 = 1 to
+                    // rounding whatever the last bits of t are).
+                    const double d = b - a, g2 = 2.0 * g;
+                    const double q2 = fma(d, d, g2 * g2);
+                    double t, c;
+                    if (q2 > 1e-30 && q2 < 1e30) {
+                        double y = (double)rsqrtf((float)q2);
+                        y = y * fma(-0.5 * q2, y * y, 1.5);
+                        y = y * fma(-0.5 * q2, y * y, 1.5);
+                        const double x = fabs(d) + q2 * y;         // |d| + sqrt(q2)
+                        double rr = (double)__frcp_rn((float)x);
+                        rr = rr * fma(-x, rr, 2.0);
+                        rr = rr * fma(-x, rr, 2.0);                // 1/x
+                        t = (d >= 0.0 ? g2 : -g2) * rr;
+                        const double u = fma(t, t, 1.0);
+                        c = (double)rsqrtf((float)u);
+                        c = c * fma(-0.5 * u, c * c, 1.5);
+                        c = c * fma(-0.5 * u, c * c, 1.5);
+                    } else {  // outside the fp32 seed range: plain fp64 sqrt / divide
+                        t = (d >= 0.0 ? g2 : -g2) / (fabs(d) + sqrt(q2));
+                        c = rsqrt(fma(t, t, 1.0));
+                    }
+                    const double sn = c * t;
+                    if (hl == 0) {
+                        nrm[p] = fmax(0.0, a - t * g);
+                        nrm[q] = fmax(0.0, b + t * g);
+                        rotated = 1;
+                    }
+                    double *vp = V + p * ld, *vq = V + q * ld;
+                    for (int i = hl; i < w; i += 16) {
+                        const double x = gp[i], y = gq[i];
+                        gp[i] = c * x - sn * y;
+                        gq[i] = sn * x + c * y;
+                        const double vx = vp[i], vy = vq[i];
+                        vp[i] = c * vx - sn * vy;
+                        vq[i] = sn * vx + c * vy;
+                    }
                 }
-                const double s = c * t;
-                if (lane == 0) {
-                    nrm[p] = fmax(0.0, a - t * g);
-                    nrm[q] = fmax(0.0, b + t * g);
-                }
-                double *vp = V + p * ld, *vq = V + q * ld;
-                for (int i = lane; i < w; i += 32) {
-                    const double x = gp[i], y = gq[i];
-                    gp[i] = c * x - s * y;
-                    gq[i] = s * x + c * y;
-                    const double vx = vp[i], vy = vq[i];
-                    vp[i] = c * vx - s * vy;
-                    vq[i] = s * vx + c * vy;
-                }
-                if (lane == 0) rotated = 1;
             }
             __syncthreads();
         }
@@ -202,8 +207,8 @@ void bsvd_launch(int w, int nu, double *B, double *P, double *Q, double *sig, do
                  double *smax_io, double tol, double svtol, int k_in, const int *flag_dev, BsvdStatus *status_dev) {
     const size_t smem = bsvd_smem_bytes(w);
     if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(bsvd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // one warp per column pair: ceil(w/2) warps, at most 32
-    int warps = std::min(32, std::max(4, (w + 1) / 2));
+    // one 16-lane half-warp per column pair: ceil(n/4) warps, at most 32
+    int warps = std::min(32, std::max(4, ((w + 1) / 2 + 1) / 2));
     KTimer kt(SVB_K_VECTOR, 8.0 * 3 * w * w);
     bsvd_kernel<<<1, warps * 32, smem, ctx().stream>>>(w, nu, B, P, Q, sig, sig_prev, nrm2F, smax_io, tol, svtol, k_in, flag_dev, status_dev);
     SVB_LAUNCH_CHECK();
