@@ -126,9 +126,10 @@ def build_workload(sv, cfg, rank, world, rows_total=None):
     return B, mu, info
 
 
-def make_operator(sv, B, mu):
+def make_operator(sv, B, mu, storage="f64"):
     h = ctypes.c_void_p()
-    sv._lib.check(sv.lib().svb_operator_create(B._h, sv._lib.ptr(np.ascontiguousarray(mu)), 0, ctypes.byref(h)))
+    vs = sv._lib.SVB_F32 if storage == "f32" else 0
+    sv._lib.check(sv.lib().svb_operator_create_ex(B._h, sv._lib.ptr(np.ascontiguousarray(mu)), 0, vs, ctypes.byref(h)))
     return h
 
 
@@ -166,7 +167,7 @@ def run_b200(args):
         n, nu = cfg["n"], cfg["nu"]
         m_local = B.shape[0]
         init = np.random.default_rng(SEED).standard_normal(n)
-        op = make_operator(sv, B, mu)
+        op = make_operator(sv, B, mu, args.storage)
 
         def barrier():
             torch.cuda.synchronize()
@@ -262,7 +263,7 @@ def run_b200(args):
                                            ctypes.byref(h)))
                 t1 = time.perf_counter()
                 o = ctypes.c_void_p()
-                L.check(lib.svb_operator_create(h, L.ptr(mu_c), 0, ctypes.byref(o)))
+                L.check(lib.svb_operator_create_ex(h, L.ptr(mu_c), 0, L.SVB_F32 if args.storage == "f32" else 0, ctypes.byref(o)))
                 lib.svb_matrix_free(h)
                 t2 = time.perf_counter()
                 it_, mp_ = ctypes.c_int64(), ctypes.c_int64()
@@ -306,7 +307,8 @@ def run_b200(args):
         out = {
             "metric": METRIC, "value": round(ms_per_step / 1e3, 6), "unit": "s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": False, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f64" if args.storage == "f64" else "f64 accumulate / f32 value storage",
+            "data": "synthetic",
             "config": {"workload": f"{args.config}: synthetic {cfg['desc']} Poisson counts, {cfg['m']} cells x {cfg['g']} genes, "
                                    f"Z={Z_total} nnz -> lognormalize -> {cfg['n']} HVGs (vst) -> scale_features(scale_max=10) -> "
                                    f"irlba nu={cfg['nu']} work={cfg['nu'] + 7} tol={TOL}",
@@ -398,6 +400,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C3", choices=sorted(CONFIGS))
+    ap.add_argument("--storage", default="f64", choices=["f64", "f32"],
+                    help="value storage of the operator layouts (f32 = optional Float32-storage / Float64-accumulate mode)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
