@@ -4,6 +4,7 @@
 // All of them are HBM-bound streams over the m x w basis; reductions are two-stage with a
 // last-block pass in a fixed order, so every result is run-to-run deterministic.
 #include "svb_internal.h"
+#include "p2p.cuh"
 
 #include <algorithm>
 
@@ -48,7 +49,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 // t[c] = sum_i X[i + c*ld] * y[i].  grid (nrb, ceil(j/CT)).
 __global__ void __launch_bounds__(TS_THREADS) ts_gemv_t_kernel(const double *__restrict__ X, int64_t ld, int64_t L, int j,
                                                                const double *__restrict__ y, double *__restrict__ t,
-                                                               double *__restrict__ partials, unsigned int *counters) {
+                                                               double *__restrict__ partials, unsigned int *counters,
+                                                               int use_p2p, P2PCtx pc) {
     __shared__ double sh[TS_THREADS / 32][CT];
     __shared__ bool is_last;
     const int c0 = blockIdx.y * CT;
@@ -99,9 +101,13 @@ __global__ void __launch_bounds__(TS_THREADS) ts_gemv_t_kernel(const double *__r
             double s = 0.0;
             for (unsigned int b = lane; b < gridDim.x; b += 32) s += __ldcg(p + (size_t)b * CT);
             s = warp_sum(s);
-            if (lane == 0) t[c0 + wid] = s;
+            if (lane == 0) {
+                if (use_p2p) p2p_store(pc, c0 + wid, s);  // fused exchange: coefficients go straight to every rank
+                else t[c0 + wid] = s;
+            }
         }
         if (threadIdx.x == 0) counters[blockIdx.y] = 0u;
+        if (use_p2p) p2p_publish_last_block(pc, gridDim.y);  // the last column tile to finish publishes the epoch
     }
 }
 
@@ -109,9 +115,17 @@ __global__ void __launch_bounds__(TS_THREADS) ts_gemv_t_kernel(const double *__r
 __global__ void __launch_bounds__(TS_THREADS) ts_gemv_n_kernel(const double *__restrict__ X, int64_t ld, int64_t L, int j,
                                                                const double *__restrict__ t, double alpha, double beta,
                                                                double *__restrict__ y, double *__restrict__ nrm2_out,
-                                                               double *__restrict__ partials, unsigned int *counter) {
+                                                               double *__restrict__ partials, unsigned int *counter,
+                                                               int t_p2p, P2PCtx pt, int nrm_p2p, P2PCtx pn) {
     __shared__ double sh[TS_THREADS / 32];
+    __shared__ double ts[TS_THREADS];
     __shared__ bool is_last;
+    const bool smem_t = j <= TS_THREADS;
+    if (t_p2p) p2p_wait(pt);  // fused exchange: every rank's coefficients are in the local mailbox
+    if (smem_t) {
+        if ((int)threadIdx.x < j) ts[threadIdx.x] = t_p2p ? p2p_sum(pt, threadIdx.x) : t[threadIdx.x];
+        __syncthreads();
+    }
     double ss = 0.0;
     const int64_t chunk = (int64_t)TS_THREADS * 2;
     for (int64_t base = (int64_t)blockIdx.x * chunk; base < L; base += (int64_t)gridDim.x * chunk) {
@@ -120,7 +134,8 @@ __global__ void __launch_bounds__(TS_THREADS) ts_gemv_n_kernel(const double *__r
         double a0 = 0.0, a1 = 0.0;
         int c = 0;
         for (; c + 4 <= j; c += 4) {
-            const double t0 = __ldg(t + c), t1 = __ldg(t + c + 1), t2 = __ldg(t + c + 2), t3 = __ldg(t + c + 3);
+            const double t0 = smem_t ? ts[c] : __ldg(t + c), t1 = smem_t ? ts[c + 1] : __ldg(t + c + 1);
+            const double t2 = smem_t ? ts[c + 2] : __ldg(t + c + 2), t3 = smem_t ? ts[c + 3] : __ldg(t + c + 3);
             const double *xp = X + (int64_t)c * ld;
             if (v0) {
                 const double x0 = __ldg(xp + i0), x1 = __ldg(xp + ld + i0), x2 = __ldg(xp + 2 * ld + i0), x3 = __ldg(xp + 3 * ld + i0);
@@ -132,7 +147,7 @@ __global__ void __launch_bounds__(TS_THREADS) ts_gemv_n_kernel(const double *__r
             }
         }
         for (; c < j; ++c) {
-            const double tc = __ldg(t + c);
+            const double tc = smem_t ? ts[c] : __ldg(t + c);
             if (v0) a0 = fma(__ldg(X + (int64_t)c * ld + i0), tc, a0);
             if (v1) a1 = fma(__ldg(X + (int64_t)c * ld + i1), tc, a1);
         }
@@ -164,15 +179,19 @@ __global__ void __launch_bounds__(TS_THREADS) ts_gemv_n_kernel(const double *__r
         is_last = (ticket == gridDim.x - 1);
     }
     __syncthreads();
-    if (is_last && wid == 0) {
-        __threadfence();
-        double s = 0.0;
-        for (unsigned int b = lane; b < gridDim.x; b += 32) s += __ldcg(partials + b);
-        s = warp_sum(s);
-        if (lane == 0) {
-            *nrm2_out = s;
-            *counter = 0u;
+    if (is_last) {
+        if (wid == 0) {
+            __threadfence();
+            double s = 0.0;
+            for (unsigned int b = lane; b < gridDim.x; b += 32) s += __ldcg(partials + b);
+            s = warp_sum(s);
+            if (lane == 0) {
+                if (nrm_p2p) p2p_store(pn, 0, s);  // fused exchange of the local |y|^2
+                else *nrm2_out = s;
+                *counter = 0u;
+            }
         }
+        if (nrm_p2p) p2p_publish_last_block(pn, 1);
     }
 }
 
@@ -190,7 +209,7 @@ static int wave_slots(K kernel, int threads) {
     return per_sm * ctx().sm_count;
 }
 
-void ts_gemv_t(const double *X, int64_t ld, int64_t L, int j, const double *y, double *t, int cls) {
+void ts_gemv_t(const double *X, int64_t ld, int64_t L, int j, const double *y, double *t, int cls, const P2PCtx *produce_t) {
     if (j <= 0) return;
     const int ctiles = (j + CT - 1) / CT;
     // keep the total CTA count near 4 waves regardless of the number of column tiles
@@ -201,19 +220,22 @@ void ts_gemv_t(const double *X, int64_t ld, int64_t L, int j, const double *y, d
     scratch_reserve((size_t)ctiles * nrb * CT + 4096, (size_t)ctiles + 8);
     KTimer kt(cls, 8.0 * ((double)L * j + (double)L * ((j + CT - 1) / CT)));
     dim3 grid((unsigned)nrb, (unsigned)ctiles);
-    ts_gemv_t_kernel<<<grid, TS_THREADS, 0, ctx().stream>>>(X, ld, L, j, y, t, g_scr.partials + 4096, g_scr.counters + 8);
+    ts_gemv_t_kernel<<<grid, TS_THREADS, 0, ctx().stream>>>(X, ld, L, j, y, t, g_scr.partials + 4096, g_scr.counters + 8,
+                                                            produce_t ? 1 : 0, produce_t ? *produce_t : P2PCtx{});
     SVB_LAUNCH_CHECK();
 }
 
 void ts_gemv_n(const double *X, int64_t ld, int64_t L, int j, const double *t, double alpha, double beta, double *y,
-               double *nrm2_out, int cls) {
+               double *nrm2_out, int cls, const P2PCtx *consume_t, const P2PCtx *produce_nrm) {
     static int slots_n = 0;
     if (!slots_n) slots_n = wave_slots(ts_gemv_n_kernel, TS_THREADS);
     const int nrb = (int)std::max<int64_t>(1, std::min<int64_t>((L + TS_THREADS * 2 - 1) / (TS_THREADS * 2), slots_n));
     scratch_reserve(4096 + 64, 8);
     KTimer kt(cls, 8.0 * ((double)L * j + 2.0 * L));
     ts_gemv_n_kernel<<<(unsigned)nrb, TS_THREADS, 0, ctx().stream>>>(X, ld, L, j, t, alpha, beta, y, nrm2_out, g_scr.partials,
-                                                                     g_scr.counters);
+                                                                     g_scr.counters, consume_t ? 1 : 0,
+                                                                     consume_t ? *consume_t : P2PCtx{}, produce_nrm ? 1 : 0,
+                                                                     produce_nrm ? *produce_nrm : P2PCtx{});
     SVB_LAUNCH_CHECK();
 }
 
@@ -407,8 +429,9 @@ void vec_sumsq(const double *x, int64_t L, double *out) {
 }
 
 __global__ void normalize_kernel(const double *__restrict__ x, int64_t L, const double *__restrict__ nrm2, double *__restrict__ y,
-                                 double *norm_out, int *flag, double eps) {
-    const double nrm = sqrt(*nrm2);
+                                 double *norm_out, int *flag, double eps, int nrm_p2p, P2PCtx pn) {
+    if (nrm_p2p) p2p_wait(pn);  // fused exchange: sum of the ranks' local |x|^2 (rank order, same bits everywhere)
+    const double nrm = sqrt(nrm_p2p ? p2p_sum(pn, 0) : *nrm2);
     const double inv = 1.0 / nrm;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += (int64_t)gridDim.x * blockDim.x) y[i] = x[i] * inv;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -417,10 +440,12 @@ __global__ void normalize_kernel(const double *__restrict__ x, int64_t L, const 
     }
 }
 
-void vec_normalize(const double *x, int64_t L, const double *nrm2_dev, double *y, double *norm_out, int *flag_dev, double eps) {
+void vec_normalize(const double *x, int64_t L, const double *nrm2_dev, double *y, double *norm_out, int *flag_dev, double eps,
+                   const P2PCtx *consume_nrm) {
     const int nrb = row_blocks(L, 256 * 4, 8);
     KTimer kt(SVB_K_VECTOR, 16.0 * L);
-    normalize_kernel<<<(unsigned)nrb, 256, 0, ctx().stream>>>(x, L, nrm2_dev, y, norm_out, flag_dev, eps);
+    normalize_kernel<<<(unsigned)nrb, 256, 0, ctx().stream>>>(x, L, nrm2_dev, y, norm_out, flag_dev, eps, consume_nrm ? 1 : 0,
+                                                              consume_nrm ? *consume_nrm : P2PCtx{});
     SVB_LAUNCH_CHECK();
 }
 

@@ -13,6 +13,7 @@
 // product. A breakdown flag set by any normalisation makes the host redo that sweep in "careful"
 // mode (norm checked on the host after every step, random restart vector from the device RNG).
 #include "svb_internal.h"
+#include "p2p.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -55,15 +56,30 @@ struct Solver {
     }
 
     // classical Gram-Schmidt of x (length L) against the first j columns of X; *nrm2 = |x|^2 after.
+    // Cell-sharded vectors (W side): the coefficients and the norm are sums over the ranks. Fused path: the
+    // producing kernels store into the peers' mailboxes and the consuming kernels wait + sum (p2p.cuh), so no
+    // stand-alone collective is launched; `nrm_pending` tells finish() that the norm is still in the mailbox.
+    bool nrm_pending = false;
+    P2PCtx nrm_ctx{};
     void orthog(const double *X, int64_t L, int j, double *x, double *nrm2, bool sharded) {
+        static const bool allow_fused = getenv("SVB_P2P_UNFUSED") == nullptr;
+        const bool multi = sharded && ctx().nranks > 1;
+        nrm_pending = false;
         if (j > 0) {
-            ts_gemv_t(X, L, L, j, x, T.p, SVB_K_REORTH);
-            if (sharded) comm_allreduce_dev(T.p, j);
-            ts_gemv_n(X, L, L, j, T.p, -1.0, 1.0, x, nrm2, SVB_K_REORTH);
+            P2PCtx pt{};
+            const bool fuse = multi && allow_fused && !careful && j <= 256 && p2p_next_ctx(j, &pt);
+            ts_gemv_t(X, L, L, j, x, T.p, SVB_K_REORTH, fuse ? &pt : nullptr);
+            if (multi && !fuse) comm_allreduce_dev(T.p, j);
+            const bool fuse_n = fuse && p2p_next_ctx(1, &nrm_ctx);
+            ts_gemv_n(X, L, L, j, T.p, -1.0, 1.0, x, nrm2, SVB_K_REORTH, fuse ? &pt : nullptr, fuse_n ? &nrm_ctx : nullptr);
+            if (fuse_n) {
+                nrm_pending = true;
+                return;
+            }
         } else {
             vec_sumsq(x, L, nrm2);
         }
-        if (sharded) comm_allreduce_dev(nrm2, 1);
+        if (multi) comm_allreduce_dev(nrm2, 1);
     }
 
     // x (|x|^2 in *nrm2) -> out = x/|x| ; |x| -> *slot. Returns false on an unrecoverable state.
@@ -84,7 +100,8 @@ struct Solver {
                 return;
             }
         }
-        vec_normalize(x, L, nrm2, out, slot, flag.p, EPS23);
+        vec_normalize(x, L, nrm2, out, slot, flag.p, EPS23, nrm_pending ? &nrm_ctx : nullptr);
+        nrm_pending = false;
     }
 };
 

@@ -11,6 +11,7 @@
 //             term -(sum w)*mu and an optional axpy are fused in the reduce epilogue.
 #include "svb_internal.h"
 #include "layout.cuh"
+#include "p2p.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(256) adj_reduce_kernel(const double *__restric
                                                          const double *__restrict__ mu, double *__restrict__ tmp, int final,
                                                          double alpha, double beta, double *__restrict__ y,
                                                          const double *__restrict__ coef, double csign,
-                                                         const double *__restrict__ cvec) {
+                                                         const double *__restrict__ cvec, int use_p2p, P2PCtx pc) {
     __shared__ double sh[8][33];
     __shared__ double shw[8];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -215,9 +216,27 @@ __global__ void __launch_bounds__(256) adj_reduce_kernel(const double *__restric
             if (beta != 0.0) r = fma(beta, y[g], r);
             if (coef != nullptr) r = fma(csign * (*coef), cvec[g], r);
             y[g] = r;
+        } else if (use_p2p) {
+            p2p_store(pc, (int)g, v);  // fused exchange: the partial goes straight into every rank's mailbox (NVLink stores)
         } else {
             tmp[g] = v;
         }
+    }
+    if (use_p2p) p2p_publish_last_block(pc, gridDim.x);
+}
+
+// consumer of the fused exchange: wait for every rank's S'w partial, sum in rank order, apply the epilogue
+// y = alpha*sum + beta*y + csign*(*coef)*cvec
+__global__ void __launch_bounds__(256) p2p_combine_kernel(int64_t L, double alpha, double beta, double *__restrict__ y,
+                                                          const double *__restrict__ coef, double csign,
+                                                          const double *__restrict__ cvec, P2PCtx pc) {
+    p2p_wait(pc);
+    const double c = coef ? csign * (*coef) : 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += (int64_t)gridDim.x * blockDim.x) {
+        double r = alpha * p2p_sum(pc, (int)i);
+        if (beta != 0.0) r = fma(beta, y[i], r);
+        if (coef) r = fma(c, cvec[i], r);
+        y[i] = r;
     }
 }
 
@@ -401,15 +420,23 @@ void op_apply(svb_operator_s *op, bool trans, double alpha, const double *dx, do
         return;
     }
     const bool multi = C.nranks > 1;
+    P2PCtx pc{};
+    static const bool allow_fused = getenv("SVB_P2P_UNFUSED") == nullptr;
+    const bool fused = multi && allow_fused && p2p_next_ctx(op->n, &pc);
     {
         KTimer kt(SVB_K_SPMV_ADJ, adj_bytes(op), 2);
         if (op->vbytes == 8) launch_adj<double>(op, dx);
         else launch_adj<float>(op, dx);
         adj_reduce_kernel<<<(unsigned)((op->n + 31) / 32), 256, 0, st>>>(op->partial, op->ntiles, op->n, op->mu, op->tmp,
-                                                                          multi ? 0 : 1, alpha, beta, dy, coef, csign, cvec);
+                                                                          multi ? 0 : 1, alpha, beta, dy, coef, csign, cvec,
+                                                                          fused ? 1 : 0, pc);
         SVB_LAUNCH_CHECK();
     }
-    if (multi) {
+    if (fused) {
+        KTimer kt(SVB_K_COMM, 8.0 * op->n, 1);
+        p2p_combine_kernel<<<grid1d(op->n), 256, 0, st>>>(op->n, alpha, beta, dy, coef, csign, cvec, pc);
+        SVB_LAUNCH_CHECK();
+    } else if (multi) {
         comm_allreduce_dev(op->tmp, op->n);
         combine_kernel<<<grid1d(op->n), 256, 0, st>>>(op->n, alpha, op->tmp, beta, dy, coef, csign, cvec, nullptr, 0.0, nullptr);
         count_launch();

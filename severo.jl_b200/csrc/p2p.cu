@@ -10,19 +10,11 @@
 // Mailbox reads bypass L1 (ld.cg): L2 is the coherence point for peer writes. Every spin is bounded.
 #define SVB_NO_ALLOC_MACROS
 #include "svb_internal.h"
+#include "p2p.cuh"
 
 #include <cstring>
 
 namespace svb {
-
-constexpr int P2P_MAX_RANKS = 16;
-constexpr int64_t P2P_CAP = 8192;  // doubles per slot (64 KB)
-
-struct Mailbox {
-    double slots[2][P2P_MAX_RANKS][P2P_CAP];
-    unsigned long long flags[2][P2P_MAX_RANKS];
-    int error;
-};
 
 struct P2PState {
     bool ready = false;
@@ -31,17 +23,9 @@ struct P2PState {
     Mailbox *peers_host[P2P_MAX_RANKS] = {nullptr};
     Mailbox **peers_dev = nullptr;  // device array of the mapped peer mailboxes (own entry = local pointer)
     unsigned long long epoch = 0;
+    unsigned int *counter = nullptr;  // last-block counter for fused producers
 };
 static P2PState g_p2p;
-
-__device__ __forceinline__ void st_flag_sys(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_flag_sys(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 
 // buf[0..n) <- sum over ranks of buf (in place). One CTA.
 __global__ void __launch_bounds__(1024) p2p_allreduce_kernel(Mailbox *const *__restrict__ peers, Mailbox *__restrict__ mine,
@@ -78,6 +62,19 @@ __global__ void __launch_bounds__(1024) p2p_allreduce_kernel(Mailbox *const *__r
 }
 
 bool p2p_ready() { return g_p2p.ready; }
+
+bool p2p_next_ctx(int64_t n, P2PCtx *out) {
+    if (!g_p2p.ready || n > P2P_CAP) return false;
+    ++g_p2p.epoch;
+    out->peers = g_p2p.peers_dev;
+    out->mine = g_p2p.mine;
+    out->nranks = g_p2p.nranks;
+    out->rank = g_p2p.rank;
+    out->epoch = g_p2p.epoch;
+    out->timeout_cycles = 20000000000ll;  // ~10 s
+    out->counter = g_p2p.counter;
+    return true;
+}
 
 bool p2p_allreduce(double *dbuf, int64_t n) {
     if (!g_p2p.ready || n > P2P_CAP) return false;
@@ -155,6 +152,9 @@ void p2p_setup(int nranks, int rank) {
         SVB_CUDA(cudaMalloc((void **)&g_p2p.peers_dev, sizeof(Mailbox *) * P2P_MAX_RANKS));
         SVB_CUDA(cudaMemcpyAsync(g_p2p.peers_dev, g_p2p.peers_host, sizeof(Mailbox *) * P2P_MAX_RANKS, cudaMemcpyHostToDevice, C.stream));
         SVB_CUDA(cudaStreamSynchronize(C.stream));
+        SVB_CUDA(cudaMalloc((void **)&g_p2p.counter, 64));
+        SVB_CUDA(cudaMemsetAsync(g_p2p.counter, 0, 64, C.stream));
+        SVB_CUDA(cudaStreamSynchronize(C.stream));
         g_p2p.nranks = nranks;
         g_p2p.rank = rank;
         g_p2p.ready = true;
@@ -169,6 +169,7 @@ void p2p_teardown() {
     for (int q = 0; q < g_p2p.nranks; ++q)
         if (q != g_p2p.rank && g_p2p.peers_host[q]) cudaIpcCloseMemHandle(g_p2p.peers_host[q]);
     if (g_p2p.peers_dev) cudaFree(g_p2p.peers_dev);
+    if (g_p2p.counter) cudaFree(g_p2p.counter);
     cudaFree(g_p2p.mine);
     g_p2p = P2PState();
 }

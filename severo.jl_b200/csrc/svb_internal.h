@@ -191,17 +191,19 @@ void op_apply_mm(svb_operator_s *op, bool trans, double alpha, const double *dX,
                  int64_t k);
 // ---- dense.cu (tall-skinny kernels; all pointers device)
 // t[0..j) = X[:, 0..j)' * y      (X col-major L x j, leading dim ld)
-void ts_gemv_t(const double *X, int64_t ld, int64_t L, int j, const double *y, double *t, int cls);
+struct P2PCtx;
+void ts_gemv_t(const double *X, int64_t ld, int64_t L, int j, const double *y, double *t, int cls,
+               const P2PCtx *produce_t = nullptr);
 // y = beta*y + alpha * X[:, 0..j) * t ; nrm2_out (optional) receives sum(y.^2) of the result
 void ts_gemv_n(const double *X, int64_t ld, int64_t L, int j, const double *t, double alpha, double beta,
-               double *y, double *nrm2_out, int cls);
+               double *y, double *nrm2_out, int cls, const P2PCtx *consume_t = nullptr, const P2PCtx *produce_nrm = nullptr);
 // out[:, 0..k) = X[:, 0..w) * P[0..w, 0..k)  (P device, col-major ldp), optional per-column scale
 void ts_gemm(const double *X, int64_t ld, int64_t L, int w, const double *P, int ldp, int k, double *out,
              int64_t ldo, const double *colscale_dev);
 void vec_sumsq(const double *x, int64_t L, double *out);            // out = sum x^2 (device scalar)
 // y = x * (1/sqrt(*nrm2)) ; also writes sqrt(*nrm2) to *norm_out (device) and flags breakdown
 void vec_normalize(const double *x, int64_t L, const double *nrm2_dev, double *y, double *norm_out,
-                   int *flag_dev, double eps);
+                   int *flag_dev, double eps, const P2PCtx *consume_nrm = nullptr);
 void vec_copy(const double *x, int64_t L, double *y);
 void vec_fill_normal(double *x, int64_t L, uint64_t seed, uint64_t offset);
 // ---- comm.cpp
