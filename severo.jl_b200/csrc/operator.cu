@@ -189,17 +189,18 @@ __global__ void __launch_bounds__(256, 5) spmv_adj_kernel(const int64_t *__restr
 // adjoint, stage 2: tmp[g] = sum_t partial[t][g] - (sum_t partial[t][n]) * mu[g]   (fixed order)
 // and, when `final` is set: y[g] = alpha*tmp[g] + beta*y[g] + csign*(*coef)*cvec[g].
 // block (32, 8): x = gene, y = tile lane.
-__global__ void __launch_bounds__(256) adj_reduce_kernel(const double *__restrict__ partial, int64_t ntiles, int64_t n,
+constexpr int ADJR_TY = 32;  // tile lanes per gene: 32 x 32 threads keep ~10 partial loads per thread at C3
+__global__ void __launch_bounds__(32 * ADJR_TY) adj_reduce_kernel(const double *__restrict__ partial, int64_t ntiles, int64_t n,
                                                          const double *__restrict__ mu, double *__restrict__ tmp, int final,
                                                          double alpha, double beta, double *__restrict__ y,
                                                          const double *__restrict__ coef, double csign,
                                                          const double *__restrict__ cvec, int use_p2p, P2PCtx pc) {
-    __shared__ double sh[8][33];
-    __shared__ double shw[8];
+    __shared__ double sh[ADJR_TY][33];
+    __shared__ double shw[ADJR_TY];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int64_t g = (int64_t)blockIdx.x * 32 + tx;
     double acc = 0.0, wacc = 0.0;
-    for (int64_t t = ty; t < ntiles; t += 8) {
+    for (int64_t t = ty; t < ntiles; t += ADJR_TY) {
         if (g < n) acc += partial[t * (n + 1) + g];
         if (tx == 0) wacc += partial[t * (n + 1) + n];
     }
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(256) adj_reduce_kernel(const double *__restric
     if (ty == 0 && g < n) {
         double s = 0.0, ws = 0.0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { s += sh[i][tx]; ws += shw[i]; }
+        for (int i = 0; i < ADJR_TY; ++i) { s += sh[i][tx]; ws += shw[i]; }
         double v = mu ? fma(-ws, mu[g], s) : s;
         if (final) {
             double r = alpha * v;
@@ -427,7 +428,7 @@ void op_apply(svb_operator_s *op, bool trans, double alpha, const double *dx, do
         KTimer kt(SVB_K_SPMV_ADJ, adj_bytes(op), 2);
         if (op->vbytes == 8) launch_adj<double>(op, dx);
         else launch_adj<float>(op, dx);
-        adj_reduce_kernel<<<(unsigned)((op->n + 31) / 32), 256, 0, st>>>(op->partial, op->ntiles, op->n, op->mu, op->tmp,
+        adj_reduce_kernel<<<(unsigned)((op->n + 31) / 32), 32 * ADJR_TY, 0, st>>>(op->partial, op->ntiles, op->n, op->mu, op->tmp,
                                                                           multi ? 0 : 1, alpha, beta, dy, coef, csign, cvec,
                                                                           fused ? 1 : 0, pc);
         SVB_LAUNCH_CHECK();
