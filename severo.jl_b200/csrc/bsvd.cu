@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(1024) bsvd_kernel(int w, int nu, double *__res
                         c = rsqrt(fma(t, t, 1.0));
                     }
                     const double sn = c * t;
+                    __syncwarp(0xffffu << (lane & 16));  // every lane of the half-warp has read nrm[p], nrm[q]
                     if (hl == 0) {
                         nrm[p] = fmax(0.0, a - t * g);
                         nrm[q] = fmax(0.0, b + t * g);

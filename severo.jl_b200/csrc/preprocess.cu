@@ -67,80 +67,153 @@ template <typename T> __device__ __forceinline__ T div_rn(T a, T b);
 template <> __device__ __forceinline__ double div_rn<double>(double a, double b) { return __ddiv_rn(a, b); }
 template <> __device__ __forceinline__ float div_rn<float>(float a, float b) { return __fdiv_rn(a, b); }
 
+// One Welford step (scaling.jl:26-29) in Float64 with the divide taken off the dependent chain: y = RN(1/count) is
+// computed ahead (count is just a counter), then q0 = RN(delta*y), r = delta - count*q0 (exact, FMA), q = RN(q0 + r*y).
+// With a correctly rounded reciprocal and a divisor whose significand is not all ones (an integer < 2^53 never is)
+// this is the correctly rounded quotient (Markstein); checked against `/` on 6.4e8 random + adversarial pairs
+// (see DESIGN.md). The dependent chain per element is 5 fp64 ops instead of a ~40-instruction software divide.
+// Zero / huge / tiny deltas take the plain IEEE divide so signed zeros, infinities and subnormals stay exact.
+__device__ __forceinline__ void welford_step_f64(double v, long long count, double y, double &mu, double &s) {
+    const double delta = __dsub_rn(v, mu);
+    const double ad = fabs(delta);
+    double q;
+    if (ad > 1e-290 && ad < 1e290) {
+        const double c = (double)count;
+        const double q0 = __dmul_rn(delta, y);
+        const double r = __fma_rn(-c, q0, delta);
+        q = __fma_rn(r, y, q0);
+    } else {
+        q = __ddiv_rn(delta, (double)count);
+    }
+    mu = __dadd_rn(mu, q);
+    s = __dadd_rn(s, __dmul_rn(delta, __dsub_rn(v, mu)));
+}
+
+// RN(1/count) for the running counter. The lane that walks a dense gene is bound by instruction issue (one warp,
+// fp64 at half rate): a correctly rounded reciprocal from scratch is ~35 fp64 instructions per element. Since the
+// counter only increments, 1/(c+1) follows from 1/c by three FMA-Newton steps (relative error 1/c -> 1/c^2 ->
+// 1/c^4 < 1 ulp for c >= 2^14; the third step is the Markstein correction that rounds correctly) — verified equal
+// to RN(1/c) for every c in [16385, 6e7] on the CPU. Below 2^14 the exact reciprocal is used.
+template <typename T> struct WelfordStep {
+    __device__ __forceinline__ void run(T v, long long count, T &mu, T &s) {
+        const T delta = sub_rn<T>(v, mu);
+        mu = add_rn<T>(mu, div_rn<T>(delta, (T)count));
+        s = add_rn<T>(s, mul_rn<T>(delta, sub_rn<T>(v, mu)));
+    }
+};
+template <> struct WelfordStep<double> {
+    double y = 0.0;
+    bool valid = false;
+    __device__ __forceinline__ void run(double v, long long count, double &mu, double &s) {
+        const double c = (double)count;
+        if (valid && count > 16384) {
+            double e = __fma_rn(-c, y, 1.0);
+            y = __fma_rn(y, e, y);
+            e = __fma_rn(-c, y, 1.0);
+            y = __fma_rn(y, e, y);
+            e = __fma_rn(-c, y, 1.0);
+            y = __fma_rn(y, e, y);
+        } else {
+            y = __drcp_rn(c);
+            valid = true;
+        }
+        welford_step_f64(v, count, y, mu, s);
+    }
+};
+
+// Streaming part shared by both Welford kernels. One warp owns 32 genes (one per lane; genes are handed out
+// longest-first, so the 32 chains have similar length). Per round the warp copies the next 32 values of each of
+// its 32 genes global -> shared with cp.async (one fully coalesced 32-element row per gene, 32 copies in flight
+// per lane, double-buffered so the next round streams in while the lanes run their dependent chains on the current
+// one); rows are padded to 33 so both the copy (row g, column lane) and the chain reads (row lane, column i) are
+// bank-conflict free. Measured at C3 (densest gene: 1.3 M stored values): 193 ms for the first version (each
+// thread walking its own gene, software divide on the chain) -> 160 ms. What remains is the dependent fp64 chain
+// itself, ~120 ns per element of the densest gene (sub, mul, 2 fma, add at fp64 latency, next to the 6-FMA
+// reciprocal recurrence): an order-exact Welford cannot go below (length of the longest gene) x (chain latency).
+template <typename VI>
+__device__ __forceinline__ void cp_async_elem(VI *smem_dst, const VI *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    if (sizeof(VI) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+constexpr int WF_WARPS = 2;  // warps per block
+
 template <typename VI, typename T>
-__global__ void __launch_bounds__(64) welford_kernel(const int64_t *__restrict__ colptr, const VI *__restrict__ val,
-                                                     const int32_t *__restrict__ order, int64_t ncol, int64_t nrow,
-                                                     double *__restrict__ mu_out, double *__restrict__ var_out) {
+__device__ __forceinline__ void welford_warp_stream(const VI *__restrict__ val, int64_t beg, int64_t len, long long &count, T &mu,
+                                                    T &s, VI (*buf)[32][33]) {
+    const int lane = threadIdx.x & 31;
+    WelfordStep<T> step;
+    int64_t maxlen = len;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+    auto issue = [&](int64_t base, int b) {
+#pragma unroll 8
+        for (int g = 0; g < 32; ++g) {
+            const int64_t bg = __shfl_sync(0xffffffffu, beg, g), lg = __shfl_sync(0xffffffffu, len, g);
+            const int64_t idx = base + lane;
+            if (idx < lg) cp_async_elem<VI>(&buf[b][g][lane], val + bg + idx);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (maxlen > 0) issue(0, 0);
+    int b = 0;
+    for (int64_t base = 0; base < maxlen; base += 32, b ^= 1) {
+        if (base + 32 < maxlen) {
+            issue(base + 32, b ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
+        const int64_t rem = len - base;
+        const int cnt = rem >= 32 ? 32 : (rem > 0 ? (int)rem : 0);
+        for (int i = 0; i < cnt; ++i) {
+            count += 1;
+            step.run((T)buf[b][lane][i], count, mu, s);
+        }
+        __syncwarp();  // everybody is done with buffer b before the round after next overwrites it
+    }
+}
+
+template <typename VI, typename T>
+__global__ void __launch_bounds__(32 * WF_WARPS) welford_kernel(const int64_t *__restrict__ colptr, const VI *__restrict__ val,
+                                                                const int32_t *__restrict__ order, int64_t ncol, int64_t nrow,
+                                                                double *__restrict__ mu_out, double *__restrict__ var_out) {
+    __shared__ VI buf[WF_WARPS][2][32][33];
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= ncol) return;
-    const int64_t c = order[g];
-    const int64_t beg = colptr[c], end = colptr[c + 1];
+    const bool have = g < ncol;
+    const int64_t c = have ? order[g] : 0;
+    const int64_t beg = have ? colptr[c] : 0, end = have ? colptr[c + 1] : 0;
     long long count = nrow - (end - beg);  // scaling.jl:21 implicit zeros first
     T mu = (T)0, s = (T)0;
-    int64_t k = beg;
-    VI nxt[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) nxt[u] = (k + u < end) ? val[k + u] : (VI)0;
-    while (k < end) {
-        VI cur[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) nxt[u] = (k + 4 + u < end) ? val[k + 4 + u] : (VI)0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (k + u < end) {
-                count += 1;
-                const T v = (T)cur[u];
-                const T delta = sub_rn<T>(v, mu);
-                mu = add_rn<T>(mu, div_rn<T>(delta, (T)count));
-                s = add_rn<T>(s, mul_rn<T>(delta, sub_rn<T>(v, mu)));
-            }
-        }
-        k += 4;
+    welford_warp_stream<VI, T>(val, beg, end - beg, count, mu, s, buf[threadIdx.x >> 5]);
+    if (have) {
+        mu_out[c] = (double)mu;
+        var_out[c] = (double)div_rn<T>(s, (T)(nrow - 1));
     }
-    mu_out[c] = (double)mu;
-    var_out[c] = (double)div_rn<T>(s, (T)(nrow - 1));
 }
 
 // Same chain, continued across cell shards: the state (count, mu, s) of every gene enters from the previous
 // rank and leaves for the next one, so the bits equal those of ONE sequential pass over all cells.
 template <typename VI>
-__global__ void __launch_bounds__(64) welford_carry_kernel(const int64_t *__restrict__ colptr, const VI *__restrict__ val,
-                                                           const int32_t *__restrict__ order, int64_t ncol,
-                                                           long long *__restrict__ count_io, double *__restrict__ mu_io,
-                                                           double *__restrict__ s_io) {
+__global__ void __launch_bounds__(32 * WF_WARPS) welford_carry_kernel(const int64_t *__restrict__ colptr, const VI *__restrict__ val,
+                                                                      const int32_t *__restrict__ order, int64_t ncol,
+                                                                      long long *__restrict__ count_io, double *__restrict__ mu_io,
+                                                                      double *__restrict__ s_io) {
+    __shared__ VI buf[WF_WARPS][2][32][33];
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= ncol) return;
-    const int64_t c = order[g];
-    const int64_t beg = colptr[c], end = colptr[c + 1];
-    long long count = count_io[c];
-    double mu = mu_io[c], s = s_io[c];
-    int64_t k = beg;
-    VI nxt[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) nxt[u] = (k + u < end) ? val[k + u] : (VI)0;
-    while (k < end) {
-        VI cur[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) nxt[u] = (k + 4 + u < end) ? val[k + 4 + u] : (VI)0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            if (k + u < end) {
-                count += 1;
-                const double v = (double)cur[u];
-                const double delta = __dsub_rn(v, mu);
-                mu = __dadd_rn(mu, __ddiv_rn(delta, (double)count));
-                s = __dadd_rn(s, __dmul_rn(delta, __dsub_rn(v, mu)));
-            }
-        }
-        k += 4;
+    const bool have = g < ncol;
+    const int64_t c = have ? order[g] : 0;
+    const int64_t beg = have ? colptr[c] : 0, end = have ? colptr[c + 1] : 0;
+    long long count = have ? count_io[c] : 0;
+    double mu = have ? mu_io[c] : 0.0, s = have ? s_io[c] : 0.0;
+    welford_warp_stream<VI, double>(val, beg, end - beg, count, mu, s, buf[threadIdx.x >> 5]);
+    if (have) {
+        count_io[c] = count;
+        mu_io[c] = mu;
+        s_io[c] = s;
     }
-    count_io[c] = count;
-    mu_io[c] = mu;
-    s_io[c] = s;
 }
 
 // ---- standardized_var_clipped: one warp per gene, double-double accumulation -----------------------
