@@ -543,15 +543,6 @@ static int operator_create_impl(svb_matrix_t a, const double *mu, int transposed
         }
         op->fwd_lps = env_int("SVB_FWD_LPS", 0);
         op->adj_lps = env_int("SVB_ADJ_LPS", 0);
-        int gs = env_int("SVB_ADJ_GS", 0);
-        if (gs <= 0) {
-            // enough CTAs for ~2 resident waves
-            const int64_t target = (int64_t)C.sm_count * 6;
-            gs = (int)std::max<int64_t>(1, std::min<int64_t>(32, (target + op->ntiles - 1) / op->ntiles));
-            const int64_t max_gs = std::max<int64_t>(1, (op->n * (op->adj_lps ? op->adj_lps : 8) + 255) / 256);
-            gs = (int)std::min<int64_t>(gs, max_gs);
-        }
-        op->adj_gs = gs;
         SVB_CUDA(cudaMalloc((void **)&op->partial, (size_t)op->ntiles * (op->n + 1) * sizeof(double)));
         SVB_CUDA(cudaMalloc((void **)&op->tmp, (size_t)std::max(op->m, op->n) * sizeof(double)));
         SVB_CUDA(cudaMalloc((void **)&op->scal, 8 * sizeof(double)));

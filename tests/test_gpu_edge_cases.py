@@ -93,3 +93,40 @@ def test_warm_restart_is_correct_and_cheaper(sv):
     np.testing.assert_allclose(S8.S, s[:8], rtol=1.5e-8)
     assert np.linalg.norm(X.T @ S8.U - S8.V * S8.S) / np.linalg.norm(X) < 1e-8
     assert S8.mprod < cold.mprod
+
+
+def test_remaining_abi_entry_points(sv):
+    # svb_row_sums (exact int64 library sizes), svb_synth_normal, device info / version, profile + launch counters,
+    # svb_mul_device
+    import ctypes
+    L = sv._lib
+    lib = sv.lib()
+    rng = np.random.default_rng(7)
+    X = sp.random(5000, 300, 0.05, random_state=9, format="csc", data_rvs=lambda k: rng.integers(1, 2_000_000, k)).astype(np.int64)
+    d = sv.DeviceMatrix.from_host(X)
+    s = np.zeros(5000, dtype=np.int64)
+    L.check(lib.svb_row_sums(d._h, L.ptr(s)))
+    np.testing.assert_array_equal(s, np.asarray(X.sum(axis=1)).ravel())
+    z = np.zeros(200_000)
+    L.check(lib.svb_synth_normal(z.shape[0], 123, L.ptr(z)))
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1.0) < 0.01
+    z2 = np.zeros(200_000)
+    L.check(lib.svb_synth_normal(z2.shape[0], 123, L.ptr(z2)))
+    np.testing.assert_array_equal(z, z2)
+    sm, mem, ma, mi = ctypes.c_int(), ctypes.c_int64(), ctypes.c_int(), ctypes.c_int()
+    L.check(lib.svb_device_info(ctypes.byref(sm), ctypes.byref(mem), ctypes.byref(ma), ctypes.byref(mi)))
+    assert sm.value > 0 and mem.value > 0 and ma.value >= 9
+    assert b"sm_100a" in lib.svb_version()
+    C = sv.CenteredMatrix(sp.random(3000, 200, 0.1, random_state=1, format="csc"), rng.standard_normal(200))
+    lib.svb_profile_enable(1)
+    lib.svb_profile_reset()
+    lib.svb_launch_count_reset()
+    v = rng.standard_normal(200)
+    y = C @ v
+    C.T @ y
+    ms, nl, by = (ctypes.c_double * 6)(), (ctypes.c_int64 * 6)(), (ctypes.c_double * 6)()
+    lib.svb_profile_get(ms, nl, by)
+    lib.svb_profile_enable(0)
+    assert nl[0] == 1 and nl[1] == 2 and ms[0] > 0 and by[0] > 0 and lib.svb_launch_count() >= 3
+    with pytest.raises(sv.SeveroB200Error):
+        L.check(lib.svb_mul(C._operator(), b"N", 1.0, None, 0.0, None, 1))
