@@ -6,7 +6,7 @@
 # exercised through the identical C ABI by the Python ctypes harness (severo.jl_b200/api.py).
 module SeveroB200
 
-using SparseArrays, LinearAlgebra, NamedArrays
+using SparseArrays, LinearAlgebra, NamedArrays, Random
 import Severo
 import Severo: CenteredMatrix, NamedCenteredMatrix, NamedCountMatrix, LinearEmbedding
 
@@ -88,6 +88,35 @@ function scale_features(X::NamedArray{T,2,SparseMatrixCSC{T,Int64}}; scale_max::
     CenteredMatrix(NamedArray(B, X.dicts, X.dimnames), NamedArray(mu, (X.dicts[2],), (X.dimnames[2],)))   # scaling.jl:344
 end
 
+# ---- variablefeatures.jl:19-50,128-161 (:vst): the two data sweeps on the device, loess + top-k on the host ----------
+import Loess: loess, predict
+
+function standardized_var_clipped(A::SparseMatrixCSC{<:Integer}, mu::Vector{Float64}, sd::Vector{Float64}; vmax=sqrt(size(A, 1)))
+    d = upload(A); out = zeros(size(A, 2))
+    check(ccall((:svb_stdvar_clipped, libsvb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}),
+        d.h, mu, sd, Float64(vmax), out))
+    out
+end
+
+function variance_stabilizing_transformation(A::SparseMatrixCSC{<:Integer}; loess_span::Real=0.5)
+    mu, var = mean_var(A)                                        # device, order-exact Welford (scaling.jl:18-34)
+    sd = sqrt.(var)
+    non_const = sd .> 0
+    xs, ys = log10.(mu[non_const]), log10.(sd[non_const])
+    model = loess(xs, ys, span=loess_span)                       # host, O(genes) (variablefeatures.jl:41)
+    expected = copy(sd)
+    expected[non_const] = 10 .^ predict(model, xs)
+    expected .= ifelse.(isnan.(expected), 0.0, expected)         # nan2zero! (variablefeatures.jl:30-32)
+    standardized_var_clipped(A, mu, expected)                    # device (variablefeatures.jl:21-28)
+end
+
+function find_variable_features(counts::NamedCountMatrix, nfeatures=2000; method=:vst, kw...)
+    Symbol(method) == :vst || error("selection method $method is outside the B200 hot path (only :vst)")
+    metric = variance_stabilizing_transformation(counts.array; kw...)
+    selected = partialsortperm(metric, 1:nfeatures, rev=true)    # variablefeatures.jl:159
+    NamedArray(selected, (names(counts, 2)[selected],), (dimnames(counts, 2),))
+end
+
 # ---- the operator + irlba.jl:47-99 -----------------------------------------------------------------------
 mutable struct DeviceOperator
     h::Ptr{Cvoid}
@@ -147,6 +176,27 @@ function _pca(X, npcs::Int64; kw...)
     Z = view(S.U, :, 1:npcs) * Diagonal(view(S.S, 1:npcs))
     stdev = view(S.S, 1:npcs) ./ sqrt(max(1, m - 1))
     Z, stdev, S.V
+end
+
+_pca(X::NamedCenteredMatrix, npcs::Int64; kw...) = _pca(CenteredMatrix(X.A.array, X.mu.array), npcs; kw...)
+
+# embedding.jl:81-94, 202-212 — same labels, same (sic) dimnames of `basis`
+function pca(X::NamedCenteredMatrix, npcs::Int64; kw...)
+    Z, stdev, loadings = _pca(X, npcs; kw...)
+    k = length(stdev)
+    latentnames = map(x -> string("PC-", x), 1:k)
+    rownames, colnames = names(X)
+    rowdim, coldim = dimnames(X)
+    coordinates = NamedArray(Z, (rownames, latentnames), (rowdim, :latent))
+    stdev = NamedArray(stdev, (latentnames,), (:latent,))
+    basis = NamedArray(loadings, (colnames, latentnames), (rowdim, :latent))
+    LinearEmbedding(X, coordinates, stdev, basis)
+end
+
+function embedding(X, ncomponents::Int64=50; method=:pca, algorithm=:irlba, kw...)
+    Symbol(method) == :pca || error("unknown reduction method: $method")
+    Symbol(algorithm) == :irlba || error("algorithm $algorithm is outside the B200 hot path (use algorithm=:irlba)")
+    pca(X, ncomponents; kw...)
 end
 
 end # module
