@@ -532,12 +532,27 @@ class LinearEmbedding:
     basis: object
 
 
-def _pca(X, npcs, algorithm="irlba", **kw):
-    """embedding.jl:46-76 with algorithm = :irlba (the reference's default :arpack and :tssvd are other
-    solvers, outside this path — SURVEY 8f #1)."""
+def _pca(X, npcs, algorithm="arpack", **kw):
+    """embedding.jl:46-76. ``algorithm``:
+
+    * ``:irlba``  — the path of this build (irlba.jl -> svb_irlba).
+    * ``:arpack`` — the reference's DEFAULT (embedding.jl:46, ``svds`` of the external Arpack.jl). Converged singular
+      triplets are unique up to sign, so the request is served by the same device solver run to Arpack-like accuracy
+      (``tol`` default 1e-10; Arpack's own default is machine eps); ``maxiter`` / ``ncv`` map to ``maxit`` / ``work``.
+      Iterates differ from Arpack's, results agree to the tolerance.
+    * ``:tssvd`` / dense ``svd`` — other solvers (Gram matrix ``C'C`` through src/mul.jl, LAPACK): outside this path.
+    """
     algorithm = str(algorithm)
-    if algorithm != "irlba":
-        raise ValueError(f"algorithm {algorithm} is outside the B200 hot path (use algorithm=:irlba)")
+    if algorithm == "arpack":
+        kw = dict(kw)
+        kw.setdefault("tol", 1e-10)
+        if "maxiter" in kw:
+            kw["maxit"] = kw.pop("maxiter")
+        if "ncv" in kw:
+            kw["work"] = kw.pop("ncv")
+        kw.pop("nsv", None)
+    elif algorithm != "irlba":
+        raise ValueError(f"algorithm {algorithm} is outside the B200 hot path (use algorithm=:irlba or :arpack)")
     C = _as_operator(X)
     m, n = C.shape
     npcs = min(min(m, n), int(npcs))
