@@ -536,13 +536,14 @@ def test_embedding_default_algorithm_is_served(sv, orc):
     # docs/src/pbmc.md:134 calls embedding(S, 15, method=:pca) with the reference default algorithm=:arpack
     X = planted_counts(4000, 900, 9, seed=31, mean_nnz=100)
     Y = sv.normalize_cells(X, scale_factor=1e4)
-    S = sv.scale_features(Y, scale_max=10.0)
-    init = np.random.default_rng(1).standard_normal(900)
+    hvf = sv.find_variable_features(X, 400)            # also drops never-expressed genes (sigma = 0 -> NaN mu, trap T3)
+    S = sv.scale_features(Y, scale_max=10.0, features=hvf)
+    init = np.random.default_rng(1).standard_normal(400)
     em = sv.embedding(S, 9, method="pca", init=init)                         # default -> :arpack selector
     em2 = sv.embedding(S, 9, method="pca", algorithm="irlba", init=init, tol=1e-10)
     sd = np.linalg.svd(S.to_dense(), compute_uv=False)[:9]
     np.testing.assert_allclose(em.stdev * np.sqrt(3999), sd, rtol=1e-9)
     np.testing.assert_allclose(em.stdev, em2.stdev, rtol=1e-12)
-    assert em.coordinates.shape == (4000, 9) and em.basis.shape == (900, 9)
+    assert em.coordinates.shape == (4000, 9) and em.basis.shape == (400, 9)
     with pytest.raises(ValueError):
         sv.embedding(S, 9, algorithm="tssvd")
