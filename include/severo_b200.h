@@ -117,6 +117,10 @@ int svb_transpose(svb_matrix_t a, svb_matrix_t *out);
  * B = scale_factor * x / s_cell (one rounded multiply, one rounded divide), then log1p. */
 int svb_normalize(svb_matrix_t counts, int method, double scale_factor, int dtype,
                   svb_matrix_t *out);
+/* The same sweep on a column subset of the counts (the HVG columns): the library sizes of the FULL matrix are
+ * supplied (libsize[nrow], from svb_row_sums) instead of being recomputed, so the values equal Y[:, hvf]. */
+int svb_normalize_libsize(svb_matrix_t counts_subset, const int64_t *libsize, int method,
+                          double scale_factor, int dtype, svb_matrix_t *out);
 /* normalize.jl:24 s = sum(A, dims=2): exact int64 library sizes (length nrow). With a communicator
  * nothing is exchanged: a cell lives on one rank. */
 int svb_row_sums(svb_matrix_t counts, int64_t *s);
@@ -150,6 +154,22 @@ int svb_operator_create_ex(svb_matrix_t a, const double *mu, int transposed, int
 /* Dense column-major A (m x n, leading dimension lda >= m) for the StridedMatrix methods. */
 int svb_operator_create_dense(int64_t m, int64_t n, const double *a, int64_t lda, const double *mu,
                               int transposed, svb_operator_t *out);
+/* The same operator built from the RAW COUNTS of the HVG columns — the scaled matrix is never materialised.
+ * Replaces scale_features + CenteredMatrix + the normalised values (normalize.jl:27,36; scaling.jl:199-232) for the
+ * PCA call: entry (i,j) of S is min(log1p(scale_factor*c_ij/libsize_i)/sd_j, scale_max + mean_j/sd_j) - mean_j/sd_j,
+ * stored as ONE 16-bit code per nonzero (2 instead of 10 bytes); the value is rebuilt in the product kernels from a
+ * per-cell table over the count levels 1..levels and the per-gene 1/sd. Counts above `levels`, counts < 1 and
+ * clipped entries keep their exact value in a small explicit residual. counts: int32 CSC, cells x HVGs (<= 65534
+ * genes). libsize[nrow]: library sizes of the FULL count matrix (svb_row_sums). mean/var[ncol]: moments of the
+ * log-normalised HVG columns (svb_mean_var), or both NULL: they are then computed here from the counts by two parallel
+ * passes (with a communicator: over the cells of all ranks) — a few ulp from the sequential Welford of scaling.jl:18-34,
+ * for the fused PCA call that keeps them internal. levels: 0 = choose (4, 8, 16 or 32). mu_out (optional, [ncol])
+ * receives the stored centre mean/sd (scaling.jl:207). Entries are within 2 ulp of the reference's (t*(1/sd) vs t/sd). */
+int svb_operator_create_counts(svb_matrix_t counts, const int64_t *libsize, double scale_factor,
+                               const double *mean, const double *var, double scale_max, int levels,
+                               double *mu_out, svb_operator_t *out);
+int svb_operator_counts_info(svb_operator_t op, int *levels, int64_t *tile_cells, int64_t *nnz_coded,
+                             int64_t *nnz_explicit, int64_t *fwd_chunks, int64_t *adj_chunks);
 int svb_operator_free(svb_operator_t op);
 int svb_operator_info(svb_operator_t op, int64_t *m, int64_t *n, int64_t *nnz, int *is_dense,
                       int *value_bytes, int *index_bytes);

@@ -59,6 +59,7 @@ SIGNATURES = {
     "svb_row_slice": (c_int, [_h, c_int64, c_int64, _ph]),
     "svb_transpose": (c_int, [_h, _ph]),
     "svb_normalize": (c_int, [_h, c_int, c_double, c_int, _ph]),
+    "svb_normalize_libsize": (c_int, [_h, c_void_p, c_int, c_double, c_int, _ph]),
     "svb_row_sums": (c_int, [_h, c_void_p]),
     "svb_mean_var": (c_int, [_h, c_void_p, c_void_p]),
     "svb_welford_carry": (c_int, [_h, c_void_p, c_void_p, c_void_p]),
@@ -68,6 +69,8 @@ SIGNATURES = {
     "svb_operator_create": (c_int, [_h, c_void_p, c_int, _ph]),
     "svb_operator_create_ex": (c_int, [_h, c_void_p, c_int, c_int, _ph]),
     "svb_operator_create_dense": (c_int, [c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int, _ph]),
+    "svb_operator_create_counts": (c_int, [_h, c_void_p, c_double, c_void_p, c_void_p, c_double, c_int, c_void_p, _ph]),
+    "svb_operator_counts_info": (c_int, [_h, _pint, _p64, _p64, _p64, _p64, _p64]),
     "svb_operator_free": (c_int, [_h]),
     "svb_operator_info": (c_int, [_h, _p64, _p64, _p64, _pint, _pint, _pint]),
     "svb_mul": (c_int, [_h, c_char, c_double, c_void_p, c_double, c_void_p, c_int64]),

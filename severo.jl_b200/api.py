@@ -30,7 +30,8 @@ from .loess import loess_fit_predict
 
 __all__ = [
     "DeviceMatrix", "NamedArray", "convert_counts", "normalize_cells", "mean_var", "mean_std",
-    "standardized_var_clipped", "find_variable_features", "scale_features", "CenteredMatrix", "irlba",
+    "standardized_var_clipped", "find_variable_features", "scale_features", "CenteredMatrix", "CountsCenteredMatrix",
+    "scale_features_counts", "irlba",
     "SVD", "svd_flip", "pca", "embedding", "LinearEmbedding", "synthetic_counts",
 ]
 
@@ -429,6 +430,96 @@ class CenteredMatrix:
             pass
 
 
+class CountsCenteredMatrix(CenteredMatrix):
+    """The operator of ``scale_features(normalize_cells(X, :lognormalize)[:, hvf]; scale_max)`` held over the RAW COUNTS:
+    the scaled matrix (scaling.jl:199-217) is never materialised, a nonzero is one 16-bit code in HBM and its value
+    ``min(log1p(sf*c/s_i)/sd_j, scale_max + mean_j/sd_j)`` is rebuilt inside the product kernels (csrc/factored.cu).
+    Same interface as CenteredMatrix (mul, T, irlba, pca). ``counts``: DeviceMatrix of int32 counts, cells x HVGs."""
+
+    def __init__(self, counts, libsize, scale_factor, scale_max=np.inf, mean=None, var=None, levels=0, names=None):
+        if not isinstance(counts, DeviceMatrix) or counts.vtype != L.SVB_I32:
+            raise TypeError("CountsCenteredMatrix expects a DeviceMatrix of integer counts")
+        m, n = counts.shape
+        libsize = np.ascontiguousarray(libsize, dtype=np.int64)
+        if libsize.shape[0] != m:
+            raise ValueError("libsize must have one entry per cell")
+        self.A = counts
+        self._names = names
+        self._parent = counts
+        self._transposed = False
+        self.shape = (m, n)
+        self._dev = None
+        self._storage = 0
+        self.libsize, self.scale_factor, self.scale_max = libsize, float(scale_factor), float(scale_max)
+        mean_c = None if mean is None else np.ascontiguousarray(mean, dtype=np.float64)
+        var_c = None if var is None else np.ascontiguousarray(var, dtype=np.float64)
+        mu = np.empty(n)
+        h = ctypes.c_void_p()
+        L.check(L.lib().svb_operator_create_counts(counts._h, L.ptr(libsize), self.scale_factor, L.ptr(mean_c), L.ptr(var_c),
+                                                    self.scale_max, int(levels), L.ptr(mu), ctypes.byref(h)))
+        self._op = h
+        self._mu = mu
+        self.mu = mu
+
+    @property
+    def names(self):
+        return self._names
+
+    def info(self):
+        lv = ctypes.c_int()
+        v = [ctypes.c_int64() for _ in range(5)]
+        L.check(L.lib().svb_operator_counts_info(self._op, lv, *v))
+        return dict(levels=lv.value, tile_cells=v[0].value, nnz_coded=v[1].value, nnz_explicit=v[2].value,
+                    fwd_chunks=v[3].value, adj_chunks=v[4].value)
+
+    def _operator(self):
+        if self._op is None:
+            raise L.SeveroB200Error(L.SVB_EARG, "operator has been freed")
+        return self._op
+
+    def to_dense(self):
+        raise TypeError("the count-level operator has no stored values; use scale_features for the explicit matrix")
+
+
+def scale_features_counts(counts, scale_factor=1e4, scale_max=np.inf, features=None, libsize=None, moments="exact", levels=0):
+    """Fused ``normalize_cells(X, :lognormalize; scale_factor)`` -> ``Y[:, features]`` -> ``scale_features(; scale_max)``
+    (normalize.jl:40-55, docs/src/pbmc.md:121, scaling.jl:335-357) returning the centred operator over the raw counts
+    (CountsCenteredMatrix) for ``irlba`` / ``embedding``. ``counts``: the full count matrix (host sparse, NamedArray or
+    DeviceMatrix); library sizes are its row sums unless ``libsize`` is given. ``moments``: "exact" = the reference's
+    sequential Welford on the log-normalised HVG columns (svb_mean_var; stored mu bit-identical to scale_features),
+    "fast" = two parallel passes inside the operator build (a few ulp away; with a communicator they span all ranks)."""
+    A, names, dimnames = _unwrap(counts)
+    dA, temp = _to_device(A)
+    if dA.vtype != L.SVB_I32:
+        raise TypeError("scale_features_counts expects integer counts")
+    lib = L.lib()
+    if libsize is None:
+        libsize = np.empty(dA.shape[0], dtype=np.int64)
+        L.check(lib.svb_row_sums(dA._h, L.ptr(libsize)))
+    sub = dA
+    if features is not None:
+        fidx = np.asarray(features.array if isinstance(features, NamedArray) else features, dtype=np.int64)
+        sub = dA.columns(fidx)
+        if names is not None:
+            names = (names[0], [names[1][i] for i in fidx])
+        if temp:
+            dA.free()
+    mean = var = None
+    if moments == "exact":
+        h = ctypes.c_void_p()
+        L.check(lib.svb_normalize_libsize(sub._h, L.ptr(np.ascontiguousarray(libsize, dtype=np.int64)), L.NORM_LOGNORMALIZE,
+                                          float(scale_factor), L.SVB_F64, ctypes.byref(h)))
+        Y = DeviceMatrix(h)
+        mean, var = np.empty(sub.shape[1]), np.empty(sub.shape[1])
+        L.check(lib.svb_mean_var(Y._h, L.ptr(mean), L.ptr(var)))
+        Y.free()
+    elif moments != "fast":
+        raise ValueError("moments must be 'exact' or 'fast'")
+    C = CountsCenteredMatrix(sub, libsize, scale_factor, scale_max, mean, var, levels, names=names)
+    C._owns_counts = sub is not counts
+    return C
+
+
 class _AdjointCentered:
     def __init__(self, parent):
         self.parent = parent
@@ -575,7 +666,7 @@ def pca(X, npcs, **kw):
     names = X.names if isinstance(X, CenteredMatrix) else (X.names if isinstance(X, NamedArray) else None)
     if names is None:
         return LinearEmbedding(X, Z, stdev, loadings)
-    rowdim = (X.A.dimnames if isinstance(X, CenteredMatrix) else X.dimnames)[0]
+    rowdim = (getattr(X.A, "dimnames", ("cells", "features")) if isinstance(X, CenteredMatrix) else X.dimnames)[0]
     coordinates = NamedArray(Z, (names[0], latent), (rowdim, "latent"))
     stdevn = NamedArray(stdev, (latent,), ("latent",))
     basis = NamedArray(loadings, (names[1], latent), (rowdim, "latent"))  # sic: (rowdim, :latent) embedding.jl:92

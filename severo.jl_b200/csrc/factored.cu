@@ -1,0 +1,993 @@
+// factored.cu — the scaled HVG operator over the RAW COUNTS ("the scaled matrix never materialised").
+//
+// The matrix the reference feeds to IRLBA is, entry by entry (normalize.jl:27,36 ; scaling.jl:211-212),
+//     B_ij = min( log1p(sf * c_ij / s_i) / sd_j ,  scale_max + mean_j / sd_j )
+// with c_ij the integer count, s_i the library size of cell i and (mean_j, sd_j) the moments of gene j. It
+// factors as  t_i[c] * (1/sd_j)  with  t_i[c] = log1p(sf*c/s_i): a per-cell table over the few distinct counts
+// times a per-gene scale. The explicit layouts of operator.cu stream 10 bytes per nonzero (f64 value + u16 index);
+// here a nonzero is ONE 16-bit code and the value is rebuilt from two tables that live in shared memory:
+//
+//   forward  y_i = sum_l t_i[l] * ( sum_{j in G_il} x_j/sd_j ) - mu.x        G_il = genes of cell i with count l
+//            layout: CSR by cell, the genes of a row grouped by count level, every group padded to whole 8-code
+//            chunks (pad code = n, xs[n] = 0); per row L group ends (u16, chunk units) and L table entries.
+//   adjoint  (S'w)_j = (1/sd_j) * sum_i T[i,c_ij] - (sum w) mu_j             T[i,l] = t_i[l] * w_i
+//            layout: cells tiled by R (R*L = 8192 table entries = 64 KB of shared memory), gene-major inside a
+//            tile, code = (c-1)*R + i_local, (tile, gene) segments padded to whole chunks (pad code = R*L -> 0).
+//
+// Entries that do not fit (count > L, count <= 0, or clipped by scale_max) are rare; each becomes one "exception
+// chunk" of the same streams that carries its exact scaled value as a Float64 (16 B instead of 2 B for that entry).
+// Values: t*(1/sd) instead of t/sd, i.e. every entry within 2 ulp of the reference's (documented in DESIGN.md; far
+// inside the 1e-6 bar on sigma).
+#include "svb_internal.h"
+#include "layout.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+
+using namespace svb;
+
+svb_factored_s::~svb_factored_s() {
+    void *ptrs[] = {tlev, tlevA, inv, f_rowptr, f_code, f_meta, a_gptr, a_code, a_meta, a_slices, counters, partial,
+                    fwd_ranges, fwd_rows};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+}
+
+namespace svb {
+
+constexpr int FCH = 8;    // codes per chunk (one 16-byte load)
+constexpr int FEXC = 63;  // level field of an exception chunk in the forward stream
+
+static inline unsigned fgrid(int64_t n, int threads = 256, int max_blocks = 148 * 16) {
+    int64_t b = (n + threads - 1) / threads;
+    return (unsigned)std::max<int64_t>(1, std::min<int64_t>(b, max_blocks));
+}
+
+// ---------------------------------------------------------------------------------------------
+// build kernels
+// ---------------------------------------------------------------------------------------------
+// per gene: sd, stored mu = mean/sd, clip = scale_max + mu (scaling.jl:205-212, same arithmetic as svb_scale), 1/sd
+__global__ void fact_prepare_kernel(const double *__restrict__ mean, const double *__restrict__ var, int64_t n, double scale_max,
+                                    double *__restrict__ sd, double *__restrict__ mus, double *__restrict__ cap,
+                                    double *__restrict__ inv, int *__restrict__ bad) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const double s = sqrt(var[j]);
+    if (!(s > 0.0) || !isfinite(s)) *bad = 1;
+    sd[j] = s;
+    const double m1 = __ddiv_rn(mean[j], s);
+    mus[j] = m1;
+    cap[j] = scale_max + m1;
+    inv[j] = __ddiv_rn(1.0, s);
+}
+
+// t_i[l] = log1p((sf * (l+1)) / s_i): the arithmetic of libnorm_kernel<double> (normalize.jl:27,36)
+// written twice: cell-major tlev[i*L + l] (forward: one row's table is contiguous) and, per adjoint tile, level-major
+// tlevA[tile*R*L + l*R + i_local] (the shared-memory table of the adjoint is level-major so that the bank of an entry is
+// its CELL, not its level: 63 % of the entries have count 1 and would otherwise all hit the same bank)
+__global__ void fact_tlev_kernel(const long long *__restrict__ s, int64_t m, int log2L, int log2R, double sf,
+                                 double *__restrict__ tlev, double *__restrict__ tlevA) {
+    const int64_t total = m << log2L;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = k >> log2L;
+        const int l = (int)(k & ((1 << log2L) - 1));
+        const long long si = s[i];
+        double v = 0.0;
+        if (si > 0) v = log1p(__ddiv_rn(__dmul_rn(sf, (double)(l + 1)), (double)si));
+        tlev[k] = v;
+        const int64_t t = i >> log2R, il = i & (((int64_t)1 << log2R) - 1);
+        tlevA[(t << (log2R + log2L)) + ((int64_t)l << log2R) + il] = v;
+    }
+}
+
+__device__ __forceinline__ double fact_block_sum(double v, double *red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    double t = 0.0;
+    for (int i = 0; i < nw; ++i) t += red[i];  // fixed order
+    return t;
+}
+
+__device__ __forceinline__ double fact_value(int c, int32_t r, int log2L, const double *__restrict__ tlev,
+                                             const long long *__restrict__ libsize, double sf) {
+    if (c >= 1 && c <= (1 << log2L)) return __ldg(tlev + (((int64_t)r) << log2L) + (c - 1));
+    return log1p(__ddiv_rn(__dmul_rn(sf, (double)c), (double)libsize[r]));
+}
+
+// Parallel two-pass moments of the log-normalised columns straight from the counts (used when the caller does not
+// supply the order-exact Welford moments of svb_mean_var: a fused PCA call keeps the moments internal, and the
+// sequential chain of the densest gene alone costs ~150 ms at 1.3 M cells). One CTA per gene, fixed-order sums.
+// pass 1: sum[j] = sum of the stored values (this rank's cells); pass 2: ss[j] = sum (v-mean)^2 + (#zeros)*mean^2.
+__global__ void __launch_bounds__(512) fact_moments_sum_kernel(const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
+                                                               const int32_t *__restrict__ val, int log2L,
+                                                               const double *__restrict__ tlev, const long long *__restrict__ libsize,
+                                                               double sf, double *__restrict__ sum) {
+    __shared__ double red[32];
+    const int64_t j = blockIdx.x;
+    const int64_t beg = colptr[j], end = colptr[j + 1];
+    double p = 0.0;
+    for (int64_t k = beg + threadIdx.x; k < end; k += blockDim.x) p += fact_value(val[k], rowidx[k], log2L, tlev, libsize, sf);
+    const double t = fact_block_sum(p, red);
+    if (threadIdx.x == 0) sum[j] = t;
+}
+
+__global__ void __launch_bounds__(512) fact_moments_ss_kernel(const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
+                                                              const int32_t *__restrict__ val, int log2L,
+                                                              const double *__restrict__ tlev, const long long *__restrict__ libsize,
+                                                              double sf, int64_t nrow_local, const double *__restrict__ sum,
+                                                              const double *__restrict__ mtot, double *__restrict__ mean,
+                                                              double *__restrict__ ss) {
+    __shared__ double red[32];
+    const int64_t j = blockIdx.x;
+    const int64_t beg = colptr[j], end = colptr[j + 1];
+    const double mu = __ddiv_rn(sum[j], *mtot);
+    double q = 0.0;
+    for (int64_t k = beg + threadIdx.x; k < end; k += blockDim.x) {
+        const double d = fact_value(val[k], rowidx[k], log2L, tlev, libsize, sf) - mu;
+        q = fma(d, d, q);
+    }
+    const double t = fact_block_sum(q, red);
+    if (threadIdx.x == 0) {
+        mean[j] = mu;
+        ss[j] = fma((double)(nrow_local - (end - beg)), mu * mu, t);
+    }
+}
+
+__global__ void fact_moments_var_kernel(const double *__restrict__ ss, const double *__restrict__ mtot, int64_t n,
+                                        double *__restrict__ var) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) var[j] = __ddiv_rn(ss[j], *mtot - 1.0);
+}
+
+// how many counts exceed 4 / 8 / 16 / 32 (chooses L)
+__global__ void fact_hist_kernel(const int32_t *__restrict__ val, int64_t nnz, unsigned long long *__restrict__ out) {
+    unsigned long long c4 = 0, c8 = 0, c16 = 0, c32 = 0;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) {
+        const int c = val[k];
+        c4 += (c > 4 || c < 1);
+        c8 += (c > 8 || c < 1);
+        c16 += (c > 16 || c < 1);
+        c32 += (c > 32 || c < 1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c4 += __shfl_xor_sync(0xffffffffu, c4, o);
+        c8 += __shfl_xor_sync(0xffffffffu, c8, o);
+        c16 += __shfl_xor_sync(0xffffffffu, c16, o);
+        c32 += __shfl_xor_sync(0xffffffffu, c32, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out + 0, c4);
+        atomicAdd(out + 1, c8);
+        atomicAdd(out + 2, c16);
+        atomicAdd(out + 3, c32);
+    }
+}
+
+// level of every stored entry, CSC order: 1..L = count level, 0 = exception (explicit residual operator).
+// grid (ncol, FY)
+__global__ void __launch_bounds__(256) fact_classify_kernel(const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
+                                                            const int32_t *__restrict__ val, int log2L,
+                                                            const double *__restrict__ tlev, const double *__restrict__ sd,
+                                                            const double *__restrict__ cap, uint8_t *__restrict__ lvl,
+                                                            unsigned long long *__restrict__ excnt) {
+    const int64_t j = blockIdx.x;
+    const int64_t beg = colptr[j], end = colptr[j + 1];
+    const double s = sd[j], cp = cap[j];
+    const int L = 1 << log2L;
+    unsigned int nexc = 0;
+    for (int64_t k = beg + (int64_t)blockIdx.y * blockDim.x + threadIdx.x; k < end; k += (int64_t)gridDim.y * blockDim.x) {
+        const int c = val[k];
+        int lv = 0;
+        if (c >= 1 && c <= L) {
+            const double t = __ldg(tlev + (((int64_t)rowidx[k]) << log2L) + (c - 1));
+            const double v = __ddiv_rn(t, s);  // scaling.jl:211
+            lv = (v > cp) ? 0 : c;             // clipped entries keep their exact value in the residual
+        }
+        lvl[k] = (uint8_t)lv;
+        nexc += (lv == 0);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nexc += __shfl_xor_sync(0xffffffffu, nexc, o);
+    if ((threadIdx.x & 31) == 0 && nexc) atomicAdd(excnt + j, (unsigned long long)nexc);
+}
+
+// the residual CSC: one warp per gene, ordered compaction of the level-0 entries with their exact scaled value
+__global__ void __launch_bounds__(256) fact_resid_fill_kernel(const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
+                                                              const int32_t *__restrict__ val, const uint8_t *__restrict__ lvl,
+                                                              int64_t ncol, const long long *__restrict__ libsize, double sf,
+                                                              const double *__restrict__ sd, const double *__restrict__ cap,
+                                                              const int64_t *__restrict__ ecolptr, int32_t *__restrict__ erow,
+                                                              double *__restrict__ eval) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t j = warp; j < ncol; j += nwarps) {
+        int64_t pos = ecolptr[j];
+        if (ecolptr[j + 1] == pos) continue;
+        const int64_t beg = colptr[j], end = colptr[j + 1];
+        const double s = sd[j], cp = cap[j];
+        for (int64_t k0 = beg; k0 < end; k0 += 32) {
+            const int64_t k = k0 + lane;
+            const bool ex = (k < end) && (lvl[k] == 0);
+            const unsigned bal = __ballot_sync(0xffffffffu, ex);
+            if (ex) {
+                const int32_t r = rowidx[k];
+                const double t = __dmul_rn(sf, (double)val[k]);
+                const double v = log1p(__ddiv_rn(t, (double)libsize[r]));
+                const double y = __ddiv_rn(v, s);
+                const int64_t dst = pos + __popc(bal & ((1u << lane) - 1u));
+                erow[dst] = r;
+                eval[dst] = ((y > cp) ? cp : y) * s;  // stored pre-multiplied by sd: the kernels apply 1/sd to everything
+            }
+            pos += __popc(bal);
+        }
+    }
+}
+
+// adjoint layout, pass 1: chunks per (tile, gene) segment (at least one: the stream kernels count segments by their
+// "last chunk" flags, so an empty segment is one all-pad chunk). Sub-warps of 8 lanes, one segment each.
+__global__ void __launch_bounds__(256) fact_seg_count_kernel(const int64_t *__restrict__ startpos, const uint8_t *__restrict__ lvl,
+                                                             const int64_t *__restrict__ estart, int64_t nseg, int64_t ncol,
+                                                             int64_t *__restrict__ gptr) {
+    const int lane = threadIdx.x & 31, sl = lane & 7;
+    const unsigned submask = 0xffu << (lane & ~7);
+    const int64_t sub = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int64_t nsub = ((int64_t)gridDim.x * blockDim.x) >> 3;
+    for (int64_t s = sub; s < nseg; s += nsub) {
+        const int64_t b = startpos[s], e = startpos[s + ncol];
+        int c = 0;
+        for (int64_t k = b + sl; k < e; k += 8) c += (lvl[k] != 0);
+        c += __shfl_xor_sync(submask, c, 4);
+        c += __shfl_xor_sync(submask, c, 2);
+        c += __shfl_xor_sync(submask, c, 1);
+        const int ne = estart ? (int)(estart[s + ncol] - estart[s]) : 0;  // one chunk per exception
+        if (sl == 0) gptr[s] = max(1, (c + FCH - 1) / FCH + ne);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) gptr[nseg] = 0;
+}
+
+// adjoint layout, pass 2: stable placement (cells ascending) of code = (level-1)*R + i_local, pads at the segment end,
+// and the per-chunk flag "last chunk of its segment"
+__global__ void __launch_bounds__(256) fact_seg_fill_kernel(const int64_t *__restrict__ startpos, const int32_t *__restrict__ rowidx,
+                                                            const uint8_t *__restrict__ lvl, int64_t nseg, int64_t ncol,
+                                                            int log2R, int log2L, const int64_t *__restrict__ gptr,
+                                                            const int64_t *__restrict__ estart, const int32_t *__restrict__ erow,
+                                                            const double *__restrict__ eval, uint16_t *__restrict__ code,
+                                                            uint8_t *__restrict__ meta) {
+    const int lane = threadIdx.x & 31, sl = lane & 7;
+    const int shift = lane & ~7;
+    const unsigned submask = 0xffu << shift;
+    const int64_t sub = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int64_t nsub = ((int64_t)gridDim.x * blockDim.x) >> 3;
+    const uint16_t padcode = (uint16_t)(1u << (log2R + log2L));
+    for (int64_t s = sub; s < nseg; s += nsub) {
+        const int64_t b = startpos[s], e = startpos[s + ncol];
+        const int64_t t = s / ncol;
+        const int64_t row0 = t << log2R;
+        const int64_t c0 = gptr[s], c1 = gptr[s + 1];
+        int64_t pos = c0 * FCH;
+        const int64_t pend = c1 * FCH;
+        for (int64_t k0 = b; k0 < e; k0 += 8) {
+            const int64_t k = k0 + sl;
+            int lv = 0;
+            if (k < e) lv = lvl[k];
+            const unsigned bal = (__ballot_sync(submask, lv != 0) >> shift) & 0xffu;
+            if (lv) {
+                const int64_t il = (int64_t)rowidx[k] - row0;
+                code[pos + __popc(bal & ((1u << sl) - 1u))] = (uint16_t)(((int64_t)(lv - 1) << log2R) + il);
+            }
+            pos += __popc(bal);
+        }
+        const int64_t eb = estart ? estart[s] : 0, ee = estart ? estart[s + ncol] : 0;
+        const int64_t cx = c1 - (ee - eb);  // first exception chunk
+        for (int64_t p = pos + sl; p < cx * FCH; p += 8) code[p] = padcode;
+        for (int64_t k = eb + sl; k < ee; k += 8) {  // {i_local, -, value*sd as Float64}
+            uint4 q;
+            q.x = (unsigned)(erow[k] - row0);
+            q.y = 0u;
+            q.z = (unsigned)__double2loint(eval[k]);
+            q.w = (unsigned)__double2hiint(eval[k]);
+            reinterpret_cast<uint4 *>(code)[cx + (k - eb)] = q;
+        }
+        for (int64_t c = c0 + sl; c < c1; c += 8) meta[c] = (uint8_t)((c == c1 - 1) | ((c >= cx) << 1));
+        (void)pend;
+    }
+}
+
+// adjoint: gene boundaries that cut every tile into K slices of equal chunk count (one slice per warp of the CTA)
+__global__ void fact_slices_kernel(const int64_t *__restrict__ gptr, int64_t ntiles, int64_t n, int K, int32_t *__restrict__ slices) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ntiles * (K + 1)) return;
+    const int64_t t = i / (K + 1);
+    const int k = (int)(i - t * (K + 1));
+    const int64_t *gp = gptr + t * n;
+    const int64_t c0 = gp[0], c1 = gp[n];
+    int64_t g;
+    if (k == 0) g = 0;
+    else if (k == K) g = n;
+    else {
+        const int64_t target = c0 + (int64_t)(((__int128)(c1 - c0) * k) / K);
+        int64_t lo = 0, hi = n;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (gp[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        g = lo;
+    }
+    slices[i] = (int32_t)g;
+}
+
+// forward layout, pass 1 (CSR by cell with the level of every entry): per row the cumulative group ends in
+// chunks (u16) and the row's chunk count (at least one chunk per row, see above). One warp per row.
+__global__ void __launch_bounds__(256) fact_row_hist_kernel(const int64_t *__restrict__ rowptr, const uint8_t *__restrict__ rlvl,
+                                                            const int64_t *__restrict__ erowptr, int64_t m, int L,
+                                                            uint16_t *__restrict__ gend, int64_t *__restrict__ rowchunks) {
+    __shared__ int hist[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t warp = (int64_t)blockIdx.x * 8 + w;
+    const int64_t nwarps = (int64_t)gridDim.x * 8;
+    for (int64_t r = warp; r < m; r += nwarps) {
+        hist[w][lane] = 0;
+        __syncwarp();
+        const int64_t b = rowptr[r], e = rowptr[r + 1];
+        for (int64_t k = b + lane; k < e; k += 32) {
+            const int lv = rlvl[k];
+            if (lv) atomicAdd(&hist[w][lv - 1], 1);
+        }
+        __syncwarp();
+        int ch = (lane < L) ? (hist[w][lane] + FCH - 1) / FCH : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, ch, o);
+            if (lane >= o) ch += y;
+        }
+        const int ne = erowptr ? (int)(erowptr[r + 1] - erowptr[r]) : 0;  // one chunk per exception, after the level groups
+        const int total = __shfl_sync(0xffffffffu, ch, 31);
+        if (total + ne == 0) ch = 1;  // empty row: one all-pad chunk in level 0
+        if (lane < L) gend[r * L + lane] = (uint16_t)ch;
+        if (lane == 31) rowchunks[r] = ch + ne;
+        __syncwarp();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) rowchunks[m] = 0;
+}
+
+// forward layout, pass 2: for every level a stable (ascending gene) ballot compaction into the group's chunks, pads
+// (gene index n, xs[n] = 0) up to the chunk boundary, and the per-chunk byte (level << 1) | last-chunk-of-the-row
+__global__ void __launch_bounds__(256) fact_row_place_kernel(const int64_t *__restrict__ rowptr, const uint16_t *__restrict__ ridx,
+                                                             const uint8_t *__restrict__ rlvl, int64_t m, int L, int padgene,
+                                                             const int64_t *__restrict__ frowptr, const uint16_t *__restrict__ gend,
+                                                             const int64_t *__restrict__ erowptr, const int32_t *__restrict__ ecol,
+                                                             const double *__restrict__ eval, uint16_t *__restrict__ code,
+                                                             uint8_t *__restrict__ meta) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < m; r += nwarps) {
+        const int64_t b = rowptr[r], e = rowptr[r + 1];
+        const int64_t cbase = frowptr[r];
+        const int64_t base = cbase * FCH;
+        const int total = (int)(frowptr[r + 1] - cbase);
+        int prev = 0;
+        for (int l = 0; l < L; ++l) {
+            const int ge = gend[r * L + l];
+            if (ge == prev) continue;
+            int64_t pos = base + (int64_t)prev * FCH;
+            const int64_t pend = base + (int64_t)ge * FCH;
+            for (int c = prev + lane; c < ge; c += 32) meta[cbase + c] = (uint8_t)((l << 1) | (c == total - 1));
+            prev = ge;
+            for (int64_t k0 = b; k0 < e; k0 += 32) {
+                const int64_t k = k0 + lane;
+                const bool hit = (k < e) && (rlvl[k] == l + 1);
+                const unsigned bal = __ballot_sync(0xffffffffu, hit);
+                if (hit) code[pos + __popc(bal & ((1u << lane) - 1u))] = ridx[k];
+                pos += __popc(bal);
+            }
+            for (int64_t p = pos + lane; p < pend; p += 32) code[p] = (uint16_t)padgene;
+        }
+        if (erowptr) {  // exception chunks {gene, -, value*sd as Float64}, level field = FEXC
+            const int64_t eb = erowptr[r], ee = erowptr[r + 1];
+            for (int64_t k = eb + lane; k < ee; k += 32) {
+                const int c = prev + (int)(k - eb);
+                uint4 q;
+                q.x = (unsigned)ecol[k];
+                q.y = 0u;
+                q.z = (unsigned)__double2loint(eval[k]);
+                q.w = (unsigned)__double2hiint(eval[k]);
+                reinterpret_cast<uint4 *>(code)[cbase + c] = q;
+                meta[cbase + c] = (uint8_t)((FEXC << 1) | (c == total - 1));
+            }
+        }
+    }
+}
+
+// warp b of NW streams the chunks of the rows [wrow[b], wrow[b+1]): whole rows, equal chunk counts
+__global__ void fact_warp_ranges_kernel(const int64_t *__restrict__ frowptr, int64_t m, int64_t nchunks, int NW,
+                                        int64_t *__restrict__ wstart, int64_t *__restrict__ wrow) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > NW) return;
+    int64_t r;
+    if (b == 0) r = 0;
+    else if (b == NW) r = m;
+    else {
+        const int64_t target = (int64_t)(((__int128)nchunks * b) / NW);
+        int64_t lo = 0, hi = m;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (frowptr[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        r = lo;
+    }
+    wrow[b] = r;
+    wstart[b] = frowptr[r];
+}
+
+// ---------------------------------------------------------------------------------------------
+// products: chunk-stream kernels. A warp streams a contiguous range of 16-byte chunks (32 chunks = 512 B per
+// iteration, loads issued PD iterations ahead), every lane turns its chunk into one partial value, and a segmented
+// warp scan over the "last chunk" flags adds the partials of a row / (tile, gene) segment; a segment that continues
+// into the next iteration is carried in a register. No per-row setup, no idle lanes on short rows, fixed summation
+// order (deterministic), and the bytes in flight do not depend on the row lengths.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double fblock_sum(double v, double *red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    double t = 0.0;
+    for (int i = 0; i < nw; ++i) t += red[i];
+    return t;
+}
+
+__device__ __forceinline__ double gather8(const double *__restrict__ T, const uint4 q) {
+    const double a0 = T[q.x & 0xffffu], a1 = T[q.x >> 16], a2 = T[q.y & 0xffffu], a3 = T[q.y >> 16];
+    const double a4 = T[q.z & 0xffffu], a5 = T[q.z >> 16], a6 = T[q.w & 0xffffu], a7 = T[q.w >> 16];
+    return ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+__device__ __forceinline__ uint4 ld_stream16(const uint4 *p) {  // streamed once: do not keep it in L1
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// inclusive segmented sum over the lanes of a warp; `lastbits` = ballot of the "segment ends at this lane" flags.
+// Returns the running sum of the lane's segment up to and including the lane; head0 = the lane's segment starts at lane 0.
+__device__ __forceinline__ double seg_scan(double v, unsigned lastbits, int lane, bool &head0) {
+    const unsigned heads = (lastbits << 1) | 1u;
+    const unsigned le = (lane == 31) ? 0xffffffffu : ((2u << lane) - 1u);
+    const int head_lane = 31 - __clz(heads & le);
+    const int d = lane - head_lane;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, v, o);
+        if (d >= o) v += t;
+    }
+    head0 = (head_lane == 0);
+    return v;
+}
+
+constexpr int FPD = 3;  // prefetch distance of the stream kernels, in iterations (3 x 16 B per lane in flight)
+
+// forward: y_i = alpha*(sum over the row's chunks of t_i[level] * sum_8 xs[gene] - mu.x) + beta*y_i + csign*(*coef)*cvec_i
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, (BLOCK == 256 ? 5 : 2))
+fwd_stream_kernel(const uint4 *__restrict__ code, const uint8_t *__restrict__ meta, const double *__restrict__ tlev, int log2L,
+                  const int64_t *__restrict__ wstart, const int64_t *__restrict__ wrow, int64_t n, const double *__restrict__ x,
+                  const double *__restrict__ inv, const double *__restrict__ mu, double alpha, double beta, double *__restrict__ y,
+                  const double *__restrict__ coef, double csign, const double *__restrict__ cvec) {
+    extern __shared__ double smem[];
+    double *red = smem;      // 32
+    double *xs = smem + 32;  // n + 1 (xs[n] = 0: the pad gene)
+    double part = 0.0;
+    for (int64_t j = threadIdx.x; j < n; j += BLOCK) {
+        const double xv = x[j];
+        xs[j] = xv * inv[j];
+        part = fma(mu[j], xv, part);
+    }
+    if (threadIdx.x == 0) xs[n] = 0.0;
+    const double mudot = fblock_sum(part, red);  // its barriers publish xs
+    const double cf = (coef != nullptr) ? csign * (*coef) : 0.0;
+
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int64_t gw = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
+    const int64_t cend = __ldg(wstart + gw + 1);
+    int64_t c = __ldg(wstart + gw) + lane;  // this lane's chunk of the current iteration
+    int64_t rowbase = __ldg(wrow + gw);     // row of the first chunk of the NEXT iteration to be decoded
+    const uint4 padq = make_uint4((unsigned)n * 0x10001u, (unsigned)n * 0x10001u, (unsigned)n * 0x10001u, (unsigned)n * 0x10001u);
+
+    uint4 q[FPD];
+    unsigned mb[FPD];
+#pragma unroll
+    for (int s = 0; s < FPD; ++s) {
+        const int64_t cc = c + 32 * s;
+        const bool ok = cc < cend;
+        q[s] = ok ? ld_stream16(code + cc) : padq;
+        mb[s] = ok ? (unsigned)__ldg(meta + cc) : 0u;
+    }
+    // decode iteration 0 and fetch its table entries
+    unsigned bal0 = __ballot_sync(0xffffffffu, (mb[0] & 1u) != 0u);
+    int64_t row0 = rowbase + __popc(bal0 & lt);
+    rowbase += __popc(bal0);
+    double t0 = (c < cend && (mb[0] >> 1) != FEXC) ? __ldg(tlev + (row0 << log2L) + (mb[0] >> 1)) : 0.0;
+    double carry = 0.0;
+    for (; c - lane < cend; c += 32) {
+        // A: loads of iteration +FPD
+        const int64_t cp = c + 32 * FPD;
+        const bool okp = cp < cend;
+        const uint4 qp = okp ? ld_stream16(code + cp) : padq;
+        const unsigned mbp = okp ? (unsigned)__ldg(meta + cp) : 0u;
+        // B: decode iteration +1 and fetch its table entries (they arrive while this iteration is processed)
+        const unsigned bal1 = __ballot_sync(0xffffffffu, (mb[1] & 1u) != 0u);
+        const int64_t row1 = rowbase + __popc(bal1 & lt);
+        rowbase += __popc(bal1);
+        const double t1 = (c + 32 < cend && (mb[1] >> 1) != FEXC) ? __ldg(tlev + (row1 << log2L) + (mb[1] >> 1)) : 0.0;
+        // C: this iteration
+        double v;
+        if ((mb[0] >> 1) == FEXC) v = __hiloint2double((int)q[0].w, (int)q[0].z) * xs[q[0].x];
+        else v = t0 * gather8(xs, q[0]);
+        bool head0;
+        v = seg_scan(v, bal0, lane, head0);
+        if (head0) v += carry;
+        if (mb[0] & 1u) {
+            double r = alpha * (v - mudot);
+            if (beta != 0.0) r = fma(beta, y[row0], r);
+            if (coef != nullptr) r = fma(cf, cvec[row0], r);
+            y[row0] = r;
+        }
+        const double v31 = __shfl_sync(0xffffffffu, v, 31);
+        carry = (bal0 >> 31) ? 0.0 : v31;
+        // rotate the pipeline
+#pragma unroll
+        for (int s = 0; s + 1 < FPD; ++s) {
+            q[s] = q[s + 1];
+            mb[s] = mb[s + 1];
+        }
+        q[FPD - 1] = qp;
+        mb[FPD - 1] = mbp;
+        bal0 = bal1;
+        row0 = row1;
+        t0 = t1;
+    }
+}
+
+// adjoint, stage 1: partial[t][g] = (1/sd_g) * sum over the chunks of segment (t,g) of sum_8 T[code], T[l*R+i] = t_i[l]*w_i;
+// partial[t][n] = sum of w over the tile. CTAs take tiles from a global counter (any order gives the same bits: every
+// tile has its own partial row); inside a tile warp k streams the k-th slice of the tile's chunks.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 3 : 1))
+adj_stream_kernel(const int64_t *__restrict__ gptr, const uint4 *__restrict__ code, const uint8_t *__restrict__ meta,
+                  const double *__restrict__ tlevA, int log2L, int log2R, int64_t m, int64_t n, int64_t ntiles,
+                  const double *__restrict__ w, const double *__restrict__ inv, double *__restrict__ partial,
+                  const int32_t *__restrict__ slices, unsigned int *__restrict__ counters) {
+    extern __shared__ double smem[];
+    __shared__ long long cur_tile;
+    double *red = smem;     // 32
+    double *T = smem + 32;  // R*L level table, [R*L] = 0 (pads), then R entries of w (exception chunks)
+    const int64_t R = (int64_t)1 << log2R;
+    const int RL = 1 << (log2R + log2L);
+    constexpr int K = BLOCK / 32;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned padc = (unsigned)RL * 0x10001u;
+    const uint4 padq = make_uint4(padc, padc, padc, padc);
+    for (;;) {
+        __syncthreads();  // everybody is done with the previous tile's table (and has read cur_tile)
+        if (threadIdx.x == 0) cur_tile = (long long)atomicAdd(&counters[0], 1u);
+        __syncthreads();
+        const int64_t t = cur_tile;
+        if (t >= ntiles) break;
+        const int64_t row0 = t << log2R;
+        const double *tl = tlevA + (row0 << log2L);  // this tile's level-major block
+#pragma unroll 4
+        for (int k = threadIdx.x; k < RL; k += BLOCK) {
+            const int64_t row = row0 + (k & (R - 1));
+            T[k] = (row < m) ? __ldg(tl + k) * __ldg(w + row) : 0.0;
+        }
+        double part = 0.0;
+        for (int64_t r = threadIdx.x; r < R; r += BLOCK) {
+            const double wv = (row0 + r < m) ? __ldg(w + row0 + r) : 0.0;
+            T[RL + 1 + r] = wv;
+            part += wv;
+        }
+        if (threadIdx.x == 0) T[RL] = 0.0;
+        // this warp's slice (loads issued before the barrier so that they overlap the table fill)
+        const int g0 = __ldg(slices + t * (K + 1) + wid), g1 = __ldg(slices + t * (K + 1) + wid + 1);
+        const int64_t cend = __ldg(gptr + t * n + g1);
+        int64_t c = __ldg(gptr + t * n + g0) + lane;
+        uint4 q[FPD];
+        unsigned mb[FPD];
+#pragma unroll
+        for (int s = 0; s < FPD; ++s) {
+            const int64_t cc = c + 32 * s;
+            const bool ok = cc < cend;
+            q[s] = ok ? ld_stream16(code + cc) : padq;
+            mb[s] = ok ? (unsigned)__ldg(meta + cc) : 0u;
+        }
+        const double wsum = fblock_sum(part, red);  // publishes T
+        if (threadIdx.x == 0) partial[t * (n + 1) + n] = wsum;
+        double *prow = partial + t * (n + 1);
+        int gbase = g0;
+        double carry = 0.0;
+        for (; c - lane < cend; c += 32) {
+            const int64_t cp = c + 32 * FPD;
+            const bool okp = cp < cend;
+            const uint4 qp = okp ? ld_stream16(code + cp) : padq;
+            const unsigned mbp = okp ? (unsigned)__ldg(meta + cp) : 0u;
+            const unsigned bal = __ballot_sync(0xffffffffu, (mb[0] & 1u) != 0u);
+            const int g = gbase + __popc(bal & lt);
+            gbase += __popc(bal);
+            double v;
+            if (mb[0] & 2u) v = __hiloint2double((int)q[0].w, (int)q[0].z) * T[RL + 1 + q[0].x];
+            else v = gather8(T, q[0]);
+            bool head0;
+            v = seg_scan(v, bal, lane, head0);
+            if (head0) v += carry;
+            if (mb[0] & 1u) prow[g] = v * __ldg(inv + g);
+            const double v31 = __shfl_sync(0xffffffffu, v, 31);
+            carry = (bal >> 31) ? 0.0 : v31;
+#pragma unroll
+            for (int s = 0; s + 1 < FPD; ++s) {
+                q[s] = q[s + 1];
+                mb[s] = mb[s + 1];
+            }
+            q[FPD - 1] = qp;
+            mb[FPD - 1] = mbp;
+        }
+    }
+    // the last CTA to leave resets the counters for the next launch
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned done = atomicAdd(&counters[1], 1u);
+        if (done == gridDim.x - 1) {
+            counters[0] = 0u;
+            counters[1] = 0u;
+            __threadfence();
+        }
+    }
+}
+
+template <typename K>
+static int fresident_grid(K kernel, size_t smem, int threads) {
+    int per_sm = 0;
+    SVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    return std::max(1, per_sm) * ctx().sm_count;
+}
+
+template <int BLOCK>
+static void launch_fact_fwd(svb_operator_s *op, double alpha, const double *dx, double beta, double *dy, const double *coef,
+                            double csign, const double *cvec) {
+    svb_factored_s *f = op->fact;
+    const size_t smem = (32 + (size_t)op->n + 1) * sizeof(double);
+    auto k = fwd_stream_kernel<BLOCK>;
+    SVB_CHECK(smem <= ctx().smem_optin, SVB_EDIM, "count-level operator: gene vector does not fit in shared memory");
+    if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (f->fwd_grid == 0) {
+        // one resident wave; fewer warps when the matrix is small (at least ~8 iterations of 32 chunks per warp)
+        int grid = fresident_grid(k, smem, BLOCK);
+        const int64_t want = std::max<int64_t>(1, f->f_chunks / (256 * (BLOCK / 32)));
+        grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid, want));
+        const int NW = grid * (BLOCK / 32);
+        SVB_CUDA(cudaMalloc((void **)&f->fwd_ranges, (size_t)(NW + 1) * sizeof(int64_t)));
+        SVB_CUDA(cudaMalloc((void **)&f->fwd_rows, (size_t)(NW + 1) * sizeof(int64_t)));
+        fact_warp_ranges_kernel<<<(NW + 256) / 256, 256, 0, ctx().stream>>>(f->f_rowptr, op->m, f->f_chunks, NW, f->fwd_ranges, f->fwd_rows);
+        count_launch();
+        SVB_LAUNCH_CHECK();
+        f->fwd_grid = grid;
+    }
+    k<<<(unsigned)f->fwd_grid, BLOCK, smem, ctx().stream>>>((const uint4 *)f->f_code, f->f_meta, f->tlev, f->log2L, f->fwd_ranges,
+                                                             f->fwd_rows, op->n, dx, f->inv, op->mu, alpha, beta, dy, coef, csign, cvec);
+    SVB_LAUNCH_CHECK();
+}
+
+constexpr int ADJ_BLOCK = 512;
+
+void fact_fwd(svb_operator_s *op, double alpha, const double *dx, double beta, double *dy, const double *coef, double csign,
+              const double *cvec) {
+    if ((size_t)op->n * 8 > 24 * 1024) launch_fact_fwd<512>(op, alpha, dx, beta, dy, coef, csign, cvec);
+    else launch_fact_fwd<256>(op, alpha, dx, beta, dy, coef, csign, cvec);
+}
+
+void fact_adj_stage1(svb_operator_s *op, const double *dx) {
+    svb_factored_s *f = op->fact;
+    const size_t smem = (32 + ((size_t)1 << (f->log2R + f->log2L)) + 1 + (size_t)f->R) * sizeof(double);
+    auto k = adj_stream_kernel<ADJ_BLOCK>;
+    if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (f->adj_grid == 0) f->adj_grid = (int)std::max<int64_t>(1, std::min<int64_t>(fresident_grid(k, smem, ADJ_BLOCK), f->ntiles));
+    k<<<(unsigned)f->adj_grid, ADJ_BLOCK, smem, ctx().stream>>>(f->a_gptr, (const uint4 *)f->a_code, f->a_meta, f->tlevA, f->log2L, f->log2R,
+                                                                 op->m, op->n, f->ntiles, dx, f->inv, f->partial, f->a_slices, f->counters);
+    SVB_LAUNCH_CHECK();
+}
+
+// algorithmic bytes of one product with THIS layout's widths: 2 B per stored entry and 1 B per chunk of 8 (pads are not
+// counted), the per-cell tables, the pointers and the vectors
+double fact_fwd_bytes(const svb_operator_s *op) {
+    const svb_factored_s *f = op->fact;
+    return 2.125 * (double)f->nnz_main + 17.0 * (double)f->nnz_exc + (double)op->m * (8.0 * f->L + 8.0) + 24.0 * (double)op->n;
+}
+double fact_adj_bytes(const svb_operator_s *op) {
+    const svb_factored_s *f = op->fact;
+    const double nseg = (double)f->ntiles * (double)op->n;
+    return 2.125 * (double)f->nnz_main + 17.0 * (double)f->nnz_exc + (double)op->m * (8.0 * f->L + 8.0) + nseg * (8.0 + 8.0) +
+           24.0 * (double)op->n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// construction
+// ---------------------------------------------------------------------------------------------
+namespace {
+// a non-owning view of a CSC matrix whose value array is replaced (the level bytes)
+struct MatrixView {
+    svb_matrix_s v;
+    MatrixView(const svb_matrix_s *a, void *val) {
+        v.nrow = a->nrow;
+        v.ncol = a->ncol;
+        v.nnz = a->nnz;
+        v.vtype = a->vtype;
+        v.colptr = a->colptr;
+        v.rowidx = a->rowidx;
+        v.val = val;
+    }
+    ~MatrixView() { v.colptr = nullptr; v.rowidx = nullptr; v.val = nullptr; }
+};
+}  // namespace
+
+static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int64_t *h_libsize, double sf, const double *h_mean,
+                           const double *h_var, double scale_max, int levels, double *mu_out) {
+    Context &C = ctx();
+    cudaStream_t st = C.stream;
+    const int64_t m = a->nrow, n = a->ncol, nnz = a->nnz;
+    auto *f = new svb_factored_s();
+    op->fact = f;
+
+    // ---- number of levels ----------------------------------------------------------------------------
+    DevBuf<long long> d_lib((size_t)std::max<int64_t>(m, 1));
+    SVB_CUDA(cudaMemcpyAsync(d_lib.p, h_libsize, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+    int L = levels;
+    if (L == 0) {
+        DevBuf<unsigned long long> d_h(4);
+        SVB_CUDA(cudaMemsetAsync(d_h.p, 0, 4 * sizeof(unsigned long long), st));
+        if (nnz > 0) {
+            fact_hist_kernel<<<fgrid(nnz), 256, 0, st>>>((const int32_t *)a->val, nnz, d_h.p);
+            count_launch();
+            SVB_LAUNCH_CHECK();
+        }
+        double h[5] = {0, 0, 0, 0, 0};
+        {
+            unsigned long long hh[4];
+            SVB_CUDA(cudaMemcpyAsync(hh, d_h.p, sizeof(hh), cudaMemcpyDeviceToHost, st));
+            SVB_CUDA(cudaStreamSynchronize(st));
+            for (int i = 0; i < 4; ++i) h[i] = (double)hh[i];
+            h[4] = (double)nnz;
+        }
+        if (C.nranks > 1) {  // every rank must choose the same L (tables are per rank, but keep the ranks in lock-step)
+            DevBuf<double> d5(5);
+            SVB_CUDA(cudaMemcpyAsync(d5.p, h, sizeof(h), cudaMemcpyHostToDevice, st));
+            comm_allreduce_dev(d5.p, 5);
+            SVB_CUDA(cudaMemcpyAsync(h, d5.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+            SVB_CUDA(cudaStreamSynchronize(st));
+        }
+        // smallest L that leaves at most 1 % of the entries to the explicit residual (10 B/nnz there, 2 B/nnz here)
+        const int cand[4] = {4, 8, 16, 32};
+        L = 32;
+        for (int i = 0; i < 4; ++i)
+            if (h[i] <= 0.01 * h[4]) { L = cand[i]; break; }
+    }
+    int log2L = 0;
+    while ((1 << log2L) < L) ++log2L;
+    f->L = L;
+    f->log2L = log2L;
+    // cells per adjoint tile: R*L = 8192 table entries (64 KB); small inputs get one small tile
+    int log2R = 13 - log2L;
+    const char *envr = getenv("SVB_FACT_LOG2R");
+    if (envr) log2R = std::max(5, std::min(atoi(envr), 14 - log2L));
+    while (log2R > 5 && (1ll << (log2R - 1)) >= m) --log2R;
+    f->log2R = log2R;
+    f->R = 1ll << log2R;
+    f->ntiles = std::max<int64_t>(1, (m + f->R - 1) / f->R);
+
+    // ---- per-cell level tables ---------------------------------------------------------------------
+    SVB_CUDA(cudaMalloc((void **)&f->tlev, (size_t)std::max<int64_t>(m << log2L, 1) * sizeof(double)));
+    SVB_CUDA(cudaMalloc((void **)&f->tlevA, (size_t)(f->ntiles << (log2R + log2L)) * sizeof(double)));
+    SVB_CUDA(cudaMemsetAsync(f->tlevA, 0, (size_t)(f->ntiles << (log2R + log2L)) * sizeof(double), st));
+    fact_tlev_kernel<<<fgrid(m << log2L), 256, 0, st>>>(d_lib.p, m, log2L, log2R, sf, f->tlev, f->tlevA);
+    count_launch();
+    SVB_LAUNCH_CHECK();
+
+    // ---- per-gene moments (given, or two parallel passes over the counts), then scale, centre, clip ------
+    DevBuf<double> d_mean((size_t)n), d_var((size_t)n), d_sd((size_t)n), d_cap((size_t)n);
+    DevBuf<int> d_bad(1);
+    SVB_CUDA(cudaMalloc((void **)&op->mu, (size_t)n * sizeof(double)));
+    SVB_CUDA(cudaMalloc((void **)&f->inv, (size_t)n * sizeof(double)));
+    if (h_mean) {
+        SVB_CUDA(cudaMemcpyAsync(d_mean.p, h_mean, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        SVB_CUDA(cudaMemcpyAsync(d_var.p, h_var, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    } else {
+        DevBuf<double> d_sum((size_t)n + 1), d_ss((size_t)n);
+        const double mloc = (double)m;
+        SVB_CUDA(cudaMemcpyAsync(d_sum.p + n, &mloc, 8, cudaMemcpyHostToDevice, st));
+        fact_moments_sum_kernel<<<(unsigned)n, 512, 0, st>>>(a->colptr, a->rowidx, (const int32_t *)a->val, log2L, f->tlev, d_lib.p, sf,
+                                                             d_sum.p);
+        count_launch();
+        SVB_LAUNCH_CHECK();
+        if (C.nranks > 1) comm_allreduce_dev(d_sum.p, n + 1);  // cells are sharded: sums and the cell count over all ranks
+        fact_moments_ss_kernel<<<(unsigned)n, 512, 0, st>>>(a->colptr, a->rowidx, (const int32_t *)a->val, log2L, f->tlev, d_lib.p, sf, m,
+                                                            d_sum.p, d_sum.p + n, d_mean.p, d_ss.p);
+        count_launch();
+        SVB_LAUNCH_CHECK();
+        if (C.nranks > 1) comm_allreduce_dev(d_ss.p, n);
+        fact_moments_var_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_ss.p, d_sum.p + n, n, d_var.p);
+        count_launch();
+        SVB_LAUNCH_CHECK();
+        SVB_CUDA(cudaStreamSynchronize(st));  // d_sum / d_ss go out of scope
+    }
+    SVB_CUDA(cudaMemsetAsync(d_bad.p, 0, sizeof(int), st));
+    fact_prepare_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_mean.p, d_var.p, n, scale_max, d_sd.p, op->mu, d_cap.p, f->inv, d_bad.p);
+    count_launch();
+    SVB_LAUNCH_CHECK();
+    int bad = 0;
+    SVB_CUDA(cudaMemcpyAsync(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (mu_out) SVB_CUDA(cudaMemcpyAsync(mu_out, op->mu, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    SVB_CUDA(cudaStreamSynchronize(st));
+    SVB_CHECK(!bad, SVB_EARG, "svb_operator_create_counts: a gene has zero (or non-finite) variance");
+
+    // ---- classify every entry (CSC order) -------------------------------------------------------------
+    DevBuf<uint8_t> lvl((size_t)std::max<int64_t>(nnz, 1));
+    DevBuf<int64_t> ecolptr((size_t)(n + 1));
+    SVB_CUDA(cudaMemsetAsync(ecolptr.p, 0, (size_t)(n + 1) * sizeof(int64_t), st));
+    if (nnz > 0) {
+        dim3 grid((unsigned)n, 8);
+        fact_classify_kernel<<<grid, 256, 0, st>>>(a->colptr, a->rowidx, (const int32_t *)a->val, log2L, f->tlev, d_sd.p, d_cap.p, lvl.p,
+                                                   (unsigned long long *)ecolptr.p);
+        count_launch();
+        SVB_LAUNCH_CHECK();
+    }
+    exclusive_scan_i64(ecolptr.p, n + 1, st);
+    int64_t nexc = 0;
+    SVB_CUDA(cudaMemcpyAsync(&nexc, ecolptr.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    SVB_CUDA(cudaStreamSynchronize(st));
+    f->nnz_exc = nexc;
+    f->nnz_main = nnz - nexc;
+
+    // ---- the exceptions with their exact value (times sd), gene-major (CSC) and cell-major (its transpose) ------
+    struct Owned {
+        svb_matrix_s *p = nullptr;
+        ~Owned() { delete p; }
+    } e, et;
+    if (nexc > 0) {
+        e.p = matrix_alloc(m, n, nexc, SVB_F64);
+        SVB_CUDA(cudaMemcpyAsync(e.p->colptr, ecolptr.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToDevice, st));
+        fact_resid_fill_kernel<<<fgrid(n * 32), 256, 0, st>>>(a->colptr, a->rowidx, (const int32_t *)a->val, lvl.p, n, d_lib.p, sf,
+                                                              d_sd.p, d_cap.p, e.p->colptr, e.p->rowidx, (double *)e.p->val);
+        count_launch();
+        SVB_LAUNCH_CHECK();
+        et.p = matrix_transpose(e.p);
+    }
+
+    // ---- adjoint layout ----------------------------------------------------------------------------------
+    {
+        const int64_t nseg = f->ntiles * n;
+        DevBuf<int64_t> startpos((size_t)((f->ntiles + 1) * n + 1)), estart;
+        tile_bounds(a, log2R, f->ntiles, startpos.p);
+        if (e.p) {
+            estart.alloc((size_t)((f->ntiles + 1) * n + 1));
+            tile_bounds(e.p, log2R, f->ntiles, estart.p);
+        }
+        SVB_CUDA(cudaMalloc((void **)&f->a_gptr, (size_t)(nseg + 1) * sizeof(int64_t)));
+        fact_seg_count_kernel<<<fgrid(nseg * 8), 256, 0, st>>>(startpos.p, lvl.p, estart.p, nseg, n, f->a_gptr);
+        count_launch();
+        SVB_LAUNCH_CHECK();
+        exclusive_scan_i64(f->a_gptr, nseg + 1, st);
+        SVB_CUDA(cudaMemcpyAsync(&f->a_chunks, f->a_gptr + nseg, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        SVB_CUDA(cudaStreamSynchronize(st));
+        SVB_CUDA(cudaMalloc((void **)&f->a_code, (size_t)std::max<int64_t>(f->a_chunks, 1) * 16));
+        SVB_CUDA(cudaMalloc((void **)&f->a_meta, (size_t)std::max<int64_t>(f->a_chunks, 1)));
+        fact_seg_fill_kernel<<<fgrid(nseg * 8), 256, 0, st>>>(startpos.p, a->rowidx, lvl.p, nseg, n, log2R, log2L, f->a_gptr, estart.p,
+                                                              e.p ? e.p->rowidx : nullptr, e.p ? (const double *)e.p->val : nullptr,
+                                                              (uint16_t *)f->a_code, f->a_meta);
+        constexpr int K = ADJ_BLOCK / 32;
+        SVB_CUDA(cudaMalloc((void **)&f->a_slices, (size_t)f->ntiles * (K + 1) * sizeof(int32_t)));
+        fact_slices_kernel<<<(unsigned)((f->ntiles * (K + 1) + 255) / 256), 256, 0, st>>>(f->a_gptr, f->ntiles, n, K, f->a_slices);
+        SVB_CUDA(cudaMalloc((void **)&f->counters, 2 * sizeof(unsigned int)));
+        SVB_CUDA(cudaMemsetAsync(f->counters, 0, 2 * sizeof(unsigned int), st));
+        count_launch(2);
+        SVB_LAUNCH_CHECK();
+        SVB_CUDA(cudaStreamSynchronize(st));
+    }
+
+    // ---- forward layout: CSR by cell of (gene, level), then level grouping -------------------------------------
+    {
+        MatrixView view(a, lvl.p);
+        TileCSC<uint8_t> tc;
+        DevBuf<int64_t> rowptr;
+        DevBuf<uint16_t> ridx;
+        DevBuf<uint8_t> rlvl;
+        int tl2 = 12;
+        while (tl2 > 8 && (1ll << (tl2 - 1)) >= m) --tl2;
+        build_tilecsc<uint8_t, uint8_t>(&view.v, tl2, tc);
+        csr_from_tilecsc<uint8_t, uint16_t>(tc, &view.v, rowptr, ridx, rlvl);
+        tc.gptr.release();
+        tc.rloc.release();
+        tc.aval.release();
+        const int64_t *erowptr = et.p ? et.p->colptr : nullptr;
+        SVB_CUDA(cudaMalloc((void **)&f->f_rowptr, (size_t)(m + 1) * sizeof(int64_t)));
+        DevBuf<uint16_t> gend((size_t)std::max<int64_t>(m * L, 1));
+        const unsigned gw = (unsigned)std::max<int64_t>(1, std::min<int64_t>((m + 7) / 8, 148 * 16));
+        fact_row_hist_kernel<<<gw, 256, 0, st>>>(rowptr.p, rlvl.p, erowptr, m, L, gend.p, f->f_rowptr);
+        count_launch();
+        SVB_LAUNCH_CHECK();
+        exclusive_scan_i64(f->f_rowptr, m + 1, st);
+        SVB_CUDA(cudaMemcpyAsync(&f->f_chunks, f->f_rowptr + m, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        SVB_CUDA(cudaStreamSynchronize(st));
+        SVB_CUDA(cudaMalloc((void **)&f->f_code, (size_t)std::max<int64_t>(f->f_chunks, 1) * 16));
+        SVB_CUDA(cudaMalloc((void **)&f->f_meta, (size_t)std::max<int64_t>(f->f_chunks, 1)));
+        fact_row_place_kernel<<<gw, 256, 0, st>>>(rowptr.p, ridx.p, rlvl.p, m, L, (int)n, f->f_rowptr, gend.p, erowptr,
+                                                  et.p ? et.p->rowidx : nullptr, et.p ? (const double *)et.p->val : nullptr,
+                                                  (uint16_t *)f->f_code, f->f_meta);
+        count_launch();
+        SVB_LAUNCH_CHECK();
+        SVB_CUDA(cudaStreamSynchronize(st));
+    }
+
+    SVB_CUDA(cudaMalloc((void **)&f->partial, (size_t)f->ntiles * (n + 1) * sizeof(double)));
+    SVB_CUDA(cudaMalloc((void **)&op->tmp, (size_t)std::max(m, n) * sizeof(double)));
+    SVB_CUDA(cudaMalloc((void **)&op->scal, 8 * sizeof(double)));
+    SVB_CUDA(cudaStreamSynchronize(st));
+}
+
+}  // namespace svb
+
+extern "C" {
+
+int svb_operator_create_counts(svb_matrix_t counts, const int64_t *libsize, double scale_factor, const double *mean,
+                               const double *var, double scale_max, int levels, double *mu_out, svb_operator_t *out) {
+    SVB_API_BEGIN
+    require_init();
+    SVB_CHECK(counts && libsize && out, SVB_EARG, "svb_operator_create_counts: null argument");
+    SVB_CHECK((mean == nullptr) == (var == nullptr), SVB_EARG, "svb_operator_create_counts: give both moments or neither");
+    SVB_CHECK(counts->vtype == SVB_I32, SVB_EARG, "svb_operator_create_counts: the matrix must hold integer counts");
+    SVB_CHECK(counts->nrow >= 1 && counts->ncol >= 1, SVB_EDIM, "svb_operator_create_counts: empty operator");
+    SVB_CHECK(counts->ncol <= 65534, SVB_EDIM, "svb_operator_create_counts: at most 65534 genes (16-bit codes); use svb_operator_create");
+    SVB_CHECK(levels == 0 || levels == 4 || levels == 8 || levels == 16 || levels == 32, SVB_EARG,
+              "svb_operator_create_counts: levels must be 0 (auto), 4, 8, 16 or 32");
+    SVB_CHECK(scale_factor > 0.0, SVB_EARG, "svb_operator_create_counts: scale_factor must be positive");
+    auto *op = new svb_operator_s();
+    try {
+        op->m = counts->nrow;
+        op->n = counts->ncol;
+        op->nnz = counts->nnz;
+        op->vbytes = 0;
+        op->ibytes = 2;
+        build_factored(op, counts, libsize, scale_factor, mean, var, scale_max, levels, mu_out);
+    } catch (...) {
+        delete op;
+        throw;
+    }
+    *out = op;
+    SVB_API_END
+}
+
+int svb_operator_counts_info(svb_operator_t op, int *levels, int64_t *tile_cells, int64_t *nnz_coded, int64_t *nnz_explicit,
+                             int64_t *fwd_chunks, int64_t *adj_chunks) {
+    SVB_API_BEGIN
+    SVB_CHECK(op && op->fact, SVB_EARG, "svb_operator_counts_info: not a count-level operator");
+    const svb_factored_s *f = op->fact;
+    if (levels) *levels = f->L;
+    if (tile_cells) *tile_cells = f->R;
+    if (nnz_coded) *nnz_coded = f->nnz_main;
+    if (nnz_explicit) *nnz_explicit = f->nnz_exc;
+    if (fwd_chunks) *fwd_chunks = f->f_chunks;
+    if (adj_chunks) *adj_chunks = f->a_chunks;
+    SVB_API_END
+}
+
+}  // extern "C"

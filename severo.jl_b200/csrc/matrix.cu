@@ -117,6 +117,12 @@ __global__ void tile_bounds_kernel(const int64_t *colptr, const int32_t *rowidx,
     }
 }
 
+void tile_bounds(const svb_matrix_s *a, int log2R, int64_t ntiles, int64_t *startpos) {
+    tile_bounds_kernel<<<grid_for((ntiles + 1) * a->ncol), 256, 0, ctx().stream>>>(a->colptr, a->rowidx, a->ncol, ntiles, log2R, startpos);
+    count_launch();
+    SVB_LAUNCH_CHECK();
+}
+
 __global__ void tile_counts_kernel(const int64_t *startpos, int64_t ncol, int64_t ntiles, int64_t *cnt) {
     const int64_t total = ntiles * ncol;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -186,57 +192,79 @@ __global__ void row_count_kernel(const int32_t *rowidx, int64_t nnz, unsigned lo
 constexpr int CSRB_ROWS = 32;
 constexpr int CSRB_GCH = 4096;  // genes per shared-memory chunk
 
+// One CTA walks the row blocks [b0, b1) of one tile. `cursor[j]` is the position inside the (tile, gene j) segment
+// of the first entry not yet consumed: found by ONE binary search when the CTA starts, then advanced as the
+// blocks go by (a per-block binary search over every gene made the 28 k-gene transposes ~50x slower than HBM).
 template <typename V, typename IdxT>
 __global__ void __launch_bounds__(1024) tile_to_csr_kernel(const int64_t *__restrict__ gptr, const uint16_t *__restrict__ rloc,
                                                            const V *__restrict__ aval, int64_t ncol, int64_t nrow, int log2R,
-                                                           const int64_t *__restrict__ rowptr, IdxT *__restrict__ fidx,
+                                                           int split, const int64_t *__restrict__ rowptr,
+                                                           int64_t *__restrict__ cursor_all, IdxT *__restrict__ fidx,
                                                            V *__restrict__ fval) {
     __shared__ uint32_t mask[CSRB_GCH];
     __shared__ int64_t aoff[CSRB_GCH];
-    const int64_t row0 = (int64_t)blockIdx.x * CSRB_ROWS;
-    const int64_t t = row0 >> log2R;
-    const int r0l = (int)(row0 - (t << log2R));  // first cell of the block, local to its tile
+    const int64_t t = blockIdx.x / split;
+    const int part = (int)(blockIdx.x - t * split);
+    const int64_t R = (int64_t)1 << log2R;
+    const int64_t tile_row0 = t << log2R;
+    const int64_t tile_rows = min(R, nrow - tile_row0);
+    const int nblocks = (int)((tile_rows + CSRB_ROWS - 1) / CSRB_ROWS);
+    const int per = (nblocks + split - 1) / split;
+    const int b0 = part * per, b1 = min(nblocks, b0 + per);
+    if (b0 >= b1) return;
+    int64_t *cursor = cursor_all + (int64_t)blockIdx.x * ncol;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t myrow = row0 + warp;
-    int64_t pos = (myrow < nrow) ? rowptr[myrow] : 0;
     const int64_t *gp = gptr + t * ncol;
-    for (int64_t g0 = 0; g0 < ncol; g0 += CSRB_GCH) {
-        const int ng = (int)min((int64_t)CSRB_GCH, ncol - g0);
-        for (int j = threadIdx.x; j < ng; j += blockDim.x) {
-            int64_t lo = __ldg(gp + g0 + j);
-            const int64_t end = __ldg(gp + g0 + j + 1);
-            int64_t hi = end;
-            while (lo < hi) {
-                const int64_t mid = (lo + hi) >> 1;
-                if ((int)__ldg(rloc + mid) < r0l) lo = mid + 1; else hi = mid;
-            }
-            uint32_t mk = 0;
-            for (int64_t k = lo; k < end; ++k) {
-                const int rr = (int)__ldg(rloc + k) - r0l;
-                if (rr >= CSRB_ROWS) break;
-                mk |= 1u << rr;
-            }
-            mask[j] = mk;
-            aoff[j] = lo;
-        }
-        __syncthreads();
-        if (myrow < nrow) {
-            const uint32_t below = (1u << warp) - 1u;
-            for (int c = 0; c < ng; c += 32) {
-                const int j = c + lane;
-                const uint32_t mk = (j < ng) ? mask[j] : 0u;
-                const bool bit = (mk >> warp) & 1u;
-                const unsigned bal = __ballot_sync(0xffffffffu, bit);
-                if (bit) {
-                    const int64_t src = aoff[j] + __popc(mk & below);
-                    const int64_t dst = pos + __popc(bal & ((1u << lane) - 1u));
-                    fidx[dst] = (IdxT)(g0 + j);
-                    fval[dst] = __ldg(aval + src);
+    for (int blk = b0; blk < b1; ++blk) {
+        const int r0l = blk * CSRB_ROWS;  // first cell of the block, local to its tile
+        const int64_t myrow = tile_row0 + r0l + warp;
+        int64_t pos = (myrow < nrow) ? rowptr[myrow] : 0;
+        for (int64_t g0 = 0; g0 < ncol; g0 += CSRB_GCH) {
+            const int ng = (int)min((int64_t)CSRB_GCH, ncol - g0);
+            for (int j = threadIdx.x; j < ng; j += blockDim.x) {
+                const int64_t end = __ldg(gp + g0 + j + 1);
+                int64_t lo;
+                if (blk == b0) {
+                    lo = __ldg(gp + g0 + j);
+                    int64_t hi = end;
+                    while (lo < hi) {
+                        const int64_t mid = (lo + hi) >> 1;
+                        if ((int)__ldg(rloc + mid) < r0l) lo = mid + 1; else hi = mid;
+                    }
+                } else {
+                    lo = cursor[g0 + j];
                 }
-                pos += __popc(bal);
+                uint32_t mk = 0;
+                int64_t k = lo;
+                for (; k < end; ++k) {
+                    const int rr = (int)__ldg(rloc + k) - r0l;
+                    if (rr >= CSRB_ROWS) break;
+                    mk |= 1u << rr;
+                }
+                mask[j] = mk;
+                aoff[j] = lo;
+                if (b1 - b0 > 1) cursor[g0 + j] = k;
             }
+            __syncthreads();
+            if (myrow < nrow) {
+                const uint32_t below = (1u << warp) - 1u;
+                for (int c = 0; c < ng; c += 32) {
+                    const int j = c + lane;
+                    const uint32_t mk = (j < ng) ? mask[j] : 0u;
+                    const bool bit = (mk >> warp) & 1u;
+                    const unsigned bal = __ballot_sync(0xffffffffu, bit);
+                    if (bal == 0u) continue;
+                    if (bit) {
+                        const int64_t src = aoff[j] + __popc(mk & below);
+                        const int64_t dst = pos + __popc(bal & ((1u << lane) - 1u));
+                        fidx[dst] = (IdxT)(g0 + j);
+                        fval[dst] = __ldg(aval + src);
+                    }
+                    pos += __popc(bal);
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 
@@ -256,8 +284,22 @@ void csr_from_tilecsc(const TileCSC<V> &tc, const svb_matrix_s *a, DevBuf<int64_
     exclusive_scan_i64(rowptr.p, a->nrow + 1, st);
     if (a->nnz > 0) {
         auto kern = tile_to_csr_kernel<V, IdxT>;
-        const int64_t nblk = (a->nrow + CSRB_ROWS - 1) / CSRB_ROWS;
-        kern<<<(unsigned)nblk, 1024, 0, st>>>(tc.gptr.p, tc.rloc.p, tc.aval.p, a->ncol, a->nrow, tc.log2R, rowptr.p, fidx.p, fval.p);
+        // Dense segments (HVG operator: ~9 entries per gene per 32-cell block): one CTA per block, the binary search
+        // costs no more than the run itself and 40 k CTAs keep the chip full. Sparse segments (raw 28 k-gene matrices,
+        // ~2 entries): tiles x split CTAs (about two resident waves) that carry per-gene cursors from block to block.
+        const int blocks_per_tile = (int)(tc.R / CSRB_ROWS);
+        const double run = (double)a->nnz / (std::max<double>(1.0, (double)a->ncol) * std::max<double>(1.0, (double)a->nrow / CSRB_ROWS));
+        int split;
+        if (run >= 4.0) {
+            split = blocks_per_tile;
+        } else {
+            split = (int)std::max<int64_t>(1, std::min<int64_t>(blocks_per_tile, ((int64_t)ctx().sm_count * 4 + tc.ntiles - 1) / tc.ntiles));
+            while (split > 1 && (int64_t)tc.ntiles * split * a->ncol * 8 > (int64_t)8 << 30) split /= 2;  // cursor memory cap: 8 GB
+        }
+        const bool need_cursor = split < blocks_per_tile;
+        DevBuf<int64_t> cursor(need_cursor ? (size_t)tc.ntiles * split * std::max<int64_t>(a->ncol, 1) : 1);
+        kern<<<(unsigned)(tc.ntiles * split), 1024, 0, st>>>(tc.gptr.p, tc.rloc.p, tc.aval.p, a->ncol, a->nrow, tc.log2R, split, rowptr.p,
+                                                          cursor.p, fidx.p, fval.p);
         count_launch();
         SVB_LAUNCH_CHECK();
     }
@@ -378,7 +420,9 @@ static svb_matrix_s *transpose_rowtiles(const svb_matrix_s *a) {
 }
 
 svb_matrix_s *matrix_transpose(const svb_matrix_s *a) {
-    const bool use_rowtiles = a->ncol <= 65536;
+    // row tiles (tile layout + cursor kernel) whenever the ntiles x ncol segment pointers stay below ~4 GB
+    const int64_t ntiles13 = std::max<int64_t>(1, (a->nrow + 8191) / 8192);
+    const bool use_rowtiles = ntiles13 * a->ncol <= ((int64_t)1 << 29);
     switch (a->vtype) {
         case SVB_I32: return use_rowtiles ? transpose_rowtiles<int32_t>(a) : transpose_coltiles<int32_t>(a);
         case SVB_F32: return use_rowtiles ? transpose_rowtiles<float>(a) : transpose_coltiles<float>(a);
@@ -427,6 +471,8 @@ template void build_tilecsc<float, float>(const svb_matrix_s *, int, TileCSC<flo
 template void build_tilecsc<int32_t, double>(const svb_matrix_s *, int, TileCSC<double> &);
 template void build_tilecsc<float, double>(const svb_matrix_s *, int, TileCSC<double> &);
 template void build_tilecsc<double, float>(const svb_matrix_s *, int, TileCSC<float> &);
+template void build_tilecsc<uint8_t, uint8_t>(const svb_matrix_s *, int, TileCSC<uint8_t> &);
+template void csr_from_tilecsc<uint8_t, uint16_t>(const TileCSC<uint8_t> &, const svb_matrix_s *, DevBuf<int64_t> &, DevBuf<uint16_t> &, DevBuf<uint8_t> &);
 template void build_tilecsc_from_transposed<double, float>(const svb_matrix_s *, int, TileCSC<float> &);
 template void build_tilecsc_from_transposed<double, double>(const svb_matrix_s *, int, TileCSC<double> &);
 template void build_tilecsc_from_transposed<float, float>(const svb_matrix_s *, int, TileCSC<float> &);

@@ -22,6 +22,7 @@ svb_operator_s::~svb_operator_s() {
     void *ptrs[] = {mu, rowptr, fidx, fval, gptr, rloc, aval, partial, dA, xdev, ydev, tmp, scal, fwd_ranges, adj_ranges};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    delete fact;
 }
 
 namespace svb {
@@ -280,7 +281,7 @@ static int resident_grid(K kernel, size_t smem, int threads = 256) {
     return std::max(1, per_sm) * ctx().sm_count;
 }
 
-static int64_t *make_ranges(const int64_t *ptr, int64_t nseg, int64_t nnz, int G) {
+int64_t *make_cta_ranges(const int64_t *ptr, int64_t nseg, int64_t nnz, int G) {
     int64_t *out = nullptr;
     SVB_CUDA(cudaMalloc((void **)&out, (size_t)(G + 1) * sizeof(int64_t)));
     cta_ranges_kernel<<<(G + 256) / 256, 256, 0, ctx().stream>>>(ptr, nseg, nnz, G, out);
@@ -296,7 +297,7 @@ static void launch_fwd_block(svb_operator_s *op, size_t smem, double alpha, cons
     if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (op->fwd_grid == 0) {
         op->fwd_grid = (int)std::min<int64_t>(resident_grid(k, smem, BLOCK), std::max<int64_t>(1, op->m / 8));
-        op->fwd_ranges = make_ranges(op->rowptr, op->m, op->nnz, op->fwd_grid);
+        op->fwd_ranges = make_cta_ranges(op->rowptr, op->m, op->nnz, op->fwd_grid);
     }
     k<<<(unsigned)op->fwd_grid, BLOCK, smem, ctx().stream>>>(op->rowptr, (const IdxT *)op->fidx, (const V *)op->fval, op->m, op->n,
                                                              op->nnz, dx, op->mu, alpha, beta, dy, coef, csign, cvec, op->fwd_ranges);
@@ -340,7 +341,7 @@ static void launch_adj_lps(svb_operator_s *op, const double *dx) {
     if (op->adj_grid == 0) {
         const int64_t nseg = op->ntiles * op->n;
         op->adj_grid = (int)std::max<int64_t>(1, std::min<int64_t>(resident_grid(k, smem), nseg / 8 + 1));
-        op->adj_ranges = make_ranges(op->gptr, nseg, op->nnz, op->adj_grid);
+        op->adj_ranges = make_cta_ranges(op->gptr, nseg, op->nnz, op->adj_grid);
     }
     k<<<(unsigned)op->adj_grid, 256, smem, C.stream>>>(op->gptr, op->rloc, (const V *)op->aval, op->m, op->n, (int)op->log2R,
                                                        op->ntiles, op->nnz, dx, op->partial, op->adj_ranges);
@@ -409,6 +410,12 @@ void op_apply(svb_operator_s *op, bool trans, double alpha, const double *dx, do
         SVB_LAUNCH_CHECK();
         return;
     }
+    svb_factored_s *fc = op->fact;
+    if (!trans && fc) {
+        KTimer kt(SVB_K_SPMV_FWD, fact_fwd_bytes(op));
+        fact_fwd(op, alpha, dx, beta, dy, coef, csign, cvec);
+        return;
+    }
     if (!trans) {
         KTimer kt(SVB_K_SPMV_FWD, fwd_bytes(op));
         if (op->vbytes == 8) {
@@ -425,10 +432,12 @@ void op_apply(svb_operator_s *op, bool trans, double alpha, const double *dx, do
     static const bool allow_fused = getenv("SVB_P2P_UNFUSED") == nullptr;
     const bool fused = multi && allow_fused && p2p_next_ctx(op->n, &pc);
     {
-        KTimer kt(SVB_K_SPMV_ADJ, adj_bytes(op), 2);
-        if (op->vbytes == 8) launch_adj<double>(op, dx);
+        KTimer kt(SVB_K_SPMV_ADJ, fc ? fact_adj_bytes(op) : adj_bytes(op), 2);
+        if (fc) fact_adj_stage1(op, dx);
+        else if (op->vbytes == 8) launch_adj<double>(op, dx);
         else launch_adj<float>(op, dx);
-        adj_reduce_kernel<<<(unsigned)((op->n + 31) / 32), 32 * ADJR_TY, 0, st>>>(op->partial, op->ntiles, op->n, op->mu, op->tmp,
+        adj_reduce_kernel<<<(unsigned)((op->n + 31) / 32), 32 * ADJR_TY, 0, st>>>(fc ? fc->partial : op->partial, fc ? fc->ntiles : op->ntiles,
+                                                                          op->n, op->mu, op->tmp,
                                                                           multi ? 0 : 1, alpha, beta, dy, coef, csign, cvec,
                                                                           fused ? 1 : 0, pc);
         SVB_LAUNCH_CHECK();

@@ -360,7 +360,7 @@ int svb_row_sums(svb_matrix_t a, int64_t *s) {
     SVB_API_END
 }
 
-int svb_normalize(svb_matrix_t a, int method, double scale_factor, int dtype, svb_matrix_t *out) {
+static int normalize_impl(svb_matrix_t a, const int64_t *h_libsize, int method, double scale_factor, int dtype, svb_matrix_t *out) {
     SVB_API_BEGIN
     require_init();
     SVB_CHECK(a && out, SVB_EARG, "svb_normalize: null argument");
@@ -374,14 +374,19 @@ int svb_normalize(svb_matrix_t a, int method, double scale_factor, int dtype, sv
         if (a->nnz > 0) {
             SVB_CUDA(cudaMemcpyAsync(b->rowidx, a->rowidx, (size_t)a->nnz * 4, cudaMemcpyDeviceToDevice, st));
             DevBuf<long long> s((size_t)std::max<int64_t>(a->nrow, 1));
-            SVB_CUDA(cudaMemsetAsync(s.p, 0, (size_t)a->nrow * 8, st));
-            row_sums_kernel<<<grid1(a->nnz), 256, 0, st>>>(a->rowidx, (const int32_t *)a->val, a->nnz, (unsigned long long *)s.p);
+            if (h_libsize) {
+                SVB_CUDA(cudaMemcpyAsync(s.p, h_libsize, (size_t)a->nrow * 8, cudaMemcpyHostToDevice, st));
+            } else {
+                SVB_CUDA(cudaMemsetAsync(s.p, 0, (size_t)a->nrow * 8, st));
+                row_sums_kernel<<<grid1(a->nnz), 256, 0, st>>>(a->rowidx, (const int32_t *)a->val, a->nnz, (unsigned long long *)s.p);
+                count_launch();
+            }
             const int do_log = method == SVB_NORM_LOGNORMALIZE;
             if (dtype == SVB_F64)
                 libnorm_kernel<double><<<grid1(a->nnz), 256, 0, st>>>(a->rowidx, (const int32_t *)a->val, a->nnz, s.p, scale_factor, do_log, (double *)b->val);
             else
                 libnorm_kernel<float><<<grid1(a->nnz), 256, 0, st>>>(a->rowidx, (const int32_t *)a->val, a->nnz, s.p, (float)scale_factor, do_log, (float *)b->val);
-            count_launch(2);
+            count_launch();
             SVB_LAUNCH_CHECK();
             SVB_CUDA(cudaStreamSynchronize(st));
         }
@@ -392,6 +397,18 @@ int svb_normalize(svb_matrix_t a, int method, double scale_factor, int dtype, sv
     }
     *out = b;
     SVB_API_END
+}
+
+int svb_normalize(svb_matrix_t a, int method, double scale_factor, int dtype, svb_matrix_t *out) {
+    return normalize_impl(a, nullptr, method, scale_factor, dtype, out);
+}
+
+int svb_normalize_libsize(svb_matrix_t a, const int64_t *libsize, int method, double scale_factor, int dtype, svb_matrix_t *out) {
+    if (!libsize) {
+        svb::set_last_error("svb_normalize_libsize: null library sizes");
+        return SVB_EARG;
+    }
+    return normalize_impl(a, libsize, method, scale_factor, dtype, out);
 }
 
 int svb_mean_var(svb_matrix_t a, double *mu, double *var) {

@@ -280,6 +280,11 @@ void launch_spmm_adj(svb_operator_s *op, const double *dW, int64_t ldw, int kc, 
 void op_apply_mm(svb_operator_s *op, bool trans, double alpha, const double *dX, int64_t ldx, double beta, double *dY, int64_t ldy,
                  int64_t k) {
     Context &C = ctx();
+    if (op->fact) {
+        // count-level operator: its matrix forms are column-by-column vector products (same 2 B/nnz stream per column)
+        for (int64_t c = 0; c < k; ++c) op_apply(op, trans, alpha, dX + c * ldx, beta, dY + c * ldy);
+        return;
+    }
     const double favg = op->m > 0 ? (double)op->nnz / (double)op->m : 0.0;
     const double aavg = (op->n > 0 && op->ntiles > 0) ? (double)op->nnz / ((double)op->n * (double)op->ntiles) : 0.0;
     DevBuf<double> partial;

@@ -139,8 +139,36 @@ struct svb_matrix_s {
     ~svb_matrix_s();
 };
 
+// count-level layouts of the scaled HVG operator (factored.cu): one 16-bit code per nonzero, the value is rebuilt from a
+// per-cell level table and a per-gene scale
+struct svb_operator_s;
+struct svb_factored_s {
+    int L = 0, log2L = 0;            // count levels 1..L are coded; everything else is an exception chunk (exact Float64 value)
+    int log2R = 0;                   // cells per adjoint tile (R*L table entries in shared memory)
+    int64_t R = 0, ntiles = 0;
+    double *tlev = nullptr;          // [m*L] t_i[l] = log1p(sf*(l+1)/s_i), cell-major (forward)
+    double *tlevA = nullptr;         // [ntiles*R*L] the same, level-major inside every adjoint tile
+    double *inv = nullptr;           // [n] 1/sd
+    int64_t *f_rowptr = nullptr;     // [m+1] forward: first chunk of a cell's row (chunk = 8 codes)
+    void *f_code = nullptr;          // [f_chunks*8] u16 gene index, pad = n
+    uint8_t *f_meta = nullptr;       // [f_chunks] (level << 1) | last chunk of the row
+    int64_t f_chunks = 0;
+    int64_t *a_gptr = nullptr;       // [ntiles*n+1] adjoint: first chunk of a (tile, gene) segment
+    void *a_code = nullptr;          // [a_chunks*8] u16 (level-1)*R + i_local, pad = R*L
+    uint8_t *a_meta = nullptr;       // [a_chunks] last chunk of the segment
+    int32_t *a_slices = nullptr;     // [ntiles*(K+1)] gene boundaries of the K per-warp slices of a tile
+    unsigned int *counters = nullptr; // [2] tile counter / finished-CTA counter of the adjoint kernel (self-resetting)
+    int64_t a_chunks = 0;
+    double *partial = nullptr;       // [ntiles*(n+1)]
+    int64_t nnz_main = 0, nnz_exc = 0;
+    int fwd_grid = 0, adj_grid = 0;
+    int64_t *fwd_ranges = nullptr, *fwd_rows = nullptr;  // [warps+1] first chunk / first row of every warp of the forward grid
+    ~svb_factored_s();
+};
+
 struct svb_operator_s {
     int64_t m = 0, n = 0, nnz = 0;  // S is m x n (cells x genes)
+    svb_factored_s *fact = nullptr; // count-level form (svb_operator_create_counts); the explicit layouts below are unused then
     bool dense = false;
     int vbytes = 8;                 // value storage width (8 = f64, 4 = f32)
     int ibytes = 2;                 // forward index width (2 = u16, 4 = i32)
@@ -186,6 +214,13 @@ size_t vtype_size(int vtype);
 // ---- operator / spmv
 void op_apply(svb_operator_s *op, bool trans, double alpha, const double *dx, double beta, double *dy,
               const double *axpy_coef_dev = nullptr, double axpy_sign = 0.0, const double *axpy_vec = nullptr);
+int64_t *make_cta_ranges(const int64_t *ptr, int64_t nseg, int64_t nnz, int G);  // [G+1] equal-work CTA boundaries
+// ---- factored.cu : products of the count-level form
+void fact_fwd(svb_operator_s *op, double alpha, const double *dx, double beta, double *dy, const double *coef, double csign,
+              const double *cvec);
+void fact_adj_stage1(svb_operator_s *op, const double *dx);
+double fact_fwd_bytes(const svb_operator_s *op);
+double fact_adj_bytes(const svb_operator_s *op);
 // ---- spmm.cu : k right-hand sides (scaling.jl:259-272), device pointers, column-major with leading dims
 void op_apply_mm(svb_operator_s *op, bool trans, double alpha, const double *dX, int64_t ldx, double beta, double *dY, int64_t ldy,
                  int64_t k);
