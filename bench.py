@@ -6,7 +6,10 @@
 
 A "step" is one full IRLBA solve (nu PCs, tol 1e-5, fixed start vector) of the implicit centred operator of
 the configuration, operator resident in HBM (`value`), or through the C ABI with HOST buffers — upload of the
-scaled CSC matrix, layout build, solve, download of U, s, V — inside the timed region (`e2e`).
+HVG count matrix + library sizes, operator build, solve, download of U, s, V — inside the timed region (`e2e`).
+Default operator: the count-level form (svb_operator_create_counts: the scaled matrix is never materialised, one
+16-bit code per nonzero); `--operator explicit` times the explicit scaled-value layouts instead, and the default
+run reports both (`explicit_operator`).
 Strong scaling: the matrix is fixed, its cells are sharded over the N ranks (one process per GPU).
 Prints ONE JSON line on rank 0.
 """
@@ -116,13 +119,16 @@ def build_workload(sv, cfg, rank, world, rows_total=None):
     metric = sharding.sharded_vst_metric(counts)
     t["hvg_metric_s"] = time.perf_counter() - t0
     hvf = np.argsort(-metric, kind="stable")[:cfg["n"]]
+    libsize = np.empty(hi - lo, dtype=np.int64)
+    sv._lib.check(sv.lib().svb_row_sums(counts._h, sv._lib.ptr(libsize)))   # a cell lives on one rank: shard-local
+    chv = counts.columns(hvf)                                               # X[:, hvf]: the raw counts of the HVGs
     counts.free()
     t0 = time.perf_counter()
     B, mu = sharding.sharded_scale_features(Y, scale_max=SCALE_MAX, features=hvf)
     sv.lib().svb_synchronize()
     t["scale_s"] = time.perf_counter() - t0
     Y.free()
-    info = dict(rows=(lo, hi), bounds=bounds, Z_local=int(Z), z_local=int(B.nnz), setup=t)
+    info = dict(rows=(lo, hi), bounds=bounds, Z_local=int(Z), z_local=int(B.nnz), setup=t, counts_hvg=chv, libsize=libsize)
     return B, mu, info
 
 
@@ -131,6 +137,64 @@ def make_operator(sv, B, mu, storage="f64"):
     vs = sv._lib.SVB_F32 if storage == "f32" else 0
     sv._lib.check(sv.lib().svb_operator_create_ex(B._h, sv._lib.ptr(np.ascontiguousarray(mu)), 0, vs, ctypes.byref(h)))
     return h
+
+
+def make_counts_operator(sv, chv, libsize):
+    """svb_operator_create_counts with internal (parallel, all-rank) moments: the fused scale_features + CenteredMatrix."""
+    h = ctypes.c_void_p()
+    mu = np.empty(chv.shape[1])
+    sv._lib.check(sv.lib().svb_operator_create_counts(chv._h, sv._lib.ptr(libsize), 1e4, None, None, SCALE_MAX, 0,
+                                                      sv._lib.ptr(mu), ctypes.byref(h)))
+    return h, mu
+
+
+def counts_info(sv, op):
+    lv = ctypes.c_int()
+    v = [ctypes.c_int64() for _ in range(5)]
+    sv._lib.check(sv.lib().svb_operator_counts_info(op, lv, *v))
+    return dict(levels=lv.value, tile_cells=v[0].value, nnz_coded=v[1].value, nnz_exception=v[2].value,
+                fwd_chunks=v[3].value, adj_chunks=v[4].value)
+
+
+def class_profile(sv, lib, op, nu, init):
+    """per-kernel-class CUDA-event timers over one extra (untimed) solve"""
+    L = sv._lib
+    lib.svb_profile_enable(1)
+    lib.svb_profile_reset()
+    r, _, _, _ = solve_device(sv, op, nu, init)
+    lib.svb_result_free(r)
+    lib.svb_profile_enable(0)
+    pms = (ctypes.c_double * 6)()
+    pl = (ctypes.c_int64 * 6)()
+    pb = (ctypes.c_double * 6)()
+    lib.svb_profile_get(pms, pl, pb)
+    classes = {}
+    for i, name in enumerate(L.K_CLASSES):
+        if pl[i]:
+            classes[name] = {"ms": round(pms[i], 4), "launches": int(pl[i]), "algorithmic_GB": round(pb[i] / 1e9, 4),
+                             "GBps": round(pb[i] / 1e9 / (pms[i] / 1e3), 1) if pms[i] > 0 else None}
+    return classes
+
+
+def roofline_of(classes, peak, peak_src, traffic_key=None, config=None, world=1):
+    dom = max(("spmv_fwd", "spmv_adj"), key=lambda k: classes.get(k, {}).get("ms", 0.0))
+    dc = classes[dom]
+    nlaunch_dom = dc["launches"] / (2 if dom == "spmv_adj" else 1)  # the adjoint is two launches per product
+    traffic = None  # dram bytes per launch from the committed ncu --set full capture of this exact configuration
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("config") == config and tj.get("n_gpus") == world:
+            traffic = tj.get((traffic_key + "_" if traffic_key else "") + dom)
+    except Exception:
+        pass
+    return {"bound": "hbm", "kernel": dom, "achieved": dc["GBps"], "peak": peak, "unit": "GB/s",
+            "frac": round(dc["GBps"] / peak, 4), "traffic": traffic, "peak_source": peak_src,
+            "bytes_per_launch": round(dc["algorithmic_GB"] * 1e9 / nlaunch_dom),
+            "avg_launch_ms": round(dc["ms"] / nlaunch_dom, 5),
+            "share_of_step": round(dc["ms"] / sum(c["ms"] for c in classes.values()), 4),
+            "other": {k: {"GBps": v["GBps"], "frac": round(v["GBps"] / peak, 4) if v["GBps"] else None, "ms": v["ms"]}
+                      for k, v in classes.items() if k != dom}}
 
 
 def solve_device(sv, op, nu, init):
@@ -167,7 +231,12 @@ def run_b200(args):
         n, nu = cfg["n"], cfg["nu"]
         m_local = B.shape[0]
         init = np.random.default_rng(SEED).standard_normal(n)
-        op = make_operator(sv, B, mu, args.storage)
+        chv, libsize = winfo.pop("counts_hvg"), winfo.pop("libsize")
+        use_counts = args.operator == "counts"
+        op_e = make_operator(sv, B, mu, args.storage)                    # explicit scaled-value layouts
+        op_c, mu_c_op = make_counts_operator(sv, chv, libsize) if use_counts else (None, None)
+        op = op_c if use_counts else op_e
+        cinfo = counts_info(sv, op_c) if use_counts else None
 
         def barrier():
             torch.cuda.synchronize()
@@ -175,95 +244,85 @@ def run_b200(args):
                 dist.barrier()
             torch.cuda.synchronize()
 
-        # ---- device-resident timing --------------------------------------------------------------
-        last = None
-        for _ in range(args.warmup):
-            r, it, mp, info = solve_device(sv, op, nu, init)
-            lib.svb_result_free(r)
-        barrier()
-        sampler = ClockSampler(local) if rank == 0 else None
-        lib.svb_launch_count_reset()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(args.steps):
-            r, it, mp, info = solve_device(sv, op, nu, init)
-            if last is not None:
-                lib.svb_result_free(last)
-            last = r
-        e1.record(stream)
-        barrier()
-        launches = int(lib.svb_launch_count())
-        clocks = sampler.stop() if sampler else None
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        ms_per_step = float(ms.item()) / args.steps
-        s_host = np.zeros(nu)
-        L.check(lib.svb_result_download(last, L.ptr(s_host), None, None, 0))
-        lib.svb_result_free(last)
+        def timed_solves(opx, warmup, steps):
+            last = None
+            for _ in range(warmup):
+                r, it, mp, info = solve_device(sv, opx, nu, init)
+                lib.svb_result_free(r)
+            barrier()
+            lib.svb_launch_count_reset()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps):
+                r, it, mp, info = solve_device(sv, opx, nu, init)
+                if last is not None:
+                    lib.svb_result_free(last)
+                last = r
+            e1.record(stream)
+            barrier()
+            launches = int(lib.svb_launch_count())
+            ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            s_host = np.zeros(nu)
+            L.check(lib.svb_result_download(last, L.ptr(s_host), None, None, 0))
+            lib.svb_result_free(last)
+            return float(ms.item()) / steps, launches, s_host, (it, mp, info)
 
-        # ---- per-kernel-class device timers (one extra, untimed solve) -------------------------------
-        lib.svb_profile_enable(1)
-        lib.svb_profile_reset()
-        r, _, _, _ = solve_device(sv, op, nu, init)
-        lib.svb_result_free(r)
-        lib.svb_profile_enable(0)
-        pms = (ctypes.c_double * 6)()
-        pl = (ctypes.c_int64 * 6)()
-        pb = (ctypes.c_double * 6)()
-        lib.svb_profile_get(pms, pl, pb)
-        classes = {}
-        for i, name in enumerate(L.K_CLASSES):
-            if pl[i]:
-                classes[name] = {"ms": round(pms[i], 4), "launches": int(pl[i]), "algorithmic_GB": round(pb[i] / 1e9, 4),
-                                 "GBps": round(pb[i] / 1e9 / (pms[i] / 1e3), 1) if pms[i] > 0 else None}
+        # ---- device-resident timing --------------------------------------------------------------
+        sampler = ClockSampler(local) if rank == 0 else None
+        ms_per_step, launches, s_host, (it, mp, info) = timed_solves(op, args.warmup, args.steps)
+        clocks = sampler.stop() if sampler else None
         peak, peak_src = measured_peak_gbs()
-        # dominant kernel = the SpMV class with the larger share of the step
-        dom = max(("spmv_fwd", "spmv_adj"), key=lambda k: classes.get(k, {}).get("ms", 0.0))
-        dc = classes[dom]
-        nlaunch_dom = dc["launches"] / (2 if dom == "spmv_adj" else 1)  # the adjoint is two launches per product
-        achieved = dc["GBps"]
-        traffic = None  # dram bytes per launch from the committed ncu --set full capture of this exact configuration
-        try:
-            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                tj = json.load(f)
-            if tj.get("config") == args.config and tj.get("n_gpus") == world:
-                traffic = tj.get(dom)
-        except Exception:
-            pass
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                    "bytes_per_launch": round(dc["algorithmic_GB"] * 1e9 / nlaunch_dom),
-                    "avg_launch_ms": round(dc["ms"] / nlaunch_dom, 5),
-                    "share_of_step": round(dc["ms"] / sum(c["ms"] for c in classes.values()), 4),
-                    "other": {k: {"GBps": v["GBps"], "frac": round(v["GBps"] / peak, 4) if v["GBps"] else None, "ms": v["ms"]}
-                              for k, v in classes.items() if k != dom}}
+        classes = class_profile(sv, lib, op, nu, init)
+        roofline = roofline_of(classes, peak, peak_src, "counts" if use_counts else None, args.config, world)
+        if use_counts:
+            roofline["note"] = ("count-level operator: 2.125 B per nonzero in HBM; ncu (profiles/r02_*) shows the kernel bound by "
+                                "shared-memory gather wavefronts (l1tex 87 %, ~3 bank-conflict wavefronts per 16 gathers), not by HBM")
+        explicit = None
+        if use_counts:
+            # the explicit scaled-value operator of the same matrix, timed beside it (HBM-bound: 10 B per nonzero)
+            ms_e, _, s_e, (it_e, mp_e, info_e) = timed_solves(op_e, 1, max(1, min(2, args.steps)))
+            cls_e = class_profile(sv, lib, op_e, nu, init)
+            explicit = {"value": round(ms_e / 1e3, 6), "unit": "s", "solve": {"restarts": it_e, "matvecs": mp_e, "info": info_e},
+                        "roofline": roofline_of(cls_e, peak, peak_src, None, args.config, world), "kernel_classes": cls_e,
+                        "sigma_max_rel_diff_vs_counts": float(np.max(np.abs(s_e / s_host - 1.0)))}
+            assert explicit["sigma_max_rel_diff_vs_counts"] < 1e-6, "count-level and explicit operators disagree"
 
         # ---- end to end through the C ABI with HOST buffers --------------------------------------------
         e2e = None
         if not args.no_e2e:
-            z = B.nnz
+            z = chv.nnz if use_counts else B.nnz
+            src = chv if use_counts else B
+            vdt, vcode = (torch.int32, L.SVB_I32) if use_counts else (torch.float64, L.SVB_F64)
             t_colptr = torch.empty(n + 1, dtype=torch.int64, pin_memory=True)
             t_rowval = torch.empty(max(z, 1), dtype=torch.int64, pin_memory=True)
-            t_nzval = torch.empty(max(z, 1), dtype=torch.float64, pin_memory=True)
+            t_nzval = torch.empty(max(z, 1), dtype=vdt, pin_memory=True)
             colptr, rowval, nzval = t_colptr.numpy(), t_rowval.numpy(), t_nzval.numpy()
-            # the caller's SparseMatrixCSC{Float64,Int64}: 1-based Int64 indices, as Julia holds it
-            L.check(lib.svb_matrix_download(B._h, L.ptr(colptr), L.ptr(rowval), L.ptr(nzval), L.SVB_F64, 1))
+            # the caller's SparseMatrixCSC{Int32 | Float64, Int64}: 1-based Int64 indices, as Julia holds it
+            L.check(lib.svb_matrix_download(src._h, L.ptr(colptr), L.ptr(rowval), L.ptr(nzval), vcode, 1))
+            t_lib = torch.empty(m_local, dtype=torch.int64, pin_memory=True)
+            t_lib.numpy()[:] = libsize
+            lib_h = t_lib.numpy()
             t_U = torch.empty((nu, m_local), dtype=torch.float64, pin_memory=True)
             t_V = torch.empty((nu, n), dtype=torch.float64, pin_memory=True)
             U, V, s = t_U.numpy().T, t_V.numpy().T, np.zeros(nu)
             mu_c = np.ascontiguousarray(mu)
+            mu_out = np.empty(n)
 
-            phases = {"upload_s": 0.0, "layout_build_s": 0.0, "solve_and_download_s": 0.0}
+            phases = {"upload_s": 0.0, "operator_build_s": 0.0, "solve_and_download_s": 0.0}
 
             def e2e_step():
                 t0 = time.perf_counter()
                 h = ctypes.c_void_p()
-                L.check(lib.svb_csc_upload(m_local, n, L.ptr(colptr), L.ptr(rowval), L.SVB_I64, L.ptr(nzval), L.SVB_F64, 1,
+                L.check(lib.svb_csc_upload(m_local, n, L.ptr(colptr), L.ptr(rowval), L.SVB_I64, L.ptr(nzval), vcode, 1,
                                            ctypes.byref(h)))
                 t1 = time.perf_counter()
                 o = ctypes.c_void_p()
-                L.check(lib.svb_operator_create_ex(h, L.ptr(mu_c), 0, L.SVB_F32 if args.storage == "f32" else 0, ctypes.byref(o)))
+                if use_counts:
+                    L.check(lib.svb_operator_create_counts(h, L.ptr(lib_h), 1e4, None, None, SCALE_MAX, 0, L.ptr(mu_out), ctypes.byref(o)))
+                else:
+                    L.check(lib.svb_operator_create_ex(h, L.ptr(mu_c), 0, L.SVB_F32 if args.storage == "f32" else 0, ctypes.byref(o)))
                 lib.svb_matrix_free(h)
                 t2 = time.perf_counter()
                 it_, mp_ = ctypes.c_int64(), ctypes.c_int64()
@@ -272,12 +331,15 @@ def run_b200(args):
                 lib.svb_operator_free(o)
                 t3 = time.perf_counter()
                 phases["upload_s"] += t1 - t0
-                phases["layout_build_s"] += t2 - t1
+                phases["operator_build_s"] += t2 - t1
                 phases["solve_and_download_s"] += t3 - t2
 
             B.free()  # the e2e call owns its own device copy
-            lib.svb_operator_free(op)
-            op = None
+            chv.free()
+            lib.svb_operator_free(op_e)
+            if op_c is not None:
+                lib.svb_operator_free(op_c)
+            op = op_e = op_c = None
             e2e_step()  # warm-up
             for k_ in phases:
                 phases[k_] = 0.0
@@ -289,11 +351,16 @@ def run_b200(args):
             dt = torch.tensor([(time.perf_counter() - t0) / args.steps], device="cuda")
             if world > 1:
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-            h2d = 8 * (n + 1) + 16 * z + 8 * n + 8 * n  # colptr + rowval + nzval + mu + init
+            if use_counts:
+                h2d = 8 * (n + 1) + 12 * z + 8 * m_local + 8 * n  # colptr + rowval(i64) + counts(i32) + library sizes + init
+                what = ("pinned-host SparseMatrixCSC{Int32,Int64} of the HVG counts + library sizes -> upload, moments, "
+                        "count-level operator build, solve, U/s/V download")
+            else:
+                h2d = 8 * (n + 1) + 16 * z + 8 * n + 8 * n  # colptr + rowval + nzval + mu + init
+                what = "pinned-host CSC{Float64,Int64} upload, device layout build, solve, U/s/V download"
             d2h = 8 * (m_local * nu + n * nu + nu)
             e2e = {"value": round(float(dt.item()), 6), "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                   "includes": "pinned-host CSC{Float64,Int64} upload, device layout build, solve, U/s/V download",
-                   "phases_rank0_s": {k_: round(v_ / args.steps, 5) for k_, v_ in phases.items()}}
+                   "includes": what, "phases_rank0_s": {k_: round(v_ / args.steps, 5) for k_, v_ in phases.items()}}
             assert np.allclose(s, s_host, rtol=1e-6), "e2e and device-resident solves disagree"
 
         # ---- totals over ranks --------------------------------------------------------------------------
@@ -313,11 +380,14 @@ def run_b200(args):
                                    f"Z={Z_total} nnz -> lognormalize -> {cfg['n']} HVGs (vst) -> scale_features(scale_max=10) -> "
                                    f"irlba nu={cfg['nu']} work={cfg['nu'] + 7} tol={TOL}",
                        "cells": cfg["m"], "genes": cfg["g"], "hvgs": cfg["n"], "nu": cfg["nu"], "hvg_nnz": z_total,
+                       "operator": ("count-level (svb_operator_create_counts: scaled matrix never materialised, 16-bit code per nonzero)"
+                                    if use_counts else "explicit scaled values (svb_operator_create)"),
                        "parallelism": f"cells sharded over {world} GPU(s), NCCL allreduce of S'w / reorth coefficients",
                        "l2_policy": "inputs larger than L2 (operator layouts 2 x %.2f GB, basis %.2f GB; L2 126 MB)" % (
-                           z_total * 10 / 1e9 / world, cfg["m"] * (cfg["nu"] + 7) * 8 / 1e9 / world)},
+                           z_total * (2.2 if use_counts else 10) / 1e9 / world, cfg["m"] * (cfg["nu"] + 7) * 8 / 1e9 / world)},
             "solve": {"restarts": it, "matvecs": mp, "info": info, "sigma_1": float(s_host[0]), "sigma_nu": float(s_host[-1])},
             "roofline": roofline, "kernel_classes": classes, "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
+            "counts_operator": cinfo, "explicit_operator": explicit,
             "setup_s": {k: round(v, 4) for k, v in winfo["setup"].items()},
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -336,6 +406,7 @@ def cpu_sample_problem(sv, cfg, cells):
     cells = min(cfg["m"], (cells // 4) * 4)
     sub = dict(cfg)
     B, mu, info = build_workload(sv, sub, 0, 1, rows_total=cells)
+    info["counts_hvg"].free()
     Bh = B.to_host()
     B.free()
     return Bh, mu, cells
@@ -402,6 +473,8 @@ def main():
     ap.add_argument("--config", default="C3", choices=sorted(CONFIGS))
     ap.add_argument("--storage", default="f64", choices=["f64", "f32"],
                     help="value storage of the operator layouts (f32 = optional Float32-storage / Float64-accumulate mode)")
+    ap.add_argument("--operator", default="counts", choices=["counts", "explicit"],
+                    help="counts = count-level operator (default); explicit = explicit scaled-value layouts only")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

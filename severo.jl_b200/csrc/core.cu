@@ -4,6 +4,7 @@
 
 #include <cstring>
 #include <mutex>
+#include <unordered_map>
 
 namespace svb {
 
@@ -22,18 +23,90 @@ void require_init() {
 
 void count_launch(int n) { ctx().launches += n; }
 
+// Device allocator. Every allocation of the library is made, used and freed in the order of ONE stream, so a freed
+// block can be handed to the next request without any driver call or synchronisation: blocks are cached in size
+// classes (8 per power of two, <= 12.5 % slack) on top of cudaMalloc and never returned to the driver before
+// svb_shutdown (or an out-of-memory retry). Round 1 used the stream-ordered pool (cudaMallocAsync, release threshold
+// unlimited): no cudaFree stall any more, but at C3 scale the pool re-maps physical memory whenever a multi-GB
+// request does not fit a free virtual range, and identical operator builds took anywhere from 0.12 s to 1.5 s
+// (profiles/r02_counts_operator.md). SVB_ALLOC=pool selects the old behaviour.
+namespace {
+struct BlockCache {
+    std::mutex mu;
+    std::unordered_map<size_t, std::vector<void *>> free_blocks;  // size class -> cached blocks
+    std::unordered_map<void *, size_t> live;                      // block -> size class
+    size_t cached_bytes = 0;
+    bool use_pool = getenv("SVB_ALLOC") != nullptr && std::string(getenv("SVB_ALLOC")) == "pool";
+};
+BlockCache &cache() {
+    static BlockCache c;
+    return c;
+}
+size_t size_class(size_t bytes) {
+    if (bytes <= 512) return 512;
+    int lg = 63 - __builtin_clzll((unsigned long long)bytes);
+    const size_t step = (size_t)1 << std::max(lg - 3, 9);
+    return (bytes + step - 1) / step * step;
+}
+void release_cached_blocks() {
+    BlockCache &B = cache();
+    for (auto &kv : B.free_blocks)
+        for (void *p : kv.second) cudaFree(p);
+    B.free_blocks.clear();
+    B.cached_bytes = 0;
+}
+}  // namespace
+
 cudaError_t dev_malloc(void **p, size_t bytes) {
     Context &C = ctx();
+    BlockCache &B = cache();
     if (bytes == 0) bytes = 8;
-    if (C.initialised && C.stream && C.pool_ok) return cudaMallocAsync(p, bytes, C.stream);
-    return cudaMalloc(p, bytes);
+    if (B.use_pool) {
+        if (C.initialised && C.stream && C.pool_ok) return cudaMallocAsync(p, bytes, C.stream);
+        return cudaMalloc(p, bytes);
+    }
+    const size_t cls = size_class(bytes);
+    std::lock_guard<std::mutex> lock(B.mu);
+    auto it = B.free_blocks.find(cls);
+    if (it != B.free_blocks.end() && !it->second.empty()) {
+        *p = it->second.back();
+        it->second.pop_back();
+        B.cached_bytes -= cls;
+        B.live[*p] = cls;
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(p, cls);
+    if (e == cudaErrorMemoryAllocation) {  // give the cached blocks back and retry once
+        cudaGetLastError();
+        if (C.stream) cudaStreamSynchronize(C.stream);
+        release_cached_blocks();
+        e = cudaMalloc(p, cls);
+    }
+    if (e == cudaSuccess) B.live[*p] = cls;
+    return e;
 }
 
 cudaError_t dev_free(void *p) {
     Context &C = ctx();
+    BlockCache &B = cache();
     if (!p) return cudaSuccess;
-    if (C.initialised && C.stream && C.pool_ok) return cudaFreeAsync(p, C.stream);
-    return cudaFree(p);  // valid for pool memory too (synchronises)
+    if (B.use_pool) {
+        if (C.initialised && C.stream && C.pool_ok) return cudaFreeAsync(p, C.stream);
+        return cudaFree(p);  // valid for pool memory too (synchronises)
+    }
+    std::lock_guard<std::mutex> lock(B.mu);
+    auto it = B.live.find(p);
+    if (it == B.live.end()) return cudaFree(p);
+    const size_t cls = it->second;
+    B.live.erase(it);
+    B.free_blocks[cls].push_back(p);  // reusable at once: the next user is ordered after this one on the library stream
+    B.cached_bytes += cls;
+    return cudaSuccess;
+}
+
+void dev_release_cache() {
+    std::lock_guard<std::mutex> lock(cache().mu);
+    release_cached_blocks();
 }
 
 KTimer::KTimer(int c, double algorithmic_bytes, int nlaunch) : cls(c), bytes(algorithmic_bytes) {
@@ -187,6 +260,7 @@ int svb_shutdown(void) {
     Context &C = ctx();
     if (C.initialised) {
         cudaDeviceSynchronize();
+        dev_release_cache();
         if (C.own_stream && C.stream) cudaStreamDestroy(C.stream);
         C.stream = nullptr;
         C.own_stream = false;
@@ -199,7 +273,7 @@ int svb_set_stream(void *s) {
     SVB_API_BEGIN
     require_init();
     Context &C = ctx();
-    SVB_CUDA(cudaStreamSynchronize(C.stream));
+    SVB_CUDA(cudaStreamSynchronize(C.stream));  // cached blocks freed under the old stream are idle from here on
     if (C.own_stream && C.stream) cudaStreamDestroy(C.stream);
     if (s) {
         C.stream = (cudaStream_t)s;

@@ -22,6 +22,7 @@
 #include "layout.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 
 using namespace svb;
@@ -169,64 +170,69 @@ __global__ void fact_hist_kernel(const int32_t *__restrict__ val, int64_t nnz, u
     }
 }
 
-// level of every stored entry, CSC order: 1..L = count level, 0 = exception (explicit residual operator).
-// grid (ncol, FY)
+// level of every stored entry, CSC order: 1..L = count level, 0 = exception (kept with its exact value).
+// grid (ncol, FSL/8), 8 warps per block: a gene's column is cut into FSL contiguous slices, one warp each, and the
+// number of exceptions of every slice is recorded so that the exception matrix can be filled in order, in parallel.
+constexpr int FSL = 64;
 __global__ void __launch_bounds__(256) fact_classify_kernel(const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
                                                             const int32_t *__restrict__ val, int log2L,
                                                             const double *__restrict__ tlev, const double *__restrict__ sd,
                                                             const double *__restrict__ cap, uint8_t *__restrict__ lvl,
-                                                            unsigned long long *__restrict__ excnt) {
+                                                            int64_t *__restrict__ excnt) {
     const int64_t j = blockIdx.x;
-    const int64_t beg = colptr[j], end = colptr[j + 1];
+    const int lane = threadIdx.x & 31;
+    const int sl = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int64_t beg = colptr[j], len = colptr[j + 1] - beg;
+    const int64_t k0 = beg + (len * sl) / FSL, k1 = beg + (len * (sl + 1)) / FSL;
     const double s = sd[j], cp = cap[j];
     const int L = 1 << log2L;
-    unsigned int nexc = 0;
-    for (int64_t k = beg + (int64_t)blockIdx.y * blockDim.x + threadIdx.x; k < end; k += (int64_t)gridDim.y * blockDim.x) {
+    int nexc = 0;
+    for (int64_t k = k0 + lane; k < k1; k += 32) {
         const int c = val[k];
         int lv = 0;
         if (c >= 1 && c <= L) {
             const double t = __ldg(tlev + (((int64_t)rowidx[k]) << log2L) + (c - 1));
             const double v = __ddiv_rn(t, s);  // scaling.jl:211
-            lv = (v > cp) ? 0 : c;             // clipped entries keep their exact value in the residual
+            lv = (v > cp) ? 0 : c;             // clipped entries keep their exact (clipped) value as exceptions
         }
         lvl[k] = (uint8_t)lv;
         nexc += (lv == 0);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nexc += __shfl_xor_sync(0xffffffffu, nexc, o);
-    if ((threadIdx.x & 31) == 0 && nexc) atomicAdd(excnt + j, (unsigned long long)nexc);
+    if (lane == 0) excnt[j * FSL + sl] = nexc;
 }
 
-// the residual CSC: one warp per gene, ordered compaction of the level-0 entries with their exact scaled value
+// the exception matrix (CSC, cells ascending inside a gene): every warp compacts the level-0 entries of its slice,
+// in order, at the offset the scan of the slice counts gives it; values are exact and pre-multiplied by sd
 __global__ void __launch_bounds__(256) fact_resid_fill_kernel(const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
                                                               const int32_t *__restrict__ val, const uint8_t *__restrict__ lvl,
-                                                              int64_t ncol, const long long *__restrict__ libsize, double sf,
+                                                              const long long *__restrict__ libsize, double sf,
                                                               const double *__restrict__ sd, const double *__restrict__ cap,
-                                                              const int64_t *__restrict__ ecolptr, int32_t *__restrict__ erow,
+                                                              const int64_t *__restrict__ exoff, int32_t *__restrict__ erow,
                                                               double *__restrict__ eval) {
+    const int64_t j = blockIdx.x;
     const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t j = warp; j < ncol; j += nwarps) {
-        int64_t pos = ecolptr[j];
-        if (ecolptr[j + 1] == pos) continue;
-        const int64_t beg = colptr[j], end = colptr[j + 1];
-        const double s = sd[j], cp = cap[j];
-        for (int64_t k0 = beg; k0 < end; k0 += 32) {
-            const int64_t k = k0 + lane;
-            const bool ex = (k < end) && (lvl[k] == 0);
-            const unsigned bal = __ballot_sync(0xffffffffu, ex);
-            if (ex) {
-                const int32_t r = rowidx[k];
-                const double t = __dmul_rn(sf, (double)val[k]);
-                const double v = log1p(__ddiv_rn(t, (double)libsize[r]));
-                const double y = __ddiv_rn(v, s);
-                const int64_t dst = pos + __popc(bal & ((1u << lane) - 1u));
-                erow[dst] = r;
-                eval[dst] = ((y > cp) ? cp : y) * s;  // stored pre-multiplied by sd: the kernels apply 1/sd to everything
-            }
-            pos += __popc(bal);
+    const int sl = blockIdx.y * 8 + (threadIdx.x >> 5);
+    int64_t pos = exoff[j * FSL + sl];
+    if (exoff[j * FSL + sl + 1] == pos) return;
+    const int64_t beg = colptr[j], len = colptr[j + 1] - beg;
+    const int64_t k0 = beg + (len * sl) / FSL, k1 = beg + (len * (sl + 1)) / FSL;
+    const double s = sd[j], cp = cap[j];
+    for (int64_t kb = k0; kb < k1; kb += 32) {
+        const int64_t k = kb + lane;
+        const bool ex = (k < k1) && (lvl[k] == 0);
+        const unsigned bal = __ballot_sync(0xffffffffu, ex);
+        if (ex) {
+            const int32_t r = rowidx[k];
+            const double t = __dmul_rn(sf, (double)val[k]);
+            const double v = log1p(__ddiv_rn(t, (double)libsize[r]));
+            const double y = __ddiv_rn(v, s);
+            const int64_t dst = pos + __popc(bal & ((1u << lane) - 1u));
+            erow[dst] = r;
+            eval[dst] = ((y > cp) ? cp : y) * s;  // stored pre-multiplied by sd: the kernels apply 1/sd to everything
         }
+        pos += __popc(bal);
     }
 }
 
@@ -326,8 +332,8 @@ __global__ void fact_slices_kernel(const int64_t *__restrict__ gptr, int64_t nti
 // forward layout, pass 1 (CSR by cell with the level of every entry): per row the cumulative group ends in
 // chunks (u16) and the row's chunk count (at least one chunk per row, see above). One warp per row.
 __global__ void __launch_bounds__(256) fact_row_hist_kernel(const int64_t *__restrict__ rowptr, const uint8_t *__restrict__ rlvl,
-                                                            const int64_t *__restrict__ erowptr, int64_t m, int L,
-                                                            uint16_t *__restrict__ gend, int64_t *__restrict__ rowchunks) {
+                                                            int64_t m, int L, uint16_t *__restrict__ gend,
+                                                            int64_t *__restrict__ rowchunks) {
     __shared__ int hist[8][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t warp = (int64_t)blockIdx.x * 8 + w;
@@ -336,10 +342,14 @@ __global__ void __launch_bounds__(256) fact_row_hist_kernel(const int64_t *__res
         hist[w][lane] = 0;
         __syncwarp();
         const int64_t b = rowptr[r], e = rowptr[r + 1];
+        int ne = 0;  // exceptions of the row (level byte 0): one chunk each, after the level groups
         for (int64_t k = b + lane; k < e; k += 32) {
             const int lv = rlvl[k];
             if (lv) atomicAdd(&hist[w][lv - 1], 1);
+            else ++ne;
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ne += __shfl_xor_sync(0xffffffffu, ne, o);
         __syncwarp();
         int ch = (lane < L) ? (hist[w][lane] + FCH - 1) / FCH : 0;
 #pragma unroll
@@ -347,7 +357,6 @@ __global__ void __launch_bounds__(256) fact_row_hist_kernel(const int64_t *__res
             const int y = __shfl_up_sync(0xffffffffu, ch, o);
             if (lane >= o) ch += y;
         }
-        const int ne = erowptr ? (int)(erowptr[r + 1] - erowptr[r]) : 0;  // one chunk per exception, after the level groups
         const int total = __shfl_sync(0xffffffffu, ch, 31);
         if (total + ne == 0) ch = 1;  // empty row: one all-pad chunk in level 0
         if (lane < L) gend[r * L + lane] = (uint16_t)ch;
@@ -362,7 +371,7 @@ __global__ void __launch_bounds__(256) fact_row_hist_kernel(const int64_t *__res
 __global__ void __launch_bounds__(256) fact_row_place_kernel(const int64_t *__restrict__ rowptr, const uint16_t *__restrict__ ridx,
                                                              const uint8_t *__restrict__ rlvl, int64_t m, int L, int padgene,
                                                              const int64_t *__restrict__ frowptr, const uint16_t *__restrict__ gend,
-                                                             const int64_t *__restrict__ erowptr, const int32_t *__restrict__ ecol,
+                                                             const int64_t *__restrict__ ecolptr, const int32_t *__restrict__ erow,
                                                              const double *__restrict__ eval, uint16_t *__restrict__ code,
                                                              uint8_t *__restrict__ meta) {
     const int lane = threadIdx.x & 31;
@@ -390,17 +399,31 @@ __global__ void __launch_bounds__(256) fact_row_place_kernel(const int64_t *__re
             }
             for (int64_t p = pos + lane; p < pend; p += 32) code[p] = (uint16_t)padgene;
         }
-        if (erowptr) {  // exception chunks {gene, -, value*sd as Float64}, level field = FEXC
-            const int64_t eb = erowptr[r], ee = erowptr[r + 1];
-            for (int64_t k = eb + lane; k < ee; k += 32) {
-                const int c = prev + (int)(k - eb);
-                uint4 q;
-                q.x = (unsigned)ecol[k];
-                q.y = 0u;
-                q.z = (unsigned)__double2loint(eval[k]);
-                q.w = (unsigned)__double2hiint(eval[k]);
-                reinterpret_cast<uint4 *>(code)[cbase + c] = q;
-                meta[cbase + c] = (uint8_t)((FEXC << 1) | (c == total - 1));
+        if (ecolptr && prev < total) {  // exception chunks {gene, -, value*sd as Float64}, level field = FEXC, ascending gene
+            int c = prev;
+            for (int64_t k0 = b; k0 < e; k0 += 32) {
+                const int64_t k = k0 + lane;
+                const bool hit = (k < e) && (rlvl[k] == 0);
+                const unsigned bal = __ballot_sync(0xffffffffu, hit);
+                if (hit) {
+                    const int g = ridx[k];
+                    // the value lives in the gene-major exception matrix: find this cell in column g
+                    int64_t lo = ecolptr[g], hi = ecolptr[g + 1];
+                    while (lo < hi) {
+                        const int64_t mid = (lo + hi) >> 1;
+                        if ((int64_t)erow[mid] < r) lo = mid + 1; else hi = mid;
+                    }
+                    const double v = eval[lo];
+                    const int cc = c + __popc(bal & ((1u << lane) - 1u));
+                    uint4 q;
+                    q.x = (unsigned)g;
+                    q.y = 0u;
+                    q.z = (unsigned)__double2loint(v);
+                    q.w = (unsigned)__double2hiint(v);
+                    reinterpret_cast<uint4 *>(code)[cbase + cc] = q;
+                    meta[cbase + cc] = (uint8_t)((FEXC << 1) | (cc == total - 1));
+                }
+                c += __popc(bal);
             }
         }
     }
@@ -748,6 +771,23 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
     const int64_t m = a->nrow, n = a->ncol, nnz = a->nnz;
     auto *f = new svb_factored_s();
     op->fact = f;
+    // SVB_FACT_TIMING=1: per-phase build times (stream-synchronised) on stderr
+    const bool timing = getenv("SVB_FACT_TIMING") != nullptr;
+    auto tlast = std::chrono::steady_clock::now();
+    auto tick = [&](const char *what) {
+        if (!timing) return;
+        cudaStreamSynchronize(st);
+        const auto now = std::chrono::steady_clock::now();
+        cudaMemPool_t pool;
+        unsigned long long reserved = 0, used = 0;
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx().device) == cudaSuccess) {
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+        }
+        fprintf(stderr, "[svb counts build] %-28s %8.3f ms   pool reserved %.2f GB used %.2f GB\n", what,
+                std::chrono::duration<double, std::milli>(now - tlast).count(), reserved / 1e9, used / 1e9);
+        tlast = std::chrono::steady_clock::now();
+    };
 
     // ---- number of levels ----------------------------------------------------------------------------
     DevBuf<long long> d_lib((size_t)std::max<int64_t>(m, 1));
@@ -795,6 +835,7 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
     f->R = 1ll << log2R;
     f->ntiles = std::max<int64_t>(1, (m + f->R - 1) / f->R);
 
+    tick("libsize upload + levels");
     // ---- per-cell level tables ---------------------------------------------------------------------
     SVB_CUDA(cudaMalloc((void **)&f->tlev, (size_t)std::max<int64_t>(m << log2L, 1) * sizeof(double)));
     SVB_CUDA(cudaMalloc((void **)&f->tlevA, (size_t)(f->ntiles << (log2R + log2L)) * sizeof(double)));
@@ -803,6 +844,7 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
     count_launch();
     SVB_LAUNCH_CHECK();
 
+    tick("level tables");
     // ---- per-gene moments (given, or two parallel passes over the counts), then scale, centre, clip ------
     DevBuf<double> d_mean((size_t)n), d_var((size_t)n), d_sd((size_t)n), d_cap((size_t)n);
     DevBuf<int> d_bad(1);
@@ -840,39 +882,43 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
     SVB_CUDA(cudaStreamSynchronize(st));
     SVB_CHECK(!bad, SVB_EARG, "svb_operator_create_counts: a gene has zero (or non-finite) variance");
 
+    tick("moments + prepare");
     // ---- classify every entry (CSC order) -------------------------------------------------------------
     DevBuf<uint8_t> lvl((size_t)std::max<int64_t>(nnz, 1));
-    DevBuf<int64_t> ecolptr((size_t)(n + 1));
-    SVB_CUDA(cudaMemsetAsync(ecolptr.p, 0, (size_t)(n + 1) * sizeof(int64_t), st));
-    if (nnz > 0) {
-        dim3 grid((unsigned)n, 8);
+    DevBuf<int64_t> exoff((size_t)(n * FSL + 1));  // exceptions per (gene, slice) -> offsets
+    SVB_CUDA(cudaMemsetAsync(exoff.p, 0, (size_t)(n * FSL + 1) * sizeof(int64_t), st));
+    {
+        dim3 grid((unsigned)n, FSL / 8);
         fact_classify_kernel<<<grid, 256, 0, st>>>(a->colptr, a->rowidx, (const int32_t *)a->val, log2L, f->tlev, d_sd.p, d_cap.p, lvl.p,
-                                                   (unsigned long long *)ecolptr.p);
+                                                   exoff.p);
         count_launch();
         SVB_LAUNCH_CHECK();
     }
-    exclusive_scan_i64(ecolptr.p, n + 1, st);
+    exclusive_scan_i64(exoff.p, n * FSL + 1, st);
     int64_t nexc = 0;
-    SVB_CUDA(cudaMemcpyAsync(&nexc, ecolptr.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    SVB_CUDA(cudaMemcpyAsync(&nexc, exoff.p + n * FSL, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     SVB_CUDA(cudaStreamSynchronize(st));
     f->nnz_exc = nexc;
     f->nnz_main = nnz - nexc;
 
-    // ---- the exceptions with their exact value (times sd), gene-major (CSC) and cell-major (its transpose) ------
+    tick("classify + scan");
+    // ---- the exceptions with their exact value (times sd), gene-major (CSC) --------------------------------
     struct Owned {
         svb_matrix_s *p = nullptr;
         ~Owned() { delete p; }
-    } e, et;
+    } e;
     if (nexc > 0) {
         e.p = matrix_alloc(m, n, nexc, SVB_F64);
-        SVB_CUDA(cudaMemcpyAsync(e.p->colptr, ecolptr.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToDevice, st));
-        fact_resid_fill_kernel<<<fgrid(n * 32), 256, 0, st>>>(a->colptr, a->rowidx, (const int32_t *)a->val, lvl.p, n, d_lib.p, sf,
-                                                              d_sd.p, d_cap.p, e.p->colptr, e.p->rowidx, (double *)e.p->val);
+        launch_strided_copy(exoff.p, FSL, n, e.p->colptr, st);
+        SVB_CUDA(cudaMemcpyAsync(e.p->colptr + n, exoff.p + n * FSL, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+        dim3 grid((unsigned)n, FSL / 8);
+        fact_resid_fill_kernel<<<grid, 256, 0, st>>>(a->colptr, a->rowidx, (const int32_t *)a->val, lvl.p, d_lib.p, sf, d_sd.p, d_cap.p,
+                                                     exoff.p, e.p->rowidx, (double *)e.p->val);
         count_launch();
         SVB_LAUNCH_CHECK();
-        et.p = matrix_transpose(e.p);
     }
 
+    tick("exceptions (CSC)");
     // ---- adjoint layout ----------------------------------------------------------------------------------
     {
         const int64_t nseg = f->ntiles * n;
@@ -904,6 +950,7 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
         SVB_CUDA(cudaStreamSynchronize(st));
     }
 
+    tick("adjoint layout");
     // ---- forward layout: CSR by cell of (gene, level), then level grouping -------------------------------------
     {
         MatrixView view(a, lvl.p);
@@ -918,11 +965,11 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
         tc.gptr.release();
         tc.rloc.release();
         tc.aval.release();
-        const int64_t *erowptr = et.p ? et.p->colptr : nullptr;
+        tick("forward: CSR of (gene, level)");
         SVB_CUDA(cudaMalloc((void **)&f->f_rowptr, (size_t)(m + 1) * sizeof(int64_t)));
         DevBuf<uint16_t> gend((size_t)std::max<int64_t>(m * L, 1));
         const unsigned gw = (unsigned)std::max<int64_t>(1, std::min<int64_t>((m + 7) / 8, 148 * 16));
-        fact_row_hist_kernel<<<gw, 256, 0, st>>>(rowptr.p, rlvl.p, erowptr, m, L, gend.p, f->f_rowptr);
+        fact_row_hist_kernel<<<gw, 256, 0, st>>>(rowptr.p, rlvl.p, m, L, gend.p, f->f_rowptr);
         count_launch();
         SVB_LAUNCH_CHECK();
         exclusive_scan_i64(f->f_rowptr, m + 1, st);
@@ -930,18 +977,20 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
         SVB_CUDA(cudaStreamSynchronize(st));
         SVB_CUDA(cudaMalloc((void **)&f->f_code, (size_t)std::max<int64_t>(f->f_chunks, 1) * 16));
         SVB_CUDA(cudaMalloc((void **)&f->f_meta, (size_t)std::max<int64_t>(f->f_chunks, 1)));
-        fact_row_place_kernel<<<gw, 256, 0, st>>>(rowptr.p, ridx.p, rlvl.p, m, L, (int)n, f->f_rowptr, gend.p, erowptr,
-                                                  et.p ? et.p->rowidx : nullptr, et.p ? (const double *)et.p->val : nullptr,
-                                                  (uint16_t *)f->f_code, f->f_meta);
+        fact_row_place_kernel<<<gw, 256, 0, st>>>(rowptr.p, ridx.p, rlvl.p, m, L, (int)n, f->f_rowptr, gend.p,
+                                                  e.p ? e.p->colptr : nullptr, e.p ? e.p->rowidx : nullptr,
+                                                  e.p ? (const double *)e.p->val : nullptr, (uint16_t *)f->f_code, f->f_meta);
         count_launch();
         SVB_LAUNCH_CHECK();
         SVB_CUDA(cudaStreamSynchronize(st));
     }
 
+    tick("forward: grouping + placement");
     SVB_CUDA(cudaMalloc((void **)&f->partial, (size_t)f->ntiles * (n + 1) * sizeof(double)));
     SVB_CUDA(cudaMalloc((void **)&op->tmp, (size_t)std::max(m, n) * sizeof(double)));
     SVB_CUDA(cudaMalloc((void **)&op->scal, 8 * sizeof(double)));
     SVB_CUDA(cudaStreamSynchronize(st));
+    tick("partial / scratch allocation");
 }
 
 }  // namespace svb
@@ -961,6 +1010,7 @@ int svb_operator_create_counts(svb_matrix_t counts, const int64_t *libsize, doub
               "svb_operator_create_counts: levels must be 0 (auto), 4, 8, 16 or 32");
     SVB_CHECK(scale_factor > 0.0, SVB_EARG, "svb_operator_create_counts: scale_factor must be positive");
     auto *op = new svb_operator_s();
+    const auto t_begin = std::chrono::steady_clock::now();
     try {
         op->m = counts->nrow;
         op->n = counts->ncol;
@@ -972,6 +1022,9 @@ int svb_operator_create_counts(svb_matrix_t counts, const int64_t *libsize, doub
         delete op;
         throw;
     }
+    if (getenv("SVB_FACT_TIMING"))
+        fprintf(stderr, "[svb counts build] %-28s %8.3f ms\n", "TOTAL (incl. temporaries freed)",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
     *out = op;
     SVB_API_END
 }

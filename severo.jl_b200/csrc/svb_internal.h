@@ -19,11 +19,11 @@ struct Error : std::runtime_error {
 
 void set_last_error(const std::string &msg);
 
-// Every device allocation of the library goes through the stream-ordered pool (cudaMallocAsync /
-// cudaFreeAsync on the library stream, release threshold = unlimited): a plain cudaFree of the
-// multi-GB Lanczos workspace costs ~100 ms per solve on a B200, the pool makes it free.
+// Every device allocation of the library goes through a block cache on top of cudaMalloc (core.cu): a plain
+// cudaFree of the multi-GB Lanczos workspace costs ~100 ms per solve on a B200, a cached block costs nothing.
 cudaError_t dev_malloc(void **p, size_t bytes);
 cudaError_t dev_free(void *p);
+void dev_release_cache();  // return every cached block to the driver
 
 #ifndef SVB_NO_ALLOC_MACROS
 #define cudaMalloc(pp, bytes) svb::dev_malloc((void **)(pp), (bytes))

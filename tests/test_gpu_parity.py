@@ -489,6 +489,21 @@ assert tot == 4000 and np.allclose(mean, mo, rtol=1e-13) and np.allclose(var, vo
 # order-exact mode: the Welford state is carried from rank to rank -> the bits of one sequential pass
 me, ve, tot = sharding.exact_mean_var(d)
 assert tot == 4000 and np.array_equal(me, mo) and np.array_equal(ve, vo)
+# count-level operator on cell shards: moments over the cells of all ranks, solve == oracle on the whole matrix
+lam = np.exp(rng.normal(-1.2, 1.0, 300))
+Xc = rng.poisson(np.exp(0.3 * rng.standard_normal(6000))[:, None] * lam[None, :] * 3.0)
+Xc[Xc.sum(axis=1) == 0, 0] = 1
+Xc = sp.csc_matrix(Xc.astype(np.int64))
+b3 = sharding.shard_bounds(6000, world)
+Cc = sv.scale_features_counts(sv.DeviceMatrix.from_host(Xc[b3[rank][0]:b3[rank][1]]), scale_factor=1e4, scale_max=10.0, moments="fast")
+Soc = orc.scale_features(orc.normalize_cells(Xc, "lognormalize", 1e4), scale_max=10.0)
+assert np.allclose(Cc.mu, Soc.mu, rtol=1e-11)
+init3 = rng.standard_normal(300)
+Sc = sv.irlba(Cc, 6, init=init3, tol=1e-9)
+Oc = orc.irlba(Soc, 6, init=init3, tol=1e-9)
+assert np.allclose(Sc.S, Oc.S, rtol=1e-6), (Sc.S, Oc.S)
+Uc = sharding.gather_rows(Sc.U, b3, rank)
+assert orc.principal_angle(Uc, Oc.U) < 1e-4 and orc.principal_angle(Sc.V, Oc.V) < 1e-4
 sv.lib().svb_comm_destroy()
 dist.destroy_process_group()
 print("OK", rank, mode)
