@@ -236,6 +236,38 @@ __global__ void __launch_bounds__(256) fact_resid_fill_kernel(const int64_t *__r
     }
 }
 
+// ---- bank-aware placement ---------------------------------------------------------------------------------------
+// The product kernels gather 8-byte table entries from shared memory; a half-warp's 16 gathers are served in one pass
+// only if they fall in 16 different 8-byte banks (bank = index mod 16), and with the entries in ascending order the
+// measured cost is ~3 passes per 16 gathers (ncu: 2/3 of the shared-load wavefronts are bank conflicts), which is what
+// bounds the kernels. The ORDER of the entries inside a (row, level) group / (tile, gene) segment is free, so the
+// builders choose it: the 16 lanes of a half-warp read element e of 16 consecutive chunks (aligned to 16 in the global
+// chunk index: the kernels start every warp on a multiple of 32 chunks) -- a "set". Entries are dealt to the sets in
+// round-robin order over the residues (the j-th entry of every residue class, class after class), and the slots are
+// filled set by set: any 16 consecutive entries of that sequence have different residues as long as no class has run
+// out, so the conflicts are confined to the tail of a group. Deterministic (ranks follow the ascending order).
+// position of the j-th entry (0-based) of residue class rho in the round-robin sequence; cnt[16] = class sizes
+__device__ __forceinline__ int rr_position(const int *__restrict__ cnt, int rho, int j) {
+    int p = 0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int c = cnt[q];
+        p += min(c, j) + ((q < rho && c > j) ? 1 : 0);
+    }
+    return p;
+}
+// slot (index into the u16 code array) of sequence position p for a group that owns the global chunks [g0, g1):
+// the slots are enumerated set by set -- aligned block of 16 chunks, then element e, then chunk
+__device__ __forceinline__ int64_t rr_slot(int64_t g0, int64_t g1, int p) {
+    const int w0 = (int)(min(g1, ((g0 >> 4) + 1) << 4) - g0);  // chunks of the group in its first block (1..16)
+    if (p < 8 * w0) return (g0 + p % w0) * FCH + p / w0;
+    const int pp = p - 8 * w0;
+    const int64_t cb = g0 + w0 + ((pp >> 7) << 4);              // every block before the last is full (128 slots)
+    const int wb = (int)min((int64_t)16, g1 - cb);
+    const int q = pp & 127;
+    return (cb + q % wb) * FCH + q / wb;
+}
+
 // adjoint layout, pass 1: chunks per (tile, gene) segment (at least one: the stream kernels count segments by their
 // "last chunk" flags, so an empty segment is one all-pad chunk). Sub-warps of 8 lanes, one segment each.
 __global__ void __launch_bounds__(256) fact_seg_count_kernel(const int64_t *__restrict__ startpos, const uint8_t *__restrict__ lvl,
@@ -266,33 +298,46 @@ __global__ void __launch_bounds__(256) fact_seg_fill_kernel(const int64_t *__res
                                                             const int64_t *__restrict__ estart, const int32_t *__restrict__ erow,
                                                             const double *__restrict__ eval, uint16_t *__restrict__ code,
                                                             uint8_t *__restrict__ meta) {
+    __shared__ int scnt[32][16], srun[32][16];  // per sub-warp: size / running rank of every residue class (cell mod 16)
     const int lane = threadIdx.x & 31, sl = lane & 7;
     const int shift = lane & ~7;
     const unsigned submask = 0xffu << shift;
+    const int sw = threadIdx.x >> 3;
+    int *cnt = scnt[sw], *run = srun[sw];
     const int64_t sub = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
     const int64_t nsub = ((int64_t)gridDim.x * blockDim.x) >> 3;
     const uint16_t padcode = (uint16_t)(1u << (log2R + log2L));
+    // every sub-warp runs the same number of outer iterations (the loop bound does not depend on the lane)
     for (int64_t s = sub; s < nseg; s += nsub) {
         const int64_t b = startpos[s], e = startpos[s + ncol];
         const int64_t t = s / ncol;
         const int64_t row0 = t << log2R;
         const int64_t c0 = gptr[s], c1 = gptr[s + 1];
-        int64_t pos = c0 * FCH;
-        const int64_t pend = c1 * FCH;
+        const int64_t eb = estart ? estart[s] : 0, ee = estart ? estart[s + ncol] : 0;
+        const int64_t cx = c1 - (ee - eb);  // first exception chunk; the coded chunks are [c0, cx)
+        cnt[sl] = 0; cnt[sl + 8] = 0; run[sl] = 0; run[sl + 8] = 0;
+        for (int64_t p = c0 * FCH + sl; p < cx * FCH; p += 8) code[p] = padcode;
+        __syncwarp(submask);
+        for (int64_t k = b + sl; k < e; k += 8)
+            if (lvl[k]) atomicAdd(&cnt[(rowidx[k] - row0) & 15], 1);
+        __syncwarp(submask);
         for (int64_t k0 = b; k0 < e; k0 += 8) {
             const int64_t k = k0 + sl;
-            int lv = 0;
-            if (k < e) lv = lvl[k];
-            const unsigned bal = (__ballot_sync(submask, lv != 0) >> shift) & 0xffu;
-            if (lv) {
-                const int64_t il = (int64_t)rowidx[k] - row0;
-                code[pos + __popc(bal & ((1u << sl) - 1u))] = (uint16_t)(((int64_t)(lv - 1) << log2R) + il);
+            int lv = 0, il = 0;
+            if (k < e) {
+                lv = lvl[k];
+                il = (int)(rowidx[k] - row0);
             }
-            pos += __popc(bal);
+            const int rho = lv ? (il & 15) : (16 + sl);  // lanes without an entry match nobody
+            const unsigned peers = (__match_any_sync(submask, rho) >> shift) & 0xffu;
+            if (lv) {
+                const int j = run[rho] + __popc(peers & ((1u << sl) - 1u));
+                code[rr_slot(c0, cx, rr_position(cnt, rho, j))] = (uint16_t)(((lv - 1) << log2R) + il);
+            }
+            __syncwarp(submask);
+            if (lv && (peers >> sl) == 1u) run[rho] += __popc(peers);  // the last lane of every class updates its counter
+            __syncwarp(submask);
         }
-        const int64_t eb = estart ? estart[s] : 0, ee = estart ? estart[s + ncol] : 0;
-        const int64_t cx = c1 - (ee - eb);  // first exception chunk
-        for (int64_t p = pos + sl; p < cx * FCH; p += 8) code[p] = padcode;
         for (int64_t k = eb + sl; k < ee; k += 8) {  // {i_local, -, value*sd as Float64}
             uint4 q;
             q.x = (unsigned)(erow[k] - row0);
@@ -302,7 +347,7 @@ __global__ void __launch_bounds__(256) fact_seg_fill_kernel(const int64_t *__res
             reinterpret_cast<uint4 *>(code)[cx + (k - eb)] = q;
         }
         for (int64_t c = c0 + sl; c < c1; c += 8) meta[c] = (uint8_t)((c == c1 - 1) | ((c >= cx) << 1));
-        (void)pend;
+        __syncwarp(submask);
     }
 }
 
@@ -366,41 +411,63 @@ __global__ void __launch_bounds__(256) fact_row_hist_kernel(const int64_t *__res
     if (blockIdx.x == 0 && threadIdx.x == 0) rowchunks[m] = 0;
 }
 
-// forward layout, pass 2: for every level a stable (ascending gene) ballot compaction into the group's chunks, pads
-// (gene index n, xs[n] = 0) up to the chunk boundary, and the per-chunk byte (level << 1) | last-chunk-of-the-row
+// forward layout, pass 2: the genes of every (row, level) group in the bank-aware order (see above), pads (gene index n,
+// xs[n] = 0) in the unused slots, and the per-chunk byte (level << 1) | last-chunk-of-the-row. One warp per row;
+// dynamic shared memory: per warp L x 16 class sizes and L x 16 running ranks.
 __global__ void __launch_bounds__(256) fact_row_place_kernel(const int64_t *__restrict__ rowptr, const uint16_t *__restrict__ ridx,
                                                              const uint8_t *__restrict__ rlvl, int64_t m, int L, int padgene,
                                                              const int64_t *__restrict__ frowptr, const uint16_t *__restrict__ gend,
                                                              const int64_t *__restrict__ ecolptr, const int32_t *__restrict__ erow,
                                                              const double *__restrict__ eval, uint16_t *__restrict__ code,
                                                              uint8_t *__restrict__ meta) {
-    const int lane = threadIdx.x & 31;
+    extern __shared__ int smi[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int *cnt = smi + (size_t)wid * 2 * L * 16;  // [L][16]
+    int *run = cnt + L * 16;                      // [L][16]
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = warp; r < m; r += nwarps) {
         const int64_t b = rowptr[r], e = rowptr[r + 1];
         const int64_t cbase = frowptr[r];
-        const int64_t base = cbase * FCH;
         const int total = (int)(frowptr[r + 1] - cbase);
-        int prev = 0;
-        for (int l = 0; l < L; ++l) {
-            const int ge = gend[r * L + l];
-            if (ge == prev) continue;
-            int64_t pos = base + (int64_t)prev * FCH;
-            const int64_t pend = base + (int64_t)ge * FCH;
-            for (int c = prev + lane; c < ge; c += 32) meta[cbase + c] = (uint8_t)((l << 1) | (c == total - 1));
-            prev = ge;
-            for (int64_t k0 = b; k0 < e; k0 += 32) {
-                const int64_t k = k0 + lane;
-                const bool hit = (k < e) && (rlvl[k] == l + 1);
-                const unsigned bal = __ballot_sync(0xffffffffu, hit);
-                if (hit) code[pos + __popc(bal & ((1u << lane) - 1u))] = ridx[k];
-                pos += __popc(bal);
+        const int coded = gend[r * L + L - 1];  // chunks of the level groups (the exception chunks follow)
+        for (int i = lane; i < 2 * L * 16; i += 32) cnt[i] = 0;
+        for (int64_t p = cbase * FCH + lane; p < (cbase + coded) * FCH; p += 32) code[p] = (uint16_t)padgene;
+        {
+            int prev = 0;
+            for (int l = 0; l < L; ++l) {
+                const int ge = gend[r * L + l];
+                for (int c = prev + lane; c < ge; c += 32) meta[cbase + c] = (uint8_t)((l << 1) | (c == total - 1));
+                prev = ge;
             }
-            for (int64_t p = pos + lane; p < pend; p += 32) code[p] = (uint16_t)padgene;
         }
-        if (ecolptr && prev < total) {  // exception chunks {gene, -, value*sd as Float64}, level field = FEXC, ascending gene
-            int c = prev;
+        __syncwarp();
+        for (int64_t k = b + lane; k < e; k += 32) {
+            const int lv = rlvl[k];
+            if (lv) atomicAdd(&cnt[(lv - 1) * 16 + (ridx[k] & 15)], 1);
+        }
+        __syncwarp();
+        for (int64_t k0 = b; k0 < e; k0 += 32) {
+            const int64_t k = k0 + lane;
+            int lv = 0, g = 0;
+            if (k < e) {
+                lv = rlvl[k];
+                g = ridx[k];
+            }
+            const int key = lv ? ((lv - 1) * 16 + (g & 15)) : (L * 16 + lane);  // lanes without a coded entry match nobody
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            if (lv) {
+                const int l = lv - 1;
+                const int j = run[key] + __popc(peers & ((1u << lane) - 1u));
+                const int64_t g0 = cbase + (l ? gend[r * L + l - 1] : 0), g1 = cbase + gend[r * L + l];
+                code[rr_slot(g0, g1, rr_position(cnt + l * 16, g & 15, j))] = (uint16_t)g;
+            }
+            __syncwarp();
+            if (lv && (peers >> lane) == 1u) run[key] += __popc(peers);  // the last lane of every class updates its counter
+            __syncwarp();
+        }
+        if (ecolptr && coded < total) {  // exception chunks {gene, -, value*sd as Float64}, level field = FEXC, ascending gene
+            int c = coded;
             for (int64_t k0 = b; k0 < e; k0 += 32) {
                 const int64_t k = k0 + lane;
                 const bool hit = (k < e) && (rlvl[k] == 0);
@@ -426,6 +493,7 @@ __global__ void __launch_bounds__(256) fact_row_place_kernel(const int64_t *__re
                 c += __popc(bal);
             }
         }
+        __syncwarp();
     }
 }
 
@@ -523,8 +591,9 @@ fwd_stream_kernel(const uint4 *__restrict__ code, const uint8_t *__restrict__ me
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const int64_t gw = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
-    const int64_t cend = __ldg(wstart + gw + 1);
-    int64_t c = __ldg(wstart + gw) + lane;  // this lane's chunk of the current iteration
+    const int64_t cbeg = __ldg(wstart + gw), cend = __ldg(wstart + gw + 1);
+    // lane = chunk index mod 32: the builder's bank-aware order assumes half-warps read aligned blocks of 16 chunks
+    int64_t c = (cbeg & ~(int64_t)31) + lane;  // this lane's chunk of the current iteration
     int64_t rowbase = __ldg(wrow + gw);     // row of the first chunk of the NEXT iteration to be decoded
     const uint4 padq = make_uint4((unsigned)n * 0x10001u, (unsigned)n * 0x10001u, (unsigned)n * 0x10001u, (unsigned)n * 0x10001u);
 
@@ -533,7 +602,7 @@ fwd_stream_kernel(const uint4 *__restrict__ code, const uint8_t *__restrict__ me
 #pragma unroll
     for (int s = 0; s < FPD; ++s) {
         const int64_t cc = c + 32 * s;
-        const bool ok = cc < cend;
+        const bool ok = cc >= cbeg && cc < cend;
         q[s] = ok ? ld_stream16(code + cc) : padq;
         mb[s] = ok ? (unsigned)__ldg(meta + cc) : 0u;
     }
@@ -541,7 +610,7 @@ fwd_stream_kernel(const uint4 *__restrict__ code, const uint8_t *__restrict__ me
     unsigned bal0 = __ballot_sync(0xffffffffu, (mb[0] & 1u) != 0u);
     int64_t row0 = rowbase + __popc(bal0 & lt);
     rowbase += __popc(bal0);
-    double t0 = (c < cend && (mb[0] >> 1) != FEXC) ? __ldg(tlev + (row0 << log2L) + (mb[0] >> 1)) : 0.0;
+    double t0 = (c >= cbeg && c < cend && (mb[0] >> 1) != FEXC) ? __ldg(tlev + (row0 << log2L) + (mb[0] >> 1)) : 0.0;
     double carry = 0.0;
     for (; c - lane < cend; c += 32) {
         // A: loads of iteration +FPD
@@ -625,14 +694,14 @@ adj_stream_kernel(const int64_t *__restrict__ gptr, const uint4 *__restrict__ co
         if (threadIdx.x == 0) T[RL] = 0.0;
         // this warp's slice (loads issued before the barrier so that they overlap the table fill)
         const int g0 = __ldg(slices + t * (K + 1) + wid), g1 = __ldg(slices + t * (K + 1) + wid + 1);
-        const int64_t cend = __ldg(gptr + t * n + g1);
-        int64_t c = __ldg(gptr + t * n + g0) + lane;
+        const int64_t cbeg = __ldg(gptr + t * n + g0), cend = __ldg(gptr + t * n + g1);
+        int64_t c = (cbeg & ~(int64_t)31) + lane;  // lane = chunk index mod 32 (bank-aware order, see the builder)
         uint4 q[FPD];
         unsigned mb[FPD];
 #pragma unroll
         for (int s = 0; s < FPD; ++s) {
             const int64_t cc = c + 32 * s;
-            const bool ok = cc < cend;
+            const bool ok = cc >= cbeg && cc < cend;
             q[s] = ok ? ld_stream16(code + cc) : padq;
             mb[s] = ok ? (unsigned)__ldg(meta + cc) : 0u;
         }
@@ -977,7 +1046,7 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
         SVB_CUDA(cudaStreamSynchronize(st));
         SVB_CUDA(cudaMalloc((void **)&f->f_code, (size_t)std::max<int64_t>(f->f_chunks, 1) * 16));
         SVB_CUDA(cudaMalloc((void **)&f->f_meta, (size_t)std::max<int64_t>(f->f_chunks, 1)));
-        fact_row_place_kernel<<<gw, 256, 0, st>>>(rowptr.p, ridx.p, rlvl.p, m, L, (int)n, f->f_rowptr, gend.p,
+        fact_row_place_kernel<<<gw, 256, (size_t)8 * 2 * L * 16 * sizeof(int), st>>>(rowptr.p, ridx.p, rlvl.p, m, L, (int)n, f->f_rowptr, gend.p,
                                                   e.p ? e.p->colptr : nullptr, e.p ? e.p->rowidx : nullptr,
                                                   e.p ? (const double *)e.p->val : nullptr, (uint16_t *)f->f_code, f->f_meta);
         count_launch();
