@@ -144,6 +144,49 @@ function operator(A::StridedMatrix{Float64}, mu=nothing)
         size(A, 1), size(A, 2), A, stride(A, 2), _mu_ptr(mu), Cint(0), h))
     DeviceOperator(h[])
 end
+# The same operator built from the RAW COUNTS of the HVG columns (svb_operator_create_counts): fuses
+# normalize_cells(:lognormalize) -> Y[:, hvf] -> scale_features(scale_max) (normalize.jl:40-55, scaling.jl:335-357);
+# the scaled matrix is never materialised. `libsize` = vec(sum(counts_all_genes, dims=2)) (normalize.jl:24).
+# moments = :exact uses the reference's sequential Welford (mean_var of the normalised columns, scaling.jl:18-34),
+# :fast lets the library compute them in two parallel passes (a few ulp away; spans all ranks of a communicator).
+function counts_operator(counts_hvg::SparseMatrixCSC{<:Integer}, libsize::Vector{Int64};
+                         scale_factor::Real=1e4, scale_max::Real=Inf, moments::Symbol=:exact, levels::Integer=0)
+    d = upload(counts_hvg)
+    n = size(counts_hvg, 2)
+    mean = var = Ptr{Float64}(C_NULL)
+    if moments == :exact
+        y = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:svb_normalize_libsize, libsvb), Cint, (Ptr{Cvoid}, Ptr{Int64}, Cint, Float64, Cint, Ref{Ptr{Cvoid}}),
+            d.h, libsize, 0, scale_factor, 3, y))
+        mean, var = zeros(n), zeros(n)
+        check(ccall((:svb_mean_var, libsvb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), y[], mean, var))
+        ccall((:svb_matrix_free, libsvb), Cint, (Ptr{Cvoid},), y[])
+    end
+    mu = zeros(n)                                    # receives mean/std, the stored centre (scaling.jl:207)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:svb_operator_create_counts, libsvb), Cint,
+        (Ptr{Cvoid}, Ptr{Int64}, Float64, Ptr{Float64}, Ptr{Float64}, Float64, Cint, Ptr{Float64}, Ref{Ptr{Cvoid}}),
+        d.h, libsize, scale_factor, mean, var, scale_max, levels, mu, h))
+    DeviceOperator(h[]), mu
+end
+
+# embedding(counts; ...) in one call: pca of the scaled HVG matrix straight from the counts
+function pca_counts(counts::SparseMatrixCSC{<:Integer}, hvf::AbstractVector{<:Integer}, npcs::Integer;
+                    scale_factor::Real=1e4, scale_max::Real=Inf, moments::Symbol=:exact, tol=1e-5, init=nothing)
+    libsize = convert(Vector{Int64}, vec(sum(counts, dims=2)))
+    sub = counts[:, hvf]
+    op, mu = counts_operator(sub, libsize; scale_factor, scale_max, moments)
+    m, n = size(sub)
+    U, s, V = zeros(m, npcs), zeros(npcs), zeros(n, npcs)
+    init === nothing && (init = randn(n))
+    iter = Ref{Int64}(0); mprod = Ref{Int64}(0)
+    info = ccall((:svb_irlba, libsvb), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Int64}, Ref{Int64}),
+        op.h, npcs, min(npcs + 7, min(m, n)), 1000, 0, tol, tol, init, s, U, V, iter, mprod)
+    info == 0 || error("convergence failed")
+    U * Diagonal(s), s ./ sqrt(max(1, m - 1)), V, mu     # coordinates, stdev, loadings (embedding.jl:67-68), centre
+end
+
 operator(S::CenteredMatrix) = operator(Severo._A_mu(S)...)
 operator(S::NamedCenteredMatrix) = operator(S.A.array, S.mu.array)
 

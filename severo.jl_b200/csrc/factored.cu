@@ -416,10 +416,10 @@ __global__ void __launch_bounds__(256) fact_row_hist_kernel(const int64_t *__res
 // dynamic shared memory: per warp L x 16 class sizes and L x 16 running ranks.
 __global__ void __launch_bounds__(256) fact_row_place_kernel(const int64_t *__restrict__ rowptr, const uint16_t *__restrict__ ridx,
                                                              const uint8_t *__restrict__ rlvl, int64_t m, int L, int padgene,
-                                                             const int64_t *__restrict__ frowptr, const uint16_t *__restrict__ gend,
-                                                             const int64_t *__restrict__ ecolptr, const int32_t *__restrict__ erow,
-                                                             const double *__restrict__ eval, uint16_t *__restrict__ code,
-                                                             uint8_t *__restrict__ meta) {
+                                                             int cshift, const int64_t *__restrict__ frowptr,
+                                                             const uint16_t *__restrict__ gend, const int64_t *__restrict__ ecolptr,
+                                                             const int32_t *__restrict__ erow, const double *__restrict__ eval,
+                                                             uint16_t *__restrict__ code, uint8_t *__restrict__ meta) {
     extern __shared__ int smi[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int *cnt = smi + (size_t)wid * 2 * L * 16;  // [L][16]
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(256) fact_row_place_kernel(const int64_t *__re
         const int total = (int)(frowptr[r + 1] - cbase);
         const int coded = gend[r * L + L - 1];  // chunks of the level groups (the exception chunks follow)
         for (int i = lane; i < 2 * L * 16; i += 32) cnt[i] = 0;
-        for (int64_t p = cbase * FCH + lane; p < (cbase + coded) * FCH; p += 32) code[p] = (uint16_t)padgene;
+        for (int64_t p = cbase * FCH + lane; p < (cbase + coded) * FCH; p += 32) code[p] = (uint16_t)(padgene << cshift);
         {
             int prev = 0;
             for (int l = 0; l < L; ++l) {
@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(256) fact_row_place_kernel(const int64_t *__re
                 const int l = lv - 1;
                 const int j = run[key] + __popc(peers & ((1u << lane) - 1u));
                 const int64_t g0 = cbase + (l ? gend[r * L + l - 1] : 0), g1 = cbase + gend[r * L + l];
-                code[rr_slot(g0, g1, rr_position(cnt + l * 16, g & 15, j))] = (uint16_t)g;
+                code[rr_slot(g0, g1, rr_position(cnt + l * 16, g & 15, j))] = (uint16_t)(g << cshift);  // index or byte offset
             }
             __syncwarp();
             if (lv && (peers >> lane) == 1u) run[key] += __popc(peers);  // the last lane of every class updates its counter
@@ -568,9 +568,22 @@ __device__ __forceinline__ double seg_scan(double v, unsigned lastbits, int lane
 
 constexpr int FPD = 3;  // prefetch distance of the stream kernels, in iterations (3 x 16 B per lane in flight)
 
+// gather with codes that are BYTE offsets (index * 8 < 65536): one instruction per code instead of two
+__device__ __forceinline__ double gather8b(const double *__restrict__ T, const uint4 q) {
+    const char *b = reinterpret_cast<const char *>(T);
+#define SVB_AT(off) (*reinterpret_cast<const double *>(b + (off)))
+    const double a0 = SVB_AT(q.x & 0xffffu), a1 = SVB_AT(q.x >> 16), a2 = SVB_AT(q.y & 0xffffu), a3 = SVB_AT(q.y >> 16);
+    const double a4 = SVB_AT(q.z & 0xffffu), a5 = SVB_AT(q.z >> 16), a6 = SVB_AT(q.w & 0xffffu), a7 = SVB_AT(q.w >> 16);
+#undef SVB_AT
+    return ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
 // forward: y_i = alpha*(sum over the row's chunks of t_i[level] * sum_8 xs[gene] - mu.x) + beta*y_i + csign*(*coef)*cvec_i
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (BLOCK == 256 ? 5 : 2))
+// BO: the codes are byte offsets (n <= 8190). After the ncu pass that showed the issue slots 70 % busy once the bank
+// conflicts were halved, the loop works on 32-bit indices relative to the warp's range and the three pipeline stages
+// are unrolled by hand (no register rotation): ~200 -> ~150 instructions per 32 chunks.
+template <int BLOCK, bool BO, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
 fwd_stream_kernel(const uint4 *__restrict__ code, const uint8_t *__restrict__ meta, const double *__restrict__ tlev, int log2L,
                   const int64_t *__restrict__ wstart, const int64_t *__restrict__ wrow, int64_t n, const double *__restrict__ x,
                   const double *__restrict__ inv, const double *__restrict__ mu, double alpha, double beta, double *__restrict__ y,
@@ -593,70 +606,89 @@ fwd_stream_kernel(const uint4 *__restrict__ code, const uint8_t *__restrict__ me
     const int64_t gw = (int64_t)blockIdx.x * (BLOCK / 32) + (threadIdx.x >> 5);
     const int64_t cbeg = __ldg(wstart + gw), cend = __ldg(wstart + gw + 1);
     // lane = chunk index mod 32: the builder's bank-aware order assumes half-warps read aligned blocks of 16 chunks
-    int64_t c = (cbeg & ~(int64_t)31) + lane;  // this lane's chunk of the current iteration
-    int64_t rowbase = __ldg(wrow + gw);     // row of the first chunk of the NEXT iteration to be decoded
-    const uint4 padq = make_uint4((unsigned)n * 0x10001u, (unsigned)n * 0x10001u, (unsigned)n * 0x10001u, (unsigned)n * 0x10001u);
+    const int64_t cbase = cbeg & ~(int64_t)31;
+    const int lo = (int)(cbeg - cbase), hi = (int)(cend - cbase);  // this warp's chunks, relative to cbase
+    const int64_t rbase = __ldg(wrow + gw);
+    const uint4 *pc = code + cbase + lane;
+    const uint8_t *pm = meta + cbase + lane;
+    const double *tl = tlev + (rbase << log2L);
+    double *yb = y + rbase;
+    const double *cvb = cvec ? cvec + rbase : nullptr;
+    const unsigned padc = (unsigned)(BO ? n * 8 : n) * 0x10001u;
+    const uint4 padq = make_uint4(padc, padc, padc, padc);
 
-    uint4 q[FPD];
-    unsigned mb[FPD];
-#pragma unroll
-    for (int s = 0; s < FPD; ++s) {
-        const int64_t cc = c + 32 * s;
-        const bool ok = cc >= cbeg && cc < cend;
-        q[s] = ok ? ld_stream16(code + cc) : padq;
-        mb[s] = ok ? (unsigned)__ldg(meta + cc) : 0u;
+    int rel = lane;   // this lane's chunk of the current iteration, relative to cbase
+    int rowrel = 0;   // row (relative to rbase) of the first chunk of the next iteration to be decoded
+    uint4 q0, q1, q2;
+    unsigned m0, m1, m2;
+    {
+        const bool ok0 = rel >= lo && rel < hi, ok1 = rel + 32 < hi, ok2 = rel + 64 < hi;
+        q0 = ok0 ? ld_stream16(pc) : padq;
+        m0 = ok0 ? (unsigned)__ldg(pm) : 0u;
+        q1 = ok1 ? ld_stream16(pc + 32) : padq;
+        m1 = ok1 ? (unsigned)__ldg(pm + 32) : 0u;
+        q2 = ok2 ? ld_stream16(pc + 64) : padq;
+        m2 = ok2 ? (unsigned)__ldg(pm + 64) : 0u;
+        pc += 96;
+        pm += 96;
     }
     // decode iteration 0 and fetch its table entries
-    unsigned bal0 = __ballot_sync(0xffffffffu, (mb[0] & 1u) != 0u);
-    int64_t row0 = rowbase + __popc(bal0 & lt);
-    rowbase += __popc(bal0);
-    double t0 = (c >= cbeg && c < cend && (mb[0] >> 1) != FEXC) ? __ldg(tlev + (row0 << log2L) + (mb[0] >> 1)) : 0.0;
+    unsigned bal0 = __ballot_sync(0xffffffffu, (m0 & 1u) != 0u);
+    int row0 = rowrel + __popc(bal0 & lt);
+    rowrel += __popc(bal0);
+    double t0 = (rel >= lo && rel < hi && (m0 >> 1) != FEXC) ? __ldg(tl + ((int64_t)row0 << log2L) + (m0 >> 1)) : 0.0;
     double carry = 0.0;
-    for (; c - lane < cend; c += 32) {
-        // A: loads of iteration +FPD
-        const int64_t cp = c + 32 * FPD;
-        const bool okp = cp < cend;
-        const uint4 qp = okp ? ld_stream16(code + cp) : padq;
-        const unsigned mbp = okp ? (unsigned)__ldg(meta + cp) : 0u;
-        // B: decode iteration +1 and fetch its table entries (they arrive while this iteration is processed)
-        const unsigned bal1 = __ballot_sync(0xffffffffu, (mb[1] & 1u) != 0u);
-        const int64_t row1 = rowbase + __popc(bal1 & lt);
-        rowbase += __popc(bal1);
-        const double t1 = (c + 32 < cend && (mb[1] >> 1) != FEXC) ? __ldg(tlev + (row1 << log2L) + (mb[1] >> 1)) : 0.0;
-        // C: this iteration
-        double v;
-        if ((mb[0] >> 1) == FEXC) v = __hiloint2double((int)q[0].w, (int)q[0].z) * xs[q[0].x];
-        else v = t0 * gather8(xs, q[0]);
-        bool head0;
-        v = seg_scan(v, bal0, lane, head0);
-        if (head0) v += carry;
-        if (mb[0] & 1u) {
-            double r = alpha * (v - mudot);
-            if (beta != 0.0) r = fma(beta, y[row0], r);
-            if (coef != nullptr) r = fma(cf, cvec[row0], r);
-            y[row0] = r;
-        }
-        const double v31 = __shfl_sync(0xffffffffu, v, 31);
-        carry = (bal0 >> 31) ? 0.0 : v31;
-        // rotate the pipeline
-#pragma unroll
-        for (int s = 0; s + 1 < FPD; ++s) {
-            q[s] = q[s + 1];
-            mb[s] = mb[s + 1];
-        }
-        q[FPD - 1] = qp;
-        mb[FPD - 1] = mbp;
-        bal0 = bal1;
-        row0 = row1;
-        t0 = t1;
+    // one iteration: QA/MA = current stage (refilled with iteration +FPD once consumed), MB = meta of the next iteration
+#define SVB_FWD_STEP(QA, MA, MB)                                                                                      \
+    {                                                                                                                 \
+        const unsigned bal1 = __ballot_sync(0xffffffffu, ((MB) & 1u) != 0u);                                          \
+        const int row1 = rowrel + __popc(bal1 & lt);                                                                  \
+        rowrel += __popc(bal1);                                                                                       \
+        const double t1 = (rel + 32 < hi && ((MB) >> 1) != FEXC) ? __ldg(tl + ((int64_t)row1 << log2L) + ((MB) >> 1)) : 0.0; \
+        double v;                                                                                                     \
+        if (((MA) >> 1) == FEXC) v = __hiloint2double((int)(QA).w, (int)(QA).z) * xs[(QA).x];                         \
+        else v = t0 * (BO ? gather8b(xs, (QA)) : gather8(xs, (QA)));                                                  \
+        const unsigned mcur = (MA);                                                                                   \
+        if (rel + 32 * FPD < hi) {                                                                                    \
+            (QA) = ld_stream16(pc);                                                                                   \
+            (MA) = (unsigned)__ldg(pm);                                                                               \
+        } else {                                                                                                      \
+            (QA) = padq;                                                                                              \
+            (MA) = 0u;                                                                                                \
+        }                                                                                                             \
+        pc += 32;                                                                                                     \
+        pm += 32;                                                                                                     \
+        bool head0;                                                                                                   \
+        v = seg_scan(v, bal0, lane, head0);                                                                           \
+        if (head0) v += carry;                                                                                        \
+        if (mcur & 1u) {                                                                                              \
+            double r = alpha * (v - mudot);                                                                           \
+            if (beta != 0.0) r = fma(beta, yb[row0], r);                                                              \
+            if (coef != nullptr) r = fma(cf, cvb[row0], r);                                                           \
+            yb[row0] = r;                                                                                             \
+        }                                                                                                             \
+        const double v31 = __shfl_sync(0xffffffffu, v, 31);                                                           \
+        carry = (bal0 >> 31) ? 0.0 : v31;                                                                             \
+        bal0 = bal1;                                                                                                  \
+        row0 = row1;                                                                                                  \
+        t0 = t1;                                                                                                      \
+        rel += 32;                                                                                                    \
     }
+    while (rel - lane < hi) {
+        SVB_FWD_STEP(q0, m0, m1)
+        if (rel - lane >= hi) break;
+        SVB_FWD_STEP(q1, m1, m2)
+        if (rel - lane >= hi) break;
+        SVB_FWD_STEP(q2, m2, m0)
+    }
+#undef SVB_FWD_STEP
 }
 
 // adjoint, stage 1: partial[t][g] = (1/sd_g) * sum over the chunks of segment (t,g) of sum_8 T[code], T[l*R+i] = t_i[l]*w_i;
 // partial[t][n] = sum of w over the tile. CTAs take tiles from a global counter (any order gives the same bits: every
 // tile has its own partial row); inside a tile warp k streams the k-th slice of the tile's chunks.
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (BLOCK == 512 ? 3 : 1))
+template <int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
 adj_stream_kernel(const int64_t *__restrict__ gptr, const uint4 *__restrict__ code, const uint8_t *__restrict__ meta,
                   const double *__restrict__ tlevA, int log2L, int log2R, int64_t m, int64_t n, int64_t ntiles,
                   const double *__restrict__ w, const double *__restrict__ inv, double *__restrict__ partial,
@@ -755,12 +787,12 @@ static int fresident_grid(K kernel, size_t smem, int threads) {
     return std::max(1, per_sm) * ctx().sm_count;
 }
 
-template <int BLOCK>
+template <int BLOCK, bool BO, int MINB>
 static void launch_fact_fwd(svb_operator_s *op, double alpha, const double *dx, double beta, double *dy, const double *coef,
                             double csign, const double *cvec) {
     svb_factored_s *f = op->fact;
     const size_t smem = (32 + (size_t)op->n + 1) * sizeof(double);
-    auto k = fwd_stream_kernel<BLOCK>;
+    auto k = fwd_stream_kernel<BLOCK, BO, MINB>;
     SVB_CHECK(smem <= ctx().smem_optin, SVB_EDIM, "count-level operator: gene vector does not fit in shared memory");
     if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (f->fwd_grid == 0) {
@@ -785,14 +817,22 @@ constexpr int ADJ_BLOCK = 512;
 
 void fact_fwd(svb_operator_s *op, double alpha, const double *dx, double beta, double *dy, const double *coef, double csign,
               const double *cvec) {
-    if ((size_t)op->n * 8 > 24 * 1024) launch_fact_fwd<512>(op, alpha, dx, beta, dy, coef, csign, cvec);
-    else launch_fact_fwd<256>(op, alpha, dx, beta, dy, coef, csign, cvec);
+    const bool bo = op->fact->f_cshift == 3;  // codes are byte offsets
+    // 64 registers per thread (4 x 256 or 2 x 512 threads per SM): 48 registers spill, and the kernel is bound by the
+    // shared-memory pipe / issue slots, not by occupancy (measured 5 vs 4 CTAs per SM: within noise)
+    if ((size_t)op->n * 8 > 24 * 1024) {
+        if (bo) launch_fact_fwd<512, true, 2>(op, alpha, dx, beta, dy, coef, csign, cvec);
+        else launch_fact_fwd<512, false, 2>(op, alpha, dx, beta, dy, coef, csign, cvec);
+    } else {
+        if (bo) launch_fact_fwd<256, true, 4>(op, alpha, dx, beta, dy, coef, csign, cvec);
+        else launch_fact_fwd<256, false, 4>(op, alpha, dx, beta, dy, coef, csign, cvec);
+    }
 }
 
 void fact_adj_stage1(svb_operator_s *op, const double *dx) {
     svb_factored_s *f = op->fact;
     const size_t smem = (32 + ((size_t)1 << (f->log2R + f->log2L)) + 1 + (size_t)f->R) * sizeof(double);
-    auto k = adj_stream_kernel<ADJ_BLOCK>;
+    auto k = adj_stream_kernel<ADJ_BLOCK, 3>;  // 3 x 512 threads per SM (2 x 512 with 60 registers measured the same)
     if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (f->adj_grid == 0) f->adj_grid = (int)std::max<int64_t>(1, std::min<int64_t>(fresident_grid(k, smem, ADJ_BLOCK), f->ntiles));
     k<<<(unsigned)f->adj_grid, ADJ_BLOCK, smem, ctx().stream>>>(f->a_gptr, (const uint4 *)f->a_code, f->a_meta, f->tlevA, f->log2L, f->log2R,
@@ -847,15 +887,8 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
         if (!timing) return;
         cudaStreamSynchronize(st);
         const auto now = std::chrono::steady_clock::now();
-        cudaMemPool_t pool;
-        unsigned long long reserved = 0, used = 0;
-        if (cudaDeviceGetDefaultMemPool(&pool, ctx().device) == cudaSuccess) {
-            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
-            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
-        }
-        fprintf(stderr, "[svb counts build] %-28s %8.3f ms   pool reserved %.2f GB used %.2f GB\n", what,
-                std::chrono::duration<double, std::milli>(now - tlast).count(), reserved / 1e9, used / 1e9);
-        tlast = std::chrono::steady_clock::now();
+        fprintf(stderr, "[svb counts build] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - tlast).count());
+        tlast = now;
     };
 
     // ---- number of levels ----------------------------------------------------------------------------
@@ -1046,7 +1079,8 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
         SVB_CUDA(cudaStreamSynchronize(st));
         SVB_CUDA(cudaMalloc((void **)&f->f_code, (size_t)std::max<int64_t>(f->f_chunks, 1) * 16));
         SVB_CUDA(cudaMalloc((void **)&f->f_meta, (size_t)std::max<int64_t>(f->f_chunks, 1)));
-        fact_row_place_kernel<<<gw, 256, (size_t)8 * 2 * L * 16 * sizeof(int), st>>>(rowptr.p, ridx.p, rlvl.p, m, L, (int)n, f->f_rowptr, gend.p,
+        f->f_cshift = (n <= 8190) ? 3 : 0;  // the codes of the forward stream are byte offsets when they fit in 16 bits
+        fact_row_place_kernel<<<gw, 256, (size_t)8 * 2 * L * 16 * sizeof(int), st>>>(rowptr.p, ridx.p, rlvl.p, m, L, (int)n, f->f_cshift, f->f_rowptr, gend.p,
                                                   e.p ? e.p->colptr : nullptr, e.p ? e.p->rowidx : nullptr,
                                                   e.p ? (const double *)e.p->val : nullptr, (uint16_t *)f->f_code, f->f_meta);
         count_launch();

@@ -150,7 +150,8 @@ struct svb_factored_s {
     double *tlevA = nullptr;         // [ntiles*R*L] the same, level-major inside every adjoint tile
     double *inv = nullptr;           // [n] 1/sd
     int64_t *f_rowptr = nullptr;     // [m+1] forward: first chunk of a cell's row (chunk = 8 codes)
-    void *f_code = nullptr;          // [f_chunks*8] u16 gene index, pad = n
+    void *f_code = nullptr;          // [f_chunks*8] u16 gene index (<< f_cshift: byte offsets when n <= 8190), pad = n
+    int f_cshift = 0;
     uint8_t *f_meta = nullptr;       // [f_chunks] (level << 1) | last chunk of the row
     int64_t f_chunks = 0;
     int64_t *a_gptr = nullptr;       // [ntiles*n+1] adjoint: first chunk of a (tile, gene) segment
