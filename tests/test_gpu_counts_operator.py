@@ -135,6 +135,27 @@ def test_counts_operator_edge_cases(sv, orc):
         sv.CountsCenteredMatrix(dm, lib[keep], 1e4, 10.0, levels=5)
 
 
+@pytest.mark.parametrize("n_genes", [4000, 9000])
+def test_counts_operator_wide_gene_sets(sv, orc, n_genes):
+    # 4000 genes: the gene vector takes the 512-thread forward kernel; 9000 genes: the 16-bit codes are indices
+    # (byte offsets no longer fit) — both against the oracle's explicit matrix
+    rng = np.random.default_rng(n_genes)
+    m = 1500
+    lam = np.exp(rng.normal(-2.2, 1.2, n_genes))
+    D = rng.poisson(np.exp(0.4 * rng.standard_normal(m))[:, None] * lam[None, :] * 2.0)
+    D[D.sum(axis=1) == 0, 0] = 1
+    D[:, D.var(axis=0) == 0] += (np.arange(m) % 3 == 0)[:, None]   # no constant genes
+    X = sp.csc_matrix(D.astype(np.int64))
+    So = _explicit_oracle(sv, orc, X, None, 10.0)
+    C = sv.scale_features_counts(X, scale_factor=1e4, scale_max=10.0)
+    np.testing.assert_array_equal(C.mu, So.mu)
+    _check_products(C, So, rng)
+    init = rng.standard_normal(n_genes)
+    G = sv.irlba(C, 5, init=init, tol=1e-9)
+    O = orc.irlba(So, 5, init=init, tol=1e-9)
+    np.testing.assert_allclose(G.S, O.S, rtol=1e-6)
+
+
 def test_counts_operator_properties_at_scale(sv):
     # 200k cells x 2000 HVGs: adjoint identity <S x, w> = <x, S' w> and agreement with the explicit operator
     counts = sv.synthetic_counts(200_000, 8000, 700.0, programs=20, seed=5)
