@@ -112,6 +112,16 @@ int svb_row_slice(svb_matrix_t a, int64_t row0, int64_t row1, svb_matrix_t *out)
 /* copy(X') : stable transpose on the device (every reader of src/input.jl ends with it). */
 int svb_transpose(svb_matrix_t a, svb_matrix_t *out);
 
+/* filtering.jl:15-35,101-106 filter_cells, then filter_features on the remaining cells (= filter_counts; with
+ * min_cells = 0 it is filter_cells alone, with the three cell thresholds 0 it is filter_features alone):
+ *   cell kept    <=> #{features with count > min_feature_count} >= min_features  and (min_umi <= 0 or UMI total > min_umi)
+ *   feature kept <=> #{kept cells with count > 0} >= min_cells
+ * cell_keep[nrow] / feature_keep[ncol] (optional) receive the 0/1 masks (the reference's CI / FI); out = A[CI, FI] with
+ * every stored entry of a kept pair, rows renumbered in order. Integer counts only. */
+int svb_filter_counts(svb_matrix_t counts, int64_t min_cells, int64_t min_features,
+                      int64_t min_feature_count, int64_t min_umi, uint8_t *cell_keep,
+                      uint8_t *feature_keep, svb_matrix_t *out);
+
 /* ---- pre-processing sweeps ---------------------------------------------------------------- */
 /* normalize.jl:17-55  row_norm / log_norm. Integer counts in; dtype = SVB_F32 | SVB_F64 out.
  * B = scale_factor * x / s_cell (one rounded multiply, one rounded divide), then log1p. */

@@ -98,6 +98,22 @@ function standardized_var_clipped(A::SparseMatrixCSC{<:Integer}, mu::Vector{Floa
     out
 end
 
+# filtering.jl:15-35,101-106 — cells first, then features on the remaining cells; returns (A[CI, FI], CI, FI)
+function filter_counts(A::SparseMatrixCSC{<:Integer}; min_cells=0, min_features=0, min_feature_count=0, min_umi=0)
+    d = upload(A)
+    CI, FI = zeros(UInt8, size(A, 1)), zeros(UInt8, size(A, 2))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:svb_filter_counts, libsvb), Cint,
+        (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Ptr{UInt8}, Ptr{UInt8}, Ref{Ptr{Cvoid}}),
+        d.h, min_cells, min_features, min_feature_count, min_umi, CI, FI, h))
+    download(DeviceMatrix(h[])), CI .!= 0, FI .!= 0
+end
+function filter_counts(A::NamedCountMatrix; kw...)
+    counts, CI, FI = filter_counts(A.array; kw...)
+    barcodes, features = names(A)
+    NamedArray(counts, (barcodes[CI], features[FI]), A.dimnames)
+end
+
 function variance_stabilizing_transformation(A::SparseMatrixCSC{<:Integer}; loess_span::Real=0.5)
     mu, var = mean_var(A)                                        # device, order-exact Welford (scaling.jl:18-34)
     sd = sqrt.(var)

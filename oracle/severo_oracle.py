@@ -105,6 +105,32 @@ def _idx64(A):
 # --------------------------------------------------------------------------------------
 # normalize.jl
 # --------------------------------------------------------------------------------------
+def filter_features(A, min_cells=0):
+    """filtering.jl:15-20: cells_per_feature = vec(sum(>(0), A, dims=1)); FI = cells_per_feature .>= min_cells."""
+    A = _csc(A)
+    cells_per_feature = np.asarray((A > 0).sum(axis=0)).ravel()
+    FI = cells_per_feature >= min_cells
+    return A[:, FI], FI
+
+
+def filter_cells(A, min_features=0, min_feature_count=0, min_umi=0):
+    """filtering.jl:22-35: features_per_cell = vec(sum(>(min_feature_count), A, dims=2)); CI = .>= min_features;
+    if min_umi > 0: CI .&= vec(sum(A, dims=2)) .> min_umi."""
+    A = _csc(A)
+    features_per_cell = np.asarray((A > min_feature_count).sum(axis=1)).ravel()
+    CI = features_per_cell >= min_features
+    if min_umi > 0:
+        CI &= np.asarray(A.sum(axis=1)).ravel() > min_umi
+    return sp.csc_matrix(A[CI, :]), CI
+
+
+def filter_counts(A, min_cells=0, min_features=0, min_feature_count=0, min_umi=0):
+    """filtering.jl:101-106: cells first, then features on what remains."""
+    counts, CI = filter_cells(A, min_features, min_feature_count, min_umi)
+    counts, FI = filter_features(counts, min_cells)
+    return sp.csc_matrix(counts), CI, FI
+
+
 def row_norm(A, scale_factor=1.0, dtype=np.float64):
     """normalize.jl:17-32. Integer counts in, ``dtype`` values out, same sparsity pattern."""
     A = _csc(A)

@@ -58,6 +58,7 @@ SIGNATURES = {
     "svb_column_subset": (c_int, [_h, c_void_p, c_int64, c_int, _ph]),
     "svb_row_slice": (c_int, [_h, c_int64, c_int64, _ph]),
     "svb_transpose": (c_int, [_h, _ph]),
+    "svb_filter_counts": (c_int, [_h, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, _ph]),
     "svb_normalize": (c_int, [_h, c_int, c_double, c_int, _ph]),
     "svb_normalize_libsize": (c_int, [_h, c_void_p, c_int, c_double, c_int, _ph]),
     "svb_row_sums": (c_int, [_h, c_void_p]),

@@ -29,7 +29,7 @@ from . import _lib as L
 from .loess import loess_fit_predict
 
 __all__ = [
-    "DeviceMatrix", "NamedArray", "convert_counts", "normalize_cells", "mean_var", "mean_std",
+    "DeviceMatrix", "NamedArray", "convert_counts", "filter_cells", "filter_features", "filter_counts", "normalize_cells", "mean_var", "mean_std",
     "standardized_var_clipped", "find_variable_features", "scale_features", "CenteredMatrix", "CountsCenteredMatrix",
     "scale_features_counts", "irlba",
     "SVD", "svd_flip", "pca", "embedding", "LinearEmbedding", "synthetic_counts",
@@ -175,6 +175,51 @@ def _to_device(A):
 
 def _rewrap(result, names, dimnames):
     return result if names is None else NamedArray(result, names, dimnames)
+
+
+# ------------------------------------------------------------------------------------------------
+# filtering.jl
+# ------------------------------------------------------------------------------------------------
+def _filter(X, min_cells, min_features, min_feature_count, min_umi):
+    A, names, dimnames = _unwrap(X)
+    dA, temp = _to_device(A)
+    if dA.vtype != L.SVB_I32:
+        raise TypeError("filtering expects a count matrix (integer values)")
+    m, n = dA.shape
+    ci, fi = np.zeros(m, dtype=np.uint8), np.zeros(n, dtype=np.uint8)
+    h = ctypes.c_void_p()
+    L.check(L.lib().svb_filter_counts(dA._h, int(min_cells), int(min_features), int(min_feature_count), int(min_umi),
+                                       L.ptr(ci), L.ptr(fi), ctypes.byref(h)))
+    out = DeviceMatrix(h)
+    CI, FI = ci.astype(bool), fi.astype(bool)
+    if temp:
+        host = out.to_host()
+        out.free()
+        dA.free()
+        out = host
+    if names is not None:
+        out = NamedArray(out, ([b for b, k in zip(names[0], CI) if k], [f for f, k in zip(names[1], FI) if k]), dimnames)
+    return out, CI, FI
+
+
+def filter_features(A, min_cells=0):
+    """filtering.jl:15-20,50-54: keep the features detected (count > 0) in at least ``min_cells`` cells.
+    Plain matrix in -> (A[:, FI], FI) like the unlabelled method; NamedArray in -> labelled matrix."""
+    out, _, FI = _filter(A, min_cells, 0, 0, 0)
+    return out if isinstance(A, NamedArray) else (out, FI)
+
+
+def filter_cells(A, min_features=0, min_feature_count=0, min_umi=0):
+    """filtering.jl:22-35,72-76: keep the cells with at least ``min_features`` features above ``min_feature_count`` and,
+    when ``min_umi > 0``, a UMI total strictly above ``min_umi``."""
+    out, CI, _ = _filter(A, 0, min_features, min_feature_count, min_umi)
+    return out if isinstance(A, NamedArray) else (out, CI)
+
+
+def filter_counts(A, min_cells=0, min_features=0, min_feature_count=0, min_umi=0):
+    """filtering.jl:101-106: filter_cells, then filter_features on the remaining cells."""
+    out, CI, FI = _filter(A, min_cells, min_features, min_feature_count, min_umi)
+    return out if isinstance(A, NamedArray) else (out, CI, FI)
 
 
 # ------------------------------------------------------------------------------------------------

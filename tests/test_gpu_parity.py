@@ -50,6 +50,57 @@ def test_upload_download_subset_slice_transpose(sv):
 
 
 # ---------------------------------------------------------------------------------------------
+# filtering.jl
+# ---------------------------------------------------------------------------------------------
+def test_filter_counts_fixed_matrix_and_random(sv, orc, golden):
+    # test/test_input.jl:25-42 through the labelled interface
+    X = sp.csc_matrix(np.array(golden["X"], dtype=np.int64))
+    C = sv.filter_counts(sv.convert_counts(X), min_features=1, min_cells=2, min_umi=2)
+    assert C.shape == (7, 4)
+    assert C.names[0] == ["cell-1", "cell-2", "cell-3", "cell-4", "cell-5", "cell-8", "cell-9"]
+    assert C.names[1] == ["gene-1", "gene-2", "gene-4", "gene-5"]
+    assert (C.array != X[np.ix_(golden["filter_cells"], golden["filter_genes"])]).nnz == 0
+    # random count matrices against the oracle, every threshold combination, explicit zeros kept, bit-exact
+    rng = np.random.default_rng(3)
+    D = rng.poisson(0.25, (4000, 700)).astype(np.int64)
+    D[rng.integers(0, 4000, 50), :] = 0                      # empty cells
+    D[:, rng.integers(0, 700, 20)] = 0                       # empty genes
+    A = sp.csc_matrix(D)
+    A.data[::97] = 0                                         # stored zeros: not "detected" (sum(>(0), ...)), but stored
+    for kw in (dict(min_cells=3, min_features=150, min_feature_count=0, min_umi=170),
+               dict(min_cells=0, min_features=0, min_feature_count=0, min_umi=0),
+               dict(min_cells=40, min_features=5, min_feature_count=1, min_umi=0),
+               dict(min_cells=10**6), dict(min_features=10**6)):
+        G, CI, FI = sv.filter_counts(A, **kw)
+        O, CIo, FIo = orc.filter_counts(A, **kw)
+        np.testing.assert_array_equal(CI, CIo)
+        np.testing.assert_array_equal(FI, FIo)
+        assert G.shape == O.shape
+        # every stored entry of a kept (cell, feature) pair survives, stored zeros included (Julia's A[CI, FI])
+        coo = A.tocoo()
+        assert G.nnz == int((CIo[coo.row] & FIo[coo.col]).sum())
+        Gs, Os = G.copy(), O.copy()
+        Gs.eliminate_zeros(); Os.eliminate_zeros()
+        Gs.sort_indices(); Os.sort_indices()
+        np.testing.assert_array_equal(Gs.indptr, Os.indptr)
+        np.testing.assert_array_equal(Gs.indices, Os.indices)
+        np.testing.assert_array_equal(Gs.data, Os.data)
+    Gc, CIc = sv.filter_cells(A, min_features=150)
+    Oc, CIoc = orc.filter_cells(A, min_features=150)
+    np.testing.assert_array_equal(CIc, CIoc)
+    assert (Gc != Oc).nnz == 0
+    Gf, FIf = sv.filter_features(A, min_cells=60)
+    Of, FIof = orc.filter_features(A, min_cells=60)
+    np.testing.assert_array_equal(FIf, FIof)
+    assert (Gf != Of).nnz == 0
+    # device in -> device out, feeding the next stage without a host copy
+    dA = sv.DeviceMatrix.from_host(sp.csc_matrix(D))
+    dG, _, _ = sv.filter_counts(dA, min_cells=3, min_features=150)
+    assert isinstance(dG, sv.DeviceMatrix)
+    assert sv.normalize_cells(dG, scale_factor=1e4).shape == dG.shape
+
+
+# ---------------------------------------------------------------------------------------------
 # normalize.jl
 # ---------------------------------------------------------------------------------------------
 def test_normalize_cells_fixed_matrix(sv, golden):

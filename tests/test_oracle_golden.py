@@ -47,6 +47,20 @@ def test_centered_operator_fixed_vectors(orc, golden):
         np.testing.assert_allclose(C.mul(y, 2.0, 1.0, r.copy(), trans=True), op["r2"], rtol=1.5e-8)
 
 
+def test_filter_counts_fixed_matrix(orc, golden):
+    # test/test_input.jl:25-42: filter_counts(min_features=1, min_cells=2, min_umi=2) keeps cells 1,2,3,4,5,8,9 and genes 1,2,4,5
+    X = sp.csc_matrix(np.array(golden["X"], dtype=np.int64))
+    C, CI, FI = orc.filter_counts(X, min_features=1, min_cells=2, min_umi=2)
+    assert C.shape == (7, 4)
+    assert list(np.nonzero(CI)[0]) == golden["filter_cells"] and list(np.nonzero(FI)[0]) == golden["filter_genes"]
+    assert (C != X[np.ix_(golden["filter_cells"], golden["filter_genes"])]).nnz == 0
+    # the order matters (filtering.jl:84): gene 3 is detected in 1 cell only once cell 5 ... stays, gene 2 in 2 cells
+    C2, FI2 = orc.filter_features(X, min_cells=2)
+    assert list(np.nonzero(FI2)[0]) == [0, 1, 3, 4]
+    C3, CI3 = orc.filter_cells(X, min_features=1, min_feature_count=2)
+    assert list(np.nonzero(CI3)[0]) == [0, 1, 2, 3, 4, 7, 8]     # cells whose largest count exceeds 2
+
+
 def test_normalize_cells_fixed_matrix(orc, golden):
     # test/test_input.jl:47-75
     X = np.array(golden["X"], dtype=np.int64)[np.ix_(golden["filter_cells"], golden["filter_genes"])]
