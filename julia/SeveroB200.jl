@@ -48,6 +48,16 @@ function download_values(d::DeviceMatrix, ::Type{R}, nnz::Integer) where {R}
     nz
 end
 
+# the whole matrix back as a SparseMatrixCSC{Int64,Int64} (counts) — 1-based indices written by the library
+function download(d::DeviceMatrix)
+    nrow = Ref{Int64}(0); ncol = Ref{Int64}(0); nz = Ref{Int64}(0); vt = Ref{Cint}(0)
+    check(ccall((:svb_matrix_info, libsvb), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Int64}, Ref{Cint}), d.h, nrow, ncol, nz, vt))
+    colptr = Vector{Int64}(undef, ncol[] + 1); rowval = Vector{Int64}(undef, nz[]); nzval = Vector{Int64}(undef, nz[])
+    check(ccall((:svb_matrix_download, libsvb), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Cvoid}, Cint, Cint),
+        d.h, colptr, rowval, nzval, SVB_I64, 1))
+    SparseMatrixCSC(nrow[], ncol[], colptr, rowval, nzval)
+end
+
 # ---- normalize.jl:40-79 ------------------------------------------------------------------------------
 function normalize_cells(X::SparseMatrixCSC{<:Integer,Int64}; method=:lognormalize, scale_factor::Real=1., dtype::Type{T}=Float64) where {T<:AbstractFloat}
     method = Symbol(method)
