@@ -169,7 +169,7 @@ int svb_operator_create_dense(int64_t m, int64_t n, const double *a, int64_t lda
  * PCA call: entry (i,j) of S is min(log1p(scale_factor*c_ij/libsize_i)/sd_j, scale_max + mean_j/sd_j) - mean_j/sd_j,
  * stored as ONE 16-bit code per nonzero (2 instead of 10 bytes); the value is rebuilt in the product kernels from a
  * per-cell table over the count levels 1..levels and the per-gene 1/sd. Counts above `levels`, counts < 1 and
- * clipped entries keep their exact value in a small explicit residual. counts: int32 CSC, cells x HVGs (<= 65534
+ * clipped entries keep their exact Float64 value as exception chunks of the same streams (17 B per such entry). counts: int32 CSC, cells x HVGs (<= 65534
  * genes). libsize[nrow]: library sizes of the FULL count matrix (svb_row_sums). mean/var[ncol]: moments of the
  * log-normalised HVG columns (svb_mean_var), or both NULL: they are then computed here from the counts by two parallel
  * passes (with a communicator: over the cells of all ranks) — a few ulp from the sequential Welford of scaling.jl:18-34,
@@ -178,8 +178,9 @@ int svb_operator_create_dense(int64_t m, int64_t n, const double *a, int64_t lda
 int svb_operator_create_counts(svb_matrix_t counts, const int64_t *libsize, double scale_factor,
                                const double *mean, const double *var, double scale_max, int levels,
                                double *mu_out, svb_operator_t *out);
+/* levels L, cells per adjoint tile, entries stored as codes / as exception chunks, 16-byte chunks of the two streams */
 int svb_operator_counts_info(svb_operator_t op, int *levels, int64_t *tile_cells, int64_t *nnz_coded,
-                             int64_t *nnz_explicit, int64_t *fwd_chunks, int64_t *adj_chunks);
+                             int64_t *nnz_exception, int64_t *fwd_chunks, int64_t *adj_chunks);
 int svb_operator_free(svb_operator_t op);
 int svb_operator_info(svb_operator_t op, int64_t *m, int64_t *n, int64_t *nnz, int *is_dense,
                       int *value_bytes, int *index_bytes);

@@ -514,7 +514,7 @@ class CountsCenteredMatrix(CenteredMatrix):
         lv = ctypes.c_int()
         v = [ctypes.c_int64() for _ in range(5)]
         L.check(L.lib().svb_operator_counts_info(self._op, lv, *v))
-        return dict(levels=lv.value, tile_cells=v[0].value, nnz_coded=v[1].value, nnz_explicit=v[2].value,
+        return dict(levels=lv.value, tile_cells=v[0].value, nnz_coded=v[1].value, nnz_exception=v[2].value,
                     fwd_chunks=v[3].value, adj_chunks=v[4].value)
 
     def _operator(self):

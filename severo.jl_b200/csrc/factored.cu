@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(256) fact_classify_kernel(const int64_t *__res
 
 // the exception matrix (CSC, cells ascending inside a gene): every warp compacts the level-0 entries of its slice,
 // in order, at the offset the scan of the slice counts gives it; values are exact and pre-multiplied by sd
-__global__ void __launch_bounds__(256) fact_resid_fill_kernel(const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
+__global__ void __launch_bounds__(256) fact_exception_fill_kernel(const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
                                                               const int32_t *__restrict__ val, const uint8_t *__restrict__ lvl,
                                                               const long long *__restrict__ libsize, double sf,
                                                               const double *__restrict__ sd, const double *__restrict__ cap,
@@ -637,7 +637,7 @@ fwd_stream_kernel(const uint4 *__restrict__ code, const uint8_t *__restrict__ me
     int row0 = rowrel + __popc(bal0 & lt);
     rowrel += __popc(bal0);
     double t0 = (rel >= lo && rel < hi && (m0 >> 1) != FEXC) ? __ldg(tl + ((int64_t)row0 << log2L) + (m0 >> 1)) : 0.0;
-    double carry = 0.0;
+    double acc = 0.0;  // this lane's share of the row that is still open (summed across lanes when the row ends)
     // one iteration: QA/MA = current stage (refilled with iteration +FPD once consumed), MB = meta of the next iteration
 #define SVB_FWD_STEP(QA, MA, MB)                                                                                      \
     {                                                                                                                 \
@@ -658,17 +658,29 @@ fwd_stream_kernel(const uint4 *__restrict__ code, const uint8_t *__restrict__ me
         }                                                                                                             \
         pc += 32;                                                                                                     \
         pm += 32;                                                                                                     \
-        bool head0;                                                                                                   \
-        v = seg_scan(v, bal0, lane, head0);                                                                           \
-        if (head0) v += carry;                                                                                        \
-        if (mcur & 1u) {                                                                                              \
-            double r = alpha * (v - mudot);                                                                           \
-            if (beta != 0.0) r = fma(beta, yb[row0], r);                                                              \
-            if (coef != nullptr) r = fma(cf, cvb[row0], r);                                                           \
-            yb[row0] = r;                                                                                             \
+        const int nends = __popc(bal0); /* rows that end in this iteration (warp-uniform) */                          \
+        if (nends == 0) {                                                                                             \
+            acc += v; /* the open row continues: lane-private partial sums, no shuffles */                            \
+        } else {                                                                                                      \
+            double r;                                                                                                 \
+            if (nends == 1) { /* the usual case for rows longer than 32 chunks: one butterfly */                      \
+                const int b1 = __ffs(bal0) - 1;                                                                       \
+                r = acc + ((lane <= b1) ? v : 0.0);                                                                   \
+                _Pragma("unroll") for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);           \
+            } else { /* several (short) rows: carried sums enter at lane 0, then the segmented scan */                \
+                double tot = acc;                                                                                     \
+                _Pragma("unroll") for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);       \
+                bool head0;                                                                                           \
+                r = seg_scan(v + (lane == 0 ? tot : 0.0), bal0, lane, head0);                                         \
+            }                                                                                                         \
+            if (mcur & 1u) {                                                                                          \
+                r = alpha * (r - mudot);                                                                              \
+                if (beta != 0.0) r = fma(beta, yb[row0], r);                                                          \
+                if (coef != nullptr) r = fma(cf, cvb[row0], r);                                                       \
+                yb[row0] = r;                                                                                         \
+            }                                                                                                         \
+            acc = (lane > 31 - __clz(bal0)) ? v : 0.0; /* the chunks after the last row end open the next row */      \
         }                                                                                                             \
-        const double v31 = __shfl_sync(0xffffffffu, v, 31);                                                           \
-        carry = (bal0 >> 31) ? 0.0 : v31;                                                                             \
         bal0 = bal1;                                                                                                  \
         row0 = row1;                                                                                                  \
         t0 = t1;                                                                                                      \
@@ -918,7 +930,7 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
             SVB_CUDA(cudaMemcpyAsync(h, d5.p, sizeof(h), cudaMemcpyDeviceToHost, st));
             SVB_CUDA(cudaStreamSynchronize(st));
         }
-        // smallest L that leaves at most 1 % of the entries to the explicit residual (10 B/nnz there, 2 B/nnz here)
+        // smallest L that leaves at most 1 % of the entries to the exception chunks (17 B per entry there, 2.1 B here)
         const int cand[4] = {4, 8, 16, 32};
         L = 32;
         for (int i = 0; i < 4; ++i)
@@ -1014,7 +1026,7 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
         launch_strided_copy(exoff.p, FSL, n, e.p->colptr, st);
         SVB_CUDA(cudaMemcpyAsync(e.p->colptr + n, exoff.p + n * FSL, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
         dim3 grid((unsigned)n, FSL / 8);
-        fact_resid_fill_kernel<<<grid, 256, 0, st>>>(a->colptr, a->rowidx, (const int32_t *)a->val, lvl.p, d_lib.p, sf, d_sd.p, d_cap.p,
+        fact_exception_fill_kernel<<<grid, 256, 0, st>>>(a->colptr, a->rowidx, (const int32_t *)a->val, lvl.p, d_lib.p, sf, d_sd.p, d_cap.p,
                                                      exoff.p, e.p->rowidx, (double *)e.p->val);
         count_launch();
         SVB_LAUNCH_CHECK();
@@ -1132,7 +1144,7 @@ int svb_operator_create_counts(svb_matrix_t counts, const int64_t *libsize, doub
     SVB_API_END
 }
 
-int svb_operator_counts_info(svb_operator_t op, int *levels, int64_t *tile_cells, int64_t *nnz_coded, int64_t *nnz_explicit,
+int svb_operator_counts_info(svb_operator_t op, int *levels, int64_t *tile_cells, int64_t *nnz_coded, int64_t *nnz_exception,
                              int64_t *fwd_chunks, int64_t *adj_chunks) {
     SVB_API_BEGIN
     SVB_CHECK(op && op->fact, SVB_EARG, "svb_operator_counts_info: not a count-level operator");
@@ -1140,7 +1152,7 @@ int svb_operator_counts_info(svb_operator_t op, int *levels, int64_t *tile_cells
     if (levels) *levels = f->L;
     if (tile_cells) *tile_cells = f->R;
     if (nnz_coded) *nnz_coded = f->nnz_main;
-    if (nnz_explicit) *nnz_explicit = f->nnz_exc;
+    if (nnz_exception) *nnz_exception = f->nnz_exc;
     if (fwd_chunks) *fwd_chunks = f->f_chunks;
     if (adj_chunks) *adj_chunks = f->a_chunks;
     SVB_API_END

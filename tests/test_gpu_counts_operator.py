@@ -44,11 +44,11 @@ def test_counts_operator_products_vs_oracle(sv, orc, levels):
     assert C.shape == So.shape
     np.testing.assert_array_equal(C.mu, So.mu)               # exact moments: the stored mean/sd is bit-identical
     info = C.info()
-    assert info["nnz_coded"] + info["nnz_explicit"] == So.P.nnz
+    assert info["nnz_coded"] + info["nnz_exception"] == So.P.nnz
     if levels:
         assert info["levels"] == levels
         big = int((X[:, hvf].data > levels).sum())
-        assert info["nnz_explicit"] >= big                    # counts above the table go to the explicit residual
+        assert info["nnz_exception"] >= big                    # counts above the table become exception chunks
     _check_products(C, So, np.random.default_rng(1))
     # matrix forms (scaling.jl:259-272)
     V = np.asfortranarray(np.random.default_rng(2).standard_normal((300, 3)))
@@ -57,7 +57,7 @@ def test_counts_operator_products_vs_oracle(sv, orc, levels):
     C.free()
 
 
-def test_counts_operator_clip_goes_to_residual(sv, orc):
+def test_counts_operator_clipped_entries_are_exceptions(sv, orc):
     # a tight scale_max clips many entries (scaling.jl:212): they must keep their exact clipped value
     X = planted_counts(2500, 600, 6, seed=11, mean_nnz=100)
     hvf = sv.find_variable_features(X, 200)
@@ -66,7 +66,7 @@ def test_counts_operator_clip_goes_to_residual(sv, orc):
     nclip = int((So.P.data == (0.5 + So.mu)[cols]).sum())
     assert nclip > 100
     C = sv.scale_features_counts(X, scale_factor=1e4, scale_max=0.5, features=hvf)
-    assert C.info()["nnz_explicit"] >= nclip
+    assert C.info()["nnz_exception"] >= nclip
     _check_products(C, So, np.random.default_rng(3))
 
 
@@ -115,7 +115,7 @@ def test_counts_operator_edge_cases(sv, orc):
     for levels in (0, 4, 32):
         C = sv.scale_features_counts(X, scale_factor=1e4, scale_max=10.0, features=hv, levels=levels)
         np.testing.assert_array_equal(C.mu, So.mu)
-        assert C.info()["nnz_explicit"] >= 1
+        assert C.info()["nnz_exception"] >= 1
         _check_products(C, So, rng)
     # IRLBA through the operator on a small dense-ish problem (work clamps to min(m, n))
     G = sv.irlba(C, 3, init=rng.standard_normal(5), tol=1e-10)
@@ -164,8 +164,8 @@ def test_counts_operator_properties_at_scale(sv):
     S = sv.scale_features(Y, scale_max=10.0, features=hvf)
     C = sv.scale_features_counts(counts, scale_factor=1e4, scale_max=10.0, features=hvf)
     info = C.info()
-    assert info["nnz_coded"] + info["nnz_explicit"] == S.A.nnz
-    assert info["nnz_explicit"] <= 0.02 * S.A.nnz
+    assert info["nnz_coded"] + info["nnz_exception"] == S.A.nnz
+    assert info["nnz_exception"] <= 0.02 * S.A.nnz
     rng = np.random.default_rng(0)
     x, w = rng.standard_normal(2000), rng.standard_normal(200_000)
     Sx, Stw = C @ x, C.T @ w
