@@ -699,7 +699,9 @@ fwd_stream_kernel(const uint4 *__restrict__ code, const uint8_t *__restrict__ me
 // adjoint, stage 1: partial[t][g] = (1/sd_g) * sum over the chunks of segment (t,g) of sum_8 T[code], T[l*R+i] = t_i[l]*w_i;
 // partial[t][n] = sum of w over the tile. CTAs take tiles from a global counter (any order gives the same bits: every
 // tile has its own partial row); inside a tile warp k streams the k-th slice of the tile's chunks.
-template <int BLOCK, int MINB>
+// LAZY: lane-private partial sums, cross-lane reduction only in iterations where a segment ends (pays when the segments
+// are longer than a warp iteration: the 1024-cell tiles); otherwise a segmented scan every iteration + a carry register.
+template <int BLOCK, int MINB, bool LAZY>
 __global__ void __launch_bounds__(BLOCK, MINB)
 adj_stream_kernel(const int64_t *__restrict__ gptr, const uint4 *__restrict__ code, const uint8_t *__restrict__ meta,
                   const double *__restrict__ tlevA, int log2L, int log2R, int64_t m, int64_t n, int64_t ntiles,
@@ -753,7 +755,7 @@ adj_stream_kernel(const int64_t *__restrict__ gptr, const uint4 *__restrict__ co
         if (threadIdx.x == 0) partial[t * (n + 1) + n] = wsum;
         double *prow = partial + t * (n + 1);
         int gbase = g0;
-        double carry = 0.0;
+        double acc = 0.0;  // LAZY: this lane's share of the open segment; else the carried sum of the open segment
         for (; c - lane < cend; c += 32) {
             const int64_t cp = c + 32 * FPD;
             const bool okp = cp < cend;
@@ -765,12 +767,35 @@ adj_stream_kernel(const int64_t *__restrict__ gptr, const uint4 *__restrict__ co
             double v;
             if (mb[0] & 2u) v = __hiloint2double((int)q[0].w, (int)q[0].z) * T[RL + 1 + q[0].x];
             else v = gather8(T, q[0]);
-            bool head0;
-            v = seg_scan(v, bal, lane, head0);
-            if (head0) v += carry;
-            if (mb[0] & 1u) prow[g] = v * __ldg(inv + g);
-            const double v31 = __shfl_sync(0xffffffffu, v, 31);
-            carry = (bal >> 31) ? 0.0 : v31;
+            if (LAZY) {
+                const int nends = __popc(bal);  // segments that end in this iteration (warp-uniform)
+                if (nends == 0) {
+                    acc += v;  // the open segment continues: lane-private partial sums
+                } else {
+                    double r;
+                    if (nends == 1) {
+                        const int b1 = __ffs(bal) - 1;
+                        r = acc + ((lane <= b1) ? v : 0.0);
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+                    } else {
+                        double tot = acc;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+                        bool head0;
+                        r = seg_scan(v + (lane == 0 ? tot : 0.0), bal, lane, head0);
+                    }
+                    if (mb[0] & 1u) prow[g] = r * __ldg(inv + g);
+                    acc = (lane > 31 - __clz(bal)) ? v : 0.0;
+                }
+            } else {
+                bool head0;
+                v = seg_scan(v, bal, lane, head0);
+                if (head0) v += acc;  // acc = the carried sum of the segment that started in an earlier iteration
+                if (mb[0] & 1u) prow[g] = v * __ldg(inv + g);
+                const double v31 = __shfl_sync(0xffffffffu, v, 31);
+                acc = (bal >> 31) ? 0.0 : v31;
+            }
 #pragma unroll
             for (int s = 0; s + 1 < FPD; ++s) {
                 q[s] = q[s + 1];
@@ -825,7 +850,9 @@ static void launch_fact_fwd(svb_operator_s *op, double alpha, const double *dx, 
     SVB_LAUNCH_CHECK();
 }
 
-constexpr int ADJ_BLOCK = 512;
+// adjoint CTA: 512 threads and a 64 KB table (R*L = 8192; three CTAs per SM), or -- SVB_FACT_LOG2R one larger -- 1024
+// threads and a 128 KB table (R*L = 16384; one CTA per SM, segments twice as long)
+static inline int adj_block_of(const svb_factored_s *f) { return (f->log2R + f->log2L >= 14) ? 1024 : 512; }
 
 void fact_fwd(svb_operator_s *op, double alpha, const double *dx, double beta, double *dy, const double *coef, double csign,
               const double *cvec) {
@@ -844,10 +871,11 @@ void fact_fwd(svb_operator_s *op, double alpha, const double *dx, double beta, d
 void fact_adj_stage1(svb_operator_s *op, const double *dx) {
     svb_factored_s *f = op->fact;
     const size_t smem = (32 + ((size_t)1 << (f->log2R + f->log2L)) + 1 + (size_t)f->R) * sizeof(double);
-    auto k = adj_stream_kernel<ADJ_BLOCK, 3>;  // 3 x 512 threads per SM (2 x 512 with 60 registers measured the same)
+    const int block = adj_block_of(f);
+    auto k = (block == 1024) ? adj_stream_kernel<1024, 1, true> : adj_stream_kernel<512, 3, false>;
     if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (f->adj_grid == 0) f->adj_grid = (int)std::max<int64_t>(1, std::min<int64_t>(fresident_grid(k, smem, ADJ_BLOCK), f->ntiles));
-    k<<<(unsigned)f->adj_grid, ADJ_BLOCK, smem, ctx().stream>>>(f->a_gptr, (const uint4 *)f->a_code, f->a_meta, f->tlevA, f->log2L, f->log2R,
+    if (f->adj_grid == 0) f->adj_grid = (int)std::max<int64_t>(1, std::min<int64_t>(fresident_grid(k, smem, block), f->ntiles));
+    k<<<(unsigned)f->adj_grid, block, smem, ctx().stream>>>(f->a_gptr, (const uint4 *)f->a_code, f->a_meta, f->tlevA, f->log2L, f->log2R,
                                                                  op->m, op->n, f->ntiles, dx, f->inv, f->partial, f->a_slices, f->counters);
     SVB_LAUNCH_CHECK();
 }
@@ -940,8 +968,10 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
     while ((1 << log2L) < L) ++log2L;
     f->L = L;
     f->log2L = log2L;
-    // cells per adjoint tile: R*L = 8192 table entries (64 KB); small inputs get one small tile
-    int log2R = 13 - log2L;
+    // cells per adjoint tile: R*L = 16384 table entries (128 KB, one 1024-thread CTA per SM; measured 0.67 vs 0.76 ms per
+    // product at C3) when there are at least 8 tiles per SM, else R*L = 8192 (64 KB, three 512-thread CTAs per SM: with
+    // fewer tiles than that the coarser tiles quantise badly over the SMs); small inputs get one small tile
+    int log2R = (m >= (int64_t)8 * C.sm_count * (16384 >> log2L)) ? 14 - log2L : 13 - log2L;
     const char *envr = getenv("SVB_FACT_LOG2R");
     if (envr) log2R = std::max(5, std::min(atoi(envr), 14 - log2L));
     while (log2R > 5 && (1ll << (log2R - 1)) >= m) --log2R;
@@ -1054,7 +1084,7 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
         fact_seg_fill_kernel<<<fgrid(nseg * 8), 256, 0, st>>>(startpos.p, a->rowidx, lvl.p, nseg, n, log2R, log2L, f->a_gptr, estart.p,
                                                               e.p ? e.p->rowidx : nullptr, e.p ? (const double *)e.p->val : nullptr,
                                                               (uint16_t *)f->a_code, f->a_meta);
-        constexpr int K = ADJ_BLOCK / 32;
+        const int K = adj_block_of(f) / 32;
         SVB_CUDA(cudaMalloc((void **)&f->a_slices, (size_t)f->ntiles * (K + 1) * sizeof(int32_t)));
         fact_slices_kernel<<<(unsigned)((f->ntiles * (K + 1) + 255) / 256), 256, 0, st>>>(f->a_gptr, f->ntiles, n, K, f->a_slices);
         SVB_CUDA(cudaMalloc((void **)&f->counters, 2 * sizeof(unsigned int)));
