@@ -329,7 +329,7 @@ def run_b200(args):
         roofline = roofline_of(classes, peak, peak_src, "counts" if use_counts else None, args.config, world)
         if use_counts:
             roofline["note"] = ("count-level operator: 2.125 B per nonzero in HBM; ncu (profiles/r02_kernels.md) shows the kernel "
-                                "bound by the shared-memory gather pipe (L1TEX 85 %, issue slots 61-73 % busy, DRAM 28 %), not by "
+                                "bound by the shared-memory gather pipe (L1TEX 75-89 %, issue slots 61-63 % busy, DRAM ~35 %), not by "
                                 "HBM; the explicit operator of the same matrix (explicit_operator) is the HBM-bound one")
         explicit = None
         if use_counts:
