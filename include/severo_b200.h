@@ -194,6 +194,13 @@ int svb_mul(svb_operator_t op, char trans, double alpha, const double *x, double
 int svb_mul_device(svb_operator_t op, char trans, double alpha, const double *dx, double beta,
                    double *dy);
 
+/* C'C (scaling.jl:274-296, over the CSC x CSC -> dense product of mul.jl:82-114): G (n x n, column-major, host) =
+ * S'S = A'A - mu q' - q mu' + M mu mu', q = column sums of A, M = cells. Explicit sparse operators: one fused pass per
+ * block of 4 genes over the adjoint layout (lower triangle only, fixed summation order, exactly symmetric result);
+ * dense and count-level operators: column j = S'(S e_j). With a communicator G is summed over the cell shards and
+ * identical on all ranks. */
+int svb_gram(svb_operator_t op, double *G);
+
 /* ---- IRLBA (replaces libcell `irlba`, src/irlba.jl:66-71) -------------------------------------- */
 /* Same buffers and return convention as the legacy call: init[n] in; s[nu], U[m x nu], V[n x nu]
  * out (column-major, caller-owned). m_b = work size (irlba.jl:50: nu+7, clamped to min(m,n)).
@@ -212,6 +219,14 @@ int svb_result_info(svb_result_t r, int64_t *m, int64_t *n, int64_t *nu, int64_t
 /* scale_u != 0 returns Z = U*Diagonal(s) (embedding.jl:67 coordinates) instead of U. */
 int svb_result_download(svb_result_t r, double *s, double *U, double *V, int scale_u);
 int svb_result_free(svb_result_t r);
+
+/* tssvd (embedding.jl:30-44, `embedding(...; algorithm=:tssvd)`): C = Hermitian(A'A) on the device (svb_gram's kernels),
+ * its nsv largest eigenpairs (lambda, phi) by the device solver applied to C (the reference calls Arpack `eigs` on the
+ * host), Sigma = sqrt(lambda), U = A*phi*inv(Diagonal(Sigma)). ncv = Lanczos basis size (the reference's default is
+ * 2*nsv; <= 0 picks nsv+7), tol <= 0 (eigs' tol = 0.0, machine precision) is served at 1e-12, init[n] = start vector. Result as for
+ * svb_irlba_solve (U local rows with a communicator); info = -2 when not converged within maxit. */
+int svb_tssvd(svb_operator_t op, int64_t nsv, int64_t ncv, int64_t maxit, double tol,
+              const double *init, svb_result_t *out);
 
 /* ---- synthetic count matrices (benchmark inputs; counter-based RNG, any shard reproducible) ---- */
 /* Poisson counts x_ij ~ Poisson(L_i * p_j * f_{c(i),j}), L_i log-normal, p_j gamma-shaped,

@@ -566,6 +566,42 @@ def irlba(A, nu, init=None, tol=1e-5, svtol=None, maxit=1000, work=None, rng=Non
 
 
 # --------------------------------------------------------------------------------------
+# C'C (scaling.jl:274-296 over mul.jl:82-114) and tssvd (embedding.jl:30-44)
+# --------------------------------------------------------------------------------------
+def gram(C: "CenteredMatrix"):
+    """scaling.jl:274-296 ``mul!(C, S', S, 1, 0)``, statement by statement: ``A'A`` (the CSC x CSC -> dense triple loop of
+    mul.jl:82-114, here scipy's product — same sums, unspecified order), ``q = sum(A, dims=1)``, ``C -= mu*q``,
+    ``q -= m*mu``, ``C -= q'*mu'``. Unpinned upstream (no reference test calls it): the tests pin it on the dense
+    ``convert(Matrix, S)`` (scaling.jl:298-303) instead."""
+    m, n = C.shape
+    if C.dense:
+        A = np.asarray(C.P, dtype=np.float64)
+        G = A.T @ A
+        q = A.sum(axis=0)
+    else:
+        A = C.P.T.tocsc() if C.transposed else C.P
+        G = np.asarray((A.T @ A).todense(), dtype=np.float64)
+        q = np.asarray(A.sum(axis=0), dtype=np.float64).ravel()
+    if C.mu is not None:
+        G = G - np.outer(C.mu, q)                 # scaling.jl:284  - M'A
+        q = q - m * C.mu                          # scaling.jl:292  axpy!(-size(Al,1), mul, q)
+        G = G - np.outer(q, C.mu)                 # scaling.jl:293  + (M'M - A'M)
+    return np.asfortranarray(G)
+
+
+def tssvd(C: "CenteredMatrix", nsv=6):
+    """embedding.jl:30-44: eigenpairs of Hermitian(A'A) (Arpack ``eigs`` upstream; LAPACK ``eigh`` here — converged
+    eigenpairs are the same up to sign), ``Sigma = sqrt(lambda)``, ``U = A*phi*inv(Diagonal(Sigma))``."""
+    G = gram(C)
+    lam, phi = np.linalg.eigh((G + G.T) * 0.5)
+    order = np.argsort(lam)[::-1][:nsv]
+    lam, phi = lam[order], phi[:, order]
+    sigma = np.sqrt(lam)
+    U = np.column_stack([C.mul(np.ascontiguousarray(phi[:, i])) for i in range(nsv)]) / sigma[None, :]
+    return IrlbaResult(np.asfortranarray(U), sigma, np.asfortranarray(phi), 0, 0, 0)
+
+
+# --------------------------------------------------------------------------------------
 # embedding.jl:46-76 _pca post-processing ; utils.jl:215-228 svd_flip!
 # --------------------------------------------------------------------------------------
 def pca_post(U, S, V, npcs, m):

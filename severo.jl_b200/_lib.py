@@ -80,6 +80,8 @@ SIGNATURES = {
                           c_void_p, c_void_p, _p64, _p64]),
     "svb_irlba_solve": (c_int, [_h, c_int64, c_int64, c_int64, c_int64, c_double, c_double, c_void_p, c_void_p,
                                 c_void_p, c_void_p, _ph]),
+    "svb_gram": (c_int, [_h, c_void_p]),
+    "svb_tssvd": (c_int, [_h, c_int64, c_int64, c_int64, c_double, c_void_p, _ph]),
     "svb_result_info": (c_int, [_h, _p64, _p64, _p64, _p64, _p64, _pint]),
     "svb_result_download": (c_int, [_h, c_void_p, c_void_p, c_void_p, c_int]),
     "svb_result_free": (c_int, [_h]),

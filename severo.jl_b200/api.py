@@ -31,7 +31,7 @@ from .loess import loess_fit_predict
 __all__ = [
     "DeviceMatrix", "NamedArray", "convert_counts", "filter_cells", "filter_features", "filter_counts", "normalize_cells", "mean_var", "mean_std",
     "standardized_var_clipped", "find_variable_features", "scale_features", "CenteredMatrix", "CountsCenteredMatrix",
-    "scale_features_counts", "irlba",
+    "scale_features_counts", "irlba", "gram", "tssvd",
     "SVD", "svd_flip", "pca", "embedding", "LinearEmbedding", "synthetic_counts",
 ]
 
@@ -646,6 +646,48 @@ def irlba(A, nu, S: Optional[SVD] = None, init=None, tol=1e-5, svtol=None, maxit
     return SVD(U, s, V.T, it.value, mp.value)
 
 
+def gram(A):
+    """``C'C`` for a CenteredMatrix (scaling.jl:274-296; plain ``A'A`` through mul.jl:82-114 when there is no centre):
+    the n x n Gram matrix, computed on the device (``svb_gram``)."""
+    C = _as_operator(A)
+    n = C.shape[1]
+    G = np.zeros((n, n), order="F")
+    L.check(L.lib().svb_gram(C._operator(), L.ptr(G)))
+    return G
+
+
+def tssvd(A, nsv=6, ritzvec=True, tol=0.0, maxiter=1000, ncv=None, init=None, rng=None):
+    """Severo.tssvd (embedding.jl:30-44): ``SVD(U, Sigma, phi')`` from the ``nsv`` largest eigenpairs of
+    ``Hermitian(A'A)``. Keywords as upstream (``ncv`` defaults to ``2*nsv``, ``tol = 0.0`` = machine precision);
+    ``init`` is Arpack's ``v0``. ``ritzvec=False`` returns an m x 0 ``U`` like embedding.jl:40-42."""
+    C = _as_operator(A)
+    m, n = C.shape
+    nsv = int(nsv)
+    ncv = 2 * nsv if ncv is None else int(ncv)
+    ncv = max(min(ncv, n), min(nsv + 1, n))
+    if init is None:
+        rng = np.random.default_rng() if rng is None else rng
+        init = rng.standard_normal(n)
+    init = np.ascontiguousarray(init, dtype=np.float64)
+    if init.shape[0] != n:
+        raise ValueError("init must have length n")
+    h = ctypes.c_void_p()
+    rc = L.lib().svb_tssvd(C._operator(), nsv, ncv, int(maxiter), float(tol), L.ptr(init), ctypes.byref(h))
+    L.check(rc)
+    try:
+        it, mp, info = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int()
+        L.check(L.lib().svb_result_info(h, None, None, None, ctypes.byref(it), ctypes.byref(mp), ctypes.byref(info)))
+        if info.value != 0:
+            raise RuntimeError("convergence failed")
+        s = np.zeros(nsv)
+        V = np.zeros((n, nsv), order="F")
+        U = np.zeros((m, nsv if ritzvec else 0), order="F")
+        L.check(L.lib().svb_result_download(h, L.ptr(s), L.ptr(U) if ritzvec else None, L.ptr(V), 0))
+    finally:
+        L.lib().svb_result_free(h)
+    return SVD(U, s, V.T, it.value, mp.value)
+
+
 def svd_flip(S: SVD, u_based_decision=True):
     """utils.jl:215-228 svd_flip!: make the max-|.| entry of every U (or V) column positive (in place)."""
     M = S.U if u_based_decision else S.V
@@ -676,7 +718,9 @@ def _pca(X, npcs, algorithm="arpack", **kw):
       triplets are unique up to sign, so the request is served by the same device solver run to Arpack-like accuracy
       (``tol`` default 1e-10; Arpack's own default is machine eps); ``maxiter`` / ``ncv`` map to ``maxit`` / ``work``.
       Iterates differ from Arpack's, results agree to the tolerance.
-    * ``:tssvd`` / dense ``svd`` — other solvers (Gram matrix ``C'C`` through src/mul.jl, LAPACK): outside this path.
+    * ``:tssvd`` — embedding.jl:30-44: the Gram matrix ``C'C`` (scaling.jl:274-296) is built on the device, its
+      eigenpairs come from the device solver (``svb_tssvd``); keywords ``tol``, ``maxiter``, ``ncv`` as upstream.
+    * dense ``svd`` — LAPACK on the host: outside this path.
     """
     algorithm = str(algorithm)
     if algorithm == "arpack":
@@ -687,16 +731,21 @@ def _pca(X, npcs, algorithm="arpack", **kw):
         if "ncv" in kw:
             kw["work"] = kw.pop("ncv")
         kw.pop("nsv", None)
-    elif algorithm != "irlba":
-        raise ValueError(f"algorithm {algorithm} is outside the B200 hot path (use algorithm=:irlba or :arpack)")
+    elif algorithm not in ("irlba", "tssvd"):
+        raise ValueError(f"algorithm {algorithm} is outside the B200 hot path (use algorithm=:irlba, :arpack or :tssvd)")
     C = _as_operator(X)
     m, n = C.shape
     npcs = min(min(m, n), int(npcs))
-    if npcs > 0.5 * min(m, n):
+    if npcs > 0.5 * min(m, n) and algorithm != "tssvd":
         # the reference switches to a dense LAPACK svd here (embedding.jl:50-53); there is no CPU fallback
         # in this build, IRLBA with work = min(m, n) spans the whole space and is exact in that regime.
         warnings.warn("Computing too large a percentage of principal components")
-    S = irlba(C, npcs, **kw)
+    if algorithm == "tssvd":
+        kw = dict(kw)
+        kw.pop("nsv", None)
+        S = tssvd(C, nsv=npcs, **kw)                       # embedding.jl:58-59
+    else:
+        S = irlba(C, npcs, **kw)
     Z = S.U[:, :npcs] * S.S[None, :npcs]                     # embedding.jl:67
     stdev = S.S[:npcs] / np.sqrt(max(1, m - 1))             # embedding.jl:68
     loadings = S.V[:, :npcs]

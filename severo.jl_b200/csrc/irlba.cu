@@ -331,6 +331,66 @@ __global__ void colscale_kernel(const double *__restrict__ U, const double *__re
         out[i] = U[i] * s[i / m];
 }
 
+__global__ void tssvd_sigma_kernel(const double *__restrict__ lambda, int64_t nu, double *__restrict__ sigma, double *__restrict__ inv) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nu) {
+        const double s = sqrt(fmax(lambda[i], 0.0));
+        sigma[i] = s;
+        inv[i] = s > 0.0 ? 1.0 / s : 0.0;
+    }
+}
+
+// tssvd (embedding.jl:30-44): C = Hermitian(A'A); (lambda, phi) = the nsv largest eigenpairs of C; Sigma = sqrt(lambda);
+// U = A*phi*inv(Diagonal(Sigma)); SVD(U, Sigma, phi'). The reference hands C to Arpack's `eigs` on the host; here C is
+// built on the device (op_gram), stays there, and its eigenpairs come from the same device IRLBA applied to the dense
+// symmetric positive semi-definite C (singular triplets of C = its eigenpairs). With cells sharded every rank holds the
+// same allreduced C and solves the n x n problem redundantly (no exchange: nranks is masked for that solve).
+static void tssvd_run(svb_operator_s *op, int64_t nu, int64_t work, int64_t maxit, double tol, const double *init, svb_result_s *res) {
+    Context &C = ctx();
+    cudaStream_t st = C.stream;
+    const int64_t n = op->n, m = op->m;
+    SVB_CHECK(nu >= 1 && nu <= n, SVB_EDIM, "tssvd: nsv must satisfy 1 <= nsv <= n");
+    svb_operator_s gop;  // dense n x n operator over C; its destructor releases the buffers
+    gop.dense = true;
+    gop.m = n;
+    gop.n = n;
+    gop.nnz = n * n;
+    gop.lda = n;
+    gop.ibytes = 0;
+    SVB_CUDA(cudaMalloc((void **)&gop.dA, (size_t)n * n * sizeof(double)));
+    SVB_CUDA(cudaMalloc((void **)&gop.tmp, (size_t)n * sizeof(double)));
+    SVB_CUDA(cudaMalloc((void **)&gop.scal, 8 * sizeof(double)));
+    op_gram(op, gop.dA);
+    svb_result_s eig;
+    {
+        struct Replicated {
+            int saved;
+            Replicated() : saved(ctx().nranks) { ctx().nranks = 1; }
+            ~Replicated() { ctx().nranks = saved; }
+        } guard;
+        irlba_run(&gop, nu, work, maxit, 0, tol, tol, init, nullptr, nullptr, nullptr, &eig);
+    }
+    res->m = m;
+    res->n = n;
+    res->nu = nu;
+    res->iter = eig.iter;
+    res->mprod = eig.mprod;
+    res->info = eig.info;
+    SVB_CUDA(cudaMalloc((void **)&res->U, (size_t)m * nu * 8));
+    SVB_CUDA(cudaMalloc((void **)&res->s, (size_t)nu * 8));
+    res->V = eig.V;  // phi
+    eig.V = nullptr;
+    DevBuf<double> inv((size_t)nu), AV((size_t)m * nu);
+    tssvd_sigma_kernel<<<(unsigned)((nu + 127) / 128), 128, 0, st>>>(eig.s, nu, res->s, inv.p);
+    count_launch();
+    SVB_LAUNCH_CHECK();
+    op_apply_cols(op, false, res->V, n, AV.p, m, nu);
+    colscale_kernel<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>((m * nu + 255) / 256, 148 * 8)), 256, 0, st>>>(AV.p, inv.p, m, nu, res->U);
+    count_launch();
+    SVB_LAUNCH_CHECK();
+    SVB_CUDA(cudaStreamSynchronize(st));
+}
+
 }  // namespace svb
 
 extern "C" {
@@ -411,6 +471,25 @@ int svb_irlba(svb_operator_t op, int64_t nu, int64_t m_b, int64_t maxit, int64_t
     if (rc != SVB_OK) return rc;
     if (info != SVB_OK) svb::set_last_error(info == SVB_ENOCONV ? "irlba: not converged within maxit" : "irlba: starting vector in the null space");
     return info;
+}
+
+int svb_tssvd(svb_operator_t op, int64_t nsv, int64_t ncv, int64_t maxit, double tol, const double *init, svb_result_t *out) {
+    SVB_API_BEGIN
+    require_init();
+    SVB_CHECK(op && init && out, SVB_EARG, "svb_tssvd: null argument");
+    // eigs' tol = 0.0 (embedding.jl:30) asks for machine precision; the restart test here also compares successive Ritz
+    // values relatively (svtol = tol), and those carry eps*lambda_max of rounding noise: 1e-12 leaves lambda_1/lambda_nsv up
+    // to ~5e3 of room and gives sqrt(lambda) to ~1e-15 (residual^2/gap).
+    if (!(tol > 0.0)) tol = 1e-12;
+    auto *r = new svb_result_s();
+    try {
+        tssvd_run(op, nsv, ncv, maxit, tol, init, r);
+    } catch (...) {
+        delete r;
+        throw;
+    }
+    *out = r;
+    SVB_API_END
 }
 
 }  // extern "C"

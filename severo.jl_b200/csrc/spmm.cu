@@ -274,6 +274,121 @@ void launch_spmm_adj(svb_operator_s *op, const double *dW, int64_t ldw, int kc, 
     SVB_LAUNCH_CHECK();
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Gram matrix C'C (scaling.jl:274-296, with the CSC x CSC product of mul.jl:82-114 underneath) — the n x n input of
+// `tssvd` (embedding.jl:30-44). One pass per block of KC genes J = [j0, j0+kc) over the adjoint layout ALONE: a CTA
+// densifies the KC columns of its cell tile into shared memory straight from their (tile, gene) segments (R x KC doubles,
+// no m x KC intermediate in HBM, no forward product), then every segment (tile, g) with g >= j0 is dotted against the KC
+// dense columns — the same gather loop as the adjoint SpMM. Only the lower triangle is computed (symmetry halves the
+// stream); per-tile partials are reduced in tile order (deterministic), written to G[g, j] and mirrored to G[j, g].
+// ---------------------------------------------------------------------------------------------
+template <typename V, int LPS>
+__global__ void __launch_bounds__(1024) gram_adj_kernel(const int64_t *__restrict__ gptr, const uint16_t *__restrict__ rloc,
+                                                        const V *__restrict__ aval, int64_t n, int log2R, int64_t ntiles, int64_t nnz,
+                                                        int64_t j0, int kc, double *__restrict__ partial /* [ntiles][n][KC] */) {
+    extern __shared__ double smem[];
+    __shared__ unsigned long long next_seg;
+    double *ws = smem;  // R*KC: the dense columns J of this cell tile, row-major
+    const int64_t R = (int64_t)1 << log2R;
+    int64_t s0, s1;
+    cta_range_mm(gptr, ntiles * n, nnz, s0, s1);
+    const int nsub = blockDim.x / LPS;
+    const int lane = threadIdx.x & 31;
+    const int sub_lane = lane & (LPS - 1);
+    const unsigned submask = (LPS == 32) ? 0xffffffffu : (((1u << LPS) - 1u) << (lane & ~(LPS - 1)));
+    for (int64_t t = s0 / n; t < ntiles && t * n < s1; ++t) {
+        const int64_t a = max(max(s0, t * n), t * n + j0), b = min(s1, (t + 1) * n);
+        if (a >= b) continue;  // uniform over the CTA
+        __syncthreads();       // every sub-warp has left the previous tile (ws, next_seg)
+        for (int64_t r = threadIdx.x; r < R * KC; r += blockDim.x) ws[r] = 0.0;
+        __syncthreads();
+        for (int c = 0; c < kc; ++c) {
+            const int64_t seg = t * n + j0 + c;
+            const int64_t k1 = __ldg(gptr + seg + 1);
+            for (int64_t k = __ldg(gptr + seg) + threadIdx.x; k < k1; k += blockDim.x)
+                ws[(size_t)__ldg(rloc + k) * KC + c] = (double)__ldg(aval + k);
+        }
+        if (threadIdx.x == 0) next_seg = (unsigned long long)(a + nsub);
+        __syncthreads();
+        double *pt = partial + (size_t)t * n * KC;
+        int64_t s = a + threadIdx.x / LPS;
+        while (s < b) {
+            double acc[KC];
+            seg_dot_mm<V, uint16_t, LPS>(aval, rloc, __ldg(gptr + s), __ldg(gptr + s + 1), ws, sub_lane, submask, acc);
+            unsigned long long nxt = 0;
+            if (sub_lane == 0) {
+#pragma unroll
+                for (int c = 0; c < KC; ++c) pt[(size_t)(s - t * n) * KC + c] = acc[c];
+                nxt = atomicAdd(&next_seg, 1ull);
+            }
+            s = (int64_t)__shfl_sync(submask, nxt, lane & ~(LPS - 1));
+        }
+    }
+}
+
+// G[g, j0+c] = G[j0+c, g] = sum_t partial[t][g][c] for g >= j0+c (tile order fixed). Tiles whose segments of gene g hold no
+// nonzero still wrote a zero partial (every segment >= j0 of every tile is visited by exactly one sub-warp).
+__global__ void __launch_bounds__(256) gram_reduce_kernel(const double *__restrict__ partial, int64_t ntiles, int64_t n, int64_t j0,
+                                                          int kc, double *__restrict__ G, int64_t ldg) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t g = j0 + i / KC;
+    const int c = (int)(i % KC);
+    if (g >= n || c >= kc || g < j0 + c) return;
+    double s = 0.0;
+    for (int64_t t = 0; t < ntiles; ++t) s += partial[((size_t)t * n + g) * KC + c];
+    G[g + (j0 + c) * ldg] = s;
+    G[(j0 + c) + g * ldg] = s;
+}
+
+// G += -mu q' - q mu' + M mu mu'   (scaling.jl:281-294; q = column sums of A, M = cells of the whole matrix). Products are
+// rounded separately so that the update — and therefore G — stays exactly symmetric.
+__global__ void __launch_bounds__(256) gram_centre_kernel(double *__restrict__ G, int64_t n, int64_t ldg, const double *__restrict__ mu,
+                                                          const double *__restrict__ q, double M) {
+    const int64_t total = n * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / n, a = i - b * n;
+        const double t = __dadd_rn(__dmul_rn(mu[a], q[b]), __dmul_rn(q[a], mu[b]));
+        const double u = __dmul_rn(M, __dmul_rn(mu[a], mu[b]));
+        G[a + b * ldg] = __dadd_rn(G[a + b * ldg], __dadd_rn(u, -t));
+    }
+}
+
+__global__ void fill_kernel(double *__restrict__ x, int64_t L, double v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += (int64_t)gridDim.x * blockDim.x) x[i] = v;
+}
+
+template <typename V, int LPS>
+void launch_gram_adj(svb_operator_s *op, int64_t j0, int kc, double *partial) {
+    Context &C = ctx();
+    const size_t smem = (size_t)op->R * KC * sizeof(double);
+    SVB_CHECK(smem + 1024 <= C.smem_optin, SVB_EDIM, "gram: tile does not fit in shared memory");
+    auto k = gram_adj_kernel<V, LPS>;
+    if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int threads = smem > 64 * 1024 ? 1024 : 256;
+    const int64_t nseg = op->ntiles * op->n;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(resident_grid_mm(k, threads, smem), nseg / 8 + 1));
+    k<<<grid, threads, smem, C.stream>>>(op->gptr, op->rloc, (const V *)op->aval, op->n, (int)op->log2R, op->ntiles, op->nnz, j0, kc, partial);
+    count_launch();
+    SVB_LAUNCH_CHECK();
+}
+
+__global__ void __launch_bounds__(256) symmetrise_kernel(double *__restrict__ G, int64_t n, int64_t ldg) {
+    const int64_t total = n * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / n, a = i - b * n;
+        if (a < b) {
+            const double v = 0.5 * (G[a + b * ldg] + G[b + a * ldg]);
+            G[a + b * ldg] = v;
+            G[b + a * ldg] = v;
+        }
+    }
+}
+
+unsigned grid1d_mm(int64_t n, int threads = 256) {
+    return (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, 148 * 8));
+}
+
 }  // namespace
 
 // Y (outL x k, ldy) = alpha * op(S) * X (inL x k, ldx) + beta * Y ; device pointers, sparse operators only
@@ -331,4 +446,97 @@ void op_apply_mm(svb_operator_s *op, bool trans, double alpha, const double *dX,
     SVB_CUDA(cudaStreamSynchronize(C.stream));  // partial / tmp are freed on return
 }
 
+// Y (outL x k) = op(S) * X (inL x k) for ANY operator kind (dense operators have no SpMM form: column by column)
+void op_apply_cols(svb_operator_s *op, bool trans, const double *dX, int64_t ldx, double *dY, int64_t ldy, int64_t k) {
+    if (op->dense) {
+        for (int64_t c = 0; c < k; ++c) op_apply(op, trans, 1.0, dX + c * ldx, 0.0, dY + c * ldy);
+        return;
+    }
+    op_apply_mm(op, trans, 1.0, dX, ldx, 0.0, dY, ldy, k);
+}
+
+// G (n x n, column-major, leading dimension n, device) = S'S of the centred operator — `C'C`, scaling.jl:274-296.
+// Explicit sparse operators: A'A by the fused tile kernels above (summed over the ranks when cells are sharded), then the
+// rank-1 terms of scaling.jl:281-294. Dense and count-level operators: column j = S'(S e_j) through the vector products.
+void op_gram(svb_operator_s *op, double *G) {
+    Context &C = ctx();
+    cudaStream_t st = C.stream;
+    const int64_t n = op->n, m = op->m;
+    if (op->dense || op->fact) {
+        DevBuf<double> e((size_t)n), y((size_t)m);
+        SVB_CUDA(cudaMemsetAsync(e.p, 0, (size_t)n * 8, st));
+        for (int64_t j = 0; j < n; ++j) {
+            fill_kernel<<<1, 32, 0, st>>>(e.p + j, 1, 1.0);
+            op_apply(op, false, 1.0, e.p, 0.0, y.p);
+            op_apply(op, true, 1.0, y.p, 0.0, G + j * n);
+            fill_kernel<<<1, 32, 0, st>>>(e.p + j, 1, 0.0);
+            count_launch(2);
+        }
+        symmetrise_kernel<<<grid1d_mm(n * n), 256, 0, st>>>(G, n, n);
+        count_launch();
+        SVB_LAUNCH_CHECK();
+        SVB_CUDA(cudaStreamSynchronize(st));
+        return;
+    }
+    {
+        DevBuf<double> partial((size_t)op->ntiles * n * KC);
+        const double aavg = (n > 0 && op->ntiles > 0) ? (double)op->nnz / ((double)n * (double)op->ntiles) : 0.0;
+        const bool wide = aavg >= 64;
+        for (int64_t j0 = 0; j0 < n; j0 += KC) {
+            const int kc = (int)std::min<int64_t>(KC, n - j0);
+            if (op->vbytes == 8) {
+                if (wide) launch_gram_adj<double, 32>(op, j0, kc, partial.p); else launch_gram_adj<double, 8>(op, j0, kc, partial.p);
+            } else {
+                if (wide) launch_gram_adj<float, 32>(op, j0, kc, partial.p); else launch_gram_adj<float, 8>(op, j0, kc, partial.p);
+            }
+            gram_reduce_kernel<<<(unsigned)(((n - j0) * KC + 255) / 256), 256, 0, st>>>(partial.p, op->ntiles, n, j0, kc, G, n);
+            count_launch();
+            SVB_LAUNCH_CHECK();
+        }
+        SVB_CUDA(cudaStreamSynchronize(st));  // partial is freed here
+    }
+    if (C.nranks > 1) comm_allreduce_dev(G, n * n);
+    if (op->mu) {
+        // q = A'1 (the operator with its centre switched off), M = cells of the whole matrix
+        DevBuf<double> ones((size_t)m), q((size_t)n), md(1);
+        fill_kernel<<<grid1d_mm(m), 256, 0, st>>>(ones.p, m, 1.0);
+        count_launch();
+        double *mu = op->mu;
+        op->mu = nullptr;
+        try {
+            op_apply(op, true, 1.0, ones.p, 0.0, q.p);
+        } catch (...) {
+            op->mu = mu;
+            throw;
+        }
+        op->mu = mu;
+        double M = (double)m;
+        if (C.nranks > 1) {
+            SVB_CUDA(cudaMemcpyAsync(md.p, &M, 8, cudaMemcpyHostToDevice, st));
+            comm_allreduce_dev(md.p, 1);
+            SVB_CUDA(cudaMemcpyAsync(&M, md.p, 8, cudaMemcpyDeviceToHost, st));
+            SVB_CUDA(cudaStreamSynchronize(st));
+        }
+        gram_centre_kernel<<<grid1d_mm(n * n), 256, 0, st>>>(G, n, n, op->mu, q.p, M);
+        count_launch();
+        SVB_LAUNCH_CHECK();
+        SVB_CUDA(cudaStreamSynchronize(st));  // ones / q are freed here
+    }
+}
+
 }  // namespace svb
+
+extern "C" {
+
+int svb_gram(svb_operator_t op, double *G) {
+    SVB_API_BEGIN
+    svb::require_init();
+    SVB_CHECK(op && G, SVB_EARG, "svb_gram: null argument");
+    svb::DevBuf<double> dG((size_t)op->n * op->n);
+    svb::op_gram(op, dG.p);
+    SVB_CUDA(cudaMemcpyAsync(G, dG.p, (size_t)op->n * op->n * 8, cudaMemcpyDeviceToHost, svb::ctx().stream));
+    SVB_CUDA(cudaStreamSynchronize(svb::ctx().stream));
+    SVB_API_END
+}
+
+}  // extern "C"

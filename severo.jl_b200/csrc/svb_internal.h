@@ -225,6 +225,8 @@ double fact_adj_bytes(const svb_operator_s *op);
 // ---- spmm.cu : k right-hand sides (scaling.jl:259-272), device pointers, column-major with leading dims
 void op_apply_mm(svb_operator_s *op, bool trans, double alpha, const double *dX, int64_t ldx, double beta, double *dY, int64_t ldy,
                  int64_t k);
+void op_apply_cols(svb_operator_s *op, bool trans, const double *dX, int64_t ldx, double *dY, int64_t ldy, int64_t k);  // any operator kind
+void op_gram(svb_operator_s *op, double *G);  // G (n x n device, ld n) = S'S  (scaling.jl:274-296)
 // ---- dense.cu (tall-skinny kernels; all pointers device)
 // t[0..j) = X[:, 0..j)' * y      (X col-major L x j, leading dim ld)
 struct P2PCtx;

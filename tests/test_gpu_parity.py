@@ -612,4 +612,4 @@ def test_embedding_default_algorithm_is_served(sv, orc):
     np.testing.assert_allclose(em.stdev, em2.stdev, rtol=1e-12)
     assert em.coordinates.shape == (4000, 9) and em.basis.shape == (400, 9)
     with pytest.raises(ValueError):
-        sv.embedding(S, 9, algorithm="tssvd")
+        sv.embedding(S, 9, algorithm="svd")      # dense LAPACK svd on the host: not served (no CPU fallback)

@@ -149,3 +149,25 @@ def test_parallel_forward_product_is_bit_identical(orc):
     C = orc.CenteredMatrix(Xs, rng.standard_normal(200))
     v = rng.standard_normal(200)
     np.testing.assert_array_equal(C.mul(v), C.mul(v, parallel=True))
+
+
+def test_gram_and_tssvd_against_dense(orc, golden):
+    # scaling.jl:274-296 C'C and embedding.jl:30-44 tssvd have no reference test: pinned on convert(Matrix, S)
+    # (scaling.jl:298-303) and the dense SVD, like test_irlba.jl pins the solver.
+    op = golden["op"]
+    Cs = orc.CenteredMatrix(sp.csc_matrix(np.array(op["A"])), op["mu"])
+    Q = np.array(op["A"]) - np.array(op["mu"])[None, :]
+    np.testing.assert_allclose(orc.gram(Cs), Q.T @ Q, rtol=1e-14, atol=1e-15)
+    rng = np.random.default_rng(11)
+    X = sp.random(700, 90, 0.08, random_state=5, format="csc")
+    mu = rng.standard_normal(90)
+    for C in (orc.CenteredMatrix(X, mu), orc.CenteredMatrix(X, None), orc.CenteredMatrix(X.toarray(), mu),
+              orc.CenteredMatrix(sp.csc_matrix(X.T), mu, transposed=True)):
+        D = C.to_dense()
+        G = orc.gram(C)
+        assert np.abs(G - D.T @ D).max() <= 1e-13 * np.abs(G).max()
+    C = orc.CenteredMatrix(X, np.asarray(X.mean(axis=0)).ravel())
+    T = orc.tssvd(C, 6)
+    U, s, Vt = np.linalg.svd(C.to_dense(), full_matrices=False)
+    np.testing.assert_allclose(T.S, s[:6], rtol=1e-12)
+    assert orc.principal_angle(T.V, Vt[:6].T) < 1e-8 and orc.principal_angle(T.U, U[:, :6]) < 1e-8
