@@ -228,6 +228,24 @@ int svb_result_free(svb_result_t r);
 int svb_tssvd(svb_operator_t op, int64_t nsv, int64_t ncv, int64_t maxit, double tol,
               const double *init, svb_result_t *out);
 
+/* ---- the step after the path: k-nearest neighbours in PCA space (neighbours.jl:19-86) ---------------------------- */
+/* Replaces libcell `FindNeighbours{Euclidean,Cosine}{32,64}` (call sites neighbours.jl:39-41,50-52,61-63,72-74): X is the
+ * n x d column-major coordinate matrix (dtype SVB_F32 | SVB_F64, column stride ldx = the reference's stride(X,2)), nn_index
+ * n x k Int32 and distances n x k (same element type as X), both column-major and caller-owned, as in `ann!`. The search is
+ * EXACT (brute force on the device) — what test/test_nn.jl compares the reference's approximate search against — so the
+ * reference's `ntables` and `seed` arguments have no counterpart. Row i lists the k nearest cells of cell i by increasing
+ * distance (ties: lower index first); include_self != 0 puts the cell itself first (distance 0), otherwise it is excluded.
+ * Euclidean = sqrt(sum (x-y)^2), cosine = max(1 - x.y/(|x||y|), 0) (Distances.jl; a zero vector is at distance 1 from
+ * everything). index_base 1 for Julia. Limits: k <= 64, d <= 128, n < 2^31. */
+#define SVB_METRIC_EUCLIDEAN 0
+#define SVB_METRIC_COSINE 1
+int svb_knn(const void *X, int dtype, int64_t n, int64_t d, int64_t ldx, int64_t k, int metric,
+            int include_self, int index_base, int32_t *nn_index, void *distances);
+/* The same search on the coordinates Z = U*Diagonal(s) (embedding.jl:67) of a solve that are still in HBM, first `dims`
+ * components (dims <= 0: all) — nearest_neighbours(em, k, dims=1:dims) without the round trip through the host. */
+int svb_knn_result(svb_result_t r, int64_t dims, int64_t k, int metric, int include_self,
+                   int index_base, int32_t *nn_index, double *distances);
+
 /* ---- synthetic count matrices (benchmark inputs; counter-based RNG, any shard reproducible) ---- */
 /* Poisson counts x_ij ~ Poisson(L_i * p_j * f_{c(i),j}), L_i log-normal, p_j gamma-shaped,
  * K planted cell programs with fold-change `fold` on ~5% of genes each. Rows [row0,row1) of the

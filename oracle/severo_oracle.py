@@ -602,6 +602,57 @@ def tssvd(C: "CenteredMatrix", nsv=6):
 
 
 # --------------------------------------------------------------------------------------
+# neighbours.jl:19-86 : k-nearest neighbours (the exact answer the reference's test holds its approximate
+# libcell search against, test/test_nn.jl:31-38)
+# --------------------------------------------------------------------------------------
+def knn(X, k, metric="euclidean", include_self=True):
+    """Exact k nearest neighbours of every row of ``X`` (n x d): ``partialsortperm`` of the pairwise distances
+    (Distances.jl ``Euclidean`` = sqrt(sum (x-y)^2), ``CosineDist`` = max(1 - x.y/(|x||y|), 0)), ties by lower index.
+    ``include_self``: the row itself comes first at distance 0 (neighbours.jl `include_self`), otherwise it is excluded.
+    Returns 0-based ``nn_index`` (n x k int32) and ``distances`` (n x k, increasing)."""
+    X = np.asarray(X, dtype=np.float64)
+    n = X.shape[0]
+    idx = np.empty((n, k), dtype=np.int32)
+    dist = np.empty((n, k))
+    nrm = np.sqrt((X * X).sum(axis=1))
+    for i0 in range(0, n, 512):
+        Q = X[i0:i0 + 512]
+        if metric == "cosine":
+            den = nrm[i0:i0 + 512, None] * nrm[None, :]
+            with np.errstate(divide="ignore", invalid="ignore"):
+                D = np.maximum(1.0 - np.where(den > 0, (Q @ X.T) / den, 0.0), 0.0)
+        elif metric == "euclidean":
+            D = np.zeros((Q.shape[0], n))
+            for c in range(X.shape[1]):                  # sum_c (q_c - x_c)^2, coordinate by coordinate
+                D += (Q[:, c, None] - X[None, :, c]) ** 2
+            D = np.sqrt(D)
+        else:
+            raise ValueError(metric)
+        rows = np.arange(Q.shape[0])
+        D[rows, i0 + rows] = -1.0 if include_self else np.inf
+        order = np.argsort(D, axis=1, kind="stable")[:, :k]
+        idx[i0:i0 + 512] = order
+        d = np.take_along_axis(D, order, axis=1)
+        if include_self:
+            d[:, 0] = 0.0
+        dist[i0:i0 + 512] = d
+    return idx, dist
+
+
+def nearest_neighbours(X, k, dims=None, metric="euclidean", include_self=True):
+    """neighbours.jl:76-80: ``sparse(vec(nn_index'), repeat(1:n, inner=k), trues)`` — entry (j, i) is set when cell j is one
+    of the k nearest neighbours of cell i ("k-neighbours are stored as rows for each cell (cols)")."""
+    X = np.asarray(X, dtype=np.float64)
+    if dims is not None:
+        X = X[:, dims]
+    idx, _ = knn(X, k, metric, include_self)
+    n = X.shape[0]
+    nn = sp.csc_matrix((np.ones(n * k, dtype=bool), idx.ravel(), np.arange(0, n * k + 1, k)), shape=(n, n))
+    nn.sort_indices()
+    return nn
+
+
+# --------------------------------------------------------------------------------------
 # embedding.jl:46-76 _pca post-processing ; utils.jl:215-228 svd_flip!
 # --------------------------------------------------------------------------------------
 def pca_post(U, S, V, npcs, m):

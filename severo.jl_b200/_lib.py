@@ -17,6 +17,7 @@ SVB_I32, SVB_I64, SVB_F32, SVB_F64 = 0, 1, 2, 3
 SVB_OK, SVB_EDIM, SVB_ENOCONV, SVB_ENOMEM, SVB_ENULLSPACE, SVB_EARG = 0, -1, -2, -3, -4, -5
 SVB_ECUDA, SVB_ENCCL = -100, -101
 NORM_LOGNORMALIZE, NORM_RELATIVECOUNTS = 0, 1
+METRIC_EUCLIDEAN, METRIC_COSINE = 0, 1
 K_CLASSES = ("spmv_fwd", "spmv_adj", "reorth", "restart", "vector", "comm")
 
 
@@ -82,6 +83,8 @@ SIGNATURES = {
                                 c_void_p, c_void_p, _ph]),
     "svb_gram": (c_int, [_h, c_void_p]),
     "svb_tssvd": (c_int, [_h, c_int64, c_int64, c_int64, c_double, c_void_p, _ph]),
+    "svb_knn": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "svb_knn_result": (c_int, [_h, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
     "svb_result_info": (c_int, [_h, _p64, _p64, _p64, _p64, _p64, _pint]),
     "svb_result_download": (c_int, [_h, c_void_p, c_void_p, c_void_p, c_int]),
     "svb_result_free": (c_int, [_h]),

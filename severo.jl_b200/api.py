@@ -31,7 +31,7 @@ from .loess import loess_fit_predict
 __all__ = [
     "DeviceMatrix", "NamedArray", "convert_counts", "filter_cells", "filter_features", "filter_counts", "normalize_cells", "mean_var", "mean_std",
     "standardized_var_clipped", "find_variable_features", "scale_features", "CenteredMatrix", "CountsCenteredMatrix",
-    "scale_features_counts", "irlba", "gram", "tssvd",
+    "scale_features_counts", "irlba", "gram", "tssvd", "ann", "nearest_neighbours",
     "SVD", "svd_flip", "pca", "embedding", "LinearEmbedding", "synthetic_counts",
 ]
 
@@ -773,6 +773,52 @@ def embedding(X, ncomponents=50, method="pca", **kw):
     if method == "pca":
         return pca(X, int(ncomponents), **kw)
     raise ValueError(f"unknown reduction method: {method}")
+
+
+# ------------------------------------------------------------------------------------------------
+# neighbours.jl (the step after the path)
+# ------------------------------------------------------------------------------------------------
+_METRICS = {"euclidean": L.METRIC_EUCLIDEAN, "euclidian": L.METRIC_EUCLIDEAN, "cosine": L.METRIC_COSINE}
+
+
+def ann(X, k, metric="euclidean", include_self=True, ntables=None, rng=None):
+    """Severo.ann (neighbours.jl:19-31): ``nn_index`` (n x k Int32) and ``distances`` (n x k, element type of ``X``) of the
+    k nearest neighbours of every row of ``X``. The search is exact on the device (``svb_knn``); ``ntables`` / ``rng``, the
+    knobs of the reference's randomised approximation, are accepted and ignored. Indices are 0-based here (the Julia
+    overlay asks for 1-based)."""
+    X = X.array if isinstance(X, NamedArray) else X
+    X = np.asarray(X)
+    if X.dtype not in (np.float32, np.float64):
+        X = X.astype(np.float64)
+    X = np.asfortranarray(X)
+    n, d = X.shape
+    nn_index = np.zeros((n, int(k)), dtype=np.int32, order="F")
+    distances = np.zeros((n, int(k)), dtype=X.dtype, order="F")
+    L.check(L.lib().svb_knn(L.ptr(X), _DT[X.dtype], n, d, X.strides[1] // X.itemsize if d > 1 else n, int(k),
+                            _METRICS[str(metric).lower()], int(bool(include_self)), 0, L.ptr(nn_index), L.ptr(distances)))
+    return nn_index, distances
+
+
+def nearest_neighbours(X, k, dims=None, metric="euclidean", include_self=True, ntables=None, rng=None):
+    """Severo.nearest_neighbours (neighbours.jl:76-86,176-180,224): the k-nearest-neighbour graph as an n x n boolean
+    sparse matrix, entry (j, i) set when cell j is among the k nearest neighbours of cell i. ``X``: coordinates (n x d),
+    a NamedArray of them, or a LinearEmbedding (its ``coordinates``); ``dims``: which coordinates to use (``:`` = all)."""
+    names = None
+    if isinstance(X, LinearEmbedding):
+        X = X.coordinates
+    rowdim = "cells"
+    if isinstance(X, NamedArray):
+        names, rowdim, X = X.names[0], X.dimnames[0], X.array
+    X = np.asarray(X)
+    if dims is not None:
+        X = X[:, dims]
+    idx, _ = ann(X, k, metric=metric, include_self=include_self)
+    n = X.shape[0]
+    nn = sp.csc_matrix((np.ones(n * int(k), dtype=bool), idx.ravel(order="C"), np.arange(0, n * int(k) + 1, int(k))), shape=(n, n))
+    nn.sort_indices()
+    if names is None:
+        return nn
+    return NamedArray(nn, (names, names), (rowdim, rowdim))           # neighbours.jl:179
 
 
 # ------------------------------------------------------------------------------------------------

@@ -171,3 +171,24 @@ def test_gram_and_tssvd_against_dense(orc, golden):
     U, s, Vt = np.linalg.svd(C.to_dense(), full_matrices=False)
     np.testing.assert_allclose(T.S, s[:6], rtol=1e-12)
     assert orc.principal_angle(T.V, Vt[:6].T) < 1e-8 and orc.principal_angle(T.U, U[:, :6]) < 1e-8
+
+
+def test_knn_restatement_meets_the_reference_criterion(orc):
+    # test/test_nn.jl:22-56: Jaccard overlap with partialsortperm of the pairwise distances, 30 % quantile == 1.0. The oracle is
+    # that exact search (k nearest by Distances.Euclidean / CosineDist), checked here against scipy's pairwise distances.
+    from scipy.spatial.distance import cdist
+    X = np.random.default_rng(3).random((100, 10))
+    for metric in ("euclidean", "cosine"):
+        D = cdist(X, X, metric)
+        idx, dist = orc.knn(X, 4, metric, include_self=True)
+        j = []
+        for i in range(100):
+            nn = set(np.argsort(D[i], kind="stable")[:4])
+            x = len(nn & set(idx[i]))
+            j.append(x / (4 + (4 - x)))
+        assert np.quantile(j, 0.3) == 1.0 and min(j) == 1.0
+        np.testing.assert_allclose(dist, np.take_along_axis(D, idx.astype(np.int64), axis=1), atol=1e-14)
+        idx2, _ = orc.knn(X, 4, metric, include_self=False)
+        assert not np.any(idx2 == np.arange(100)[:, None])
+    nn = orc.nearest_neighbours(X, 4)
+    assert nn.shape == (100, 100) and nn.nnz == 400 and np.all(np.asarray(nn.sum(axis=0)).ravel() == 4)   # k rows per cell column
