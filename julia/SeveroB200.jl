@@ -8,7 +8,7 @@ module SeveroB200
 
 using SparseArrays, LinearAlgebra, NamedArrays, Random
 import Severo
-import Severo: CenteredMatrix, NamedCenteredMatrix, NamedCountMatrix, LinearEmbedding
+import Severo: CenteredMatrix, NamedCenteredMatrix, NamedCountMatrix, LinearEmbedding  # Severo re-exports Distances' Euclidean / CosineDist
 
 const libsvb = get(ENV, "SEVERO_B200_LIB", joinpath(@__DIR__, "..", "severo.jl_b200", "libsevero_b200.so"))
 const SVB_I32, SVB_I64, SVB_F32, SVB_F64 = Cint(0), Cint(1), Cint(2), Cint(3)
@@ -237,11 +237,54 @@ function irlba(A, nu::Integer; kw...)
     irlba!(Random.default_rng(), A, zeros(m, nu), zeros(nu), zeros(n, nu); kw...)
 end
 
-# embedding.jl:46-94 with algorithm = :irlba
-function _pca(X, npcs::Int64; kw...)
+# scaling.jl:274-296  C'C  (mul!(C, S', S, 1, 0)): the n x n Gram matrix of the centred operator, built on the device
+function gram(A)
+    n = size(A, 2)
+    G = Matrix{Float64}(undef, n, n)
+    op = operator(A)
+    check(ccall((:svb_gram, libsvb), Cint, (Ptr{Cvoid}, Ptr{Float64}), op.h, G))
+    G
+end
+
+# embedding.jl:30-44 tssvd: same keywords and return type; C'C and its eigenpairs are computed on the device
+function tssvd(A::AbstractMatrix; nsv::Int=6, ritzvec::Bool=true, tol::Float64=0.0, maxiter::Int=1000, ncv::Int=2*nsv, v0=nothing)
+    m, n = size(A)
+    v0 === nothing && (v0 = randn(n))
+    op = operator(A)
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:svb_tssvd, libsvb), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Float64, Ptr{Float64}, Ref{Ptr{Cvoid}}),
+        op.h, nsv, min(ncv, n), maxiter, tol, convert(Vector{Float64}, v0), r))
+    info = Ref{Cint}(0)
+    ccall((:svb_result_info, libsvb), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ref{Cint}),
+        r[], C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, info)
+    Sigma = Vector{Float64}(undef, nsv); phi = Matrix{Float64}(undef, n, nsv)
+    U = Matrix{Float64}(undef, m, ritzvec ? nsv : 0)                     # embedding.jl:37-42
+    rc = ccall((:svb_result_download, libsvb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint),
+        r[], Sigma, ritzvec ? pointer(U) : Ptr{Float64}(C_NULL), phi, 0)
+    ccall((:svb_result_free, libsvb), Cint, (Ptr{Cvoid},), r[])
+    check(rc)
+    info[] == 0 || error("convergence failed")
+    SVD(U, Sigma, phi')                                                  # embedding.jl:44
+end
+
+# embedding.jl:46-76: algorithm = :irlba (this path), :arpack (the reference default: served by the same device solver at
+# Arpack-like accuracy, maxiter/ncv mapped to maxit/work), :tssvd (Gram matrix + eigenpairs on the device)
+function _pca(X, npcs::Int64; algorithm=:arpack, kw...)
     m, n = size(X)
     npcs = min(min(m, n), npcs)
-    S = irlba(X, npcs; kw...)
+    S = if algorithm == :irlba
+        irlba(X, npcs; kw...)
+    elseif algorithm == :arpack
+        kwd = Dict{Symbol,Any}(kw)
+        haskey(kwd, :maxiter) && (kwd[:maxit] = pop!(kwd, :maxiter))
+        pop!(kwd, :ncv, nothing); pop!(kwd, :nsv, nothing)
+        get!(kwd, :tol, 1e-10)
+        irlba(X, npcs; kwd...)
+    elseif algorithm == :tssvd
+        tssvd(X; nsv=npcs, kw...)
+    else
+        error("algorithm $algorithm is outside the B200 hot path (use :irlba, :arpack or :tssvd)")
+    end
     Z = view(S.U, :, 1:npcs) * Diagonal(view(S.S, 1:npcs))
     stdev = view(S.S, 1:npcs) ./ sqrt(max(1, m - 1))
     Z, stdev, S.V
@@ -262,10 +305,42 @@ function pca(X::NamedCenteredMatrix, npcs::Int64; kw...)
     LinearEmbedding(X, coordinates, stdev, basis)
 end
 
-function embedding(X, ncomponents::Int64=50; method=:pca, algorithm=:irlba, kw...)
+function embedding(X, ncomponents::Int64=50; method=:pca, kw...)
     Symbol(method) == :pca || error("unknown reduction method: $method")
-    Symbol(algorithm) == :irlba || error("algorithm $algorithm is outside the B200 hot path (use algorithm=:irlba)")
     pca(X, ncomponents; kw...)
 end
+
+# ---- neighbours.jl:19-86 : the step after the path ------------------------------------------------------------
+# Same buffers as Severo.ann! (nn_index n x k Int32, distances n x k of eltype(X), X with unit row stride); the four
+# `ccall(("FindNeighbours...", libcell), ...)` become one call of the exact device search. `rng` / `ntables` drove the
+# reference's randomised approximation and are accepted for signature compatibility only.
+_metric(::Severo.Euclidean) = Cint(0)
+_metric(::Severo.CosineDist) = Cint(1)
+
+function ann!(rng, nn_index::Matrix{Int32}, distances::Matrix{T}, metric, X::StridedMatrix{T}, k::Int64,
+        include_self::Bool, ntables::Int64) where {T<:Union{Float32,Float64}}
+    n, d = size(X)
+    @assert stride(X, 1) == 1
+    check(ccall((:svb_knn, libsvb), Cint,
+        (Ptr{Cvoid}, Cint, Int64, Int64, Int64, Int64, Cint, Cint, Cint, Ptr{Int32}, Ptr{Cvoid}),
+        X, svbtype(T), n, d, stride(X, 2), k, _metric(metric), Cint(include_self), Cint(1), nn_index, distances))
+    nn_index, distances
+end
+
+function ann(rng, X::AbstractMatrix{T}, k::Int64, metric=Severo.Euclidean(), include_self::Bool=true, ntables::Int64=2*size(X,2)) where {T<:AbstractFloat}
+    n, d = size(X)
+    ann!(rng, Matrix{Int32}(undef, n, k), Matrix{T}(undef, n, k), metric, X, k, include_self, ntables)
+end
+
+function nearest_neighbours(rng, X::NamedArray{T,2}, k::Int64; dims=:, metric=Severo.Euclidean(), include_self::Bool=true,
+        ntables::Int64=2*size(X,2)) where {T}
+    Z = dims === Colon() ? X.array : X.array[:, dims]
+    nn_index, _ = ann(rng, Z, k, metric, include_self, ntables)
+    nn = sparse(vec(nn_index'), repeat(1:size(nn_index, 1), inner=k), trues(length(nn_index)))   # neighbours.jl:79
+    NamedArray(nn, (X.dicts[1], X.dicts[1]), (X.dimnames[1], X.dimnames[1]))
+end
+nearest_neighbours(X::NamedArray, k::Int64; kw...) = nearest_neighbours(Random.default_rng(), X, k; kw...)
+nearest_neighbours(rng, em::LinearEmbedding, k::Int64; kw...) = nearest_neighbours(rng, em.coordinates, k; kw...)
+nearest_neighbours(em::LinearEmbedding, k::Int64; kw...) = nearest_neighbours(Random.default_rng(), em, k; kw...)
 
 end # module

@@ -146,8 +146,11 @@ def test_two_gpu_gram_and_tssvd(tmp_path):
     import os
     import subprocess
     import sys
-    import torch
-    if torch.cuda.device_count() < 2:
+    try:
+        ngpu = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=60).stdout.count("GPU ")
+    except Exception:
+        ngpu = 0
+    if ngpu < 2:
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     script = tmp_path / "two_rank_gram.py"

@@ -13,8 +13,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import torch  # noqa: E402
-
 import severo_jl_b200 as sv  # noqa: E402
 from bench import CONFIGS, SCALE_MAX, SEED, solve_device  # noqa: E402
 from severo_jl_b200 import sharding  # noqa: E402
@@ -26,7 +24,6 @@ def main():
     cfg = dict(CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "C2"])
     if len(sys.argv) > 2:
         cfg["m"] = int(sys.argv[2])
-    torch.cuda.set_device(0)
     lib = sv.init(0)
     out = {"config": cfg}
     m, n, nu = cfg["m"], cfg["n"], cfg["nu"]

@@ -1,0 +1,49 @@
+"""tools/knn_check.py — timing of the exact device k-nearest-neighbour search (svb_knn) at scale, 1 GPU.
+usage: python tools/knn_check.py n d k [metric]
+Prints one JSON line: wall time of the call (host buffers in, host buffers out), n^2*D fp64 FMAs per second against the
+fp64 pipe, and a spot check of 64 random queries against a numpy brute-force search."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import severo_jl_b200 as sv  # noqa: E402
+
+
+def main():
+    n, d, k = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+    metric = sys.argv[4] if len(sys.argv) > 4 else "euclidean"
+    sv.init(0)
+    rng = np.random.default_rng(1)
+    centres = rng.standard_normal((64, d)) * 3.0
+    X = np.asfortranarray(centres[rng.integers(0, 64, n)] + rng.standard_normal((n, d)))
+    sv.ann(X[:4096], k, metric=metric)  # warm-up: module load, allocations
+    t0 = time.perf_counter()
+    idx, dist = sv.ann(X, k, metric=metric)
+    dt = time.perf_counter() - t0
+    D = (d + 7) // 8 * 8 if d <= 64 else (96 if d <= 96 else 128)
+    out = {"n": n, "d": d, "D": D, "k": k, "metric": metric, "seconds": round(dt, 4), "fp64_fma_per_s": round(n * n * D / dt, 0),
+           "fp64_tflops": round(2.0 * n * n * D / dt / 1e12, 2)}
+    bad = 0
+    for i in rng.integers(0, n, 64):
+        if metric == "euclidean":
+            dd = np.sqrt(((X - X[i]) ** 2).sum(axis=1))
+        else:
+            dd = np.maximum(1.0 - (X @ X[i]) / (np.linalg.norm(X, axis=1) * np.linalg.norm(X[i])), 0.0)
+        dd[i] = -1.0
+        ref = np.argsort(dd, kind="stable")[:k]
+        bad += int(set(ref) != set(idx[i]))
+    out["spot_check_mismatching_rows_of_64"] = bad
+    line = json.dumps(out)
+    print(line, flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "knn_check_%d_%d.json" % (n, d)), "w") as f:
+        f.write(line + "\n")
+
+
+if __name__ == "__main__":
+    main()
