@@ -25,6 +25,8 @@ namespace {
 constexpr int KNN_THREADS = 128;
 constexpr int KNN_KMAX = 64;
 constexpr int KNN_TILE_DOUBLES = 4096;  // 32 KB of packed points per tile
+constexpr bool KNN_AUTO_MMA = false;    // fp64 tensor-core variant for D <= 64 when SVB_KNN_MMA is unset
+constexpr bool KNN_AUTO_Q2 = true;      // two queries per thread for D <= 32 when unset SVB_KNN_Q (see launch_knn)
 
 __host__ __device__ constexpr int knn_tile_points(int D) { return (KNN_TILE_DOUBLES / D) & ~3; }
 
@@ -66,31 +68,37 @@ __device__ __forceinline__ void knn_insert(double *bs, int *bi, int k, double s,
     worst = bs[k - 1];
 }
 
-template <int D>
+// Q queries per thread: one 16-byte shared load of a point then feeds 2*Q fp64 FMAs (Q = 2 when the coordinates of two
+// queries fit the register file, D <= 32).
+template <int D, int Q>
 __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const double *__restrict__ P, const double *__restrict__ cn, int64_t n,
                                                           int64_t npad, int k, int include_self, int *__restrict__ nbr /* [n][k] */) {
     constexpr int TP = knn_tile_points(D);
     extern __shared__ double sm[];
     double *tile = sm;            // TP x D, row-major
     double *cs = sm + TP * D;     // TP
-    const int64_t qi = (int64_t)blockIdx.x * KNN_THREADS + threadIdx.x;
-    const bool active = qi < n;
-    const int64_t qrow = active ? qi : n - 1;
-    double q[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) q[i] = P[qrow * D + i];
-    double bs[KNN_KMAX];
-    int bi[KNN_KMAX];
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
-    for (int r = 0; r < k; ++r) {
-        bs[r] = inf;
-        bi[r] = -1;
+    int64_t qi[Q];
+    double q[Q][D];
+    double bs[Q][KNN_KMAX];
+    int bi[Q][KNN_KMAX];
+    double worst[Q];
+#pragma unroll
+    for (int s = 0; s < Q; ++s) {
+        qi[s] = ((int64_t)blockIdx.x * Q + s) * KNN_THREADS + threadIdx.x;
+        const int64_t qrow = qi[s] < n ? qi[s] : n - 1;
+#pragma unroll
+        for (int i = 0; i < D; ++i) q[s][i] = P[qrow * D + i];
+        for (int r = 0; r < k; ++r) {
+            bs[s][r] = inf;
+            bi[s][r] = -1;
+        }
+        if (include_self) {  // neighbours.jl `include_self`: the cell itself is its first neighbour (distance 0)
+            bs[s][0] = -inf;
+            bi[s][0] = (int)qrow;
+        }
+        worst[s] = bs[s][k - 1];
     }
-    if (include_self) {  // neighbours.jl `include_self`: the cell itself is its first neighbour (distance 0)
-        bs[0] = -inf;
-        bi[0] = (int)qrow;
-    }
-    double worst = bs[k - 1];
     for (int64_t p0 = 0; p0 < npad; p0 += TP) {
         __syncthreads();
         {
@@ -102,33 +110,164 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const double *__restri
         __syncthreads();
         for (int j = 0; j < TP; j += 4) {
             const double *t0 = tile + j * D;
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            double a[Q][4];
+#pragma unroll
+            for (int s = 0; s < Q; ++s)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a[s][u] = 0.0;
 #pragma unroll
             for (int i = 0; i < D; i += 2) {
-                const double2 v0 = *reinterpret_cast<const double2 *>(t0 + i);
-                const double2 v1 = *reinterpret_cast<const double2 *>(t0 + D + i);
-                const double2 v2 = *reinterpret_cast<const double2 *>(t0 + 2 * D + i);
-                const double2 v3 = *reinterpret_cast<const double2 *>(t0 + 3 * D + i);
-                a0 = fma(q[i], v0.x, a0);
-                a1 = fma(q[i], v1.x, a1);
-                a2 = fma(q[i], v2.x, a2);
-                a3 = fma(q[i], v3.x, a3);
-                a0 = fma(q[i + 1], v0.y, a0);
-                a1 = fma(q[i + 1], v1.y, a1);
-                a2 = fma(q[i + 1], v2.y, a2);
-                a3 = fma(q[i + 1], v3.y, a3);
+                double2 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const double2 *>(t0 + u * D + i);
+#pragma unroll
+                for (int s = 0; s < Q; ++s)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) a[s][u] = fma(q[s][i], v[u].x, a[s][u]);
+#pragma unroll
+                for (int s = 0; s < Q; ++s)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) a[s][u] = fma(q[s][i + 1], v[u].y, a[s][u]);
             }
-            const double s0 = fma(-2.0, a0, cs[j]), s1 = fma(-2.0, a1, cs[j + 1]);
-            const double s2 = fma(-2.0, a2, cs[j + 2]), s3 = fma(-2.0, a3, cs[j + 3]);
             const int64_t pj = p0 + j;
-            if (s0 < worst && pj != qi) knn_insert(bs, bi, k, s0, (int)pj, worst);
-            if (s1 < worst && pj + 1 != qi) knn_insert(bs, bi, k, s1, (int)(pj + 1), worst);
-            if (s2 < worst && pj + 2 != qi) knn_insert(bs, bi, k, s2, (int)(pj + 2), worst);
-            if (s3 < worst && pj + 3 != qi) knn_insert(bs, bi, k, s3, (int)(pj + 3), worst);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double c = cs[j + u];
+#pragma unroll
+                for (int s = 0; s < Q; ++s) {
+                    const double key = fma(-2.0, a[s][u], c);
+                    if (key < worst[s] && pj + u != qi[s]) knn_insert(bs[s], bi[s], k, key, (int)(pj + u), worst[s]);
+                }
+            }
         }
     }
-    if (active)
-        for (int r = 0; r < k; ++r) nbr[qi * k + r] = bi[r];
+#pragma unroll
+    for (int s = 0; s < Q; ++s)
+        if (qi[s] < n)
+            for (int r = 0; r < k; ++r) nbr[qi[s] * k + r] = bi[s][r];
+}
+
+// ---- fp64 tensor-core variant (mma.sync.m8n8k4 DMMA; tcgen05 has no fp64) -------------------------------------------
+// ncu on the kernel above (profiles/r03_knn_gram.md): a broadcast 16-byte shared load costs two LSU wavefronts and feeds two
+// warp-wide fp64 FMAs, so with one query per thread the shared pipe saturates (86 %) at 44 % of the fp64 pipe. Here a warp
+// owns 32 queries as four 8 x 4 A-fragments per 4 coordinates (D doubles per lane, loaded once), streams the points as
+// 4 x 8 B-fragments (one 8-byte shared load per lane per 4 DMMAs: 512 FMAs per wavefront instead of 32) and gets 8 x 8 blocks of
+// dot products. Lane (g, t) of the accumulator layout sees, for query row g of each of its four query groups, the points
+// 2t, 2t+1 of every 8: it keeps a private top-k list per group over that quarter of the points, and the four lanes of a row
+// merge their lists at the end with two shuffles per output (lexicographic (key, index) minimum: same tie rule).
+__device__ __forceinline__ void knn_dmma(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__host__ __device__ constexpr int knn_mma_stride(int D) { return (D % 16 == 0) ? D + 4 : D + 12; }  // == 4 (mod 16): conflict-free B loads
+__host__ __device__ constexpr int knn_mma_tile_points(int D) { return (KNN_TILE_DOUBLES / knn_mma_stride(D)) & ~15; }
+
+template <int D>
+__global__ void __launch_bounds__(KNN_THREADS) knn_mma_kernel(const double *__restrict__ P, const double *__restrict__ cn, int64_t n,
+                                                              int64_t npad, int k, int include_self, int *__restrict__ nbr /* [n][k] */) {
+    constexpr int DS = knn_mma_stride(D);
+    constexpr int TP = knn_mma_tile_points(D);
+    constexpr int KS = D / 4;
+    extern __shared__ double sm[];
+    double *tile = sm;             // TP x DS
+    double *cs = sm + TP * DS;     // TP
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t qb = ((int64_t)blockIdx.x * (KNN_THREADS / 32) + warp) * 32;
+    int64_t qi[4];
+    double aq[4][KS];
+    double bs[4][KNN_KMAX];
+    int bi[4][KNN_KMAX];
+    double worst[4];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+        qi[mt] = qb + mt * 8 + g;
+        const int64_t qrow = qi[mt] < n ? qi[mt] : n - 1;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) aq[mt][ks] = P[qrow * D + 4 * ks + t];
+        for (int r = 0; r < k; ++r) {
+            bs[mt][r] = inf;
+            bi[mt][r] = -1;
+        }
+        if (include_self && t == 0) {  // the cell itself, once among the four lanes of its row
+            bs[mt][0] = -inf;
+            bi[mt][0] = (int)qrow;
+        }
+        worst[mt] = bs[mt][k - 1];
+    }
+    for (int64_t p0 = 0; p0 < npad; p0 += TP) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < TP * (D / 2); idx += KNN_THREADS) {
+            const int row = idx / (D / 2), c2 = idx - row * (D / 2);
+            reinterpret_cast<double2 *>(tile + row * DS)[c2] = reinterpret_cast<const double2 *>(P + (p0 + row) * D)[c2];
+        }
+        for (int idx = threadIdx.x; idx < TP; idx += KNN_THREADS) cs[idx] = cn[p0 + idx];
+        __syncthreads();
+        for (int j = 0; j < TP; j += 16) {
+            double acc[4][2][2];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb) acc[mt][nb][0] = acc[mt][nb][1] = 0.0;
+            const double *b0 = tile + (j + g) * DS + t, *b1 = b0 + 8 * DS;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const double v0 = b0[4 * ks], v1 = b1[4 * ks];
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) {
+                    knn_dmma(acc[mt][0][0], acc[mt][0][1], aq[mt][ks], v0);
+                    knn_dmma(acc[mt][1][0], acc[mt][1][1], aq[mt][ks], v1);
+                }
+            }
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb) {
+                const int col = j + nb * 8 + 2 * t;
+                const double c0 = cs[col], c1 = cs[col + 1];
+                const int64_t pj = p0 + col;
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) {
+                    const double k0 = fma(-2.0, acc[mt][nb][0], c0), k1 = fma(-2.0, acc[mt][nb][1], c1);
+                    if (k0 < worst[mt] && pj != qi[mt]) knn_insert(bs[mt], bi[mt], k, k0, (int)pj, worst[mt]);
+                    if (k1 < worst[mt] && pj + 1 != qi[mt]) knn_insert(bs[mt], bi[mt], k, k1, (int)(pj + 1), worst[mt]);
+                }
+            }
+        }
+    }
+    // merge the four partial lists of every query row (lanes t = 0..3 of the row are adjacent lanes)
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+        int head = 0;
+        for (int r = 0; r < k; ++r) {
+            double key = head < k ? bs[mt][head] : inf;
+            int idx = head < k ? bi[mt][head] : 0x7fffffff;
+            if (idx < 0) idx = 0x7fffffff;  // unfilled slot: loses every tie
+            double mk = key;
+            int mi = idx;
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+                const double ok = __shfl_xor_sync(0xffffffffu, mk, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+                if (ok < mk || (ok == mk && oi < mi)) {
+                    mk = ok;
+                    mi = oi;
+                }
+            }
+            if (mk == key && mi == idx) ++head;  // this lane's head won (indices are unique across the four lists)
+            if (t == 0 && qi[mt] < n) nbr[qi[mt] * k + r] = mi;
+        }
+    }
+}
+
+template <int D>
+void launch_knn_mma(const double *P, const double *cn, int64_t n, int64_t npad, int k, int include_self, int *nbr) {
+    constexpr int TP = knn_mma_tile_points(D);
+    const size_t smem = (size_t)(TP * knn_mma_stride(D) + TP) * sizeof(double);
+    knn_mma_kernel<D><<<(unsigned)((n + KNN_THREADS - 1) / KNN_THREADS), KNN_THREADS, smem, ctx().stream>>>(P, cn, n, npad, k, include_self, nbr);
+    count_launch();
+    SVB_LAUNCH_CHECK();
 }
 
 // exact distances of the k winners from the packed coordinates; outputs column-major n x k like the reference's buffers
@@ -142,7 +281,9 @@ __global__ void __launch_bounds__(256) knn_finalize_kernel(const double *__restr
     const int j = nbr[t];
     const double *a = P + i * D, *b = P + (int64_t)j * D;
     double dist;
-    if (metric == SVB_METRIC_COSINE) {
+    if (j == i) {
+        dist = 0.0;  // the cell itself (include_self): 1 - q^.q^ is only 0 to rounding
+    } else if (metric == SVB_METRIC_COSINE) {
         double dot = 0.0;
         for (int c = 0; c < D; ++c) dot = fma(a[c], b[c], dot);
         dist = fmax(1.0 - dot, 0.0);  // Distances.CosineDist clamps at 0
@@ -165,13 +306,28 @@ __global__ void __launch_bounds__(256) knn_coords_kernel(const double *__restric
         Z[i] = U[i] * s[i / m];
 }
 
-template <int D>
-void launch_knn(const double *P, const double *cn, int64_t n, int64_t npad, int k, int include_self, int *nbr) {
+template <int D, int Q>
+void launch_knn_q(const double *P, const double *cn, int64_t n, int64_t npad, int k, int include_self, int *nbr) {
     constexpr int TP = knn_tile_points(D);
     const size_t smem = (size_t)(TP * D + TP) * sizeof(double);
-    knn_kernel<D><<<(unsigned)((n + KNN_THREADS - 1) / KNN_THREADS), KNN_THREADS, smem, ctx().stream>>>(P, cn, n, npad, k, include_self, nbr);
+    const int64_t per_cta = (int64_t)KNN_THREADS * Q;
+    knn_kernel<D, Q><<<(unsigned)((n + per_cta - 1) / per_cta), KNN_THREADS, smem, ctx().stream>>>(P, cn, n, npad, k, include_self, nbr);
     count_launch();
     SVB_LAUNCH_CHECK();
+}
+
+template <int D>
+void launch_knn(const double *P, const double *cn, int64_t n, int64_t npad, int k, int include_self, int *nbr) {
+    const int q_env = getenv("SVB_KNN_Q") ? atoi(getenv("SVB_KNN_Q")) : 0;  // 1 / 2 force the variant, 0 = choose
+    if constexpr (D <= 32) {
+        // two queries per thread need enough queries to fill the machine with half as many threads
+        const bool auto_q2 = KNN_AUTO_Q2 && n >= (int64_t)ctx().sm_count * KNN_THREADS * 4;
+        if (q_env == 2 || (q_env == 0 && auto_q2)) {
+            launch_knn_q<D, 2>(P, cn, n, npad, k, include_self, nbr);
+            return;
+        }
+    }
+    launch_knn_q<D, 1>(P, cn, n, npad, k, include_self, nbr);
 }
 
 int knn_padded_dims(int d) {
@@ -191,7 +347,9 @@ void knn_device(const double *Xd, int64_t ldx, int64_t n, int d, int k, int metr
     SVB_CHECK(k <= n - (include_self ? 0 : 1), SVB_EDIM, "knn: fewer than k candidate neighbours");
     SVB_CHECK(dist_type == SVB_F64 || dist_type == SVB_F32, SVB_EARG, "knn: distances must be Float32 or Float64");
     const int D = knn_padded_dims(d);
-    const int TP = knn_tile_points(D);
+    const int mma_env = getenv("SVB_KNN_MMA") ? atoi(getenv("SVB_KNN_MMA")) : -1;  // 1 / 0 force the variant, unset = choose
+    const bool use_mma = D <= 64 && (mma_env == 1 || (mma_env < 0 && KNN_AUTO_MMA));
+    const int TP = use_mma ? knn_mma_tile_points(D) : knn_tile_points(D);
     const int64_t npad = (n + TP - 1) / TP * TP;
     DevBuf<double> P((size_t)npad * D), cn((size_t)npad), dist((size_t)n * k);
     DevBuf<int> nbr((size_t)n * k);
@@ -199,6 +357,20 @@ void knn_device(const double *Xd, int64_t ldx, int64_t n, int d, int k, int metr
     knn_pack_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, st>>>(Xd, ldx, n, npad, d, D, metric, P.p, cn.p);
     count_launch();
     SVB_LAUNCH_CHECK();
+    {
+    KTimer kt(SVB_K_VECTOR, 8.0 * (double)npad * D * (double)((n + KNN_THREADS - 1) / KNN_THREADS), 0);  // tile bytes read by all CTAs (L2 mostly)
+    if (use_mma) {
+        switch (D) {
+            case 8: launch_knn_mma<8>(P.p, cn.p, n, npad, k, include_self, nbr.p); break;
+            case 16: launch_knn_mma<16>(P.p, cn.p, n, npad, k, include_self, nbr.p); break;
+            case 24: launch_knn_mma<24>(P.p, cn.p, n, npad, k, include_self, nbr.p); break;
+            case 32: launch_knn_mma<32>(P.p, cn.p, n, npad, k, include_self, nbr.p); break;
+            case 40: launch_knn_mma<40>(P.p, cn.p, n, npad, k, include_self, nbr.p); break;
+            case 48: launch_knn_mma<48>(P.p, cn.p, n, npad, k, include_self, nbr.p); break;
+            case 56: launch_knn_mma<56>(P.p, cn.p, n, npad, k, include_self, nbr.p); break;
+            default: launch_knn_mma<64>(P.p, cn.p, n, npad, k, include_self, nbr.p); break;
+        }
+    } else
     switch (D) {
         case 8: launch_knn<8>(P.p, cn.p, n, npad, k, include_self, nbr.p); break;
         case 16: launch_knn<16>(P.p, cn.p, n, npad, k, include_self, nbr.p); break;
@@ -210,6 +382,7 @@ void knn_device(const double *Xd, int64_t ldx, int64_t n, int d, int k, int metr
         case 64: launch_knn<64>(P.p, cn.p, n, npad, k, include_self, nbr.p); break;
         case 96: launch_knn<96>(P.p, cn.p, n, npad, k, include_self, nbr.p); break;
         default: launch_knn<128>(P.p, cn.p, n, npad, k, include_self, nbr.p); break;
+    }
     }
     knn_finalize_kernel<<<(unsigned)((n * k + 255) / 256), 256, 0, st>>>(P.p, D, n, k, metric, nbr.p, index_base, oidx.p, dist.p);
     count_launch();

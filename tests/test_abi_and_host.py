@@ -25,6 +25,61 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/severo_b200.h but not exported"
     assert sorted(sv.SIGNATURES) == syms, "python binding table out of sync with the header"
+    counts = _header_param_counts()
+    for name, (_, argtypes) in sv.SIGNATURES.items():
+        assert len(argtypes) == counts[name], f"{name}: ctypes table has {len(argtypes)} arguments, C declares {counts[name]}"
+
+
+def _header_param_counts():
+    txt = open(os.path.join(ROOT, "include", "severo_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    out = {}
+    for name, params in re.findall(r"\b(svb_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", txt, flags=re.S):
+        params = params.strip()
+        out[name] = 0 if params in ("", "void") else params.count(",") + 1
+    return out
+
+
+def _split_top_level(text):
+    parts, depth, cur = [], 0, ""
+    for ch in text:
+        if ch in "({[":
+            depth += 1
+        elif ch in ")}]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            parts.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        parts.append(cur.strip())
+    return parts
+
+
+def test_julia_overlay_binds_declared_symbols_with_matching_arity():
+    # Julia is not in the image: the overlay cannot run here, but every `ccall` in it must name a symbol the header
+    # declares and pass as many argument types as the C declaration has parameters.
+    counts = _header_param_counts()
+    src = open(os.path.join(ROOT, "julia", "SeveroB200.jl")).read()
+    seen = 0
+    for m in re.finditer(r"ccall\(\(:(svb_[a-z0-9_]+), libsvb\),", src):
+        name = m.group(1)
+        assert name in counts, f"julia overlay calls {name}, which include/severo_b200.h does not declare"
+        rest = src[m.end():]
+        # rest = " RetType, (T1, T2, ...), args...)": the argument-type tuple is the first top-level parenthesis group
+        start = rest.index("(")
+        depth, end = 0, None
+        for i in range(start, len(rest)):
+            depth += rest[i] == "("
+            depth -= rest[i] == ")"
+            if depth == 0:
+                end = i
+                break
+        types = _split_top_level(rest[start + 1:end])
+        assert len(types) == counts[name], f"{name}: julia passes {len(types)} argument types, C declares {counts[name]}"
+        seen += 1
+    assert seen >= 20
 
 
 def test_no_cpu_fallback_without_device():

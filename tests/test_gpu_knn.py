@@ -116,3 +116,36 @@ def test_nearest_neighbours_of_an_embedding(sv, orc):
     same = np.mean([set(a) == set(b) for a, b in zip(idx, ref_idx)])
     assert same >= 0.999
     np.testing.assert_allclose(np.sort(dist, axis=1), ref_dist, rtol=1e-8, atol=1e-10)
+
+
+_Q2 = r"""
+import sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+import severo_jl_b200 as sv
+from oracle import severo_oracle as orc
+sv.init(0)
+for (n, d, k) in ((3000, 7, 5), (2049, 10, 20), (1500, 30, 4), (257, 32, 64)):
+    rng = np.random.default_rng(n + d)
+    X = rng.standard_normal((8, d))[rng.integers(0, 8, n)] * 3.0 + rng.standard_normal((n, d))
+    for metric in ("euclidean", "cosine"):
+        for include_self in (True, False):
+            idx, dist = sv.ann(X, k, metric=metric, include_self=include_self)
+            ref_idx, ref_dist = orc.knn(X, k, metric, include_self)
+            assert np.array_equal(np.sort(idx, axis=1), np.sort(ref_idx, axis=1)), (n, d, k, metric, include_self)
+            np.testing.assert_allclose(np.sort(dist, axis=1), ref_dist, rtol=1e-11, atol=1e-13)
+print("OK")
+"""
+
+
+def test_knn_two_queries_per_thread_variant(tmp_path):
+    # the D <= 32 kernels with two query cells per thread (SVB_KNN_Q=2 forces them at any n)
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "knn_q2.py"
+    script.write_text(_Q2)
+    r = subprocess.run([sys.executable, str(script), root], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, SVB_KNN_Q="2"))
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -21,13 +21,37 @@ def main():
     rng = np.random.default_rng(1)
     centres = rng.standard_normal((64, d)) * 3.0
     X = np.asfortranarray(centres[rng.integers(0, 64, n)] + rng.standard_normal((n, d)))
+    import ctypes
+    L = sv._lib
+    lib = sv.lib()
     sv.ann(X[:4096], k, metric=metric)  # warm-up: module load, allocations
-    t0 = time.perf_counter()
-    idx, dist = sv.ann(X, k, metric=metric)
-    dt = time.perf_counter() - t0
     D = (d + 7) // 8 * 8 if d <= 64 else (96 if d <= 96 else 128)
-    out = {"n": n, "d": d, "D": D, "k": k, "metric": metric, "seconds": round(dt, 4), "fp64_fma_per_s": round(n * n * D / dt, 0),
-           "fp64_tflops": round(2.0 * n * n * D / dt / 1e12, 2)}
+    out = {"n": n, "d": d, "D": D, "k": k, "metric": metric}
+    # the kernel variants back to back in one process (same box, same clocks): SVB_KNN_Q / SVB_KNN_MMA are read per call.
+    # seconds = wall time of the whole call (pageable host buffers in and out); kernel_ms = CUDA events around the search kernel
+    variants = [("default", {}), ("simt_q1", {"SVB_KNN_Q": "1", "SVB_KNN_MMA": "0"}), ("simt_q2", {"SVB_KNN_Q": "2", "SVB_KNN_MMA": "0"}),
+                ("dmma", {"SVB_KNN_MMA": "1"})]
+    if os.environ.get("KNN_VARIANTS") == "default":
+        variants = variants[:1]
+    lib.svb_profile_enable(1)
+    for name, env in variants:
+        for key in ("SVB_KNN_Q", "SVB_KNN_MMA"):
+            os.environ.pop(key, None)
+        os.environ.update(env)
+        lib.svb_profile_reset()
+        t0 = time.perf_counter()
+        idx, dist = sv.ann(X, k, metric=metric)
+        dt = time.perf_counter() - t0
+        ms = (ctypes.c_double * 6)()
+        ln = (ctypes.c_int64 * 6)()
+        by = (ctypes.c_double * 6)()
+        L.check(lib.svb_profile_get(ms, ln, by))
+        kms = ms[4]
+        out[name] = {"seconds": round(dt, 4), "kernel_ms": round(kms, 2), "kernel_fp64_tflops": round(2.0 * n * n * D / (kms * 1e-3) / 1e12, 2)}
+    for key in ("SVB_KNN_Q", "SVB_KNN_MMA"):
+        os.environ.pop(key, None)
+    lib.svb_profile_enable(0)
+    idx, dist = sv.ann(X, k, metric=metric)
     bad = 0
     for i in rng.integers(0, n, 64):
         if metric == "euclidean":
