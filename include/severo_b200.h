@@ -246,6 +246,18 @@ int svb_knn(const void *X, int dtype, int64_t n, int64_t d, int64_t ldx, int64_t
 int svb_knn_result(svb_result_t r, int64_t dims, int64_t k, int metric, int include_self,
                    int index_base, int32_t *nn_index, double *distances);
 
+/* ---- the consumer of the kNN graph: Jaccard index / shared nearest neighbours (neighbours.jl:88-131,263-270) -------- */
+/* Replaces `_jaccard_index` (neighbours.jl:88-94 with a fixed k, :96-110 without): snn = nn' * nn — entry (i, j) = number
+ * of neighbours cells i and j share — each stored x mapped to x / (k + (k - x)) in the output element type, then
+ * `droptol!(snn, prune)` (entries with abs(x) <= prune removed). nn: the n x n neighbour graph as uploaded by
+ * svb_csc_upload (column i = the neighbours of cell i, the layout `nearest_neighbours` returns, neighbours.jl:79; only the
+ * PATTERN is read — upload the `true` entries; rows strictly ascending inside a column, as SparseMatrixCSC guarantees,
+ * else SVB_EDIM). k > 0: the fixed neighbourhood size of `jaccard_index(nn, k)` / `shared_nearest_neighbours`; k <= 0: the
+ * form without k, where column j uses diag(snn)[j] = its own number of neighbours (:99,103-106). dtype SVB_F32 | SVB_F64
+ * = the reference's `dtype` (prune is rounded to it first, :128). out: n x n CSC handle with ascending rows and values of
+ * that type (svb_matrix_download / svb_matrix_free). The sparse product is never formed: see csrc/snn.cu. */
+int svb_jaccard_index(svb_matrix_t nn, int64_t k, double prune, int dtype, svb_matrix_t *out);
+
 /* ---- synthetic count matrices (benchmark inputs; counter-based RNG, any shard reproducible) ---- */
 /* Poisson counts x_ij ~ Poisson(L_i * p_j * f_{c(i),j}), L_i log-normal, p_j gamma-shaped,
  * K planted cell programs with fold-change `fold` on ~5% of genes each. Rows [row0,row1) of the

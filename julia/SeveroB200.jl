@@ -343,4 +343,44 @@ nearest_neighbours(X::NamedArray, k::Int64; kw...) = nearest_neighbours(Random.d
 nearest_neighbours(rng, em::LinearEmbedding, k::Int64; kw...) = nearest_neighbours(rng, em.coordinates, k; kw...)
 nearest_neighbours(em::LinearEmbedding, k::Int64; kw...) = nearest_neighbours(Random.default_rng(), em, k; kw...)
 
+
+# ---- neighbours.jl:88-152,263-270 : Jaccard index / shared nearest neighbours, the consumer of the kNN graph ------------
+# `_jaccard_index` forms nn' * nn with the generic sparse product; the device computes the same entries from the neighbour
+# lists directly (csrc/snn.cu) and returns them in SparseMatrixCSC order. k <= 0 selects the form without k (:96-110).
+function _jaccard_index(::Type{T}, nn::SparseMatrixCSC, k::Integer, prune::T) where {T<:Union{Float32,Float64}}
+    n = size(nn, 2)
+    pattern = SparseMatrixCSC(size(nn, 1), n, nn.colptr, nn.rowval, ones(Int32, length(nn.rowval)))   # `trues` graph: pattern only
+    d = upload(pattern)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:svb_jaccard_index, libsvb), Cint, (Ptr{Cvoid}, Int64, Cdouble, Cint, Ref{Ptr{Cvoid}}),
+        d.h, k, Float64(prune), svbtype(T), h))
+    o = DeviceMatrix(h[])
+    nz = Ref{Int64}(0)
+    check(ccall((:svb_matrix_info, libsvb), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ref{Int64}, Ptr{Cint}), o.h, C_NULL, C_NULL, nz, C_NULL))
+    colptr = Vector{Int64}(undef, n + 1); rowval = Vector{Int64}(undef, nz[]); nzval = Vector{T}(undef, nz[])
+    check(ccall((:svb_matrix_download, libsvb), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Cvoid}, Cint, Cint),
+        o.h, colptr, rowval, nzval, svbtype(T), 1))
+    SparseMatrixCSC(n, n, colptr, rowval, nzval)
+end
+_jaccard_index(::Type{T}, nn::SparseMatrixCSC, prune::T) where {T<:Union{Float32,Float64}} = _jaccard_index(T, nn, 0, prune)
+
+function jaccard_index(nn::NamedArray; prune::Real=1/15, dtype::Type{R}=Float64) where {R<:AbstractFloat}
+    snn = _jaccard_index(dtype, nn.array, convert(dtype, prune))
+    NamedArray(snn, (nn.dicts[1], nn.dicts[1]), (nn.dimnames[1], nn.dimnames[1]))
+end
+function jaccard_index(nn::NamedArray, k::Int64; prune::Real=1/15, dtype::Type{R}=Float64) where {R<:AbstractFloat}
+    snn = _jaccard_index(dtype, nn.array, k, convert(dtype, prune))
+    NamedArray(snn, (nn.dicts[1], nn.dicts[1]), (nn.dimnames[1], nn.dimnames[1]))
+end
+
+function shared_nearest_neighbours(rng, X::NamedArray{T,2}, k::Int64; dims=:, metric=Severo.Euclidean(), include_self::Bool=true,
+        ntables::Int64=2*size(X,2), prune::Real=1/15) where {T}
+    nn = nearest_neighbours(rng, X, k; dims=dims, metric=metric, include_self=include_self, ntables=ntables)
+    snn = _jaccard_index(T, nn.array, k, convert(T, prune))                                          # neighbours.jl:267-268
+    NamedArray(snn, (X.dicts[1], X.dicts[1]), (X.dimnames[1], X.dimnames[1]))
+end
+shared_nearest_neighbours(X::NamedArray, k::Int64; kw...) = shared_nearest_neighbours(Random.default_rng(), X, k; kw...)
+shared_nearest_neighbours(rng, em::LinearEmbedding, k::Int64; kw...) = shared_nearest_neighbours(rng, em.coordinates, k; kw...)
+shared_nearest_neighbours(em::LinearEmbedding, k::Int64; kw...) = shared_nearest_neighbours(Random.default_rng(), em, k; kw...)
+
 end # module

@@ -653,6 +653,40 @@ def nearest_neighbours(X, k, dims=None, metric="euclidean", include_self=True):
 
 
 # --------------------------------------------------------------------------------------
+# neighbours.jl:88-110 : Jaccard index of the neighbour sets (shared-nearest-neighbour graph), the consumer of the kNN graph
+# --------------------------------------------------------------------------------------
+def jaccard_index(nn, k=None, prune=1.0 / 15.0, dtype=np.float64):
+    """``_jaccard_index`` (neighbours.jl:88-94 with a fixed ``k``, :96-110 without): ``snn = nn' * nn`` — entry (i, j) =
+    number of neighbours cells i and j share — converted to ``dtype``; every stored x becomes ``x / (k + (k - x))`` with
+    ``k`` the given neighbourhood size or, without it, ``diag(snn)[j]`` of the entry's COLUMN j (:103-106); then
+    ``droptol!(snn, prune)`` removes the entries with ``abs(x) <= prune`` (:92,108). ``nn``: n x n sparse pattern, column i =
+    the neighbours of cell i (stored entries count as ``true``). Returns CSC with ascending row indices."""
+    T = np.dtype(dtype).type
+    nn = sp.csc_matrix(nn)
+    nn.sort_indices()
+    n = nn.shape[1]
+    P = sp.csc_matrix((np.ones(nn.nnz, dtype=np.int64), nn.indices, nn.indptr), shape=nn.shape)
+    snn = sp.csc_matrix(P.T @ P)
+    snn.sort_indices()
+    x = snn.data.astype(T)
+    col = np.repeat(np.arange(n), np.diff(snn.indptr))
+    kk = np.full(x.shape, T(k), dtype=T) if k is not None else snn.diagonal().astype(T)[col]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        v = x / (kk + (kk - x))
+    keep = ~(np.abs(v) <= T(prune))
+    indptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(np.bincount(col[keep], minlength=n), out=indptr[1:])
+    return sp.csc_matrix((v[keep], snn.indices[keep], indptr), shape=(n, n))
+
+
+def shared_nearest_neighbours(X, k, dims=None, metric="euclidean", include_self=True, prune=1.0 / 15.0):
+    """neighbours.jl:263-270: the kNN graph of ``X`` and its Jaccard index with the fixed ``k``, in the element type of X."""
+    X = np.asarray(X)
+    T = X.dtype if X.dtype in (np.float32, np.float64) else np.float64
+    return jaccard_index(nearest_neighbours(X, k, dims, metric, include_self), k, prune, T)
+
+
+# --------------------------------------------------------------------------------------
 # embedding.jl:46-76 _pca post-processing ; utils.jl:215-228 svd_flip!
 # --------------------------------------------------------------------------------------
 def pca_post(U, S, V, npcs, m):

@@ -85,6 +85,7 @@ SIGNATURES = {
     "svb_tssvd": (c_int, [_h, c_int64, c_int64, c_int64, c_double, c_void_p, _ph]),
     "svb_knn": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
     "svb_knn_result": (c_int, [_h, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "svb_jaccard_index": (c_int, [_h, c_int64, c_double, c_int, _ph]),
     "svb_result_info": (c_int, [_h, _p64, _p64, _p64, _p64, _p64, _pint]),
     "svb_result_download": (c_int, [_h, c_void_p, c_void_p, c_void_p, c_int]),
     "svb_result_free": (c_int, [_h]),

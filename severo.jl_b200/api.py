@@ -31,7 +31,7 @@ from .loess import loess_fit_predict
 __all__ = [
     "DeviceMatrix", "NamedArray", "convert_counts", "filter_cells", "filter_features", "filter_counts", "normalize_cells", "mean_var", "mean_std",
     "standardized_var_clipped", "find_variable_features", "scale_features", "CenteredMatrix", "CountsCenteredMatrix",
-    "scale_features_counts", "irlba", "gram", "tssvd", "ann", "nearest_neighbours",
+    "scale_features_counts", "irlba", "gram", "tssvd", "ann", "nearest_neighbours", "jaccard_index", "shared_nearest_neighbours",
     "SVD", "svd_flip", "pca", "embedding", "LinearEmbedding", "synthetic_counts",
 ]
 
@@ -819,6 +819,58 @@ def nearest_neighbours(X, k, dims=None, metric="euclidean", include_self=True, n
     if names is None:
         return nn
     return NamedArray(nn, (names, names), (rowdim, rowdim))           # neighbours.jl:179
+
+
+def _jaccard(nn, k, prune, dtype):
+    nn = sp.csc_matrix(nn)
+    if nn.shape[0] != nn.shape[1]:
+        raise ValueError("jaccard_index: the neighbour graph must be square (cells x cells)")
+    if nn.dtype != np.bool_ or nn.nnz != int(np.count_nonzero(nn.data)):
+        nn = nn.copy()
+        nn.eliminate_zeros()                          # only `true` entries are neighbours
+    if not nn.has_sorted_indices:
+        nn = nn.copy()
+        nn.sort_indices()
+    dt = np.dtype(dtype)
+    if dt not in (np.dtype(np.float32), np.dtype(np.float64)):
+        raise TypeError("jaccard_index: dtype must be Float32 or Float64")
+    pattern = sp.csc_matrix((np.ones(nn.nnz, dtype=np.int32), nn.indices, nn.indptr), shape=nn.shape)
+    dN = DeviceMatrix.from_host(pattern)
+    h = ctypes.c_void_p()
+    try:
+        L.check(L.lib().svb_jaccard_index(dN._h, 0 if k is None else int(k), float(prune), _DT[dt], ctypes.byref(h)))
+    finally:
+        dN.free()
+    out = DeviceMatrix(h)
+    snn = out.to_host(dt)
+    out.free()
+    return snn
+
+
+def jaccard_index(nn, k=None, prune=1.0 / 15.0, dtype=np.float64):
+    """Severo.jaccard_index (neighbours.jl:112-131,133-152 over ``_jaccard_index`` :88-110): the shared-nearest-neighbour
+    graph of a neighbour graph ``nn`` (n x n boolean sparse, column i = the neighbours of cell i, as ``nearest_neighbours``
+    returns it). Entry (i, j) = |N(i) ∩ N(j)| / |N(i) ∪ N(j)| computed as ``x / (k + (k - x))`` with the given ``k`` or,
+    without it, the size of N(j); entries with a value <= ``prune`` are removed. Computed on the device (``svb_jaccard_index``)
+    without forming ``nn' * nn``. Returns CSC of ``dtype`` (labelled like the input when that is a NamedArray)."""
+    A, names, dimnames = _unwrap(nn)
+    if k is not None and int(k) <= 0:
+        raise ValueError("jaccard_index: k must be positive")
+    snn = _jaccard(A, k, prune, dtype)
+    if names is None:
+        return snn
+    return NamedArray(snn, (names[0], names[0]), (dimnames[0], dimnames[0]))      # neighbours.jl:130
+
+
+def shared_nearest_neighbours(X, k, dims=None, metric="euclidean", include_self=True, ntables=None, prune=1.0 / 15.0, rng=None):
+    """Severo.shared_nearest_neighbours (neighbours.jl:263-270,289,308,327): ``nearest_neighbours`` followed by the Jaccard
+    index with the fixed ``k``, in the element type of the coordinates (``prune = convert(T, prune)``, :267)."""
+    nn = nearest_neighbours(X, k, dims=dims, metric=metric, include_self=include_self)
+    if isinstance(X, LinearEmbedding):
+        X = X.coordinates
+    arr = X.array if isinstance(X, NamedArray) else np.asarray(X)
+    dt = arr.dtype if arr.dtype in (np.float32, np.float64) else np.dtype(np.float64)
+    return jaccard_index(nn, int(k), prune, dt)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -192,3 +192,81 @@ def test_knn_restatement_meets_the_reference_criterion(orc):
         assert not np.any(idx2 == np.arange(100)[:, None])
     nn = orc.nearest_neighbours(X, 4)
     assert nn.shape == (100, 100) and nn.nnz == 400 and np.all(np.asarray(nn.sum(axis=0)).ravel() == 4)   # k rows per cell column
+
+
+def _device_snn_algorithm(indptr, indices, n, k, prune, T):
+    """Pure-Python twin of csrc/snn.cu: reverse lists, a pair (i, j) emitted only at its smallest common neighbour (with an
+    early exit on a common element below it), survivors rank-sorted inside the column. Validates the ALGORITHM on the CPU."""
+    N = [list(indices[indptr[i]:indptr[i + 1]]) for i in range(n)]
+    R = [[] for _ in range(n)]
+    for j in range(n):
+        for p in N[j]:
+            R[p].append(j)
+    R = [r[::-1] for r in R]                     # any order must do
+    cols = []
+    for j in range(n):
+        kk = T(k if k is not None else len(N[j]))
+        surv = []
+        for p in N[j]:
+            for i in R[p]:
+                c, first = 0, True
+                for q in N[i]:
+                    if q in N[j]:
+                        if q < p:
+                            first = False
+                            break
+                        c += 1
+                if first:
+                    x = T(c)
+                    v = x / (kk + (kk - x))
+                    if not abs(v) <= T(prune):
+                        surv.append((i, v))
+        keys = [s[0] for s in surv]
+        assert len(set(keys)) == len(keys)       # every pair is emitted exactly once
+        out = [None] * len(surv)
+        for (i, v) in surv:
+            out[sum(1 for u in keys if u < i)] = (i, v)
+        cols.append(out)
+    return cols
+
+
+def test_jaccard_index_restatement(orc):
+    # neighbours.jl:88-110. Hand-computed case: N(0)={0,1,2}, N(1)={0,1,2}, N(2)={1,2,3}, N(3)={2,3,4}, N(4)={0,3,4}
+    nbrs = [[0, 1, 2], [0, 1, 2], [1, 2, 3], [2, 3, 4], [0, 3, 4]]
+    nn = sp.csc_matrix((np.ones(15, dtype=bool), np.concatenate(nbrs), np.arange(0, 16, 3)), shape=(5, 5))
+    j = {3: 1.0, 2: 0.5, 1: 0.2}                                   # x / (3 + (3 - x))
+    shared = np.array([[3, 3, 2, 1, 1], [3, 3, 2, 1, 1], [2, 2, 3, 2, 1], [1, 1, 2, 3, 2], [1, 1, 1, 2, 3]])
+    expect = np.vectorize(j.get)(shared)
+    S = orc.jaccard_index(nn, 3, prune=1.0 / 15.0)
+    assert np.array_equal(S.toarray(), expect) and S.nnz == 25
+    S = orc.jaccard_index(nn, 3, prune=0.2)                         # droptol!: abs(x) <= tol is dropped, 0.2 itself goes
+    assert np.array_equal(S.toarray(), np.where(expect > 0.2, expect, 0.0)) and S.nnz == 15
+    assert np.array_equal(orc.jaccard_index(nn, None, prune=1.0 / 15.0).toarray(), expect)   # diag(snn) = 3 everywhere
+    # ragged neighbourhoods: the form without k divides by the size of the COLUMN's neighbourhood (neighbours.jl:103-106)
+    nbrs = [[0, 1], [0, 1, 2, 3], [2], [], [1, 2, 4]]
+    ptr = np.concatenate([[0], np.cumsum([len(v) for v in nbrs])])
+    nn = sp.csc_matrix((np.ones(ptr[-1], dtype=bool), np.concatenate(nbrs).astype(np.int64), ptr), shape=(5, 5))
+    S = orc.jaccard_index(nn, None, prune=0.0).toarray()
+    for jcol in range(5):
+        for i in range(5):
+            x = len(set(nbrs[i]) & set(nbrs[jcol]))
+            kj = len(nbrs[jcol])
+            assert S[i, jcol] == (x / (kj + (kj - x)) if x else 0.0)
+    # the device algorithm (emit at the smallest common neighbour, rank sort) gives the same entries, both element types
+    rng = np.random.default_rng(3)
+    X = rng.random((70, 4))
+    for k, T in ((5, np.float64), (5, np.float32), (None, np.float64)):
+        nnk = orc.nearest_neighbours(X, 5)
+        if k is None:                                              # make it ragged
+            nnk = sp.csc_matrix(nnk.multiply(sp.csc_matrix(rng.random((70, 70)) < 0.8)))
+            nnk.eliminate_zeros()
+            nnk.sort_indices()
+        S = orc.jaccard_index(nnk, k, 1.0 / 15.0, T)
+        assert S.dtype == T
+        cols = _device_snn_algorithm(nnk.indptr, nnk.indices, 70, k, 1.0 / 15.0, T)
+        for jcol in range(70):
+            a, b = S.indptr[jcol], S.indptr[jcol + 1]
+            assert [c[0] for c in cols[jcol]] == list(S.indices[a:b])
+            assert [c[1] for c in cols[jcol]] == list(S.data[a:b])
+    Sn = orc.shared_nearest_neighbours(X.astype(np.float32), 5)
+    assert Sn.dtype == np.float32 and np.array_equal(Sn.toarray(), orc.jaccard_index(orc.nearest_neighbours(X.astype(np.float32), 5), 5, 1 / 15, np.float32).toarray())
