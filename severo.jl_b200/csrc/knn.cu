@@ -4,7 +4,7 @@
 // EXACT brute force instead of the reference's randomised multi-table approximation (`ntables`, `seed` have no role) —
 // the answer the reference's own test compares against (test/test_nn.jl:31-38: partialsortperm of the pairwise distances).
 //
-// One thread owns one query cell: its coordinates sit in registers (D = d rounded up to 8, compile-time), the points
+// One thread owns one query cell: its coordinates sit in registers (D = d zero-padded, compile-time: knn_padded_dims), the points
 // stream through shared memory in 32 KB tiles that every thread of the CTA reads at the same address (broadcast, no bank
 // conflicts: one 16-byte shared load feeds two fp64 FMAs of all 32 lanes — the ratio at which the shared pipe keeps the
 // fp64 pipe busy), four points at a time for instruction-level parallelism. Ranking key: |p|^2 - 2 q.p (Euclidean; |q|^2 is
@@ -330,7 +330,18 @@ void launch_knn(const double *P, const double *cn, int64_t n, int64_t npad, int 
     launch_knn_q<D, 1>(P, cn, n, npad, k, include_self, nbr);
 }
 
-int knn_padded_dims(int d) {
+// Compile-time coordinate count the search runs with (zero-padded). Multiples of 8 in general; the widths the pipeline
+// actually uses get their own even-sized instance so that no FMA is spent on padding: dims = 1:10 (docs/src/pbmc.md:157)
+// runs with D = 10 instead of 16, 20 PCs with 20 instead of 24, 50 PCs with 50 instead of 56. The tensor-core variant
+// needs multiples of 8 (k-steps of 4, two per B fragment pair).
+constexpr bool KNN_EXACT_WIDTHS = true;
+int knn_padded_dims(int d, bool mma) {
+    if (KNN_EXACT_WIDTHS && !mma) {
+        if (d == 9 || d == 10) return 10;
+        if (d == 11 || d == 12) return 12;
+        if (d >= 17 && d <= 20) return 20;
+        if (d == 49 || d == 50) return 50;
+    }
     if (d <= 64) return (d + 7) & ~7;
     return d <= 96 ? 96 : 128;
 }
@@ -346,9 +357,9 @@ void knn_device(const double *Xd, int64_t ldx, int64_t n, int d, int k, int metr
     SVB_CHECK(k >= 1 && k <= KNN_KMAX, SVB_EDIM, "knn: k must satisfy 1 <= k <= 64");
     SVB_CHECK(k <= n - (include_self ? 0 : 1), SVB_EDIM, "knn: fewer than k candidate neighbours");
     SVB_CHECK(dist_type == SVB_F64 || dist_type == SVB_F32, SVB_EARG, "knn: distances must be Float32 or Float64");
-    const int D = knn_padded_dims(d);
     const int mma_env = getenv("SVB_KNN_MMA") ? atoi(getenv("SVB_KNN_MMA")) : -1;  // 1 / 0 force the variant, unset = choose
-    const bool use_mma = D <= 64 && (mma_env == 1 || (mma_env < 0 && KNN_AUTO_MMA));
+    const bool use_mma = d <= 64 && (mma_env == 1 || (mma_env < 0 && KNN_AUTO_MMA));
+    const int D = knn_padded_dims(d, use_mma);
     const int TP = use_mma ? knn_mma_tile_points(D) : knn_tile_points(D);
     const int64_t npad = (n + TP - 1) / TP * TP;
     DevBuf<double> P((size_t)npad * D), cn((size_t)npad), dist((size_t)n * k);
@@ -373,11 +384,15 @@ void knn_device(const double *Xd, int64_t ldx, int64_t n, int d, int k, int metr
     } else
     switch (D) {
         case 8: launch_knn<8>(P.p, cn.p, n, npad, k, include_self, nbr.p); break;
+        case 10: launch_knn<10>(P.p, cn.p, n, npad, k, include_self, nbr.p); break;
+        case 12: launch_knn<12>(P.p, cn.p, n, npad, k, include_self, nbr.p); break;
         case 16: launch_knn<16>(P.p, cn.p, n, npad, k, include_self, nbr.p); break;
+        case 20: launch_knn<20>(P.p, cn.p, n, npad, k, include_self, nbr.p); break;
         case 24: launch_knn<24>(P.p, cn.p, n, npad, k, include_self, nbr.p); break;
         case 32: launch_knn<32>(P.p, cn.p, n, npad, k, include_self, nbr.p); break;
         case 40: launch_knn<40>(P.p, cn.p, n, npad, k, include_self, nbr.p); break;
         case 48: launch_knn<48>(P.p, cn.p, n, npad, k, include_self, nbr.p); break;
+        case 50: launch_knn<50>(P.p, cn.p, n, npad, k, include_self, nbr.p); break;
         case 56: launch_knn<56>(P.p, cn.p, n, npad, k, include_self, nbr.p); break;
         case 64: launch_knn<64>(P.p, cn.p, n, npad, k, include_self, nbr.p); break;
         case 96: launch_knn<96>(P.p, cn.p, n, npad, k, include_self, nbr.p); break;

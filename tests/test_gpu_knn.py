@@ -36,9 +36,10 @@ def test_ann_reference_cases(sv, orc, metric):
     np.testing.assert_allclose(dist, ref_dist, rtol=1e-6, atol=1e-7)
 
 
-@pytest.mark.parametrize("case", [(3000, 7, 5), (3000, 50, 20), (2049, 10, 20), (700, 64, 64), (1500, 33, 1), (300, 80, 4), (400, 100, 10), (130, 128, 3)])
+@pytest.mark.parametrize("case", [(3000, 7, 5), (3000, 50, 20), (2049, 10, 20), (700, 64, 64), (1500, 33, 1), (300, 80, 4), (400, 100, 10), (130, 128, 3), (500, 11, 5), (640, 19, 6)])
 def test_knn_exact_against_oracle(sv, orc, case):
-    # every padded width of the kernel family (8, 56, 16, 64, 40, 96, 128-with-spills), n not a multiple of the tile or CTA size
+    # every kind of padded width of the kernel family (8, 50, 10, 64, 40, 96, 128-with-spills, 12, 20: knn_padded_dims), n not a multiple of
+    # the tile or CTA size
     n, d, k = case
     rng = np.random.default_rng(n + d)
     centres = rng.standard_normal((8, d)) * 3.0

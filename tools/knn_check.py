@@ -25,7 +25,12 @@ def main():
     L = sv._lib
     lib = sv.lib()
     sv.ann(X[:4096], k, metric=metric)  # warm-up: module load, allocations
-    D = (d + 7) // 8 * 8 if d <= 64 else (96 if d <= 96 else 128)
+    def padded(d, mma):      # knn_padded_dims (csrc/knn.cu)
+        if not mma and d in (9, 10, 11, 12, 17, 18, 19, 20, 49, 50):
+            return {9: 10, 10: 10, 11: 12, 12: 12, 49: 50, 50: 50}.get(d, 20)
+        return (d + 7) // 8 * 8 if d <= 64 else (96 if d <= 96 else 128)
+
+    D = padded(d, False)
     out = {"n": n, "d": d, "D": D, "k": k, "metric": metric}
     # the kernel variants back to back in one process (same box, same clocks): SVB_KNN_Q / SVB_KNN_MMA are read per call.
     # seconds = wall time of the whole call (pageable host buffers in and out); kernel_ms = CUDA events around the search kernel
@@ -47,7 +52,7 @@ def main():
         by = (ctypes.c_double * 6)()
         L.check(lib.svb_profile_get(ms, ln, by))
         kms = ms[4]
-        out[name] = {"seconds": round(dt, 4), "kernel_ms": round(kms, 2), "kernel_fp64_tflops": round(2.0 * n * n * D / (kms * 1e-3) / 1e12, 2)}
+        out[name] = {"seconds": round(dt, 4), "kernel_ms": round(kms, 2), "kernel_fp64_tflops": round(2.0 * n * n * padded(d, name == "dmma") / (kms * 1e-3) / 1e12, 2)}
     for key in ("SVB_KNN_Q", "SVB_KNN_MMA"):
         os.environ.pop(key, None)
     lib.svb_profile_enable(0)
