@@ -7,19 +7,26 @@
 // reached once per common neighbour; it is EMITTED only at its smallest common neighbour — the lane that holds the
 // occurrence (p, i) walks the ascending list N(i), looks every element up in the ascending list N(j) by binary search,
 // stops when a common element below p turns up (a later occurrence owns the pair) and otherwise ends with the full
-// intersection count. So there is no hash table and no de-duplication pass, integer work only. Survivors of the prune
-// test are counted (pass 1), scanned into the output column pointers, written in enumeration order (pass 2) and put in
-// ascending row order by rank counting inside each column (distinct keys, typically < 100 per column).
+// intersection count: no de-duplication storage at all, integer work only. That is the GENERAL path (any neighbourhood
+// sizes, hubs of any in-degree). Measured on a B200 (262,144 cells, k = 20) it is bound by the divergent 4-byte loads of
+// the lists N(i) — 0.11 s — so columns whose candidate count fits take the FAST path instead: the warp counts the
+// occurrences of every i in a private shared-memory hash table (one coalesced read of each reverse list, one shared
+// atomic per occurrence; the count of i IS |N(i) ∩ N(j)|) and never touches N(i). Either way the survivors of the prune
+// test are counted (pass 1), scanned into the output column pointers, written (pass 2) and put in ascending row order by
+// rank counting inside each column (distinct keys, typically < 100 per column), so the result does not depend on the path.
 // Values are computed exactly as the reference does, in the output element type: one rounded division per entry, so the
 // result is bit-identical to the reference's (Float32 or Float64).
 #include "svb_internal.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 using namespace svb;
 
 namespace svb {
 namespace {
+
+constexpr bool SNN_HASH_DEFAULT = true;  // columns whose candidates fit a per-warp hash table are counted there (see below)
 
 inline unsigned snn_grid(int64_t n, int threads = 256) {
     return (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, 148 * 16));
@@ -79,15 +86,113 @@ __device__ __forceinline__ T snn_value(int c, T kk) {
     return x / (kk + (kk - x));
 }
 
-// WRITE = false: cnt[j] = number of surviving entries of column j.
-// WRITE = true : cnt = exclusive scan of those counts; the survivors (row, intersection count) go to tmp_row / tmp_cnt at
-//                cnt[j] + their position in enumeration order. Both passes enumerate identically.
+// WRITE = false: returns the number of surviving entries of column j.
+// WRITE = true : the survivors (row, intersection count) go to tmp_row / tmp_cnt at base + their position in enumeration
+//                order; returns the same number. Both passes enumerate identically. Warp-collective (j is warp-uniform).
 template <typename T, bool WRITE>
+__device__ __forceinline__ int64_t snn_column_general(const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
+                                                      const int64_t *__restrict__ rptr, const int32_t *__restrict__ rev, const int32_t *Nj,
+                                                      int dj, T kk, T prune, int64_t base, int32_t *__restrict__ tmp_row,
+                                                      int32_t *__restrict__ tmp_cnt, int lane) {
+    int64_t total = 0;
+    for (int a = 0; a < dj; ++a) {
+        const int32_t p = __ldg(Nj + a);
+        const int64_t r0 = rptr[p], r1 = rptr[p + 1];
+        for (int64_t rb = r0; rb < r1; rb += 32) {  // warp-uniform trip count: the ballot below is collective
+            const int64_t r = rb + lane;
+            bool keep = false;
+            int32_t i = 0;
+            int c = 0;
+            if (r < r1) {
+                i = rev[r];
+                const int64_t i0 = colptr[i], i1 = colptr[i + 1];
+                bool first = true;  // p is the smallest common neighbour of i and j
+                for (int64_t e = i0; e < i1; ++e) {
+                    const int32_t q = __ldg(rowidx + e);
+                    if (snn_contains(Nj, dj, q)) {
+                        if (q < p) {
+                            first = false;
+                            break;
+                        }
+                        ++c;
+                    }
+                }
+                if (first) keep = !(fabs((double)snn_value<T>(c, kk)) <= (double)prune);  // droptol!: abs(x) <= tol goes
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (WRITE && keep) {
+                const int64_t dst = base + total + __popc(bal & ((1u << lane) - 1u));
+                tmp_row[dst] = i;
+                tmp_cnt[dst] = c;
+            }
+            total += __popc(bal);
+        }
+    }
+    return total;
+}
+
+// Fast path: occurrences of every candidate counted in the warp's hash table (open addressing, linear probing; the caller
+// guarantees candidates <= SNN_HASH_LIMIT < SNN_HASH_SLOTS, so a free slot always exists). hkey = -1 marks a free slot.
+constexpr int SNN_HASH_SLOTS = 2048;                       // per warp: 2048 x (key, count) = 16 KB
+constexpr int SNN_HASH_LIMIT = SNN_HASH_SLOTS * 3 / 4;     // candidate occurrences (>= distinct candidates) per column
+constexpr int SNN_HASH_WARPS = 4;                          // warps per CTA on the hash path (64 KB of shared memory)
+
+template <typename T, bool WRITE>
+__device__ __forceinline__ int64_t snn_column_hash(const int64_t *__restrict__ rptr, const int32_t *__restrict__ rev, const int32_t *Nj, int dj,
+                                                   T kk, T prune, int64_t base, int32_t *__restrict__ tmp_row,
+                                                   int32_t *__restrict__ tmp_cnt, int lane, int *hkey, int *hcnt) {
+    for (int t = lane; t < SNN_HASH_SLOTS; t += 32) {
+        hkey[t] = -1;
+        hcnt[t] = 0;
+    }
+    __syncwarp();
+    for (int a = 0; a < dj; ++a) {
+        const int32_t p = __ldg(Nj + a);
+        const int64_t r1 = rptr[p + 1];
+        for (int64_t r = rptr[p] + lane; r < r1; r += 32) {
+            const int i = rev[r];
+            unsigned h = ((unsigned)i * 2654435761u) >> 21;  // 11 bits
+            while (true) {
+                const int old = atomicCAS(&hkey[h], -1, i);
+                if (old == -1 || old == i) {
+                    atomicAdd(&hcnt[h], 1);
+                    break;
+                }
+                h = (h + 1) & (SNN_HASH_SLOTS - 1);
+            }
+        }
+    }
+    __syncwarp();
+    int64_t total = 0;
+    for (int t0 = 0; t0 < SNN_HASH_SLOTS; t0 += 32) {
+        const int i = hkey[t0 + lane];
+        const int c = hcnt[t0 + lane];
+        const bool keep = i >= 0 && !(fabs((double)snn_value<T>(c, kk)) <= (double)prune);
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (WRITE && keep) {
+            const int64_t dst = base + total + __popc(bal & ((1u << lane) - 1u));
+            tmp_row[dst] = i;
+            tmp_cnt[dst] = c;
+        }
+        total += __popc(bal);
+    }
+    __syncwarp();  // the table is cleared again for the warp's next column
+    return total;
+}
+
+// WRITE = false: cnt[j] = number of surviving entries of column j.
+// WRITE = true : cnt = exclusive scan of those counts; survivors written at cnt[j] + position.
+// HASH: dynamic shared memory = (blockDim.x / 32) tables; columns with more than SNN_HASH_LIMIT candidate occurrences
+// (hubs) take the general path inside the same kernel.
+template <typename T, bool WRITE, bool HASH>
 __global__ void __launch_bounds__(256) snn_enumerate_kernel(const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
                                                             int64_t n, const int64_t *__restrict__ rptr, const int32_t *__restrict__ rev,
                                                             int64_t kfixed, T prune, int64_t *__restrict__ cnt,
                                                             int32_t *__restrict__ tmp_row, int32_t *__restrict__ tmp_cnt) {
+    extern __shared__ int snn_tables[];
     const int lane = threadIdx.x & 31;
+    int *hkey = snn_tables + (threadIdx.x >> 5) * 2 * SNN_HASH_SLOTS;
+    int *hcnt = hkey + SNN_HASH_SLOTS;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < n; j += nwarps) {  // j is warp-uniform
         const int64_t j0 = colptr[j];
@@ -95,40 +200,23 @@ __global__ void __launch_bounds__(256) snn_enumerate_kernel(const int64_t *__res
         const int32_t *Nj = rowidx + j0;
         const T kk = (T)(kfixed > 0 ? kfixed : (int64_t)dj);
         const int64_t base = WRITE ? cnt[j] : 0;
-        int64_t total = 0;
-        for (int a = 0; a < dj; ++a) {
-            const int32_t p = __ldg(Nj + a);
-            const int64_t r0 = rptr[p], r1 = rptr[p + 1];
-            for (int64_t rb = r0; rb < r1; rb += 32) {  // warp-uniform trip count: the ballot below is collective
-                const int64_t r = rb + lane;
-                bool keep = false;
-                int32_t i = 0;
-                int c = 0;
-                if (r < r1) {
-                    i = rev[r];
-                    const int64_t i0 = colptr[i], i1 = colptr[i + 1];
-                    bool first = true;  // p is the smallest common neighbour of i and j
-                    for (int64_t e = i0; e < i1; ++e) {
-                        const int32_t q = __ldg(rowidx + e);
-                        if (snn_contains(Nj, dj, q)) {
-                            if (q < p) {
-                                first = false;
-                                break;
-                            }
-                            ++c;
-                        }
-                    }
-                    if (first) keep = !(fabs((double)snn_value<T>(c, kk)) <= (double)prune);  // droptol!: abs(x) <= tol goes
-                }
-                const unsigned bal = __ballot_sync(0xffffffffu, keep);
-                if (WRITE && keep) {
-                    const int64_t dst = base + total + __popc(bal & ((1u << lane) - 1u));
-                    tmp_row[dst] = i;
-                    tmp_cnt[dst] = c;
-                }
-                total += __popc(bal);
+        int64_t total;
+        bool general = true;
+        if (HASH) {
+            // candidate occurrences of the column = sum of the in-degrees of its neighbours (warp-uniform after the reduction)
+            long long cand = 0;
+            for (int a = lane; a < dj; a += 32) {
+                const int32_t p = __ldg(Nj + a);
+                cand += rptr[p + 1] - rptr[p];
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cand += __shfl_xor_sync(0xffffffffu, cand, o);
+            general = cand > SNN_HASH_LIMIT;
         }
+        if (general)
+            total = snn_column_general<T, WRITE>(colptr, rowidx, rptr, rev, Nj, dj, kk, prune, base, tmp_row, tmp_cnt, lane);
+        else
+            total = snn_column_hash<T, WRITE>(rptr, rev, Nj, dj, kk, prune, base, tmp_row, tmp_cnt, lane, hkey, hcnt);
         if (!WRITE && lane == 0) cnt[j] = total;
     }
 }
@@ -187,10 +275,21 @@ svb_matrix_s *jaccard_run(const svb_matrix_s *nn, int64_t k, double prune, int v
         count_launch();
         SVB_LAUNCH_CHECK();
     }
-    // pass 1: survivors per column -> output column pointers
-    const unsigned egrid = snn_grid(n * 32);
+    // pass 1: survivors per column -> output column pointers. SVB_SNN_HASH=0 / 1 forces the general / hash kernels.
+    const int hash_env = getenv("SVB_SNN_HASH") ? atoi(getenv("SVB_SNN_HASH")) : -1;
+    const bool hash = hash_env < 0 ? SNN_HASH_DEFAULT : hash_env != 0;
+    const int ethreads = hash ? SNN_HASH_WARPS * 32 : 256;
+    const size_t esmem = hash ? (size_t)SNN_HASH_WARPS * 2 * SNN_HASH_SLOTS * sizeof(int) : 0;
+    const unsigned egrid = snn_grid(n * 32, ethreads);
+    if (hash) {
+        SVB_CUDA(cudaFuncSetAttribute(snn_enumerate_kernel<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
+        SVB_CUDA(cudaFuncSetAttribute(snn_enumerate_kernel<T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
+    }
     if (nnz > 0) {
-        snn_enumerate_kernel<T, false><<<egrid, 256, 0, st>>>(nn->colptr, nn->rowidx, n, rptr.p, rev.p, k, (T)prune, cnt.p, nullptr, nullptr);
+        if (hash)
+            snn_enumerate_kernel<T, false, true><<<egrid, ethreads, esmem, st>>>(nn->colptr, nn->rowidx, n, rptr.p, rev.p, k, (T)prune, cnt.p, nullptr, nullptr);
+        else
+            snn_enumerate_kernel<T, false, false><<<egrid, ethreads, 0, st>>>(nn->colptr, nn->rowidx, n, rptr.p, rev.p, k, (T)prune, cnt.p, nullptr, nullptr);
         count_launch();
         SVB_LAUNCH_CHECK();
     }
@@ -204,8 +303,11 @@ svb_matrix_s *jaccard_run(const svb_matrix_s *nn, int64_t k, double prune, int v
         SVB_CUDA(cudaMemcpyAsync(out->colptr, cnt.p, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
         if (onnz > 0) {
             DevBuf<int32_t> tmp_row((size_t)onnz), tmp_cnt((size_t)onnz);
-            snn_enumerate_kernel<T, true><<<egrid, 256, 0, st>>>(nn->colptr, nn->rowidx, n, rptr.p, rev.p, k, (T)prune, cnt.p, tmp_row.p, tmp_cnt.p);
-            snn_finalize_kernel<T><<<egrid, 256, 0, st>>>(out->colptr, nn->colptr, n, k, tmp_row.p, tmp_cnt.p, out->rowidx, (T *)out->val);
+            if (hash)
+                snn_enumerate_kernel<T, true, true><<<egrid, ethreads, esmem, st>>>(nn->colptr, nn->rowidx, n, rptr.p, rev.p, k, (T)prune, cnt.p, tmp_row.p, tmp_cnt.p);
+            else
+                snn_enumerate_kernel<T, true, false><<<egrid, ethreads, 0, st>>>(nn->colptr, nn->rowidx, n, rptr.p, rev.p, k, (T)prune, cnt.p, tmp_row.p, tmp_cnt.p);
+            snn_finalize_kernel<T><<<snn_grid(n * 32), 256, 0, st>>>(out->colptr, nn->colptr, n, k, tmp_row.p, tmp_cnt.p, out->rowidx, (T *)out->val);
             count_launch(2);
             SVB_LAUNCH_CHECK();
             SVB_CUDA(cudaStreamSynchronize(st));  // tmp_row / tmp_cnt are freed here

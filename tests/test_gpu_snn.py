@@ -22,7 +22,15 @@ def _clustered(n, d, seed):
     return centres[rng.integers(0, 6, n)] + rng.standard_normal((n, d))
 
 
-def test_jaccard_hand_computed_case(sv):
+@pytest.fixture(params=["hash", "general"])
+def snn_path(request, monkeypatch):
+    """Both device paths of csrc/snn.cu: per-warp hash tables (default; hub columns fall back inside the kernel) and the
+    general smallest-common-neighbour enumeration for every column (SVB_SNN_HASH=0, read per call)."""
+    monkeypatch.setenv("SVB_SNN_HASH", "1" if request.param == "hash" else "0")
+    return request.param
+
+
+def test_jaccard_hand_computed_case(sv, snn_path):
     # same case as tests/test_oracle_golden.py::test_jaccard_index_restatement
     nbrs = [[0, 1, 2], [0, 1, 2], [1, 2, 3], [2, 3, 4], [0, 3, 4]]
     nn = sp.csc_matrix((np.ones(15, dtype=bool), np.concatenate(nbrs), np.arange(0, 16, 3)), shape=(5, 5))
@@ -36,7 +44,7 @@ def test_jaccard_hand_computed_case(sv):
 
 
 @pytest.mark.parametrize("case", [(300, 5, 4), (2000, 10, 20), (1500, 8, 33), (4097, 6, 15)])
-def test_jaccard_index_against_oracle(sv, orc, case):
+def test_jaccard_index_against_oracle(sv, orc, case, snn_path):
     n, d, k = case
     X = _clustered(n, d, n + k)
     nn = orc.nearest_neighbours(X, k)
@@ -49,7 +57,7 @@ def test_jaccard_index_against_oracle(sv, orc, case):
     assert (abs(S - S.T)).nnz == 0 and np.all(S.diagonal() == 1.0)
 
 
-def test_jaccard_ragged_hubs_and_empty_columns(sv, orc):
+def test_jaccard_ragged_hubs_and_empty_columns(sv, orc, snn_path):
     rng = np.random.default_rng(11)
     n = 900
     # ragged neighbourhoods, some empty, and a hub that a third of the cells point at (long reverse list: several
@@ -79,6 +87,22 @@ def test_jaccard_ragged_hubs_and_empty_columns(sv, orc):
     # empty graph
     E = sv.jaccard_index(sp.csc_matrix((50, 50), dtype=bool), 5)
     assert E.shape == (50, 50) and E.nnz == 0
+
+
+def test_jaccard_hub_columns_leave_the_hash_path(sv, orc):
+    # a cell that 2,500 others point at: every column holding it has more candidate occurrences than a warp's hash table
+    # takes (1,536) and is enumerated by the general path inside the hash kernel; the other columns stay on the hash path
+    rng = np.random.default_rng(5)
+    n, k = 5000, 8
+    idx = np.array([rng.choice(n, k, replace=False) for _ in range(n)])
+    hub_cols = rng.choice(n, 2500, replace=False)
+    idx[hub_cols, 0] = 42
+    idx = np.array([np.unique(r) for r in idx], dtype=object)
+    ptr = np.concatenate([[0], np.cumsum([len(r) for r in idx])])
+    nn = sp.csc_matrix((np.ones(ptr[-1], dtype=bool), np.concatenate(idx).astype(np.int64), ptr), shape=(n, n))
+    assert np.bincount(nn.indices, minlength=n)[42] >= 2500
+    for kk, prune in ((k, 1.0 / 15.0), (None, 0.0)):
+        assert _same_csc(sv.jaccard_index(nn, kk, prune=prune), orc.jaccard_index(nn, kk, prune))
 
 
 def test_shared_nearest_neighbours_and_errors(sv, orc):

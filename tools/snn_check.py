@@ -1,7 +1,7 @@
 """tools/snn_check.py — timing of the device Jaccard index / shared-nearest-neighbour graph (svb_jaccard_index) at scale, 1 GPU.
 usage: python tools/snn_check.py n d k
 Builds the exact kNN graph of n clustered points on the device (svb_knn), then times svb_jaccard_index on the resident
-graph (device-synchronised on both sides, second call) and the whole host call (upload of the pattern, compute, download of
+graph (device-synchronised on both sides, two calls per device path) and the whole host call (upload of the pattern, compute, download of
 the CSC result). Spot check: 64 random columns recomputed on the host with Python set intersections. One JSON line."""
 import ctypes
 import json
@@ -32,18 +32,23 @@ def main():
     srt = np.sort(idx, axis=1)
     pattern = sp.csc_matrix((np.ones(n * k, dtype=np.int32), srt.ravel(), np.arange(0, n * k + 1, k, dtype=np.int64)), shape=(n, n))
     dN = sv.DeviceMatrix.from_host(pattern)
-    times = []
+    times = {}
     nnz = 0
-    for _ in range(2):
-        h = ctypes.c_void_p()
-        lib.svb_synchronize()
-        t0 = time.perf_counter()
-        L.check(lib.svb_jaccard_index(dN._h, k, prune, L.SVB_F64, ctypes.byref(h)))
-        lib.svb_synchronize()
-        times.append(time.perf_counter() - t0)
-        o = sv.DeviceMatrix(h)
-        nnz = o.nnz
-        o.free()
+    # both device paths back to back (SVB_SNN_HASH is read per call): per-warp hash tables (default) / general enumeration
+    for name, env in (("hash", "1"), ("general", "0")):
+        os.environ["SVB_SNN_HASH"] = env
+        times[name] = []
+        for _ in range(2):
+            h = ctypes.c_void_p()
+            lib.svb_synchronize()
+            t0 = time.perf_counter()
+            L.check(lib.svb_jaccard_index(dN._h, k, prune, L.SVB_F64, ctypes.byref(h)))
+            lib.svb_synchronize()
+            times[name].append(round(time.perf_counter() - t0, 5))
+            o = sv.DeviceMatrix(h)
+            nnz = o.nnz
+            o.free()
+    os.environ.pop("SVB_SNN_HASH", None)
     dN.free()
     t0 = time.perf_counter()
     S = sv.jaccard_index(pattern.astype(bool), k, prune)
@@ -71,7 +76,7 @@ def main():
         a, b = S.indptr[j], S.indptr[j + 1]
         got = dict(zip(S.indices[a:b].tolist(), S.data[a:b].tolist()))
         bad += int(got != ref or list(S.indices[a:b]) != sorted(ref))
-    out = {"n": n, "d": d, "k": k, "prune": prune, "knn_s": round(knn_s, 4), "jaccard_device_s": [round(t, 5) for t in times],
+    out = {"n": n, "d": d, "k": k, "prune": prune, "knn_s": round(knn_s, 4), "jaccard_device_s": times,
            "jaccard_host_call_s": round(host_s, 4), "snn_nnz": int(nnz), "snn_nnz_per_cell": round(nnz / n, 2),
            "candidate_pairs": float((indeg ** 2).sum()), "max_indegree": int(indeg.max()),
            "spot_check_mismatching_columns_of_64": bad}
