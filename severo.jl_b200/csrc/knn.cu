@@ -336,7 +336,8 @@ void launch_knn(const double *P, const double *cn, int64_t n, int64_t npad, int 
 // needs multiples of 8 (k-steps of 4, two per B fragment pair).
 constexpr bool KNN_EXACT_WIDTHS = true;
 int knn_padded_dims(int d, bool mma) {
-    if (KNN_EXACT_WIDTHS && !mma) {
+    const bool exact = getenv("SVB_KNN_WIDTHS") ? atoi(getenv("SVB_KNN_WIDTHS")) != 0 : KNN_EXACT_WIDTHS;  // 0: multiples of 8 only
+    if (exact && !mma) {
         if (d == 9 || d == 10) return 10;
         if (d == 11 || d == 12) return 12;
         if (d >= 17 && d <= 20) return 20;

@@ -25,8 +25,8 @@ def main():
     L = sv._lib
     lib = sv.lib()
     sv.ann(X[:4096], k, metric=metric)  # warm-up: module load, allocations
-    def padded(d, mma):      # knn_padded_dims (csrc/knn.cu)
-        if not mma and d in (9, 10, 11, 12, 17, 18, 19, 20, 49, 50):
+    def padded(d, mma, exact=True):      # knn_padded_dims (csrc/knn.cu)
+        if exact and not mma and d in (9, 10, 11, 12, 17, 18, 19, 20, 49, 50):
             return {9: 10, 10: 10, 11: 12, 12: 12, 49: 50, 50: 50}.get(d, 20)
         return (d + 7) // 8 * 8 if d <= 64 else (96 if d <= 96 else 128)
 
@@ -35,12 +35,14 @@ def main():
     # the kernel variants back to back in one process (same box, same clocks): SVB_KNN_Q / SVB_KNN_MMA are read per call.
     # seconds = wall time of the whole call (pageable host buffers in and out); kernel_ms = CUDA events around the search kernel
     variants = [("default", {}), ("simt_q1", {"SVB_KNN_Q": "1", "SVB_KNN_MMA": "0"}), ("simt_q2", {"SVB_KNN_Q": "2", "SVB_KNN_MMA": "0"}),
-                ("dmma", {"SVB_KNN_MMA": "1"})]
+                ("dmma", {"SVB_KNN_MMA": "1"}), ("pad8", {"SVB_KNN_WIDTHS": "0"})]
     if os.environ.get("KNN_VARIANTS") == "default":
         variants = variants[:1]
+    elif os.environ.get("KNN_VARIANTS") == "widths":     # exact-width instance against the multiple-of-8 one
+        variants = [variants[0], variants[4]]
     lib.svb_profile_enable(1)
     for name, env in variants:
-        for key in ("SVB_KNN_Q", "SVB_KNN_MMA"):
+        for key in ("SVB_KNN_Q", "SVB_KNN_MMA", "SVB_KNN_WIDTHS"):
             os.environ.pop(key, None)
         os.environ.update(env)
         lib.svb_profile_reset()
@@ -52,8 +54,9 @@ def main():
         by = (ctypes.c_double * 6)()
         L.check(lib.svb_profile_get(ms, ln, by))
         kms = ms[4]
-        out[name] = {"seconds": round(dt, 4), "kernel_ms": round(kms, 2), "kernel_fp64_tflops": round(2.0 * n * n * padded(d, name == "dmma") / (kms * 1e-3) / 1e12, 2)}
-    for key in ("SVB_KNN_Q", "SVB_KNN_MMA"):
+        out[name] = {"seconds": round(dt, 4), "kernel_ms": round(kms, 2), "D": padded(d, name == "dmma", name != "pad8"),
+                     "kernel_fp64_tflops": round(2.0 * n * n * padded(d, name == "dmma", name != "pad8") / (kms * 1e-3) / 1e12, 2)}
+    for key in ("SVB_KNN_Q", "SVB_KNN_MMA", "SVB_KNN_WIDTHS"):
         os.environ.pop(key, None)
     lib.svb_profile_enable(0)
     idx, dist = sv.ann(X, k, metric=metric)
