@@ -6,7 +6,7 @@
 # exercised through the identical C ABI by the Python ctypes harness (severo.jl_b200/api.py).
 module SeveroB200
 
-using SparseArrays, LinearAlgebra, NamedArrays, Random
+using SparseArrays, LinearAlgebra, NamedArrays, Random, Statistics
 import Severo
 import Severo: CenteredMatrix, NamedCenteredMatrix, NamedCountMatrix, LinearEmbedding  # Severo re-exports Distances' Euclidean / CosineDist
 
@@ -136,9 +136,49 @@ function variance_stabilizing_transformation(A::SparseMatrixCSC{<:Integer}; loes
     standardized_var_clipped(A, mu, expected)                    # device (variablefeatures.jl:21-28)
 end
 
+# the selectors next to :vst (variablefeatures.jl:52-103,135-155): row_norm(counts, 1) and its per-gene moments on the
+# device (svb_normalize / svb_mean_var, svb_row_sums for :saunders), the gene-length arithmetic by Severo's own functions
+function _log_VMR(norm::SparseMatrixCSC)
+    mu, var = mean_var(norm)                                     # device; same Welford as mean_var(T, identity, A) scaling.jl:157-187
+    log1p.(mu), log.(var ./ mu)                                  # scaling.jl:190-193
+end
+
+function _variable_feature_metric(counts::SparseMatrixCSC{<:Integer}, method::Symbol; kw...)
+    norm = if :norm in keys(kw)
+        n = kw[:norm]; isa(n, NamedArray) ? n.array : n
+    else
+        normalize_cells(counts; method=:relativecounts, scale_factor=1.0)        # row_norm(counts.array, one(dtype)) :140
+    end
+    if method == :saunders
+        ncells, ngenes = size(counts)
+        trx = zeros(Int64, ncells)
+        check(ccall((:svb_row_sums, libsvb), Cint, (Ptr{Cvoid}, Ptr{Int64}), upload(counts).h, trx))
+        mu, var = mean_var(norm)
+        nolan = Statistics.mean(1 ./ trx)
+        alpha = get(kw, :alpha_thresh, 0.1) / ngenes
+        upper = mu .+ Severo.qnorm(1 - alpha / 2) .* sqrt.(mu .* nolan ./ ncells)
+        metric = zeros(ngenes)
+        J = (var ./ nolan) .> upper
+        metric[J] = log10.(var[J]) .- log10.(mu[J] .* nolan)
+        metric
+    elseif method == :dispersion
+        Severo.nan2zero!(_log_VMR(norm)[2])
+    elseif method == :meanvarplot
+        mu, disp = _log_VMR(norm)
+        mu = Severo.nan2zero!(mu); disp = Severo.nan2zero!(disp)
+        num_bins = get(kw, :num_bins, 20)
+        _, bins = Severo.cut(mu, num_bins; method=get(kw, :binning_method, :width))
+        bin_mean, bin_std = Severo.mean_std(disp, bins, num_bins)
+        Severo.nan2zero!((disp .- bin_mean[bins]) ./ bin_std[bins])
+    else
+        error("unknown selection method: $method")
+    end
+end
+
 function find_variable_features(counts::NamedCountMatrix, nfeatures=2000; method=:vst, kw...)
-    Symbol(method) == :vst || error("selection method $method is outside the B200 hot path (only :vst)")
-    metric = variance_stabilizing_transformation(counts.array; kw...)
+    method = Symbol(method)
+    metric = method == :vst ? variance_stabilizing_transformation(counts.array; kw...) :
+                              _variable_feature_metric(counts.array, method; kw...)
     selected = partialsortperm(metric, 1:nfeatures, rev=true)    # variablefeatures.jl:159
     NamedArray(selected, (names(counts, 2)[selected],), (dimnames(counts, 2),))
 end

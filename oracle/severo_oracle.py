@@ -288,6 +288,117 @@ def standardized_var_clipped(A, mu, sd, vmax=None):
 
 
 # --------------------------------------------------------------------------------------
+# variablefeatures.jl:52-103 — the selectors next to :vst (:saunders, :dispersion, :meanvarplot). Data sweeps = row sums,
+# row_norm and mean_var (above); everything else is arithmetic on gene-length vectors, restated literally (loops).
+# --------------------------------------------------------------------------------------
+def log_VMR(norm):
+    """scaling.jl:190-197: (log1p.(mu), log.(var ./ mu)) of the per-gene moments."""
+    mu, var = mean_var(norm)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.log1p(mu), np.log(var / mu)
+
+
+def _nan2zero(v):
+    """variablefeatures.jl:30-32."""
+    return np.where(np.isnan(v), 0.0, v)
+
+
+def cut_width(v, nbreaks):
+    """utils.jl:140-148,155 with utils.jl:110-128 (`_cut!`, right = true): equal-width breaks over [min, max], the two outer
+    breaks moved out by dx/1000; label = searchsortedlast(breaks, x), minus one when x sits exactly on that break; 0 outside."""
+    v = np.asarray(v, dtype=np.float64)
+    lo, hi = float(v.min()), float(v.max())
+    dx = hi - lo
+    from fractions import Fraction
+    # range(min, max, length = n+1): Julia evaluates it in twice-precision arithmetic, i.e. (almost always) the correctly
+    # rounded min + i*(max-min)/n — restated with exact rationals
+    breaks = [float(Fraction(lo) + (Fraction(hi) - Fraction(lo)) * i / nbreaks) for i in range(nbreaks + 1)]
+    breaks[0] -= dx / 1000
+    breaks[-1] += dx / 1000
+    labels = np.zeros(v.shape[0], dtype=np.int64)
+    for i, x in enumerate(v):
+        if breaks[0] <= x <= breaks[-1]:
+            idx = 0                                   # searchsortedlast: number of breaks <= x (1-based index of the last one)
+            for b in breaks:
+                if b <= x:
+                    idx += 1
+            if x == breaks[idx - 1]:
+                idx -= 1
+            labels[i] = idx
+    return np.array(breaks), labels
+
+
+def mean_std_labels(x, lbls, nlabels):
+    """scaling.jl:89-112: Welford per label over a dense vector, unbiased, std = sqrt(var). Labels are 1-based."""
+    mu = np.zeros(nlabels)
+    var = np.zeros(nlabels)
+    n = np.zeros(nlabels, dtype=np.int64)
+    for v, k in zip(x, lbls):
+        k = int(k) - 1
+        if k < 0:
+            raise IndexError("label 0: the reference indexes out of bounds here (utils.jl:122, scaling.jl:96)")
+        n[k] += 1
+        delta = v - mu[k]
+        mu[k] += delta / n[k]
+        var[k] += delta * (v - mu[k])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        var = var / (n - 1)
+        return mu, np.sqrt(var)
+
+
+def select_dispersion(norm):
+    """variablefeatures.jl:73-76."""
+    _, disp = log_VMR(norm)
+    return _nan2zero(disp)
+
+
+def select_meanvarplot(norm, num_bins=20):
+    """variablefeatures.jl:78-92 (binning_method = :width)."""
+    mu, disp = log_VMR(norm)
+    mu = _nan2zero(mu)
+    disp = _nan2zero(disp)
+    _, bins = cut_width(mu, num_bins)
+    bin_mean, bin_std = mean_std_labels(disp, bins, num_bins)
+    out = np.empty_like(disp)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for i in range(disp.shape[0]):
+            k = bins[i] - 1
+            out[i] = (disp[i] - bin_mean[k]) / bin_std[k]
+    return _nan2zero(out)
+
+
+def select_features_saunders(counts, norm, alpha_thresh=0.99):
+    """variablefeatures.jl:54-71."""
+    from scipy.stats import norm as _normal
+    counts = _csc(counts)
+    ncells, ngenes = counts.shape
+    trx_per_cell = np.asarray(counts.sum(axis=1)).ravel().astype(np.float64)
+    mu, var = mean_var(norm)
+    nolan = float(np.mean(1.0 / trx_per_cell))
+    corrected = float(alpha_thresh) / ngenes
+    z = float(_normal.ppf(1.0 - corrected / 2.0))
+    metric = np.zeros(ngenes)
+    for j in range(ngenes):
+        upper = mu[j] + z * np.sqrt(mu[j] * nolan / ncells)
+        if var[j] / nolan > upper:
+            metric[j] = np.log10(var[j]) - np.log10(mu[j] * nolan)
+    return metric
+
+
+def variable_feature_metric(counts, method, norm=None, **kw):
+    """variablefeatures.jl:128-157 for the three selectors above: ``norm`` defaults to row_norm(counts, 1) (:136-141)."""
+    if norm is None:
+        norm = row_norm(counts, 1.0)
+    if method == "saunders":
+        return select_features_saunders(counts, norm, kw.get("alpha_thresh", 0.1))          # default of the call site, :144
+    if method == "dispersion":
+        return select_dispersion(norm)
+    if method == "meanvarplot":
+        return select_meanvarplot(norm, kw.get("num_bins", 20))
+    raise ValueError(f"unknown selection method: {method}")
+
+
+# --------------------------------------------------------------------------------------
 # scaling.jl — scale_data / CenteredMatrix
 # --------------------------------------------------------------------------------------
 def scale_data(A, scale_max=np.inf):

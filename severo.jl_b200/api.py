@@ -308,15 +308,126 @@ def variance_stabilizing_transformation(A, loess_span=0.5, expected_std_fn=None)
     return standardized_var_clipped(A, mu, expected)
 
 
+def _nan2zero(v):
+    return np.where(np.isnan(v), 0.0, v)                      # variablefeatures.jl:30-32
+
+
+def _log_vmr(mu, var):
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.log1p(mu), np.log(var / mu)                 # scaling.jl:190-193
+
+
+def _cut(v, nbreaks, method="width"):
+    """utils.jl:140-156 + `_cut!` :110-128 (right = true): (breaks, 1-based bin labels, 0 = outside)."""
+    v = np.asarray(v, dtype=np.float64)
+    method = str(method)
+    if method == "width":
+        from fractions import Fraction
+        lo, hi = float(v.min()), float(v.max())
+        dx = hi - lo
+        # collect(range(lo, hi, length = nbreaks + 1)): Julia's twice-precision range, restated exactly (nbreaks + 1 values)
+        breaks = np.array([float(Fraction(lo) + (Fraction(hi) - Fraction(lo)) * i / nbreaks) for i in range(nbreaks + 1)])
+        breaks[0] -= dx / 1000
+        breaks[-1] += dx / 1000
+    elif method == "frequency":
+        breaks = np.quantile(v, np.linspace(0.0, 1.0, nbreaks))
+    else:
+        raise ValueError(f"unknown binning method: {method}")
+    idx = np.searchsorted(breaks, v, side="right")            # searchsortedlast
+    on_break = breaks[np.maximum(idx, 1) - 1] == v
+    labels = np.where((v >= breaks[0]) & (v <= breaks[-1]), idx - (on_break & (idx > 0)), 0)
+    return breaks, labels.astype(np.int64)
+
+
+def _mean_std_labels(x, labels, nlabels):
+    """scaling.jl:89-112 on a dense vector: Welford per label in index order, unbiased variance, sqrt."""
+    if labels.size and labels.min() < 1:
+        # :frequency binning labels the smallest mean 0 (utils.jl:120-122) and the reference then indexes out of bounds
+        raise IndexError("meanvarplot: a feature fell outside every bin (label 0) — the reference fails here as well")
+    mu, var, n = np.zeros(nlabels), np.zeros(nlabels), np.zeros(nlabels, dtype=np.int64)
+    for v, k in zip(x.tolist(), (labels - 1).tolist()):
+        n[k] += 1
+        delta = v - mu[k]
+        mu[k] += delta / n[k]
+        var[k] += delta * (v - mu[k])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return mu, np.sqrt(var / (n - 1))
+
+
+def _dispersion_metric(mu, var):
+    """select_dispersion, variablefeatures.jl:73-76."""
+    return _nan2zero(_log_vmr(mu, var)[1])
+
+
+def _meanvarplot_metric(mu, var, num_bins=20, binning_method="width"):
+    """select_meanvarplot, variablefeatures.jl:78-92: z-score of the dispersion inside equal-width bins of log1p(mean)."""
+    lmu, disp = _log_vmr(mu, var)
+    lmu, disp = _nan2zero(lmu), _nan2zero(disp)
+    _, bins = _cut(lmu, int(num_bins), binning_method)
+    bin_mean, bin_std = _mean_std_labels(disp, bins, int(num_bins))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return _nan2zero((disp - bin_mean[bins - 1]) / bin_std[bins - 1])
+
+
+def _saunders_metric(mu, var, trx_per_cell, ncells, alpha_thresh=0.99):
+    """select_features_saunders, variablefeatures.jl:54-71."""
+    from scipy.stats import norm as _normal
+    ngenes = mu.shape[0]
+    nolan = float(np.mean(1.0 / np.asarray(trx_per_cell, dtype=np.float64)))
+    z = float(_normal.ppf(1.0 - (float(alpha_thresh) / ngenes) / 2.0))      # qnorm, :52
+    with np.errstate(divide="ignore", invalid="ignore"):
+        upper = mu + z * np.sqrt(mu * nolan / ncells)
+        J = (var / nolan) > upper
+        metric = np.zeros(ngenes)
+        metric[J] = np.log10(var[J]) - np.log10(mu[J] * nolan)
+    return metric
+
+
+def _variable_feature_metric(A, method, kw):
+    """The selectors next to :vst (variablefeatures.jl:135-155). Data sweeps on the device: row_norm(counts, 1) =
+    ``normalize_cells(:relativecounts)``, ``mean_var`` of it, the UMI totals; the rest is gene-length host arithmetic."""
+    kw = dict(kw)
+    norm = kw.pop("norm", None)
+    if norm is not None:
+        norm = norm.array if isinstance(norm, NamedArray) else norm
+    dA, temp = _to_device(A)
+    dN = None
+    try:
+        if norm is None:
+            dN = normalize_cells(dA, method="relativecounts", scale_factor=1.0)      # row_norm(counts.array, one(dtype)) :140
+            norm = dN
+        mu, var = mean_var(norm)
+        mu, var = np.asarray(mu, dtype=np.float64), np.asarray(var, dtype=np.float64)
+        if method == "saunders":
+            m = dA.shape[0]
+            trx = np.zeros(m, dtype=np.int64)
+            L.check(L.lib().svb_row_sums(dA._h, L.ptr(trx)))
+            metric = _saunders_metric(mu, var, trx, m, kw.pop("alpha_thresh", 0.1))   # call-site default :144
+        elif method == "dispersion":
+            kw.pop("num_bins", None), kw.pop("binning_method", None)                  # read and unused upstream too (:146-148)
+            metric = _dispersion_metric(mu, var)
+        else:
+            metric = _meanvarplot_metric(mu, var, kw.pop("num_bins", 20), kw.pop("binning_method", "width"))
+    finally:
+        if dN is not None:
+            dN.free()
+        if temp:
+            dA.free()
+    return metric
+
+
 def find_variable_features(counts, nfeatures=2000, method="vst", **kw):
-    """variablefeatures.jl:128-161, ``:vst`` only (the other selectors are out of this path's scope).
+    """variablefeatures.jl:128-161: ``:vst`` (default), ``:dispersion``, ``:meanvarplot``, ``:saunders``; ``norm=`` passes a
+    precomputed normalised matrix to the last three (:136-141). Float64 only.
     Returns 0-based gene indices ordered by DEcreasing metric (partialsortperm(..., rev=true), :159)."""
     method = str(method)
-    if method != "vst":
-        raise ValueError(f"unknown selection method: {method}" if method not in ("dispersion", "meanvarplot", "saunders")
-                         else f"selection method {method} is outside the B200 hot path (only :vst)")
     A, names, dimnames = _unwrap(counts)
-    metric = variance_stabilizing_transformation(A, **kw)
+    if method == "vst":
+        metric = variance_stabilizing_transformation(A, **kw)
+    elif method in ("dispersion", "meanvarplot", "saunders"):
+        metric = _variable_feature_metric(A, method, kw)
+    else:
+        raise ValueError(f"unknown selection method: {method}")
     nfeatures = min(int(nfeatures), metric.shape[0])
     selected = np.argsort(-metric, kind="stable")[:nfeatures]
     if names is None:

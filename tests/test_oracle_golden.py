@@ -270,3 +270,37 @@ def test_jaccard_index_restatement(orc):
             assert [c[1] for c in cols[jcol]] == list(S.data[a:b])
     Sn = orc.shared_nearest_neighbours(X.astype(np.float32), 5)
     assert Sn.dtype == np.float32 and np.array_equal(Sn.toarray(), orc.jaccard_index(orc.nearest_neighbours(X.astype(np.float32), 5), 5, 1 / 15, np.float32).toarray())
+
+
+def test_variable_feature_selectors_host_arithmetic(orc):
+    # variablefeatures.jl:52-103. The product's gene-length host arithmetic (vectorised) against the oracle's literal
+    # loop restatement, both fed with the oracle's moments of row_norm(counts, 1). No device involved.
+    import severo_jl_b200 as sv
+    from conftest import planted_counts
+    api = sv.api
+    X = planted_counts(400, 900, 5, seed=21, mean_nnz=40.0)
+    X = sp.csc_matrix(X)
+    X[:, 17] = 0                                                    # an undetected gene: mu = var = 0 -> NaN -> 0
+    X.eliminate_zeros()
+    norm = orc.row_norm(X, 1.0)
+    mu, var = orc.mean_var(norm)
+    assert np.array_equal(api._dispersion_metric(mu, var), orc.select_dispersion(norm))
+    assert api._dispersion_metric(mu, var)[17] == 0.0
+    for nb in (20, 7):
+        assert np.array_equal(api._meanvarplot_metric(mu, var, nb), orc.select_meanvarplot(norm, nb))
+    brk, lab = api._cut(np.log1p(mu), 20)
+    obrk, olab = orc.cut_width(np.log1p(mu), 20)
+    assert np.array_equal(brk, obrk) and np.array_equal(lab, olab) and lab.min() >= 1 and lab.max() == 20
+    # a value exactly on an inner break belongs to the bin on its left (right = true, utils.jl:120-122)
+    v = np.array([0.0, 0.25, 0.5, 1.0])
+    assert list(api._cut(v, 4)[1]) == [1, 1, 2, 4] and list(orc.cut_width(v, 4)[1]) == [1, 1, 2, 4]
+    trx = np.asarray(X.sum(axis=1)).ravel()
+    for alpha in (0.1, 0.99):
+        assert np.array_equal(api._saunders_metric(mu, var, trx, X.shape[0], alpha), orc.select_features_saunders(X, norm, alpha))
+    assert np.count_nonzero(orc.select_features_saunders(X, norm, 0.1)) > 10
+    # :frequency binning puts the smallest mean outside every bin; the reference then indexes out of bounds
+    import pytest
+    with pytest.raises(IndexError):
+        api._meanvarplot_metric(mu, var, 20, "frequency")
+    with pytest.raises(ValueError):
+        api._cut(mu, 20, "nope")
