@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const double *__restri
 }
 
 // ---- fp64 tensor-core variant (mma.sync.m8n8k4 DMMA; tcgen05 has no fp64) -------------------------------------------
-// ncu on the kernel above (profiles/r03_knn_gram.md): a broadcast 16-byte shared load costs two LSU wavefronts and feeds two
+// ncu on the kernel above (profiles/r03_gram_knn.md): a broadcast 16-byte shared load costs two LSU wavefronts and feeds two
 // warp-wide fp64 FMAs, so with one query per thread the shared pipe saturates (86 %) at 44 % of the fp64 pipe. Here a warp
 // owns 32 queries as four 8 x 4 A-fragments per 4 coordinates (D doubles per lane, loaded once), streams the points as
 // 4 x 8 B-fragments (one 8-byte shared load per lane per 4 DMMAs: 512 FMAs per wavefront instead of 32) and gets 8 x 8 blocks of
