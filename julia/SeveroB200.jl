@@ -152,7 +152,8 @@ function _variable_feature_metric(counts::SparseMatrixCSC{<:Integer}, method::Sy
     if method == :saunders
         ncells, ngenes = size(counts)
         trx = zeros(Int64, ncells)
-        check(ccall((:svb_row_sums, libsvb), Cint, (Ptr{Cvoid}, Ptr{Int64}), upload(counts).h, trx))
+        d = upload(counts)
+        GC.@preserve d check(ccall((:svb_row_sums, libsvb), Cint, (Ptr{Cvoid}, Ptr{Int64}), d.h, trx))
         mu, var = mean_var(norm)
         nolan = Statistics.mean(1 ./ trx)
         alpha = get(kw, :alpha_thresh, 0.1) / ngenes
