@@ -113,6 +113,38 @@ def test_shard_bounds():
     assert sharding.shard_bounds(10, 1) == [(0, 10)]
 
 
+def test_shard_bounds_properties():
+    # any sizes: the ranges tile [0, m) in order, inner boundaries are multiples of 4, nnz-balanced cuts stay within one cell
+    # quad + one cell of the ideal split
+    from hypothesis import given, settings, strategies as st
+    from severo_jl_b200 import sharding
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.integers(0, 5000), st.integers(1, 9), st.booleans(), st.integers(0, 2 ** 31))
+    def check(m, nranks, weighted, seed):
+        nnz = np.random.default_rng(seed).integers(0, 50, m) if weighted else None
+        b = sharding.shard_bounds(m, nranks, row_nnz=nnz)
+        assert len(b) == nranks and b[0][0] == 0 and b[-1][1] == m
+        assert all(lo <= hi for lo, hi in b) and all(b[i][1] == b[i + 1][0] for i in range(nranks - 1))
+        assert all(lo % 4 == 0 for lo, _ in b[1:])
+        if weighted and m:
+            csum = np.concatenate([[0], np.cumsum(nnz)])
+            for r in range(1, nranks):
+                ideal = int(np.searchsorted(csum, csum[-1] * r / nranks))
+                assert ideal - 4 < b[r][0] <= ideal
+    check()
+    with pytest.raises(ValueError):
+        sharding.shard_bounds(10, 0)
+
+
+def test_tools_and_studies_parse():
+    import ast
+    for d in ("tools", os.path.join("tests", "studies")):
+        for f in sorted(os.listdir(os.path.join(ROOT, d))):
+            if f.endswith(".py"):
+                ast.parse(open(os.path.join(ROOT, d, f)).read(), filename=f)
+
+
 def test_loess_recovers_smooth_trend():
     from severo_jl_b200.loess import loess_fit_predict
     rng = np.random.default_rng(0)
