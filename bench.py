@@ -11,7 +11,9 @@ Default operator: the count-level form (svb_operator_create_counts: the scaled m
 16-bit code per nonzero); `--operator explicit` times the explicit scaled-value layouts instead, and the default
 run reports both (`explicit_operator`).
 Strong scaling: the matrix is fixed, its cells are sharded over the N ranks (one process per GPU).
-Prints ONE JSON line on rank 0.
+Prints ONE JSON line on rank 0. A default 1-GPU C3 run also carries `after_path`: the kNN graph and Jaccard index timings of
+tools/knn_check.py / tools/snn_check.py at the same cell count, run in their own processes after every timed region
+(informational; `--no-after-path` skips them).
 """
 import argparse
 import ctypes
@@ -444,6 +446,8 @@ def run_b200(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(sv, cfg, steps=1, warmup=0)
+        if world == 1 and args.config == "C3" and not (args.no_after_path or args.no_e2e or args.no_cpu_baseline):
+            out["after_path"] = after_path(cfg["m"])
         emit(out)
     if world > 1:
         dist.barrier()
@@ -519,6 +523,24 @@ def run_reference(args):
 _REAL_STDOUT = None
 
 
+def after_path(cells):
+    """Informational, OUTSIDE every timed region: the two steps that consume the PCA coordinates (exact kNN graph of 10
+    coordinates, docs/src/pbmc.md:157, and its Jaccard index, :158) timed at the configuration's cell count by the tools that
+    produced profiles/r03_*; each runs in its own process under a timeout, so a failure there cannot touch the bench line."""
+    res = {}
+    for key, cmd, env, limit in (
+            ("knn_10_coordinates_k20", ["tools/knn_check.py", str(cells), "10", "20"], {"KNN_VARIANTS": "widths"}, 180),
+            ("jaccard_index_k20", ["tools/snn_check.py", str(cells), "10", "20"], {}, 240)):
+        try:
+            p = subprocess.run([sys.executable, os.path.join(ROOT, cmd[0])] + cmd[1:], env=dict(os.environ, **env), cwd=ROOT,
+                               stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=limit)
+            lines = [ln for ln in p.stdout.decode(errors="replace").splitlines() if ln.startswith("{")]
+            res[key] = json.loads(lines[-1]) if lines else {"error": "no result (exit code %d)" % p.returncode}
+        except Exception as e:  # noqa: BLE001 — never let the side measurement break the bench line
+            res[key] = {"error": "%s: %s" % (type(e).__name__, e)}
+    return res
+
+
 def emit(obj):
     """The ONE JSON line, on the real stdout."""
     line = (json.dumps(obj) + "\n").encode()
@@ -548,6 +570,7 @@ def main():
                     help="counts = count-level operator (default); explicit = explicit scaled-value layouts only")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-after-path", action="store_true", help="skip the informational kNN / Jaccard timings after the bench")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
