@@ -530,6 +530,7 @@ def after_path(cells):
     res = {}
     for key, cmd, env, limit in (
             ("knn_10_coordinates_k20", ["tools/knn_check.py", str(cells), "10", "20"], {"KNN_VARIANTS": "widths"}, 180),
+            ("knn_50_coordinates_k20_262144_cells", ["tools/knn_check.py", "262144", "50", "20"], {"KNN_VARIANTS": "widths"}, 120),
             ("jaccard_index_k20", ["tools/snn_check.py", str(cells), "10", "20"], {}, 240)):
         try:
             p = subprocess.run([sys.executable, os.path.join(ROOT, cmd[0])] + cmd[1:], env=dict(os.environ, **env), cwd=ROOT,
