@@ -44,24 +44,49 @@ import numpy as np
 import scipy.sparse as sp
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SRC = os.path.join(_HERE, "csrc", "severo_oracle.c")
+_SRCS = [os.path.join(_HERE, "csrc", "severo_oracle.c"), os.path.join(_HERE, "csrc", "synth_twin.c")]
 _BUILD = os.path.join(_HERE, "_build")
 _LIB = os.path.join(_BUILD, "libsevero_oracle.so")
+_STAMP = os.path.join(_BUILD, "cpu_flags.txt")
 
 _i64p = ctypes.POINTER(ctypes.c_int64)
 _i32p = ctypes.POINTER(ctypes.c_int32)
 _f64p = ctypes.POINTER(ctypes.c_double)
 _f32p = ctypes.POINTER(ctypes.c_float)
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+
+
+def _cpu_flags() -> str:
+    """The instruction-set flags of this host: the library is built -march=native, so a copy built on another machine
+    (the container builds, the GPU box runs) is rebuilt when the flags differ."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return " ".join(sorted(line.split(":", 1)[1].split()))
+    except OSError:
+        pass
+    return "unknown"
 
 
 def build(force: bool = False) -> str:
-    """Compile csrc/severo_oracle.c -> _build/libsevero_oracle.so (gcc, no FMA contraction)."""
-    if not force and os.path.exists(_LIB) and os.path.getmtime(_LIB) >= os.path.getmtime(_SRC):
+    """Compile csrc/*.c -> _build/libsevero_oracle.so: gcc -O3 -march=native, no FMA contraction, no fast-math
+    (BASELINE.md section 4's flags for the CPU baseline)."""
+    flags = _cpu_flags()
+    fresh = os.path.exists(_LIB) and all(os.path.getmtime(_LIB) >= os.path.getmtime(src) for src in _SRCS)
+    if fresh and os.path.exists(_STAMP):
+        with open(_STAMP) as f:
+            fresh = f.read() == flags
+    else:
+        fresh = False
+    if fresh and not force:
         return _LIB
     os.makedirs(_BUILD, exist_ok=True)
-    cmd = ["gcc", "-O2", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-shared", "-fPIC",
-           "-fvisibility=hidden", "-o", _LIB, _SRC, "-lm"]
+    cmd = ["gcc", "-O3", "-march=native", "-ffp-contract=off", "-fno-fast-math", "-fopenmp", "-shared", "-fPIC",
+           "-fvisibility=hidden", "-o", _LIB] + _SRCS + ["-lm"]
     subprocess.run(cmd, check=True)
+    with open(_STAMP, "w") as f:
+        f.write(flags)
     return _LIB
 
 
