@@ -32,6 +32,11 @@ mutable struct DeviceMatrix
     end
 end
 
+# GC safety: handles are passed to `ccall` as the OBJECT, never as the raw field `d.h`. `ccall` keeps every argument it
+# converts (Base.cconvert) rooted until the foreign call returns, so the finalizer cannot free the device matrix / operator
+# while a kernel that reads it is still running; passing `d.h` would leave `d` unreferenced after the field load.
+Base.unsafe_convert(::Type{Ptr{Cvoid}}, d::DeviceMatrix) = d.h
+
 # SparseMatrixCSC{T,Int64}: colptr / rowval are 1-based Int64 — passed as they are (index_base = 1)
 function upload(A::SparseMatrixCSC{T,Int64}) where {T<:Union{Int32,Int64,Float32,Float64}}
     h = Ref{Ptr{Cvoid}}(C_NULL)
@@ -44,17 +49,17 @@ end
 function download_values(d::DeviceMatrix, ::Type{R}, nnz::Integer) where {R}
     nz = Vector{R}(undef, nnz)
     check(ccall((:svb_matrix_download, libsvb), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Cvoid}, Cint, Cint),
-        d.h, C_NULL, C_NULL, nz, svbtype(R), 1))
+        d, C_NULL, C_NULL, nz, svbtype(R), 1))
     nz
 end
 
 # the whole matrix back as a SparseMatrixCSC{Int64,Int64} (counts) — 1-based indices written by the library
 function download(d::DeviceMatrix)
     nrow = Ref{Int64}(0); ncol = Ref{Int64}(0); nz = Ref{Int64}(0); vt = Ref{Cint}(0)
-    check(ccall((:svb_matrix_info, libsvb), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Int64}, Ref{Cint}), d.h, nrow, ncol, nz, vt))
+    check(ccall((:svb_matrix_info, libsvb), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Int64}, Ref{Cint}), d, nrow, ncol, nz, vt))
     colptr = Vector{Int64}(undef, ncol[] + 1); rowval = Vector{Int64}(undef, nz[]); nzval = Vector{Int64}(undef, nz[])
     check(ccall((:svb_matrix_download, libsvb), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Cvoid}, Cint, Cint),
-        d.h, colptr, rowval, nzval, SVB_I64, 1))
+        d, colptr, rowval, nzval, SVB_I64, 1))
     SparseMatrixCSC(nrow[], ncol[], colptr, rowval, nzval)
 end
 
@@ -65,7 +70,7 @@ function normalize_cells(X::SparseMatrixCSC{<:Integer,Int64}; method=:lognormali
     d = upload(X)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:svb_normalize, libsvb), Cint, (Ptr{Cvoid}, Cint, Float64, Cint, Ref{Ptr{Cvoid}}),
-        d.h, code, Float64(convert(dtype, scale_factor)), svbtype(dtype), h))
+        d, code, Float64(convert(dtype, scale_factor)), svbtype(dtype), h))
     out = DeviceMatrix(h[])
     SparseMatrixCSC(size(X, 1), size(X, 2), copy(X.colptr), copy(X.rowval), download_values(out, dtype, nnz(X)))
 end
@@ -78,14 +83,14 @@ end
 # ---- scaling.jl:119-147, 199-217, 335-357 ------------------------------------------------------------
 function mean_var(A::SparseMatrixCSC)
     d = upload(A); mu = zeros(size(A, 2)); var = zeros(size(A, 2))
-    check(ccall((:svb_mean_var, libsvb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), d.h, mu, var))
+    check(ccall((:svb_mean_var, libsvb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), d, mu, var))
     mu, var
 end
 
 function scale_data(A::SparseMatrixCSC, scale_max::R=Inf) where {R<:AbstractFloat}
     d = upload(A); mu = zeros(Float64, size(A, 2)); h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:svb_scale, libsvb), Cint, (Ptr{Cvoid}, Float64, Cint, Ref{Ptr{Cvoid}}, Ptr{Float64}),
-        d.h, Float64(scale_max), svbtype(R), h, mu))
+        d, Float64(scale_max), svbtype(R), h, mu))
     out = DeviceMatrix(h[])
     B = SparseMatrixCSC(size(A, 1), size(A, 2), copy(A.colptr), copy(A.rowval), download_values(out, R, nnz(A)))
     B, convert(Vector{R}, mu)
@@ -104,7 +109,7 @@ import Loess: loess, predict
 function standardized_var_clipped(A::SparseMatrixCSC{<:Integer}, mu::Vector{Float64}, sd::Vector{Float64}; vmax=sqrt(size(A, 1)))
     d = upload(A); out = zeros(size(A, 2))
     check(ccall((:svb_stdvar_clipped, libsvb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}),
-        d.h, mu, sd, Float64(vmax), out))
+        d, mu, sd, Float64(vmax), out))
     out
 end
 
@@ -115,7 +120,7 @@ function filter_counts(A::SparseMatrixCSC{<:Integer}; min_cells=0, min_features=
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:svb_filter_counts, libsvb), Cint,
         (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Ptr{UInt8}, Ptr{UInt8}, Ref{Ptr{Cvoid}}),
-        d.h, min_cells, min_features, min_feature_count, min_umi, CI, FI, h))
+        d, min_cells, min_features, min_feature_count, min_umi, CI, FI, h))
     download(DeviceMatrix(h[])), CI .!= 0, FI .!= 0
 end
 function filter_counts(A::NamedCountMatrix; kw...)
@@ -153,7 +158,7 @@ function _variable_feature_metric(counts::SparseMatrixCSC{<:Integer}, method::Sy
         ncells, ngenes = size(counts)
         trx = zeros(Int64, ncells)
         d = upload(counts)
-        GC.@preserve d check(ccall((:svb_row_sums, libsvb), Cint, (Ptr{Cvoid}, Ptr{Int64}), d.h, trx))
+        check(ccall((:svb_row_sums, libsvb), Cint, (Ptr{Cvoid}, Ptr{Int64}), d, trx))
         mu, var = mean_var(norm)
         nolan = Statistics.mean(1 ./ trx)
         alpha = get(kw, :alpha_thresh, 0.1) / ngenes
@@ -193,6 +198,8 @@ mutable struct DeviceOperator
     end
 end
 
+Base.unsafe_convert(::Type{Ptr{Cvoid}}, o::DeviceOperator) = o.h   # rooted by ccall for the whole call (see DeviceMatrix)
+
 _mu_ptr(mu::Nothing) = Ptr{Float64}(C_NULL)
 _mu_ptr(mu::AbstractVector) = convert(Vector{Float64}, mu)
 
@@ -200,7 +207,7 @@ function operator(A::SparseMatrixCSC, mu=nothing; transposed::Bool=false)
     d = upload(A isa SparseMatrixCSC{<:AbstractFloat} ? A : convert(SparseMatrixCSC{Float64,Int64}, A))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:svb_operator_create, libsvb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Ref{Ptr{Cvoid}}),
-        d.h, _mu_ptr(mu), Cint(transposed), h))
+        d, _mu_ptr(mu), Cint(transposed), h))
     DeviceOperator(h[])
 end
 operator(A::Adjoint{<:Any,<:SparseMatrixCSC}, mu=nothing) = operator(parent(A), mu; transposed=true)   # test_irlba.jl:111
@@ -224,7 +231,7 @@ function counts_operator(counts_hvg::SparseMatrixCSC{<:Integer}, libsize::Vector
     if moments == :exact
         y = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:svb_normalize_libsize, libsvb), Cint, (Ptr{Cvoid}, Ptr{Int64}, Cint, Float64, Cint, Ref{Ptr{Cvoid}}),
-            d.h, libsize, 0, scale_factor, 3, y))
+            d, libsize, 0, scale_factor, 3, y))
         mean, var = zeros(n), zeros(n)
         check(ccall((:svb_mean_var, libsvb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), y[], mean, var))
         ccall((:svb_matrix_free, libsvb), Cint, (Ptr{Cvoid},), y[])
@@ -233,7 +240,7 @@ function counts_operator(counts_hvg::SparseMatrixCSC{<:Integer}, libsize::Vector
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:svb_operator_create_counts, libsvb), Cint,
         (Ptr{Cvoid}, Ptr{Int64}, Float64, Ptr{Float64}, Ptr{Float64}, Float64, Cint, Ptr{Float64}, Ref{Ptr{Cvoid}}),
-        d.h, libsize, scale_factor, mean, var, scale_max, levels, mu, h))
+        d, libsize, scale_factor, mean, var, scale_max, levels, mu, h))
     DeviceOperator(h[]), mu
 end
 
@@ -249,7 +256,7 @@ function pca_counts(counts::SparseMatrixCSC{<:Integer}, hvf::AbstractVector{<:In
     iter = Ref{Int64}(0); mprod = Ref{Int64}(0)
     info = ccall((:svb_irlba, libsvb), Cint,
         (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Int64}, Ref{Int64}),
-        op.h, npcs, min(npcs + 7, min(m, n)), 1000, 0, tol, tol, init, s, U, V, iter, mprod)
+        op, npcs, min(npcs + 7, min(m, n)), 1000, 0, tol, tol, init, s, U, V, iter, mprod)
     info == 0 || error("convergence failed")
     U * Diagonal(s), s ./ sqrt(max(1, m - 1)), V, mu     # coordinates, stdev, loadings (embedding.jl:67-68), centre
 end
@@ -268,7 +275,7 @@ function irlba!(rng, A, U::Matrix{Float64}, s::Vector{Float64}, V::Matrix{Float6
     iter = Ref{Int64}(0); mprod = Ref{Int64}(0)
     info = ccall((:svb_irlba, libsvb), Cint,
         (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Int64}, Ref{Int64}),
-        op.h, nu, m_b, maxit, restart, tol, svtol, init, s, U, V, iter, mprod)
+        op, nu, m_b, maxit, restart, tol, svtol, init, s, U, V, iter, mprod)
     info == 0 || error("convergence failed")                  # irlba.jl:73
     SVD(U, s, V')                                              # irlba.jl:75
 end
@@ -283,7 +290,7 @@ function gram(A)
     n = size(A, 2)
     G = Matrix{Float64}(undef, n, n)
     op = operator(A)
-    check(ccall((:svb_gram, libsvb), Cint, (Ptr{Cvoid}, Ptr{Float64}), op.h, G))
+    check(ccall((:svb_gram, libsvb), Cint, (Ptr{Cvoid}, Ptr{Float64}), op, G))
     G
 end
 
@@ -294,14 +301,14 @@ function tssvd(A::AbstractMatrix; nsv::Int=6, ritzvec::Bool=true, tol::Float64=0
     op = operator(A)
     r = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:svb_tssvd, libsvb), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Float64, Ptr{Float64}, Ref{Ptr{Cvoid}}),
-        op.h, nsv, min(ncv, n), maxiter, tol, convert(Vector{Float64}, v0), r))
+        op, nsv, min(ncv, n), maxiter, tol, convert(Vector{Float64}, v0), r))
     info = Ref{Cint}(0)
     ccall((:svb_result_info, libsvb), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ref{Cint}),
         r[], C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, info)
     Sigma = Vector{Float64}(undef, nsv); phi = Matrix{Float64}(undef, n, nsv)
     U = Matrix{Float64}(undef, m, ritzvec ? nsv : 0)                     # embedding.jl:37-42
     rc = ccall((:svb_result_download, libsvb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint),
-        r[], Sigma, ritzvec ? pointer(U) : Ptr{Float64}(C_NULL), phi, 0)
+        r[], Sigma, ritzvec ? U : Ptr{Float64}(C_NULL), phi, 0)   # arrays are rooted by ccall; no bare pointer(U)
     ccall((:svb_result_free, libsvb), Cint, (Ptr{Cvoid},), r[])
     check(rc)
     info[] == 0 || error("convergence failed")
@@ -394,13 +401,13 @@ function _jaccard_index(::Type{T}, nn::SparseMatrixCSC, k::Integer, prune::T) wh
     d = upload(pattern)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:svb_jaccard_index, libsvb), Cint, (Ptr{Cvoid}, Int64, Cdouble, Cint, Ref{Ptr{Cvoid}}),
-        d.h, k, Float64(prune), svbtype(T), h))
+        d, k, Float64(prune), svbtype(T), h))
     o = DeviceMatrix(h[])
     nz = Ref{Int64}(0)
-    check(ccall((:svb_matrix_info, libsvb), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ref{Int64}, Ptr{Cint}), o.h, C_NULL, C_NULL, nz, C_NULL))
+    check(ccall((:svb_matrix_info, libsvb), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ref{Int64}, Ptr{Cint}), o, C_NULL, C_NULL, nz, C_NULL))
     colptr = Vector{Int64}(undef, n + 1); rowval = Vector{Int64}(undef, nz[]); nzval = Vector{T}(undef, nz[])
     check(ccall((:svb_matrix_download, libsvb), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Cvoid}, Cint, Cint),
-        o.h, colptr, rowval, nzval, svbtype(T), 1))
+        o, colptr, rowval, nzval, svbtype(T), 1))
     SparseMatrixCSC(n, n, colptr, rowval, nzval)
 end
 _jaccard_index(::Type{T}, nn::SparseMatrixCSC, prune::T) where {T<:Union{Float32,Float64}} = _jaccard_index(T, nn, 0, prune)

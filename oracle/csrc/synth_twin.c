@@ -64,6 +64,7 @@ static inline double det_exp(double x) {
 }
 
 static inline int poisson_count(double lam, uint32_t bits) {
+    if (lam > 600.0) lam = 600.0; /* keeps p0 = exp(-lam) a normal number; part of the generator's definition */
     const double u = ((double)bits + 0.5) * (1.0 / 4294967296.0);
     if (u < 1.0 - lam) return 0;
     double p = det_exp(-lam);
@@ -146,12 +147,38 @@ EXPORT void orc_synth_cell_params(int64_t row0, int64_t rows, int K, uint64_t se
     }
 }
 
-/* the four counts of cell quad q (cells 4q .. 4q+3, global numbering) in gene g */
-static inline void quad_counts(uint64_t q, int64_t g, uint64_t seed, const double *lib4, const uint8_t *prog4, const double *lg,
-                               int nvalid, int x[4]) {
-    uint32_t u[4];
-    philox4((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)g, 2u, (uint32_t)seed, (uint32_t)(seed >> 32), u);
-    for (int e = 0; e < 4; ++e) x[e] = (e < nvalid) ? poisson_count(lib4[e] * lg[prog4[e]], u[e]) : 0;
+/* The counts of gene g for a block of cells [r, r + nb) (r a multiple of 4, nb <= GB): three phases so that the first two
+ * vectorise — Philox for every cell quad; lam and the pre-filter u < 1 - lam for every cell; the sampler proper only for the
+ * few cells that pass. Writes x[0..nb) (0 for the filtered cells). Same arithmetic per pair as poisson_count alone. */
+#define GB 1024
+static inline void block_counts(int64_t row0, int64_t r, int nb, int64_t g, uint64_t seed, const double *lib, const uint8_t *prog,
+                                const double *lg, uint32_t *bits, int32_t *x) {
+    const int nq = (nb + 3) / 4;
+    const uint64_t q0 = (uint64_t)(row0 + r) >> 2;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int qi = 0; qi < nq; ++qi) {
+        const uint64_t q = q0 + (uint64_t)qi;
+        uint32_t c0 = (uint32_t)q, c1 = (uint32_t)(q >> 32), c2 = (uint32_t)g, c3 = 2u, a0 = k0, a1 = k1;
+        for (int rd = 0; rd < 10; ++rd) {
+            const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+            const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+            const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ a0;
+            const uint32_t n1 = (uint32_t)p1;
+            const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ a1;
+            const uint32_t n3 = (uint32_t)p0;
+            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+            a0 += 0x9E3779B9u;
+            a1 += 0xBB67AE85u;
+        }
+        bits[4 * qi + 0] = c0; bits[4 * qi + 1] = c1; bits[4 * qi + 2] = c2; bits[4 * qi + 3] = c3;
+    }
+    for (int i = 0; i < nb; ++i) {
+        const double lam = lib[r + i] * lg[prog[r + i]];
+        const double u = ((double)bits[i] + 0.5) * (1.0 / 4294967296.0);
+        x[i] = !(u < 1.0 - lam); /* candidates (NaN-safe: the same sense as the sampler's test) */
+    }
+    for (int i = 0; i < nb; ++i)
+        if (x[i]) x[i] = poisson_count(lib[r + i] * lg[prog[r + i]], bits[i]);
 }
 
 /* One streaming pass over ALL genes (row0 must be a multiple of 4, as in the device generator):
@@ -172,7 +199,6 @@ EXPORT int orc_synth_pass_stats(int64_t row0, int64_t rows, int64_t genes, int K
     if (!libs) return -1;
     int64_t over = 0;
     int fail = 0;
-    const int64_t nquads = (rows + 3) / 4;
 #pragma omp parallel reduction(+ : over)
     {
         int tid = 0;
@@ -191,12 +217,12 @@ EXPORT int orc_synth_pass_stats(int64_t row0, int64_t rows, int64_t genes, int K
             const double *lg = lamtab + (size_t)g * K;
             int64_t *hg = hist + (size_t)g * HB;
             int64_t nnz = 0;
-            for (int64_t qi = 0; qi < nquads; ++qi) {
-                const int64_t r = qi * 4;
-                const int nvalid = (rows - r) < 4 ? (int)(rows - r) : 4;
-                int x[4];
-                quad_counts((uint64_t)(row0 + r) >> 2, g, seed, lib + r, prog + r, lg, nvalid, x);
-                for (int e = 0; e < nvalid; ++e) {
+            for (int64_t r = 0; r < rows; r += GB) {
+                const int nb = (rows - r) < GB ? (int)(rows - r) : GB;
+                uint32_t bits[GB];
+                int32_t x[GB];
+                block_counts(row0, r, nb, g, seed, lib, prog, lg, bits, x);
+                for (int e = 0; e < nb; ++e) {
                     if (x[e]) {
                         buf[nnz++] = x[e];
                         mylib[r + e] += x[e];
@@ -230,18 +256,17 @@ EXPORT int orc_synth_pass_stats(int64_t row0, int64_t rows, int64_t genes, int K
 /* the columns sel[0..nsel) as CSC (cells ascending inside a gene): pass 0 counts, pass 1 fills */
 EXPORT void orc_synth_columns_count(int64_t row0, int64_t rows, int K, uint64_t seed, const double *lamtab, const double *lib,
                                     const uint8_t *prog, const int64_t *sel, int64_t nsel, int64_t *colnnz) {
-    const int64_t nquads = (rows + 3) / 4;
 #pragma omp parallel for schedule(dynamic, 4)
     for (int64_t c = 0; c < nsel; ++c) {
         const int64_t g = sel[c];
         const double *lg = lamtab + (size_t)g * K;
         int64_t nnz = 0;
-        for (int64_t qi = 0; qi < nquads; ++qi) {
-            const int64_t r = qi * 4;
-            const int nvalid = (rows - r) < 4 ? (int)(rows - r) : 4;
-            int x[4];
-            quad_counts((uint64_t)(row0 + r) >> 2, g, seed, lib + r, prog + r, lg, nvalid, x);
-            nnz += (x[0] != 0) + (x[1] != 0) + (x[2] != 0) + (x[3] != 0);
+        for (int64_t r = 0; r < rows; r += GB) {
+            const int nb = (rows - r) < GB ? (int)(rows - r) : GB;
+            uint32_t bits[GB];
+            int32_t x[GB];
+            block_counts(row0, r, nb, g, seed, lib, prog, lg, bits, x);
+            for (int e = 0; e < nb; ++e) nnz += (x[e] != 0);
         }
         colnnz[c] = nnz;
     }
@@ -250,18 +275,17 @@ EXPORT void orc_synth_columns_count(int64_t row0, int64_t rows, int K, uint64_t 
 EXPORT void orc_synth_columns_fill(int64_t row0, int64_t rows, int K, uint64_t seed, const double *lamtab, const double *lib,
                                    const uint8_t *prog, const int64_t *sel, int64_t nsel, const int64_t *colptr,
                                    int64_t *rowval, int32_t *val) {
-    const int64_t nquads = (rows + 3) / 4;
 #pragma omp parallel for schedule(dynamic, 4)
     for (int64_t c = 0; c < nsel; ++c) {
         const int64_t g = sel[c];
         const double *lg = lamtab + (size_t)g * K;
         int64_t pos = colptr[c];
-        for (int64_t qi = 0; qi < nquads; ++qi) {
-            const int64_t r = qi * 4;
-            const int nvalid = (rows - r) < 4 ? (int)(rows - r) : 4;
-            int x[4];
-            quad_counts((uint64_t)(row0 + r) >> 2, g, seed, lib + r, prog + r, lg, nvalid, x);
-            for (int e = 0; e < nvalid; ++e)
+        for (int64_t r = 0; r < rows; r += GB) {
+            const int nb = (rows - r) < GB ? (int)(rows - r) : GB;
+            uint32_t bits[GB];
+            int32_t x[GB];
+            block_counts(row0, r, nb, g, seed, lib, prog, lg, bits, x);
+            for (int e = 0; e < nb; ++e)
                 if (x[e]) {
                     rowval[pos] = r + e;
                     val[pos] = x[e];

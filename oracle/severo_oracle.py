@@ -847,3 +847,126 @@ def principal_angle(X, Y):
     # sin of the largest angle = ||(I - Qx Qx') Qy||_2 : accurate for small angles
     R = Qy - Qx @ (Qx.T @ Qy)
     return float(np.arcsin(min(1.0, np.linalg.norm(R, 2))))
+
+
+# --------------------------------------------------------------------------------------
+# Host twin of the benchmark's synthetic generator (csrc/synth_twin.c) — the input of bench.py's reference arm
+# --------------------------------------------------------------------------------------
+@dataclass
+class SynthTables:
+    """Gene / cell tables of one synthetic configuration (the host part of svb_synth_counts)."""
+    m_total: int
+    genes: int
+    K: int
+    seed: int
+    row0: int
+    rows: int
+    lamtab: np.ndarray   # [genes*K] Float64
+    lib: np.ndarray      # [rows] Float64 library factors L_i
+    prog: np.ndarray     # [rows] uint8 program of every cell
+    scale: float
+
+
+def synth_tables(m_total, genes, mean_nnz_per_cell, programs=64, fold=6.0, seed=20260101, rows=None) -> SynthTables:
+    L = lib()
+    L.orc_synth_gene_tables.restype = ctypes.c_double
+    lo, hi = (0, m_total) if rows is None else rows
+    assert lo % 4 == 0 and 1 <= programs <= 255
+    K = int(programs)
+    lamtab = np.empty(genes * K)
+    scale = L.orc_synth_gene_tables(ctypes.c_int64(genes), K, ctypes.c_double(mean_nnz_per_cell), ctypes.c_double(fold),
+                                    ctypes.c_uint64(seed), _p(lamtab, _f64p))
+    n = hi - lo
+    libf = np.empty(max(n, 1))
+    prog = np.empty(max(n, 1), dtype=np.uint8)
+    L.orc_synth_cell_params(ctypes.c_int64(lo), ctypes.c_int64(n), K, ctypes.c_uint64(seed), _p(libf, _f64p), _p(prog, _u8p))
+    return SynthTables(m_total, genes, K, seed, lo, n, lamtab, libf, prog, scale)
+
+
+def synth_stats(t: SynthTables, hist_bins=1024):
+    """One streaming pass over ALL genes: (libsize, gene_nnz, mean, var, hist) — see orc_synth_pass_stats."""
+    libsize = np.zeros(t.rows, dtype=np.int64)
+    gene_nnz = np.zeros(t.genes, dtype=np.int64)
+    mean, var = np.zeros(t.genes), np.zeros(t.genes)
+    hist = np.zeros(t.genes * hist_bins, dtype=np.int64)
+    over = ctypes.c_int64()
+    rc = lib().orc_synth_pass_stats(ctypes.c_int64(t.row0), ctypes.c_int64(t.rows), ctypes.c_int64(t.genes), t.K,
+                                    ctypes.c_uint64(t.seed), _p(t.lamtab, _f64p), _p(t.lib, _f64p), _p(t.prog, _u8p), hist_bins,
+                                    _p(libsize, _i64p), _p(gene_nnz, _i64p), _p(mean, _f64p), _p(var, _f64p), _p(hist, _i64p),
+                                    ctypes.byref(over))
+    if rc != 0:
+        raise MemoryError("orc_synth_pass_stats")
+    if over.value:
+        raise ValueError(f"{over.value} counts >= {hist_bins}: raise hist_bins")
+    return libsize, gene_nnz, mean, var, hist.reshape(t.genes, hist_bins)
+
+
+def stdvar_clipped_hist(nrow, hist, gene_nnz, mu, sd, vmax=None):
+    """variablefeatures.jl:19-28 from per-gene count histograms (orc_stdvar_clipped_hist)."""
+    genes, HB = hist.shape
+    if vmax is None:
+        vmax = np.sqrt(float(nrow))
+    out = np.zeros(genes)
+    mu = np.ascontiguousarray(mu, dtype=np.float64)
+    sd = np.ascontiguousarray(sd, dtype=np.float64)
+    h = np.ascontiguousarray(hist)
+    lib().orc_stdvar_clipped_hist(ctypes.c_int64(nrow), ctypes.c_int64(genes), HB, _p(h, _i64p), _p(gene_nnz, _i64p), _p(mu, _f64p),
+                                  _p(sd, _f64p), ctypes.c_double(float(vmax)), _p(out, _f64p))
+    return out
+
+
+def synth_columns(t: SynthTables, sel):
+    """The gene columns ``sel`` (0-based, any order) as raw CSC arrays (colptr int64, rowval int64, counts int32)."""
+    sel = np.ascontiguousarray(sel, dtype=np.int64)
+    n = sel.shape[0]
+    L = lib()
+    colnnz = np.zeros(n, dtype=np.int64)
+    args = (ctypes.c_int64(t.row0), ctypes.c_int64(t.rows), t.K, ctypes.c_uint64(t.seed), _p(t.lamtab, _f64p), _p(t.lib, _f64p),
+            _p(t.prog, _u8p), _p(sel, _i64p), ctypes.c_int64(n))
+    L.orc_synth_columns_count(*args, _p(colnnz, _i64p))
+    colptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(colnnz, out=colptr[1:])
+    nnz = int(colptr[-1])
+    rowval = np.empty(max(nnz, 1), dtype=np.int64)
+    val = np.empty(max(nnz, 1), dtype=np.int32)
+    L.orc_synth_columns_fill(*args, _p(colptr, _i64p), _p(rowval, _i64p), _p(val, _i32p))
+    return colptr, rowval[:nnz], val[:nnz]
+
+
+def synthetic_counts(m_total, genes, mean_nnz_per_cell, programs=64, fold=6.0, seed=20260101, rows=None):
+    """Host twin of severo_jl_b200.synthetic_counts: the same matrix, bit for bit (scipy CSC, int64 counts)."""
+    t = synth_tables(m_total, genes, mean_nnz_per_cell, programs, fold, seed, rows)
+    colptr, rowval, val = synth_columns(t, np.arange(genes))
+    return sp.csc_matrix((val.astype(np.int64), rowval, colptr), shape=(t.rows, genes))
+
+
+def lognorm_columns(rowval, counts_i32, libsize, scale_factor=1e4):
+    """normalize.jl:25-29,36 on HVG columns with the library sizes of the full matrix (Y[:, hvf] without forming Y)."""
+    out = np.empty(counts_i32.shape[0])
+    lib().orc_lognorm_i32(ctypes.c_int64(counts_i32.shape[0]), _p(rowval, _i64p), _p(counts_i32, _i32p), _p(libsize, _i64p),
+                          ctypes.c_double(scale_factor), _p(out, _f64p))
+    return out
+
+
+def scale_data_arrays(nrow, colptr, nzval, scale_max=np.inf):
+    """scaling.jl:199-217 on raw CSC arrays (no scipy copies: the full-size reference arm holds 7.5e8 nonzeros)."""
+    ncol = colptr.shape[0] - 1
+    out = np.empty(nzval.shape[0])
+    mu = np.empty(ncol)
+    lib().orc_scale_data_f64(ctypes.c_int64(nrow), ctypes.c_int64(ncol), _p(colptr, _i64p), _p(nzval, _f64p),
+                             ctypes.c_double(float(scale_max)), _p(out, _f64p), _p(mu, _f64p))
+    return out, mu
+
+
+def centered_from_arrays(nrow, colptr, rowval, nzval, mu):
+    """CenteredMatrix over caller-owned CSC arrays (int64 indices, Float64 values) without copying them."""
+    C = CenteredMatrix.__new__(CenteredMatrix)
+    ncol = colptr.shape[0] - 1
+    C.dense = False
+    C.transposed = False
+    C.P = sp.csc_matrix((nzval, rowval, colptr), shape=(nrow, ncol), copy=False)
+    C.colptr, C.rowval, C.nz = colptr, rowval, nzval
+    C._csr = None
+    C.shape = (nrow, ncol)
+    C.mu = np.ascontiguousarray(mu, dtype=np.float64)
+    return C
