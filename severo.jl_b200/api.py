@@ -290,6 +290,17 @@ def standardized_var_clipped(A, mu, sd, vmax=None):
     return out
 
 
+def _call_trend(fn, mu, sd):
+    """``expected_std_fn(mu)`` or ``expected_std_fn(mu, sd)``: a deterministic replacement of the loess trend of :vst."""
+    import inspect
+    try:
+        nargs = len([p for p in inspect.signature(fn).parameters.values()
+                     if p.default is inspect.Parameter.empty and p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD)])
+    except (TypeError, ValueError):
+        nargs = 1
+    return fn(mu, sd) if nargs >= 2 else fn(mu)
+
+
 def variance_stabilizing_transformation(A, loess_span=0.5, expected_std_fn=None):
     """variablefeatures.jl:34-50. The two data sweeps run on the device; the loess fit between them
     is host code (Loess.jl in the reference: third-party and un-pinned). A deterministic
@@ -300,7 +311,7 @@ def variance_stabilizing_transformation(A, loess_span=0.5, expected_std_fn=None)
     non_const = sd > 0
     expected = sd.copy()
     if expected_std_fn is not None:
-        expected[non_const] = expected_std_fn(mu[non_const])
+        expected[non_const] = _call_trend(expected_std_fn, mu[non_const], sd[non_const])
     else:
         xs, ys = np.log10(mu[non_const]), np.log10(sd[non_const])
         expected[non_const] = 10.0 ** loess_fit_predict(xs, ys, span=float(loess_span))

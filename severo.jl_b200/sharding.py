@@ -118,14 +118,14 @@ def merged_mean_var(dA):
 
 def sharded_vst_metric(counts, loess_span=0.5, expected_std_fn=None):
     """variance_stabilizing_transformation (variablefeatures.jl:34-50) over a row-sharded count matrix."""
-    from .api import standardized_var_clipped
+    from .api import standardized_var_clipped, _call_trend
     from .loess import loess_fit_predict
     mu, var, m_total = merged_mean_var(counts)
     sd = np.sqrt(var)
     non_const = sd > 0
     expected = sd.copy()
     if expected_std_fn is not None:
-        expected[non_const] = expected_std_fn(mu[non_const])
+        expected[non_const] = _call_trend(expected_std_fn, mu[non_const], sd[non_const])
     else:
         expected[non_const] = 10.0 ** loess_fit_predict(np.log10(mu[non_const]), np.log10(sd[non_const]), span=loess_span)
     expected = np.where(np.isnan(expected), 0.0, expected)
