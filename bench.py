@@ -249,8 +249,12 @@ def counts_info(sv, op):
     lv = ctypes.c_int()
     v = [ctypes.c_int64() for _ in range(5)]
     sv._lib.check(sv.lib().svb_operator_counts_info(op, lv, *v))
+    fr, ar, al = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    fp, apass = ctypes.c_double(), ctypes.c_double()
+    sv._lib.check(sv.lib().svb_operator_counts_layout(op, fr, fp, ar, al, apass))
     return dict(levels=lv.value, tile_cells=v[0].value, nnz_coded=v[1].value, nnz_exception=v[2].value,
-                fwd_chunks=v[3].value, adj_chunks=v[4].value)
+                fwd_chunks=v[3].value, adj_chunks=v[4].value, fwd_replicas=fr.value, fwd_passes_per_set=round(fp.value, 4),
+                adj_replicas=ar.value, adj_replicated_levels=al.value, adj_passes_per_set=round(apass.value, 4))
 
 
 def class_profile(sv, lib, op, nu, init):

@@ -181,6 +181,16 @@ int svb_operator_create_counts(svb_matrix_t counts, const int64_t *libsize, doub
 /* levels L, cells per adjoint tile, entries stored as codes / as exception chunks, 16-byte chunks of the two streams */
 int svb_operator_counts_info(svb_operator_t op, int *levels, int64_t *tile_cells, int64_t *nnz_coded,
                              int64_t *nnz_exception, int64_t *fwd_chunks, int64_t *adj_chunks);
+/* Shared-memory layout of the count-level operator's gathered tables: the forward kernel holds fwd_replicas bank-shifted copies
+ * of x/sd, the adjoint kernel adj_replicas copies of the first adj_replicated_levels levels of its tile table; *_passes = the
+ * average number of shared-memory passes per set of 16 gathers after the build-time replica assignment (1 = conflict-free;
+ * 0 = not evaluated: no replicas and SVB_FACT_STATS unset). Any pointer may be NULL. */
+int svb_operator_counts_layout(svb_operator_t op, int *fwd_replicas, double *fwd_passes,
+                               int *adj_replicas, int *adj_replicated_levels, double *adj_passes);
+/* Debug / study aid: copies one stream of the count-level operator to the host — adjoint = 0: the forward (cell-major) stream,
+ * 1: the adjoint (tile, gene) stream. code[chunks*8] (16-bit codes, or the 16 bytes of an exception chunk), meta[chunks].
+ * Either pointer may be NULL. Used by the layout tests and tools/studies/. */
+int svb_operator_counts_stream(svb_operator_t op, int adjoint, uint16_t *code, uint8_t *meta);
 int svb_operator_free(svb_operator_t op);
 int svb_operator_info(svb_operator_t op, int64_t *m, int64_t *n, int64_t *nnz, int *is_dense,
                       int *value_bytes, int *index_bytes);
@@ -193,6 +203,20 @@ int svb_mul(svb_operator_t op, char trans, double alpha, const double *x, double
 /* Device-pointer variant for benchmarking one product (x, y already in HBM). */
 int svb_mul_device(svb_operator_t op, char trans, double alpha, const double *dx, double beta,
                    double *dy);
+
+/* ---- the stand-alone sparse products of src/mul.jl ------------------------------------------------------------- */
+/* mul.jl:50-77  mul!(y, A::SparseMatrixCSC, x::SparseVector, alpha, beta): y = beta*y + alpha*A*x. A: m x n handle (values of any
+ * uploaded type, promoted to Float64); x: its nx stored entries (x_nzind ascending, index_base 1 for Julia's nonzeroinds; stored
+ * zeros take part, as in the reference); y: host Float64[m], in and out. Same terms, same order, same roundings as the reference
+ * loop ((alpha*a)*x added to y[i] in ascending j): bit-identical and deterministic (csrc/spmul.cu). */
+int svb_spmspv(svb_matrix_t A, const int64_t *x_nzind, const double *x_nzval, int64_t nx, int index_base,
+               double alpha, double beta, double *y);
+/* mul.jl:82-114  mul!(C::StridedMatrix, A::CSC, B::CSC, alpha, beta): C = beta*C + alpha*A*B, C host Float64 column-major
+ * (size(A,1) x size(B,2), leading dimension ldc). transpose_a != 0: the Transpose / Adjoint methods of mul.jl:79-80,
+ * C = beta*C + alpha*A'*B (the reference materialises copy(A'); here the rows of A' are the columns of A as stored).
+ * Bit-identical to the reference's triple loop (every C[row, col] receives (alpha*a)*b in ascending inner index). */
+int svb_spgemm_dense(svb_matrix_t A, int transpose_a, svb_matrix_t B, double alpha, double beta,
+                     double *C, int64_t ldc);
 
 /* C'C (scaling.jl:274-296, over the CSC x CSC -> dense product of mul.jl:82-114): G (n x n, column-major, host) =
  * S'S = A'A - mu q' - q mu' + M mu mu', q = column sums of A, M = cells. Explicit sparse operators: one fused pass per

@@ -278,3 +278,43 @@ EXPORT void orc_csc_to_csr(int64_t nrow, int64_t ncol, const int64_t *colptr,
         }
     __builtin_free(cursor);
 }
+
+/* ---- mul.jl:50-77  mul!(y, A::CSC, x::SparseVector, alpha, beta): the reference loop, literally.
+ *      beta != 1: fill!(y, 0) or rmul!(y, beta); alpha == 0: return; for jp over the stored x: for kp in column rvx[jp]:
+ *      y[i] += alpha * nzvA[kp] * nzx   (Julia's n-ary * is (alpha*a)*x) ---- */
+EXPORT void orc_spmspv(int64_t m, int64_t n, const int64_t *colptr, const int64_t *rowval, const double *nzval,
+                       const int64_t *xind, const double *xval, int64_t nx, double alpha, double beta, double *y) {
+    (void)n;
+    if (beta != 1.0) {
+        if (beta == 0.0) memset(y, 0, (size_t)m * sizeof(double));
+        else for (int64_t i = 0; i < m; ++i) y[i] *= beta;
+    }
+    if (alpha == 0.0) return;
+    for (int64_t jp = 0; jp < nx; ++jp) {
+        const double nzx = xval[jp];
+        const int64_t j = xind[jp];
+        for (int64_t kp = colptr[j]; kp < colptr[j + 1]; ++kp) {
+            const int64_t i = rowval[kp];
+            y[i] += (alpha * nzval[kp]) * nzx;
+        }
+    }
+}
+
+/* ---- mul.jl:82-114  mul!(C::Dense, A::CSC, B::CSC, alpha, beta): the reference triple loop, literally (C column-major) ---- */
+EXPORT void orc_spgemm_dense(int64_t m, int64_t p, const int64_t *acolptr, const int64_t *arowval, const double *anzval,
+                             const int64_t *bcolptr, const int64_t *browval, const double *bnzval, double alpha, double beta,
+                             double *C) {
+    if (beta != 1.0) {
+        if (beta != 0.0) for (int64_t i = 0; i < m * p; ++i) C[i] *= beta;
+        else memset(C, 0, (size_t)(m * p) * sizeof(double));
+    }
+    for (int64_t col = 0; col < p; ++col)
+        for (int64_t jp = bcolptr[col]; jp < bcolptr[col + 1]; ++jp) {
+            const double nzB = bnzval[jp];
+            const int64_t j = browval[jp];
+            for (int64_t kp = acolptr[j]; kp < acolptr[j + 1]; ++kp) {
+                const int64_t row = arowval[kp];
+                C[row + col * m] += (alpha * anzval[kp]) * nzB;
+            }
+        }
+}

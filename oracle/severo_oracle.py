@@ -970,3 +970,37 @@ def centered_from_arrays(nrow, colptr, rowval, nzval, mu):
     C.shape = (nrow, ncol)
     C.mu = np.ascontiguousarray(mu, dtype=np.float64)
     return C
+
+
+# --------------------------------------------------------------------------------------
+# mul.jl:50-77 (SpMSpV) and mul.jl:79-114 (CSC x CSC -> dense): the reference loops, literally (csrc/severo_oracle.c)
+# --------------------------------------------------------------------------------------
+def spmspv(y, A, x, alpha=1.0, beta=0.0):
+    """mul!(y, A::SparseMatrixCSC, x::SparseVector, alpha, beta) — in place. ``x``: scipy sparse n x 1 (stored entries count)."""
+    A = _csc(A).astype(np.float64)
+    xs = sp.csc_matrix(x)
+    xs.sort_indices()
+    m, n = A.shape
+    assert xs.shape == (n, 1) and y.shape == (m,)          # DimensionMismatch
+    colptr, rowval = _idx64(A)
+    nz = np.ascontiguousarray(A.data, dtype=np.float64)
+    xi = np.ascontiguousarray(xs.indices, dtype=np.int64)
+    xv = np.ascontiguousarray(xs.data, dtype=np.float64)
+    lib().orc_spmspv(ctypes.c_int64(m), ctypes.c_int64(n), _p(colptr, _i64p), _p(rowval, _i64p), _p(nz, _f64p), _p(xi, _i64p),
+                     _p(xv, _f64p), ctypes.c_int64(xi.shape[0]), ctypes.c_double(alpha), ctypes.c_double(beta), _p(y, _f64p))
+    return y
+
+
+def spgemm_dense(C, A, B, alpha=1.0, beta=0.0, transpose_a=False):
+    """mul!(C, A, B, alpha, beta) for CSC A, B and dense column-major C; ``transpose_a``: mul.jl:79-80, mul!(C, copy(A'), B, ...)."""
+    A = _csc(sp.csc_matrix(A).T) if transpose_a else _csc(A)
+    A = A.astype(np.float64)
+    B = _csc(B).astype(np.float64)
+    m, p = A.shape[0], B.shape[1]
+    assert A.shape[1] == B.shape[0] and C.shape == (m, p) and C.flags.f_contiguous
+    acp, arv = _idx64(A)
+    bcp, brv = _idx64(B)
+    lib().orc_spgemm_dense(ctypes.c_int64(m), ctypes.c_int64(p), _p(acp, _i64p), _p(arv, _i64p),
+                           _p(np.ascontiguousarray(A.data), _f64p), _p(bcp, _i64p), _p(brv, _i64p),
+                           _p(np.ascontiguousarray(B.data), _f64p), ctypes.c_double(alpha), ctypes.c_double(beta), _p(C, _f64p))
+    return C

@@ -73,6 +73,8 @@ SIGNATURES = {
     "svb_operator_create_dense": (c_int, [c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int, _ph]),
     "svb_operator_create_counts": (c_int, [_h, c_void_p, c_double, c_void_p, c_void_p, c_double, c_int, c_void_p, _ph]),
     "svb_operator_counts_info": (c_int, [_h, _pint, _p64, _p64, _p64, _p64, _p64]),
+    "svb_operator_counts_stream": (c_int, [_h, c_int, c_void_p, c_void_p]),
+    "svb_operator_counts_layout": (c_int, [_h, _pint, _pf64, _pint, _pint, _pf64]),
     "svb_operator_free": (c_int, [_h]),
     "svb_operator_info": (c_int, [_h, _p64, _p64, _p64, _pint, _pint, _pint]),
     "svb_mul": (c_int, [_h, c_char, c_double, c_void_p, c_double, c_void_p, c_int64]),
@@ -81,6 +83,8 @@ SIGNATURES = {
                           c_void_p, c_void_p, _p64, _p64]),
     "svb_irlba_solve": (c_int, [_h, c_int64, c_int64, c_int64, c_int64, c_double, c_double, c_void_p, c_void_p,
                                 c_void_p, c_void_p, _ph]),
+    "svb_spmspv": (c_int, [_h, c_void_p, c_void_p, c_int64, c_int, c_double, c_double, c_void_p]),
+    "svb_spgemm_dense": (c_int, [_h, c_int, _h, c_double, c_double, c_void_p, c_int64]),
     "svb_gram": (c_int, [_h, c_void_p]),
     "svb_tssvd": (c_int, [_h, c_int64, c_int64, c_int64, c_double, c_void_p, _ph]),
     "svb_knn": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),

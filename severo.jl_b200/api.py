@@ -31,7 +31,7 @@ from .loess import loess_fit_predict
 __all__ = [
     "DeviceMatrix", "NamedArray", "convert_counts", "filter_cells", "filter_features", "filter_counts", "normalize_cells", "mean_var", "mean_std",
     "standardized_var_clipped", "find_variable_features", "scale_features", "CenteredMatrix", "CountsCenteredMatrix",
-    "scale_features_counts", "irlba", "gram", "tssvd", "ann", "nearest_neighbours", "jaccard_index", "shared_nearest_neighbours",
+    "scale_features_counts", "irlba", "mul_sparse_vector", "mul_sparse_dense", "gram", "tssvd", "ann", "nearest_neighbours", "jaccard_index", "shared_nearest_neighbours",
     "SVD", "svd_flip", "pca", "embedding", "LinearEmbedding", "synthetic_counts",
 ]
 
@@ -636,8 +636,12 @@ class CountsCenteredMatrix(CenteredMatrix):
         lv = ctypes.c_int()
         v = [ctypes.c_int64() for _ in range(5)]
         L.check(L.lib().svb_operator_counts_info(self._op, lv, *v))
+        fr, ar, al = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        fp, apass = ctypes.c_double(), ctypes.c_double()
+        L.check(L.lib().svb_operator_counts_layout(self._op, fr, fp, ar, al, apass))
         return dict(levels=lv.value, tile_cells=v[0].value, nnz_coded=v[1].value, nnz_exception=v[2].value,
-                    fwd_chunks=v[3].value, adj_chunks=v[4].value)
+                    fwd_chunks=v[3].value, adj_chunks=v[4].value, fwd_replicas=fr.value, fwd_passes_per_set=fp.value,
+                    adj_replicas=ar.value, adj_replicated_levels=al.value, adj_passes_per_set=apass.value)
 
     def _operator(self):
         if self._op is None:
@@ -766,6 +770,51 @@ def irlba(A, nu, S: Optional[SVD] = None, init=None, tol=1e-5, svtol=None, maxit
         raise RuntimeError("convergence failed")  # irlba.jl:73
     L.check(rc)
     return SVD(U, s, V.T, it.value, mp.value)
+
+
+def mul_sparse_vector(y, A, x, alpha=1.0, beta=0.0):
+    """mul.jl:50-77 ``mul!(y, A::SparseMatrixCSC, x::SparseVector, alpha, beta)``: y = beta*y + alpha*A*x in place (and returned).
+    ``A``: scipy sparse / DeviceMatrix (m x n); ``x``: a scipy sparse column or row vector of length n (its STORED entries take
+    part, zeros included); ``y``: Float64[m]. Raises ValueError on a size mismatch (the reference's DimensionMismatch)."""
+    dA, temp = _to_device(A)
+    m, n = dA.shape
+    xs = sp.csc_matrix(x) if sp.issparse(x) else sp.csc_matrix(np.asarray(x, dtype=np.float64).reshape(-1, 1))
+    if xs.shape[1] != 1:
+        xs = sp.csc_matrix(xs.T)
+    if xs.shape != (n, 1) or y.shape != (m,):
+        raise ValueError("DimensionMismatch")
+    if not (y.dtype == np.float64 and y.flags.c_contiguous):
+        raise ValueError("y must be a contiguous Float64 vector")
+    xs.sort_indices()
+    idx = np.ascontiguousarray(xs.indices, dtype=np.int64)
+    val = np.ascontiguousarray(xs.data, dtype=np.float64)
+    L.check(L.lib().svb_spmspv(dA._h, L.ptr(idx), L.ptr(val), idx.shape[0], 0, float(alpha), float(beta), L.ptr(y)))
+    if temp:
+        dA.free()
+    return y
+
+
+def mul_sparse_dense(C, A, B, alpha=1.0, beta=0.0):
+    """mul.jl:82-114 ``mul!(C::StridedMatrix, A::SparseMatrixCSC, B::SparseMatrixCSC, alpha, beta)``: C = beta*C + alpha*A*B in
+    place (and returned); ``A`` may be given as ``X.T`` of a CSC (a scipy CSR) for the Transpose / Adjoint methods of
+    mul.jl:79-80. ``C``: column-major Float64 (size(A,1) x size(B,2))."""
+    trans = sp.issparse(A) and A.format == "csr"
+    if trans:                                            # X' of a CSC: keep the parent, ask for A' * B
+        A = sp.csc_matrix((A.data, A.indices, A.indptr), shape=(A.shape[1], A.shape[0]))
+    dA, ta = _to_device(A)
+    dB, tb = _to_device(B)
+    m = dA.shape[1] if trans else dA.shape[0]
+    inner = dA.shape[0] if trans else dA.shape[1]
+    if inner != dB.shape[0] or C.shape != (m, dB.shape[1]):
+        raise ValueError("DimensionMismatch")
+    if not (C.dtype == np.float64 and C.flags.f_contiguous):
+        raise ValueError("C must be a column-major Float64 matrix")
+    L.check(L.lib().svb_spgemm_dense(dA._h, int(trans), dB._h, float(alpha), float(beta), L.ptr(C), max(m, 1)))
+    if ta:
+        dA.free()
+    if tb:
+        dB.free()
+    return C
 
 
 def gram(A):

@@ -268,6 +268,165 @@ __device__ __forceinline__ int64_t rr_slot(int64_t g0, int64_t g1, int p) {
     return (cb + q % wb) * FCH + q / wb;
 }
 
+// ---- replica assignment (round 2) --------------------------------------------------------------------------------
+// What the round-robin order leaves (the tails of the groups, sets shared by two groups / segments: 1.9 passes per set in the
+// forward stream, 1.55 in the adjoint at C3) is removed with bank-shifted REPLICAS of the gathered table: replica r of a table
+// region starts 5r banks later, so an entry can be read from any of nrep banks, and the builder decides which — per SET (element
+// e of an aligned block of 16 chunks = the 16 gathers a half-warp issues together), one thread per set: entries with a single
+// copy take their bank first; the others are matched to the free banks by augmenting paths (Kuhn's bipartite matching, 16 x 16);
+// what cannot be matched goes to its least-loaded candidate. The chosen replica is written into the code, so the product
+// kernels are unchanged apart from a larger table. Host simulation on the C3 matrix (tools/studies/bank_sim.py): forward,
+// 4 replicas of xs (64 KB): 1.91 -> 1.10 passes per set; adjoint, 4 replicas of levels 1-2 only (176 KB table): 1.55 -> 1.10.
+// The pads of a set share one address and count as ONE entry. Exception chunks are left untouched.
+struct AssignGeom {
+    int adjoint;   // 0: forward stream (codes are byte offsets of xs entries); 1: adjoint stream (canonical (level-1)*R + i)
+    int nrep;      // replicas of the replicated region
+    int step;      // entries between two replicas (= 5 mod 16)
+    int padcanon;  // canonical pad: gene n (forward) / R*L (adjoint)
+    int log2R, nlr, baseB, pad;  // adjoint: cells per tile, replicated levels, first single-copy entry, physical pad entry
+};
+
+__global__ void __launch_bounds__(256) fact_assign_kernel(uint16_t *__restrict__ code, const uint8_t *__restrict__ meta,
+                                                          int64_t nchunks, AssignGeom G, unsigned long long *__restrict__ stats) {
+    const int64_t nsets = ((nchunks + 15) >> 4) << 3;
+    unsigned long long mypasses = 0, mysets = 0;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nsets; s += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t blk = s >> 3;
+        const int e = (int)(s & 7);
+        int base[16], nc[16], choice[16], owner[16], load[16];
+        unsigned present = 0, dup = 0;
+        int padrep = -1;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            owner[c] = -1;
+            load[c] = 0;
+            choice[c] = 0;
+            base[c] = 0;
+            nc[c] = 1;
+            const int64_t ch = (blk << 4) + c;
+            if (ch >= nchunks) continue;
+            const unsigned mb = meta[ch];
+            if (G.adjoint ? (mb & 2u) != 0u : (mb >> 1) == (unsigned)FEXC) continue;  // exception chunk: another format
+            const int v = code[ch * FCH + e];
+            present |= 1u << c;
+            if (!G.adjoint) {
+                const int idx = v >> 3;
+                base[c] = idx;
+                nc[c] = G.nrep;
+                if (idx == G.padcanon) {
+                    if (padrep < 0) padrep = c; else dup |= 1u << c;
+                }
+            } else if (v == G.padcanon) {
+                base[c] = G.pad;
+                if (padrep < 0) padrep = c; else dup |= 1u << c;
+            } else {
+                const int l = v >> G.log2R, il = v & ((1 << G.log2R) - 1);
+                if (l < G.nlr) {
+                    base[c] = l * G.nrep * G.step + il;
+                    nc[c] = G.nrep;
+                } else {
+                    base[c] = G.baseB + ((l - G.nlr) << G.log2R) + il;
+                }
+            }
+        }
+        const unsigned live = present & ~dup;
+        // single-copy entries first
+        for (int c = 0; c < 16; ++c)
+            if (((live >> c) & 1u) && nc[c] == 1) {
+                const int b = base[c] & 15;
+                load[b] += 1;
+                owner[b] = -2;
+            }
+        // matching of the replicated entries
+        unsigned unmatched = 0;
+        for (int c = 0; c < 16; ++c) {
+            if (!((live >> c) & 1u) || nc[c] == 1) continue;
+            int se[17], sr[17], pb[17];
+            unsigned seen = 0;
+            int sp = 0;
+            se[0] = c;
+            sr[0] = 0;
+            bool found = false;
+            while (sp >= 0) {
+                const int en = se[sp];
+                if (sr[sp] >= nc[en]) {
+                    --sp;
+                    continue;
+                }
+                const int r = sr[sp]++;
+                const int b = (base[en] + r * G.step) & 15;
+                if ((seen >> b) & 1u) continue;
+                seen |= 1u << b;
+                if (owner[b] == -2) continue;
+                pb[sp] = b;
+                if (owner[b] == -1) {
+                    for (int k = 0; k <= sp; ++k) {
+                        owner[pb[k]] = se[k];
+                        choice[se[k]] = sr[k] - 1;
+                    }
+                    found = true;
+                    break;
+                }
+                se[sp + 1] = owner[b];
+                sr[sp + 1] = 0;
+                ++sp;
+            }
+            if (!found) unmatched |= 1u << c;
+        }
+        for (int b = 0; b < 16; ++b)
+            if (owner[b] >= 0) load[b] += 1;
+        for (int c = 0; c < 16; ++c)
+            if ((unmatched >> c) & 1u) {
+                int best = 0, bl = 1 << 30;
+                for (int r = 0; r < nc[c]; ++r) {
+                    const int b = (base[c] + r * G.step) & 15;
+                    if (load[b] < bl) {
+                        bl = load[b];
+                        best = r;
+                    }
+                }
+                choice[c] = best;
+                load[(base[c] + best * G.step) & 15] += 1;
+            }
+        int passes = 0;
+        for (int b = 0; b < 16; ++b) passes = max(passes, load[b]);
+        if (present) {
+            mypasses += (unsigned long long)passes;
+            mysets += 1;
+        }
+        for (int c = 0; c < 16; ++c)
+            if ((present >> c) & 1u) {
+                const int src = ((dup >> c) & 1u) ? padrep : c;
+                const int phys = base[src] + choice[src] * G.step;
+                code[((blk << 4) + c) * FCH + e] = (uint16_t)(G.adjoint ? phys : (phys << 3));
+            }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mypasses += __shfl_xor_sync(0xffffffffu, mypasses, o);
+        mysets += __shfl_xor_sync(0xffffffffu, mysets, o);
+    }
+    if ((threadIdx.x & 31) == 0 && mysets) {
+        atomicAdd(stats + 0, mypasses);
+        atomicAdd(stats + 1, mysets);
+    }
+}
+
+// passes per set of a stream WITHOUT touching it (statistics of the placement: the "before" figure / streams without replicas)
+static double run_assign(uint16_t *code, const uint8_t *meta, int64_t nchunks, const AssignGeom &G, cudaStream_t st) {
+    if (nchunks <= 0) return 0.0;
+    DevBuf<unsigned long long> d(2);
+    SVB_CUDA(cudaMemsetAsync(d.p, 0, 2 * sizeof(unsigned long long), st));
+    const int64_t nsets = ((nchunks + 15) >> 4) << 3;
+    fact_assign_kernel<<<fgrid(nsets, 256, 148 * 32), 256, 0, st>>>(code, meta, nchunks, G, d.p);
+    count_launch();
+    SVB_LAUNCH_CHECK();
+    unsigned long long h[2];
+    SVB_CUDA(cudaMemcpyAsync(h, d.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    SVB_CUDA(cudaStreamSynchronize(st));
+    return h[1] ? (double)h[0] / (double)h[1] : 0.0;
+}
+
 // adjoint layout, pass 1: chunks per (tile, gene) segment (at least one: the stream kernels count segments by their
 // "last chunk" flags, so an empty segment is one all-pad chunk). Sub-warps of 8 lanes, one segment each.
 __global__ void __launch_bounds__(256) fact_seg_count_kernel(const int64_t *__restrict__ startpos, const uint8_t *__restrict__ lvl,
@@ -587,17 +746,18 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 fwd_stream_kernel(const uint4 *__restrict__ code, const uint8_t *__restrict__ meta, const double *__restrict__ tlev, int log2L,
                   const int64_t *__restrict__ wstart, const int64_t *__restrict__ wrow, int64_t n, const double *__restrict__ x,
                   const double *__restrict__ inv, const double *__restrict__ mu, double alpha, double beta, double *__restrict__ y,
-                  const double *__restrict__ coef, double csign, const double *__restrict__ cvec) {
+                  const double *__restrict__ coef, double csign, const double *__restrict__ cvec, int nrep, int stride) {
     extern __shared__ double smem[];
     double *red = smem;      // 32
-    double *xs = smem + 32;  // n + 1 (xs[n] = 0: the pad gene)
+    double *xs = smem + 32;  // nrep bank-shifted replicas of {x_j / sd_j, j < n ; 0 (the pad gene)}, `stride` entries apart
     double part = 0.0;
     for (int64_t j = threadIdx.x; j < n; j += BLOCK) {
         const double xv = x[j];
-        xs[j] = xv * inv[j];
+        const double v = xv * inv[j];
+        for (int r = 0; r < nrep; ++r) xs[(int64_t)r * stride + j] = v;
         part = fma(mu[j], xv, part);
     }
-    if (threadIdx.x == 0) xs[n] = 0.0;
+    if ((int)threadIdx.x < nrep) xs[(int64_t)threadIdx.x * stride + n] = 0.0;
     const double mudot = fblock_sum(part, red);  // its barriers publish xs
     const double cf = (coef != nullptr) ? csign * (*coef) : 0.0;
 
@@ -696,6 +856,11 @@ fwd_stream_kernel(const uint4 *__restrict__ code, const uint8_t *__restrict__ me
 #undef SVB_FWD_STEP
 }
 
+// physical layout of the adjoint tile table (see the replica assignment above); identity = {0, 1, 0, 0, R*L, R*L + 1}
+struct AdjGeom {
+    int nlr, nrep, strideA, baseB, pad, wbase;
+};
+
 // adjoint, stage 1: partial[t][g] = (1/sd_g) * sum over the chunks of segment (t,g) of sum_8 T[code], T[l*R+i] = t_i[l]*w_i;
 // partial[t][n] = sum of w over the tile. CTAs take tiles from a global counter (any order gives the same bits: every
 // tile has its own partial row); inside a tile warp k streams the k-th slice of the tile's chunks.
@@ -706,17 +871,17 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 adj_stream_kernel(const int64_t *__restrict__ gptr, const uint4 *__restrict__ code, const uint8_t *__restrict__ meta,
                   const double *__restrict__ tlevA, int log2L, int log2R, int64_t m, int64_t n, int64_t ntiles,
                   const double *__restrict__ w, const double *__restrict__ inv, double *__restrict__ partial,
-                  const int32_t *__restrict__ slices, unsigned int *__restrict__ counters) {
+                  const int32_t *__restrict__ slices, unsigned int *__restrict__ counters, AdjGeom G) {
     extern __shared__ double smem[];
     __shared__ long long cur_tile;
     double *red = smem;     // 32
-    double *T = smem + 32;  // R*L level table, [R*L] = 0 (pads), then R entries of w (exception chunks)
+    double *T = smem + 32;  // level table (levels 1..nlr in nrep bank-shifted replicas), T[pad] = 0, then R entries of w (exceptions)
     const int64_t R = (int64_t)1 << log2R;
     const int RL = 1 << (log2R + log2L);
     constexpr int K = BLOCK / 32;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
-    const unsigned padc = (unsigned)RL * 0x10001u;
+    const unsigned padc = (unsigned)G.pad * 0x10001u;
     const uint4 padq = make_uint4(padc, padc, padc, padc);
     for (;;) {
         __syncthreads();  // everybody is done with the previous tile's table (and has read cur_tile)
@@ -726,18 +891,26 @@ adj_stream_kernel(const int64_t *__restrict__ gptr, const uint4 *__restrict__ co
         if (t >= ntiles) break;
         const int64_t row0 = t << log2R;
         const double *tl = tlevA + (row0 << log2L);  // this tile's level-major block
-#pragma unroll 4
-        for (int k = threadIdx.x; k < RL; k += BLOCK) {
-            const int64_t row = row0 + (k & (R - 1));
-            T[k] = (row < m) ? __ldg(tl + k) * __ldg(w + row) : 0.0;
-        }
+        // table fill: a thread owns a cell — w_i once, then its L table entries (all loads independent, coalesced per level)
         double part = 0.0;
-        for (int64_t r = threadIdx.x; r < R; r += BLOCK) {
-            const double wv = (row0 + r < m) ? __ldg(w + row0 + r) : 0.0;
-            T[RL + 1 + r] = wv;
+        const int Lv = 1 << log2L;
+        for (int il = threadIdx.x; il < (int)R; il += BLOCK) {
+            const int64_t row = row0 + il;
+            const double wv = (row < m) ? __ldg(w + row) : 0.0;
+            T[G.wbase + il] = wv;
             part += wv;
+#pragma unroll 4
+            for (int l = 0; l < Lv; ++l) {
+                const double v = __ldg(tl + (l << log2R) + il) * wv;  // tlevA is zero beyond the last cell
+                if (l < G.nlr) {
+                    double *dst = T + l * G.nrep * G.strideA + il;
+                    for (int r = 0; r < G.nrep; ++r) dst[r * G.strideA] = v;
+                } else {
+                    T[G.baseB + ((l - G.nlr) << log2R) + il] = v;
+                }
+            }
         }
-        if (threadIdx.x == 0) T[RL] = 0.0;
+        if (threadIdx.x == 0) T[G.pad] = 0.0;
         // this warp's slice (loads issued before the barrier so that they overlap the table fill)
         const int g0 = __ldg(slices + t * (K + 1) + wid), g1 = __ldg(slices + t * (K + 1) + wid + 1);
         const int64_t cbeg = __ldg(gptr + t * n + g0), cend = __ldg(gptr + t * n + g1);
@@ -765,7 +938,7 @@ adj_stream_kernel(const int64_t *__restrict__ gptr, const uint4 *__restrict__ co
             const int g = gbase + __popc(bal & lt);
             gbase += __popc(bal);
             double v;
-            if (mb[0] & 2u) v = __hiloint2double((int)q[0].w, (int)q[0].z) * T[RL + 1 + q[0].x];
+            if (mb[0] & 2u) v = __hiloint2double((int)q[0].w, (int)q[0].z) * T[G.wbase + q[0].x];
             else v = gather8(T, q[0]);
             if (LAZY) {
                 const int nends = __popc(bal);  // segments that end in this iteration (warp-uniform)
@@ -828,7 +1001,7 @@ template <int BLOCK, bool BO, int MINB>
 static void launch_fact_fwd(svb_operator_s *op, double alpha, const double *dx, double beta, double *dy, const double *coef,
                             double csign, const double *cvec) {
     svb_factored_s *f = op->fact;
-    const size_t smem = (32 + (size_t)op->n + 1) * sizeof(double);
+    const size_t smem = (32 + (size_t)(f->f_nrep - 1) * f->f_stride + (size_t)op->n + 1) * sizeof(double);
     auto k = fwd_stream_kernel<BLOCK, BO, MINB>;
     SVB_CHECK(smem <= ctx().smem_optin, SVB_EDIM, "count-level operator: gene vector does not fit in shared memory");
     if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -846,7 +1019,8 @@ static void launch_fact_fwd(svb_operator_s *op, double alpha, const double *dx, 
         f->fwd_grid = grid;
     }
     k<<<(unsigned)f->fwd_grid, BLOCK, smem, ctx().stream>>>((const uint4 *)f->f_code, f->f_meta, f->tlev, f->log2L, f->fwd_ranges,
-                                                             f->fwd_rows, op->n, dx, f->inv, op->mu, alpha, beta, dy, coef, csign, cvec);
+                                                             f->fwd_rows, op->n, dx, f->inv, op->mu, alpha, beta, dy, coef, csign, cvec,
+                                                             f->f_nrep, f->f_stride);
     SVB_LAUNCH_CHECK();
 }
 
@@ -859,7 +1033,7 @@ void fact_fwd(svb_operator_s *op, double alpha, const double *dx, double beta, d
     const bool bo = op->fact->f_cshift == 3;  // codes are byte offsets
     // 64 registers per thread (4 x 256 or 2 x 512 threads per SM): 48 registers spill, and the kernel is bound by the
     // shared-memory pipe / issue slots, not by occupancy (measured 5 vs 4 CTAs per SM: within noise)
-    if ((size_t)op->n * 8 > 24 * 1024) {
+    if (((size_t)(op->fact->f_nrep - 1) * op->fact->f_stride + (size_t)op->n) * 8 > 24 * 1024) {
         if (bo) launch_fact_fwd<512, true, 2>(op, alpha, dx, beta, dy, coef, csign, cvec);
         else launch_fact_fwd<512, false, 2>(op, alpha, dx, beta, dy, coef, csign, cvec);
     } else {
@@ -870,13 +1044,14 @@ void fact_fwd(svb_operator_s *op, double alpha, const double *dx, double beta, d
 
 void fact_adj_stage1(svb_operator_s *op, const double *dx) {
     svb_factored_s *f = op->fact;
-    const size_t smem = (32 + ((size_t)1 << (f->log2R + f->log2L)) + 1 + (size_t)f->R) * sizeof(double);
+    const size_t smem = (32 + (size_t)f->a_tabsize) * sizeof(double);
     const int block = adj_block_of(f);
+    const AdjGeom G{f->a_nlr, f->a_nrep, f->a_strideA, f->a_baseB, f->a_pad, f->a_wbase};
     auto k = (block == 1024) ? adj_stream_kernel<1024, 1, true> : adj_stream_kernel<512, 3, false>;
     if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (f->adj_grid == 0) f->adj_grid = (int)std::max<int64_t>(1, std::min<int64_t>(fresident_grid(k, smem, block), f->ntiles));
     k<<<(unsigned)f->adj_grid, block, smem, ctx().stream>>>(f->a_gptr, (const uint4 *)f->a_code, f->a_meta, f->tlevA, f->log2L, f->log2R,
-                                                                 op->m, op->n, f->ntiles, dx, f->inv, f->partial, f->a_slices, f->counters);
+                                                                 op->m, op->n, f->ntiles, dx, f->inv, f->partial, f->a_slices, f->counters, G);
     SVB_LAUNCH_CHECK();
 }
 
@@ -958,11 +1133,12 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
             SVB_CUDA(cudaMemcpyAsync(h, d5.p, sizeof(h), cudaMemcpyDeviceToHost, st));
             SVB_CUDA(cudaStreamSynchronize(st));
         }
-        // smallest L that leaves at most 1 % of the entries to the exception chunks (17 B per entry there, 2.1 B here)
+        // smallest L that leaves at most 2 % of the entries to the exception chunks (17 B and a whole lane slot per entry
+        // there, 2.1 B here; doubling L halves the cells per adjoint tile, which costs more than 2 % of exceptions)
         const int cand[4] = {4, 8, 16, 32};
         L = 32;
         for (int i = 0; i < 4; ++i)
-            if (h[i] <= 0.01 * h[4]) { L = cand[i]; break; }
+            if (h[i] <= 0.02 * h[4]) { L = cand[i]; break; }
     }
     int log2L = 0;
     while ((1 << log2L) < L) ++log2L;
@@ -978,6 +1154,39 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
     f->log2R = log2R;
     f->R = 1ll << log2R;
     f->ntiles = std::max<int64_t>(1, (m + f->R - 1) / f->R);
+    // ---- bank-shifted replicas of the gathered tables (see fact_assign_kernel) ------------------------------------------
+    static const bool replicas = !(getenv("SVB_FACT_REPLICAS") && atoi(getenv("SVB_FACT_REPLICAS")) == 0);
+    {
+        // forward: xs replicas while the byte-offset codes still fit in 16 bits; replica r starts at entry r*stride, stride = 5 mod 16
+        int stride = (int)n + 1;
+        while ((stride & 15) != 5) ++stride;
+        f->f_stride = stride;
+        f->f_nrep = 1;
+        if (replicas && n <= 8190) f->f_nrep = (int)std::max<int64_t>(1, std::min<int64_t>(4, (8191 - n) / stride + 1));
+        // adjoint: only the one-CTA-per-SM kernel (R*L = 16384) has the shared memory for it: levels 1..2 in 4 replicas
+        const int RL = 1 << (log2R + log2L);
+        f->a_nlr = 0;
+        f->a_nrep = 1;
+        f->a_strideA = 0;
+        f->a_baseB = 0;
+        if (replicas && log2R + log2L >= 14 && log2R >= 4 && L >= 2) {
+            f->a_nlr = 2;
+            f->a_nrep = 4;
+            f->a_strideA = (int)f->R + 5;
+            f->a_baseB = (f->a_nlr * f->a_nrep * f->a_strideA + 15) & ~15;
+        }
+        f->a_pad = f->a_baseB + RL - (f->a_nlr << log2R);
+        f->a_wbase = f->a_pad + 1;
+        f->a_tabsize = f->a_wbase + (int)f->R;
+        if ((size_t)(32 + f->a_tabsize) * sizeof(double) > C.smem_optin || f->a_tabsize > 65535) {  // does not fit: single copies
+            f->a_nlr = 0;
+            f->a_nrep = 1;
+            f->a_baseB = 0;
+            f->a_pad = RL;
+            f->a_wbase = RL + 1;
+            f->a_tabsize = RL + 1 + (int)f->R;
+        }
+    }
 
     tick("libsize upload + levels");
     // ---- per-cell level tables ---------------------------------------------------------------------
@@ -1084,12 +1293,19 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
         fact_seg_fill_kernel<<<fgrid(nseg * 8), 256, 0, st>>>(startpos.p, a->rowidx, lvl.p, nseg, n, log2R, log2L, f->a_gptr, estart.p,
                                                               e.p ? e.p->rowidx : nullptr, e.p ? (const double *)e.p->val : nullptr,
                                                               (uint16_t *)f->a_code, f->a_meta);
+        count_launch();
+        SVB_LAUNCH_CHECK();
+        static const bool stats = getenv("SVB_FACT_STATS") != nullptr;
+        if (f->a_nrep > 1 || stats) {
+            const AssignGeom G{1, f->a_nrep, f->a_strideA ? f->a_strideA : 5, 1 << (log2R + log2L), log2R, f->a_nlr, f->a_baseB, f->a_pad};
+            f->a_passes = run_assign((uint16_t *)f->a_code, f->a_meta, f->a_chunks, G, st);
+        }
         const int K = adj_block_of(f) / 32;
         SVB_CUDA(cudaMalloc((void **)&f->a_slices, (size_t)f->ntiles * (K + 1) * sizeof(int32_t)));
         fact_slices_kernel<<<(unsigned)((f->ntiles * (K + 1) + 255) / 256), 256, 0, st>>>(f->a_gptr, f->ntiles, n, K, f->a_slices);
         SVB_CUDA(cudaMalloc((void **)&f->counters, 2 * sizeof(unsigned int)));
         SVB_CUDA(cudaMemsetAsync(f->counters, 0, 2 * sizeof(unsigned int), st));
-        count_launch(2);
+        count_launch();
         SVB_LAUNCH_CHECK();
         SVB_CUDA(cudaStreamSynchronize(st));
     }
@@ -1127,6 +1343,11 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
                                                   e.p ? (const double *)e.p->val : nullptr, (uint16_t *)f->f_code, f->f_meta);
         count_launch();
         SVB_LAUNCH_CHECK();
+        static const bool stats = getenv("SVB_FACT_STATS") != nullptr;
+        if (f->f_cshift == 3 && (f->f_nrep > 1 || stats)) {
+            const AssignGeom G{0, f->f_nrep, f->f_stride, (int)n, 0, 0, 0, 0};
+            f->f_passes = run_assign((uint16_t *)f->f_code, f->f_meta, f->f_chunks, G, st);
+        }
         SVB_CUDA(cudaStreamSynchronize(st));
     }
 
@@ -1185,6 +1406,32 @@ int svb_operator_counts_info(svb_operator_t op, int *levels, int64_t *tile_cells
     if (nnz_exception) *nnz_exception = f->nnz_exc;
     if (fwd_chunks) *fwd_chunks = f->f_chunks;
     if (adj_chunks) *adj_chunks = f->a_chunks;
+    SVB_API_END
+}
+
+int svb_operator_counts_stream(svb_operator_t op, int adjoint, uint16_t *code, uint8_t *meta) {
+    SVB_API_BEGIN
+    require_init();
+    SVB_CHECK(op && op->fact, SVB_EARG, "svb_operator_counts_stream: not a count-level operator");
+    const svb_factored_s *f = op->fact;
+    const int64_t nch = adjoint ? f->a_chunks : f->f_chunks;
+    cudaStream_t st = ctx().stream;
+    if (code) SVB_CUDA(cudaMemcpyAsync(code, adjoint ? f->a_code : f->f_code, (size_t)nch * 16, cudaMemcpyDeviceToHost, st));
+    if (meta) SVB_CUDA(cudaMemcpyAsync(meta, adjoint ? f->a_meta : f->f_meta, (size_t)nch, cudaMemcpyDeviceToHost, st));
+    SVB_CUDA(cudaStreamSynchronize(st));
+    SVB_API_END
+}
+
+int svb_operator_counts_layout(svb_operator_t op, int *fwd_replicas, double *fwd_passes, int *adj_replicas,
+                               int *adj_replicated_levels, double *adj_passes) {
+    SVB_API_BEGIN
+    SVB_CHECK(op && op->fact, SVB_EARG, "svb_operator_counts_layout: not a count-level operator");
+    const svb_factored_s *f = op->fact;
+    if (fwd_replicas) *fwd_replicas = f->f_nrep;
+    if (fwd_passes) *fwd_passes = f->f_passes;
+    if (adj_replicas) *adj_replicas = f->a_nrep;
+    if (adj_replicated_levels) *adj_replicated_levels = f->a_nlr;
+    if (adj_passes) *adj_passes = f->a_passes;
     SVB_API_END
 }
 

@@ -162,6 +162,13 @@ struct svb_factored_s {
     int64_t a_chunks = 0;
     double *partial = nullptr;       // [ntiles*(n+1)]
     int64_t nnz_main = 0, nnz_exc = 0;
+    // bank-shifted replicas of the gathered tables (round 2): the builder picks, set by set, the replica of every entry so that
+    // the 16 gathers of a half-warp fall in 16 different 8-byte banks (bipartite matching at build time, see factored.cu)
+    int f_nrep = 1, f_stride = 0;    // forward: xs replica r starts at entry r*f_stride (f_stride = 5 mod 16); code = byte offset
+    int a_nlr = 0, a_nrep = 1;       // adjoint: levels 1..a_nlr have a_nrep replicas, the others one copy
+    int a_strideA = 0, a_baseB = 0;  // entry of (l < a_nlr, r, i): (l*a_nrep + r)*a_strideA + i ; (l >= a_nlr, i): a_baseB + (l-a_nlr)*R + i
+    int a_pad = 0, a_wbase = 0, a_tabsize = 0;  // pad entry (0.0), first of the R entries of w (exception chunks), table entries
+    double f_passes = 0.0, a_passes = 0.0;      // average shared-memory passes per set of 16 gathers after the assignment (1 = no conflict)
     int fwd_grid = 0, adj_grid = 0;
     int64_t *fwd_ranges = nullptr, *fwd_rows = nullptr;  // [warps+1] first chunk / first row of every warp of the forward grid
     ~svb_factored_s();

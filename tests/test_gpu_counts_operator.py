@@ -176,3 +176,47 @@ def test_counts_operator_properties_at_scale(sv):
     # run-to-run determinism (fixed-order reductions, no floating-point atomics)
     np.testing.assert_array_equal(C @ x, Sx)
     np.testing.assert_array_equal(C.T @ w, Stw)
+
+
+@pytest.mark.parametrize("levels,log2r", [(16, 10), (8, 11), (32, 9), (4, 12)])
+def test_counts_operator_replica_tables(sv, orc, monkeypatch, levels, log2r):
+    """Round 2: bank-shifted replicas of the gathered tables + build-time matching. SVB_FACT_LOG2R forces the one-CTA-per-SM
+    adjoint kernel (R*L = 16384 table entries, levels 1-2 in four replicas) that only the 1.3 M-cell configurations reach on
+    their own; the forward replicas (four copies of x/sd for <= 2,046 genes) are always on. Products must equal the oracle's,
+    and the assignment must leave fewer shared-memory passes per set than the unassigned order."""
+    X = planted_counts(9000, 900, 8, seed=21, mean_nnz=170)
+    hvf = sv.find_variable_features(X, 400)
+    So = _explicit_oracle(sv, orc, X, hvf, 10.0)
+    monkeypatch.setenv("SVB_FACT_LOG2R", str(log2r))
+    C = sv.scale_features_counts(X, scale_factor=1e4, scale_max=10.0, features=hvf, levels=levels)
+    info = C.info()
+    assert info["tile_cells"] == 1 << log2r and info["levels"] == levels
+    assert info["fwd_replicas"] == 4 and info["adj_replicas"] == 4 and info["adj_replicated_levels"] == 2
+    assert 1.0 <= info["fwd_passes_per_set"] < 1.35 and 1.0 <= info["adj_passes_per_set"] < 1.35
+    _check_products(C, So, np.random.default_rng(5))
+    init = np.random.default_rng(6).standard_normal(400)
+    G = sv.irlba(C, 8, init=init, tol=1e-9)
+    O = orc.irlba(So, 8, init=init, tol=1e-9)
+    np.testing.assert_allclose(G.S, O.S, rtol=1e-6)
+    assert orc.principal_angle(G.V, O.V) < 1e-4
+    C.free()
+
+
+def test_counts_operator_forward_replicas_by_gene_count(sv, orc):
+    # the number of x/sd replicas follows from the 16-bit byte-offset code space: 4 up to 2,046 genes, then 3, 2, 1
+    for n_hvg, want in ((500, 4), (2300, 3), (3000, 2), (4500, 1)):
+        X = planted_counts(1500, n_hvg + 200, 4, seed=n_hvg, mean_nnz=80)
+        hvf = np.arange(n_hvg)
+        keep = np.asarray((X[:, hvf] > 0).sum(axis=0)).ravel() > 1
+        hvf = hvf[keep]
+        C = sv.scale_features_counts(X, scale_factor=1e4, scale_max=10.0, features=hvf)
+        nrep = C.info()["fwd_replicas"]
+        n = len(hvf)
+        stride = n + 1
+        while stride % 16 != 5:
+            stride += 1
+        assert nrep == max(1, min(4, (8191 - n) // stride + 1)), (n, nrep)
+        assert abs(n - n_hvg) > 50 or nrep == want
+        So = _explicit_oracle(sv, orc, X, hvf, 10.0)
+        _check_products(C, So, np.random.default_rng(n_hvg))
+        C.free()

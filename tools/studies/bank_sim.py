@@ -156,7 +156,7 @@ def adjoint_chunks(colptr, rowval, counts, R, tiles, L):
     return np.array(out)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1].isdigit():
     d = np.load("/tmp/hvg_sample.npz")
     colptr, rowval, counts = d["colptr"], d["rowval"], d["counts"]
     L = int(sys.argv[1]) if len(sys.argv) > 1 else 16
@@ -231,3 +231,68 @@ if __name__ == "__main__" and len(sys.argv) > 2 and sys.argv[2] == "partial":
                 "lev1-2 x3 {0,5,10}": ((0, 5, 10), 2), "lev1 x4": ((0, 5, 10, 15), 1), "all x2 {0,5}": ((0, 5), 16),
                 "lev1-4 x3": ((0, 5, 10), 4), "lev1-3 x4": ((0, 5, 10, 15), 3)}
         simulate_partial(ch, R, f"adj R={R}", cfgs)
+
+
+def device_like(chunks, R, nlev, shifts, pad_flex, dedupe):
+    nblocks = len(chunks) // 16
+    tot = sets = 0
+    for b in range(nblocks):
+        blk = chunks[b * 16:(b + 1) * 16]
+        for e in range(8):
+            addrs = [int(x) for x in blk[:, e]]
+            pads = [a for a in addrs if a == PAD]
+            real = [a for a in addrs if a != PAD]
+            if dedupe:
+                real = list(set(real))
+            ent = real + ([PAD] if pads else [])
+            fixed = [a for a in ent if not ((a == PAD and pad_flex) or (a != PAD and (a // R) < nlev))]
+            flex = [a for a in ent if a not in fixed or (a == PAD and pad_flex)]
+            flex = [a for a in ent if ((a == PAD and pad_flex) or (a != PAD and (a // R) < nlev))]
+            load = [0] * 16
+            owner = [-1] * 16
+            for a in fixed:
+                bb = 0 if a == PAD else (a & 15)
+                load[bb] += 1
+                owner[bb] = -2
+            choice = {}
+            unmatched = []
+            fl = list(range(len(flex)))
+            own = {}
+
+            def bank(i, r):
+                a = flex[i]
+                return ((0 if a == PAD else a) + shifts[r]) & 15
+
+            def aug(i, seen):
+                for r in range(len(shifts)):
+                    bb = bank(i, r)
+                    if bb in seen:
+                        continue
+                    seen.add(bb)
+                    if owner[bb] == -2:
+                        continue
+                    if owner[bb] == -1 or aug(owner[bb], seen):
+                        owner[bb] = i
+                        return True
+                return False
+
+            for i in fl:
+                if not aug(i, set()):
+                    unmatched.append(i)
+            for bb in range(16):
+                if owner[bb] >= 0:
+                    load[bb] += 1
+            for i in unmatched:
+                r = min(range(len(shifts)), key=lambda r: load[bank(i, r)])
+                load[bank(i, r)] += 1
+            sets += 1
+            tot += max(load) if ent else 0
+    return tot / sets
+
+
+if __name__ == "__main__" and len(sys.argv) > 2 and sys.argv[2] == "device":
+    R = 1024
+    ch = adjoint_chunks(colptr, rowval, counts, R, 1, L)
+    for pf in (False, True):
+        for dd in (False, True):
+            print("adj device-like: pad_flex", pf, "dedupe", dd, device_like(ch, R, 2, (0, 5, 10, 15), pf, dd))
