@@ -20,6 +20,7 @@
 // inside the 1e-6 bar on sigma).
 #include "svb_internal.h"
 #include "layout.cuh"
+#include "assign.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -278,14 +279,6 @@ __device__ __forceinline__ int64_t rr_slot(int64_t g0, int64_t g1, int p) {
 // kernels are unchanged apart from a larger table. Host simulation on the C3 matrix (tools/studies/bank_sim.py): forward,
 // 4 replicas of xs (64 KB): 1.91 -> 1.10 passes per set; adjoint, 4 replicas of levels 1-2 only (176 KB table): 1.55 -> 1.10.
 // The pads of a set share one address and count as ONE entry. Exception chunks are left untouched.
-struct AssignGeom {
-    int adjoint;   // 0: forward stream (codes are byte offsets of xs entries); 1: adjoint stream (canonical (level-1)*R + i)
-    int nrep;      // replicas of the replicated region
-    int step;      // entries between two replicas (= 5 mod 16)
-    int padcanon;  // canonical pad: gene n (forward) / R*L (adjoint)
-    int log2R, nlr, baseB, pad;  // adjoint: cells per tile, replicated levels, first single-copy entry, physical pad entry
-};
-
 __global__ void __launch_bounds__(256) fact_assign_kernel(uint16_t *__restrict__ code, const uint8_t *__restrict__ meta,
                                                           int64_t nchunks, AssignGeom G, unsigned long long *__restrict__ stats) {
     const int64_t nsets = ((nchunks + 15) >> 4) << 3;
@@ -293,113 +286,24 @@ __global__ void __launch_bounds__(256) fact_assign_kernel(uint16_t *__restrict__
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nsets; s += (int64_t)gridDim.x * blockDim.x) {
         const int64_t blk = s >> 3;
         const int e = (int)(s & 7);
-        int base[16], nc[16], choice[16], owner[16], load[16];
-        unsigned present = 0, dup = 0;
-        int padrep = -1;
+        int v[16];
+        unsigned present = 0;
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
-            owner[c] = -1;
-            load[c] = 0;
-            choice[c] = 0;
-            base[c] = 0;
-            nc[c] = 1;
+            v[c] = 0;
             const int64_t ch = (blk << 4) + c;
             if (ch >= nchunks) continue;
             const unsigned mb = meta[ch];
             if (G.adjoint ? (mb & 2u) != 0u : (mb >> 1) == (unsigned)FEXC) continue;  // exception chunk: another format
-            const int v = code[ch * FCH + e];
+            v[c] = code[ch * FCH + e];
             present |= 1u << c;
-            if (!G.adjoint) {
-                const int idx = v >> 3;
-                base[c] = idx;
-                nc[c] = G.nrep;
-                if (idx == G.padcanon) {
-                    if (padrep < 0) padrep = c; else dup |= 1u << c;
-                }
-            } else if (v == G.padcanon) {
-                base[c] = G.pad;
-                if (padrep < 0) padrep = c; else dup |= 1u << c;
-            } else {
-                const int l = v >> G.log2R, il = v & ((1 << G.log2R) - 1);
-                if (l < G.nlr) {
-                    base[c] = l * G.nrep * G.step + il;
-                    nc[c] = G.nrep;
-                } else {
-                    base[c] = G.baseB + ((l - G.nlr) << G.log2R) + il;
-                }
-            }
         }
-        const unsigned live = present & ~dup;
-        // single-copy entries first
+        if (!present) continue;
+        mypasses += (unsigned long long)assign_set(G, v, present);
+        mysets += 1;
+#pragma unroll
         for (int c = 0; c < 16; ++c)
-            if (((live >> c) & 1u) && nc[c] == 1) {
-                const int b = base[c] & 15;
-                load[b] += 1;
-                owner[b] = -2;
-            }
-        // matching of the replicated entries
-        unsigned unmatched = 0;
-        for (int c = 0; c < 16; ++c) {
-            if (!((live >> c) & 1u) || nc[c] == 1) continue;
-            int se[17], sr[17], pb[17];
-            unsigned seen = 0;
-            int sp = 0;
-            se[0] = c;
-            sr[0] = 0;
-            bool found = false;
-            while (sp >= 0) {
-                const int en = se[sp];
-                if (sr[sp] >= nc[en]) {
-                    --sp;
-                    continue;
-                }
-                const int r = sr[sp]++;
-                const int b = (base[en] + r * G.step) & 15;
-                if ((seen >> b) & 1u) continue;
-                seen |= 1u << b;
-                if (owner[b] == -2) continue;
-                pb[sp] = b;
-                if (owner[b] == -1) {
-                    for (int k = 0; k <= sp; ++k) {
-                        owner[pb[k]] = se[k];
-                        choice[se[k]] = sr[k] - 1;
-                    }
-                    found = true;
-                    break;
-                }
-                se[sp + 1] = owner[b];
-                sr[sp + 1] = 0;
-                ++sp;
-            }
-            if (!found) unmatched |= 1u << c;
-        }
-        for (int b = 0; b < 16; ++b)
-            if (owner[b] >= 0) load[b] += 1;
-        for (int c = 0; c < 16; ++c)
-            if ((unmatched >> c) & 1u) {
-                int best = 0, bl = 1 << 30;
-                for (int r = 0; r < nc[c]; ++r) {
-                    const int b = (base[c] + r * G.step) & 15;
-                    if (load[b] < bl) {
-                        bl = load[b];
-                        best = r;
-                    }
-                }
-                choice[c] = best;
-                load[(base[c] + best * G.step) & 15] += 1;
-            }
-        int passes = 0;
-        for (int b = 0; b < 16; ++b) passes = max(passes, load[b]);
-        if (present) {
-            mypasses += (unsigned long long)passes;
-            mysets += 1;
-        }
-        for (int c = 0; c < 16; ++c)
-            if ((present >> c) & 1u) {
-                const int src = ((dup >> c) & 1u) ? padrep : c;
-                const int phys = base[src] + choice[src] * G.step;
-                code[((blk << 4) + c) * FCH + e] = (uint16_t)(G.adjoint ? phys : (phys << 3));
-            }
+            if ((present >> c) & 1u) code[((blk << 4) + c) * FCH + e] = (uint16_t)v[c];
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -856,9 +760,9 @@ fwd_stream_kernel(const uint4 *__restrict__ code, const uint8_t *__restrict__ me
 #undef SVB_FWD_STEP
 }
 
-// physical layout of the adjoint tile table (see the replica assignment above); identity = {0, 1, 0, 0, R*L, R*L + 1}
+// physical layout of the adjoint tile table (see the replica assignment above); identity = {0, 1, 0, 0, 0, R*L, R*L + 1}
 struct AdjGeom {
-    int nlr, nrep, strideA, baseB, pad, wbase;
+    int nlr, nrep, strideA, levstride, baseB, pad, wbase;
 };
 
 // adjoint, stage 1: partial[t][g] = (1/sd_g) * sum over the chunks of segment (t,g) of sum_8 T[code], T[l*R+i] = t_i[l]*w_i;
@@ -903,7 +807,7 @@ adj_stream_kernel(const int64_t *__restrict__ gptr, const uint4 *__restrict__ co
             for (int l = 0; l < Lv; ++l) {
                 const double v = __ldg(tl + (l << log2R) + il) * wv;  // tlevA is zero beyond the last cell
                 if (l < G.nlr) {
-                    double *dst = T + l * G.nrep * G.strideA + il;
+                    double *dst = T + l * G.levstride + il;
                     for (int r = 0; r < G.nrep; ++r) dst[r * G.strideA] = v;
                 } else {
                     T[G.baseB + ((l - G.nlr) << log2R) + il] = v;
@@ -914,69 +818,94 @@ adj_stream_kernel(const int64_t *__restrict__ gptr, const uint4 *__restrict__ co
         // this warp's slice (loads issued before the barrier so that they overlap the table fill)
         const int g0 = __ldg(slices + t * (K + 1) + wid), g1 = __ldg(slices + t * (K + 1) + wid + 1);
         const int64_t cbeg = __ldg(gptr + t * n + g0), cend = __ldg(gptr + t * n + g1);
-        int64_t c = (cbeg & ~(int64_t)31) + lane;  // lane = chunk index mod 32 (bank-aware order, see the builder)
-        uint4 q[FPD];
-        unsigned mb[FPD];
-#pragma unroll
-        for (int s = 0; s < FPD; ++s) {
-            const int64_t cc = c + 32 * s;
-            const bool ok = cc >= cbeg && cc < cend;
-            q[s] = ok ? ld_stream16(code + cc) : padq;
-            mb[s] = ok ? (unsigned)__ldg(meta + cc) : 0u;
+        // lane = chunk index mod 32 (bank-aware order, see the builder); 32-bit indices relative to the aligned start of the
+        // slice and the FPD = 3 pipeline stages unrolled by hand — the first version rotated the stages through registers
+        // (q[s] = q[s+1]) and did 64-bit index arithmetic: ncu counted 24 moves and ~12 carry instructions in the 112 of an
+        // iteration (profiles/r04_spmv.md)
+        const int64_t cbase = cbeg & ~(int64_t)31;
+        const int lo = (int)(cbeg - cbase), hi = (int)(cend - cbase);
+        const uint4 *pc = code + cbase + lane;
+        const uint8_t *pm = meta + cbase + lane;
+        int rel = lane;
+        // stages in flight: 3 for the one-CTA-per-SM kernel (56 registers), 2 for the three-CTAs-per-SM one (40-register cap)
+        constexpr int NS = LAZY ? 3 : 2;
+        uint4 q0, q1, q2 = padq;
+        unsigned m0, m1, m2 = 0u;
+        {
+            const bool ok0 = rel >= lo && rel < hi, ok1 = rel + 32 < hi, ok2 = NS == 3 && rel + 64 < hi;
+            q0 = ok0 ? ld_stream16(pc) : padq;
+            m0 = ok0 ? (unsigned)__ldg(pm) : 0u;
+            q1 = ok1 ? ld_stream16(pc + 32) : padq;
+            m1 = ok1 ? (unsigned)__ldg(pm + 32) : 0u;
+            if (NS == 3) {
+                q2 = ok2 ? ld_stream16(pc + 64) : padq;
+                m2 = ok2 ? (unsigned)__ldg(pm + 64) : 0u;
+            }
+            pc += 32 * NS;
+            pm += 32 * NS;
         }
         const double wsum = fblock_sum(part, red);  // publishes T
         if (threadIdx.x == 0) partial[t * (n + 1) + n] = wsum;
         double *prow = partial + t * (n + 1);
         int gbase = g0;
         double acc = 0.0;  // LAZY: this lane's share of the open segment; else the carried sum of the open segment
-        for (; c - lane < cend; c += 32) {
-            const int64_t cp = c + 32 * FPD;
-            const bool okp = cp < cend;
-            const uint4 qp = okp ? ld_stream16(code + cp) : padq;
-            const unsigned mbp = okp ? (unsigned)__ldg(meta + cp) : 0u;
-            const unsigned bal = __ballot_sync(0xffffffffu, (mb[0] & 1u) != 0u);
-            const int g = gbase + __popc(bal & lt);
-            gbase += __popc(bal);
-            double v;
-            if (mb[0] & 2u) v = __hiloint2double((int)q[0].w, (int)q[0].z) * T[G.wbase + q[0].x];
-            else v = gather8(T, q[0]);
-            if (LAZY) {
-                const int nends = __popc(bal);  // segments that end in this iteration (warp-uniform)
-                if (nends == 0) {
-                    acc += v;  // the open segment continues: lane-private partial sums
-                } else {
-                    double r;
-                    if (nends == 1) {
-                        const int b1 = __ffs(bal) - 1;
-                        r = acc + ((lane <= b1) ? v : 0.0);
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-                    } else {
-                        double tot = acc;
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-                        bool head0;
-                        r = seg_scan(v + (lane == 0 ? tot : 0.0), bal, lane, head0);
-                    }
-                    if (mb[0] & 1u) prow[g] = r * __ldg(inv + g);
-                    acc = (lane > 31 - __clz(bal)) ? v : 0.0;
-                }
-            } else {
-                bool head0;
-                v = seg_scan(v, bal, lane, head0);
-                if (head0) v += acc;  // acc = the carried sum of the segment that started in an earlier iteration
-                if (mb[0] & 1u) prow[g] = v * __ldg(inv + g);
-                const double v31 = __shfl_sync(0xffffffffu, v, 31);
-                acc = (bal >> 31) ? 0.0 : v31;
+#define SVB_ADJ_STEP(QA, MA)                                                                                          \
+    {                                                                                                                 \
+        const unsigned mcur = (MA);                                                                                   \
+        const unsigned bal = __ballot_sync(0xffffffffu, (mcur & 1u) != 0u);                                           \
+        const int g = gbase + __popc(bal & lt);                                                                       \
+        gbase += __popc(bal);                                                                                         \
+        double v;                                                                                                     \
+        if (mcur & 2u) v = __hiloint2double((int)(QA).w, (int)(QA).z) * T[G.wbase + (QA).x];                          \
+        else v = gather8(T, (QA));                                                                                    \
+        if (rel + 32 * NS < hi) { /* refill this stage with the chunk of iteration + NS */                            \
+            (QA) = ld_stream16(pc);                                                                                   \
+            (MA) = (unsigned)__ldg(pm);                                                                               \
+        } else {                                                                                                      \
+            (QA) = padq;                                                                                              \
+            (MA) = 0u;                                                                                                \
+        }                                                                                                             \
+        pc += 32;                                                                                                     \
+        pm += 32;                                                                                                     \
+        if (LAZY) {                                                                                                   \
+            const int nends = __popc(bal); /* segments that end in this iteration (warp-uniform) */                   \
+            if (nends == 0) {                                                                                         \
+                acc += v; /* the open segment continues: lane-private partial sums */                                 \
+            } else {                                                                                                  \
+                double r;                                                                                             \
+                if (nends == 1) {                                                                                     \
+                    const int b1 = __ffs(bal) - 1;                                                                    \
+                    r = acc + ((lane <= b1) ? v : 0.0);                                                               \
+                    _Pragma("unroll") for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);       \
+                } else {                                                                                              \
+                    double tot = acc;                                                                                 \
+                    _Pragma("unroll") for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);   \
+                    bool head0;                                                                                       \
+                    r = seg_scan(v + (lane == 0 ? tot : 0.0), bal, lane, head0);                                      \
+                }                                                                                                     \
+                if (mcur & 1u) prow[g] = r * __ldg(inv + g);                                                          \
+                acc = (lane > 31 - __clz(bal)) ? v : 0.0;                                                             \
+            }                                                                                                         \
+        } else {                                                                                                      \
+            bool head0;                                                                                               \
+            v = seg_scan(v, bal, lane, head0);                                                                        \
+            if (head0) v += acc; /* acc = the carried sum of the segment that started in an earlier iteration */      \
+            if (mcur & 1u) prow[g] = v * __ldg(inv + g);                                                              \
+            const double v31 = __shfl_sync(0xffffffffu, v, 31);                                                       \
+            acc = (bal >> 31) ? 0.0 : v31;                                                                            \
+        }                                                                                                             \
+        rel += 32;                                                                                                    \
+    }
+        while (rel - lane < hi) {
+            SVB_ADJ_STEP(q0, m0)
+            if (rel - lane >= hi) break;
+            SVB_ADJ_STEP(q1, m1)
+            if (NS == 3) {
+                if (rel - lane >= hi) break;
+                SVB_ADJ_STEP(q2, m2)
             }
-#pragma unroll
-            for (int s = 0; s + 1 < FPD; ++s) {
-                q[s] = q[s + 1];
-                mb[s] = mb[s + 1];
-            }
-            q[FPD - 1] = qp;
-            mb[FPD - 1] = mbp;
         }
+#undef SVB_ADJ_STEP
     }
     // the last CTA to leave resets the counters for the next launch
     if (threadIdx.x == 0) {
@@ -1046,7 +975,7 @@ void fact_adj_stage1(svb_operator_s *op, const double *dx) {
     svb_factored_s *f = op->fact;
     const size_t smem = (32 + (size_t)f->a_tabsize) * sizeof(double);
     const int block = adj_block_of(f);
-    const AdjGeom G{f->a_nlr, f->a_nrep, f->a_strideA, f->a_baseB, f->a_pad, f->a_wbase};
+    const AdjGeom G{f->a_nlr, f->a_nrep, f->a_strideA, f->a_levstride, f->a_baseB, f->a_pad, f->a_wbase};
     auto k = (block == 1024) ? adj_stream_kernel<1024, 1, true> : adj_stream_kernel<512, 3, false>;
     if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (f->adj_grid == 0) f->adj_grid = (int)std::max<int64_t>(1, std::min<int64_t>(fresident_grid(k, smem, block), f->ntiles));
@@ -1165,29 +1094,31 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
         if (replicas && n <= 8190) f->f_nrep = (int)std::max<int64_t>(1, std::min<int64_t>(4, (8191 - n) / stride + 1));
         // adjoint: only the one-CTA-per-SM kernel (R*L = 16384) has the shared memory for it: levels 1..2 in 4 replicas
         const int RL = 1 << (log2R + log2L);
-        f->a_nlr = 0;
-        f->a_nrep = 1;
-        f->a_strideA = 0;
-        f->a_baseB = 0;
-        if (replicas && log2R + log2L >= 14 && log2R >= 4 && L >= 2) {
-            f->a_nlr = 2;
-            f->a_nrep = 4;
-            f->a_strideA = (int)f->R + 5;
-            f->a_baseB = (f->a_nlr * f->a_nrep * f->a_strideA + 15) & ~15;
-        }
-        f->a_pad = f->a_baseB + RL - (f->a_nlr << log2R);
-        f->a_wbase = f->a_pad + 1;
-        f->a_tabsize = f->a_wbase + (int)f->R;
-        if ((size_t)(32 + f->a_tabsize) * sizeof(double) > C.smem_optin || f->a_tabsize > 65535) {  // does not fit: single copies
-            f->a_nlr = 0;
-            f->a_nrep = 1;
-            f->a_baseB = 0;
-            f->a_pad = RL;
-            f->a_wbase = RL + 1;
-            f->a_tabsize = RL + 1 + (int)f->R;
-        }
+        // the largest replica configuration that fits the shared memory of an SM (simulated passes per set at C3, L = 16,
+        // R = 1024: {levels 1-2 x 4: 1.10, 1-2 x 3: 1.19, level 1 x 4: 1.19, 1-2 x 2: ~1.3}; no replicas: 1.55)
+        const int cand[6][2] = {{2, 4}, {2, 3}, {1, 4}, {2, 2}, {1, 3}, {1, 2}};
+        auto set_geom = [&](int nlr, int nrep) {
+            f->a_nlr = nlr;
+            f->a_nrep = nrep;
+            f->a_strideA = nrep > 1 ? (int)f->R + 5 : 0;                              // replica r of a level: 5r banks later
+            f->a_levstride = nrep > 1 ? (nrep * f->a_strideA + 15) & ~15 : 0;          // levels 16-aligned: replica 0 keeps bank = cell mod 16
+            f->a_baseB = nlr * f->a_levstride;
+            f->a_pad = f->a_baseB + RL - (nlr << log2R);
+            f->a_wbase = f->a_pad + 1;
+            f->a_tabsize = f->a_wbase + (int)f->R;
+            return (size_t)(32 + f->a_tabsize) * sizeof(double) <= C.smem_optin && f->a_tabsize <= 65535;
+        };
+        bool done = false;
+        if (replicas && log2R + log2L >= 14 && log2R >= 4)
+            for (int i = 0; i < 6 && !done; ++i)
+                if (cand[i][0] <= L) done = set_geom(cand[i][0], cand[i][1]);
+        if (!done) set_geom(0, 1);
     }
 
+    if (timing)
+        fprintf(stderr, "[svb counts build] L %d log2R %d tiles %lld | fwd replicas %d stride %d | adj nlr %d nrep %d strideA %d levstride %d baseB %d pad %d table %d entries (%zu B of %zu)\n",
+                L, log2R, (long long)f->ntiles, f->f_nrep, f->f_stride, f->a_nlr, f->a_nrep, f->a_strideA, f->a_levstride, f->a_baseB,
+                f->a_pad, f->a_tabsize, (size_t)(32 + f->a_tabsize) * sizeof(double), (size_t)C.smem_optin);
     tick("libsize upload + levels");
     // ---- per-cell level tables ---------------------------------------------------------------------
     SVB_CUDA(cudaMalloc((void **)&f->tlev, (size_t)std::max<int64_t>(m << log2L, 1) * sizeof(double)));
@@ -1297,7 +1228,7 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
         SVB_LAUNCH_CHECK();
         static const bool stats = getenv("SVB_FACT_STATS") != nullptr;
         if (f->a_nrep > 1 || stats) {
-            const AssignGeom G{1, f->a_nrep, f->a_strideA ? f->a_strideA : 5, 1 << (log2R + log2L), log2R, f->a_nlr, f->a_baseB, f->a_pad};
+            const AssignGeom G{1, f->a_nrep, f->a_strideA ? f->a_strideA : 5, 1 << (log2R + log2L), log2R, f->a_nlr, f->a_baseB, f->a_pad, f->a_levstride};
             f->a_passes = run_assign((uint16_t *)f->a_code, f->a_meta, f->a_chunks, G, st);
         }
         const int K = adj_block_of(f) / 32;
@@ -1345,7 +1276,7 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
         SVB_LAUNCH_CHECK();
         static const bool stats = getenv("SVB_FACT_STATS") != nullptr;
         if (f->f_cshift == 3 && (f->f_nrep > 1 || stats)) {
-            const AssignGeom G{0, f->f_nrep, f->f_stride, (int)n, 0, 0, 0, 0};
+            const AssignGeom G{0, f->f_nrep, f->f_stride, (int)n, 0, 0, 0, 0, 0};
             f->f_passes = run_assign((uint16_t *)f->f_code, f->f_meta, f->f_chunks, G, st);
         }
         SVB_CUDA(cudaStreamSynchronize(st));

@@ -166,7 +166,8 @@ struct svb_factored_s {
     // the 16 gathers of a half-warp fall in 16 different 8-byte banks (bipartite matching at build time, see factored.cu)
     int f_nrep = 1, f_stride = 0;    // forward: xs replica r starts at entry r*f_stride (f_stride = 5 mod 16); code = byte offset
     int a_nlr = 0, a_nrep = 1;       // adjoint: levels 1..a_nlr have a_nrep replicas, the others one copy
-    int a_strideA = 0, a_baseB = 0;  // entry of (l < a_nlr, r, i): (l*a_nrep + r)*a_strideA + i ; (l >= a_nlr, i): a_baseB + (l-a_nlr)*R + i
+    int a_strideA = 0, a_levstride = 0, a_baseB = 0;  // entry of (l < a_nlr, r, i): l*a_levstride + r*a_strideA + i (a_levstride = 0 mod 16,
+                                     // a_strideA = 5 mod 16: replica 0 keeps bank = cell mod 16); (l >= a_nlr, i): a_baseB + (l-a_nlr)*R + i
     int a_pad = 0, a_wbase = 0, a_tabsize = 0;  // pad entry (0.0), first of the R entries of w (exception chunks), table entries
     double f_passes = 0.0, a_passes = 0.0;      // average shared-memory passes per set of 16 gathers after the assignment (1 = no conflict)
     int fwd_grid = 0, adj_grid = 0;

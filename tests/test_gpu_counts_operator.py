@@ -178,12 +178,13 @@ def test_counts_operator_properties_at_scale(sv):
     np.testing.assert_array_equal(C.T @ w, Stw)
 
 
-@pytest.mark.parametrize("levels,log2r", [(16, 10), (8, 11), (32, 9), (4, 12)])
-def test_counts_operator_replica_tables(sv, orc, monkeypatch, levels, log2r):
+@pytest.mark.parametrize("levels,log2r,want", [(16, 10, (2, 4)), (8, 11, (2, 3)), (32, 9, (2, 4)), (4, 12, (2, 2))])
+def test_counts_operator_replica_tables(sv, orc, monkeypatch, levels, log2r, want):
     """Round 2: bank-shifted replicas of the gathered tables + build-time matching. SVB_FACT_LOG2R forces the one-CTA-per-SM
-    adjoint kernel (R*L = 16384 table entries, levels 1-2 in four replicas) that only the 1.3 M-cell configurations reach on
-    their own; the forward replicas (four copies of x/sd for <= 2,046 genes) are always on. Products must equal the oracle's,
-    and the assignment must leave fewer shared-memory passes per set than the unassigned order."""
+    adjoint kernel (R*L = 16384 table entries; levels 1-2 in as many replicas as the 227 KB of shared memory hold: `want` =
+    (replicated levels, replicas)) that only the 1.3 M-cell configurations reach on their own; the forward replicas (four copies
+    of x/sd for <= 2,046 genes) are always on. Products must equal the oracle's, and the assignment must leave (almost) no
+    shared-memory conflicts (1.5-1.9 passes per set without it)."""
     X = planted_counts(9000, 900, 8, seed=21, mean_nnz=170)
     hvf = sv.find_variable_features(X, 400)
     So = _explicit_oracle(sv, orc, X, hvf, 10.0)
@@ -191,8 +192,9 @@ def test_counts_operator_replica_tables(sv, orc, monkeypatch, levels, log2r):
     C = sv.scale_features_counts(X, scale_factor=1e4, scale_max=10.0, features=hvf, levels=levels)
     info = C.info()
     assert info["tile_cells"] == 1 << log2r and info["levels"] == levels
-    assert info["fwd_replicas"] == 4 and info["adj_replicas"] == 4 and info["adj_replicated_levels"] == 2
-    assert 1.0 <= info["fwd_passes_per_set"] < 1.35 and 1.0 <= info["adj_passes_per_set"] < 1.35
+    assert info["fwd_replicas"] == 4 and (info["adj_replicated_levels"], info["adj_replicas"]) == want
+    assert 1.0 <= info["fwd_passes_per_set"] < 1.2
+    assert 1.0 <= info["adj_passes_per_set"] < (1.25 if want[1] >= 3 else 1.45)
     _check_products(C, So, np.random.default_rng(5))
     init = np.random.default_rng(6).standard_normal(400)
     G = sv.irlba(C, 8, init=init, tol=1e-9)
