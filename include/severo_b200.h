@@ -12,8 +12,9 @@
  * The reference-side bindings (Julia `ccall` overlay, Python ctypes) are shown in INTEGRATION.md.
  *
  * Conventions
- *   - One process drives ONE GPU (svb_init(device)); N GPUs = N processes, each holding a
- *     contiguous range of cells, joined by svb_comm_init (NCCL over NVLink).
+ *   - svb_init(device): the calling process drives ONE GPU; N GPUs = N processes, each holding a
+ *     contiguous range of cells, joined by svb_comm_init (NCCL over NVLink). OR svb_init_devices:
+ *     one process and one calling thread drive N GPUs through worker threads inside the library.
  *   - Matrices follow Severo's orientation: rows = cells, columns = genes, CSC (column = gene),
  *     exactly the layout of `SparseMatrixCSC{T,Int64}` (src/Severo.jl:26-34). Index arrays may be
  *     Julia's 1-based Int64 (index_base = 1) or 0-based.
@@ -91,6 +92,31 @@ int svb_comm_init(int nranks, int rank, const unsigned char id[128]);
 int svb_comm_destroy(void);
 int svb_comm_info(int *nranks, int *rank);
 int svb_comm_allreduce_f64(double *host_buf, int64_t n); /* sum over ranks, in place (host buffer) */
+
+/* ---- multi-GPU: ONE process, ONE calling thread, N GPUs (csrc/multi.cu) ---------------------------------------------------- */
+/* The reference's boundary is one synchronous call from one host thread (src/irlba.jl:66-71); these entry points keep that
+ * shape on a whole node: svb_init_devices starts one worker thread per GPU inside the library (devices = NULL: 0..ndev-1;
+ * ndev <= 0: every visible GPU), joins them with ncclCommInitAll and maps their mailboxes through peer access. The
+ * *_devices calls then take the caller's WHOLE SparseMatrixCSC on the host, shard it by cells internally, solve on all the
+ * GPUs and fill the caller's s[nu], U[m x nu], V[n x nu] (column-major) — the Julia drop-in reaches 8 GPUs without a launcher.
+ * Independent of svb_init (the one-GPU context of the calling thread); both may be active. */
+int svb_init_devices(int ndev, const int *devices);
+int svb_devices_info(int *ndev, int *devices, int *peer_mailboxes);
+int svb_shutdown_devices(void);
+/* irlba(CenteredMatrix(A, mu), nu) for a host SparseMatrixCSC{Float64|Float32} A (m cells x n genes; rowval Int32 or Int64,
+ * index_base 1 for Julia), mu[n] or NULL: same buffers and return convention as svb_irlba. */
+int svb_irlba_csc_devices(int64_t m, int64_t n, const int64_t *colptr, const void *rowval, int rowval_type,
+                          const void *nzval, int vtype, int index_base, const double *mu, int64_t nu,
+                          int64_t m_b, int64_t maxit, double tol, double svtol, const double *init,
+                          double *s, double *U, double *V, int64_t *iter, int64_t *mprod);
+/* The fused PCA call over the RAW COUNTS of the HVG columns (svb_operator_create_counts on every device, moments over the
+ * cells of all devices): counts Int32 / Int64 CSC (m x n), libsize[m] = library sizes of the full matrix; mu_out[n]
+ * (optional) receives the stored centre mean/sd. */
+int svb_pca_counts_devices(int64_t m, int64_t n, const int64_t *colptr, const void *rowval, int rowval_type,
+                           const void *counts, int vtype, int index_base, const int64_t *libsize,
+                           double scale_factor, double scale_max, int64_t nu, int64_t m_b, int64_t maxit,
+                           double tol, double svtol, const double *init, double *mu_out, double *s,
+                           double *U, double *V, int64_t *iter, int64_t *mprod);
 
 /* ---- sparse matrices (CSC, cells x genes) ----------------------------------------------------- */
 /* Upload a SparseMatrixCSC. colptr: int64[ncol+1]. rowval: int32 or int64 (rowval_type), nzval:

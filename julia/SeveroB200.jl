@@ -431,4 +431,40 @@ shared_nearest_neighbours(X::NamedArray, k::Int64; kw...) = shared_nearest_neigh
 shared_nearest_neighbours(rng, em::LinearEmbedding, k::Int64; kw...) = shared_nearest_neighbours(rng, em.coordinates, k; kw...)
 shared_nearest_neighbours(em::LinearEmbedding, k::Int64; kw...) = shared_nearest_neighbours(Random.default_rng(), em, k; kw...)
 
+# ---- one process, one calling thread, N GPUs (csrc/multi.cu) -------------------------------------------------------------
+# The call shape of irlba.jl:66-71 on a whole node: `init_devices()` once, then the WHOLE SparseMatrixCSC goes down in one
+# `ccall`; the library shards it by cells over its worker threads (one per GPU) and fills U, s, V. No launcher, no MPI.
+init_devices(ndev::Integer=0) = check(ccall((:svb_init_devices, libsvb), Cint, (Cint, Ptr{Cint}), ndev, C_NULL))
+shutdown_devices() = check(ccall((:svb_shutdown_devices, libsvb), Cint, ()))
+
+function irlba_devices(A::SparseMatrixCSC{T,Int64}, nu::Integer; mu=nothing, tol::Real=1e-5, maxit::Integer=1000,
+                       init::AbstractVector=randn(size(A, 2))) where {T<:Union{Float32,Float64}}
+    m, n = size(A)
+    U = zeros(m, nu); s = zeros(nu); V = zeros(n, nu)
+    iter = Ref{Int64}(0); mprod = Ref{Int64}(0)
+    info = ccall((:svb_irlba_csc_devices, libsvb), Cint,
+        (Int64, Int64, Ptr{Int64}, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Int64, Int64, Int64, Float64, Float64,
+         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Int64}, Ref{Int64}),
+        m, n, A.colptr, A.rowval, SVB_I64, A.nzval, svbtype(T), 1, _mu_ptr(mu), nu, min(nu + 7, min(m, n)), maxit, tol, tol,
+        convert(Vector{Float64}, init), s, U, V, iter, mprod)
+    info == 0 || error("convergence failed")                                   # irlba.jl:73
+    SVD(U, s, V')                                                                # irlba.jl:75
+end
+irlba_devices(C::CenteredMatrix, nu::Integer; kw...) = irlba_devices(C.A isa NamedArray ? C.A.array : C.A, nu; mu=C.mu isa NamedArray ? C.mu.array : C.mu, kw...)
+
+# the fused PCA over the raw counts of the HVG columns on all GPUs: (SVD, stored centre mean/sd)
+function pca_counts_devices(counts_hvg::SparseMatrixCSC{T,Int64}, libsize::Vector{Int64}, npcs::Integer; scale_factor::Real=1e4,
+                            scale_max::Real=Inf, tol::Real=1e-5, maxit::Integer=1000, init::AbstractVector=randn(size(counts_hvg, 2))) where {T<:Union{Int32,Int64}}
+    m, n = size(counts_hvg)
+    U = zeros(m, npcs); s = zeros(npcs); V = zeros(n, npcs); mu = zeros(n)
+    iter = Ref{Int64}(0); mprod = Ref{Int64}(0)
+    info = ccall((:svb_pca_counts_devices, libsvb), Cint,
+        (Int64, Int64, Ptr{Int64}, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint, Cint, Ptr{Int64}, Float64, Float64, Int64, Int64, Int64, Float64,
+         Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Int64}, Ref{Int64}),
+        m, n, counts_hvg.colptr, counts_hvg.rowval, SVB_I64, counts_hvg.nzval, svbtype(T), 1, libsize, scale_factor, scale_max, npcs,
+        min(npcs + 7, min(m, n)), maxit, tol, tol, convert(Vector{Float64}, init), mu, s, U, V, iter, mprod)
+    info == 0 || error("convergence failed")
+    SVD(U, s, V'), mu
+end
+
 end # module

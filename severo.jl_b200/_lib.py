@@ -52,6 +52,14 @@ SIGNATURES = {
     "svb_comm_destroy": (c_int, []),
     "svb_comm_info": (c_int, [_pint, _pint]),
     "svb_comm_allreduce_f64": (c_int, [c_void_p, c_int64]),
+    "svb_init_devices": (c_int, [c_int, c_void_p]),
+    "svb_devices_info": (c_int, [_pint, c_void_p, _pint]),
+    "svb_shutdown_devices": (c_int, []),
+    "svb_irlba_csc_devices": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int64, c_int64,
+                                      c_int64, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p, _p64, _p64]),
+    "svb_pca_counts_devices": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_double, c_double,
+                                       c_int64, c_int64, c_int64, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, _p64, _p64]),
     "svb_csc_upload": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, _ph]),
     "svb_matrix_free": (c_int, [_h]),
     "svb_matrix_info": (c_int, [_h, _p64, _p64, _p64, _pint]),

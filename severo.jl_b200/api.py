@@ -33,6 +33,7 @@ __all__ = [
     "standardized_var_clipped", "find_variable_features", "scale_features", "CenteredMatrix", "CountsCenteredMatrix",
     "scale_features_counts", "irlba", "mul_sparse_vector", "mul_sparse_dense", "gram", "tssvd", "ann", "nearest_neighbours", "jaccard_index", "shared_nearest_neighbours",
     "SVD", "svd_flip", "pca", "embedding", "LinearEmbedding", "synthetic_counts",
+    "init_devices", "shutdown_devices", "devices_info", "irlba_devices", "pca_counts_devices",
 ]
 
 _DT = {np.dtype(np.float32): L.SVB_F32, np.dtype(np.float64): L.SVB_F64,
@@ -815,6 +816,108 @@ def mul_sparse_dense(C, A, B, alpha=1.0, beta=0.0):
     if tb:
         dB.free()
     return C
+
+
+# ------------------------------------------------------------------------------------------------
+# one process, one calling thread, N GPUs (csrc/multi.cu): the call shape of src/irlba.jl:66-71 on a whole node
+# ------------------------------------------------------------------------------------------------
+def init_devices(ndev=0, devices=None):
+    """svb_init_devices: one worker thread per GPU inside the library (ndev <= 0: every visible GPU)."""
+    d = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+    L.check(L.load().svb_init_devices(int(ndev if devices is None else len(d)), L.ptr(d)))
+
+
+def shutdown_devices():
+    L.check(L.load().svb_shutdown_devices())
+
+
+def devices_info():
+    n, pm = ctypes.c_int(), ctypes.c_int()
+    dev = np.zeros(16, dtype=np.int32)
+    L.check(L.load().svb_devices_info(ctypes.byref(n), L.ptr(dev), ctypes.byref(pm)))
+    return dict(ndev=n.value, devices=dev[:n.value].tolist(), peer_mailboxes=bool(pm.value))
+
+
+def _host_csc(A, want_float):
+    A = sp.csc_matrix(A)
+    if not A.has_sorted_indices:
+        A = A.copy()
+        A.sort_indices()
+    if want_float and A.dtype not in (np.float32, np.float64):
+        A = A.astype(np.float64)
+    if not want_float and A.dtype not in (np.int32, np.int64):
+        raise TypeError("integer counts required")
+    return A
+
+
+def irlba_devices(A, nu, mu=None, init=None, tol=1e-5, svtol=None, maxit=1000, rng=None, work=None):
+    """``irlba(CenteredMatrix(A, mu), nu)`` (irlba.jl:47-85) on the device group of ``init_devices``: the WHOLE host matrix
+    goes in one call from one thread; the library shards it by cells over its GPUs. ``A``: scipy sparse, cells x genes."""
+    A = _host_csc(A, True)
+    m, n = A.shape
+    nu = int(nu)
+    m_b = nu + 7 if work is None else int(work)
+    if svtol is None:
+        svtol = tol
+    if init is None:
+        rng = np.random.default_rng() if rng is None else rng
+        init = rng.standard_normal(n)
+    init = np.ascontiguousarray(init, dtype=np.float64)
+    muv = None if mu is None else np.ascontiguousarray(mu, dtype=np.float64)
+    colptr = np.ascontiguousarray(A.indptr, dtype=np.int64)
+    rowval = np.ascontiguousarray(A.indices)
+    rt = L.SVB_I64 if rowval.dtype == np.int64 else L.SVB_I32
+    if rowval.dtype not in (np.int32, np.int64):
+        rowval, rt = rowval.astype(np.int64), L.SVB_I64
+    nz = np.ascontiguousarray(A.data)
+    U = np.zeros((m, nu), order="F")
+    s = np.zeros(nu)
+    V = np.zeros((n, nu), order="F")
+    it, mp = ctypes.c_int64(), ctypes.c_int64()
+    rc = L.load().svb_irlba_csc_devices(m, n, L.ptr(colptr), L.ptr(rowval), rt, L.ptr(nz), _DT[nz.dtype], 0, L.ptr(muv), nu, m_b,
+                                        int(maxit), float(tol), float(svtol), L.ptr(init), L.ptr(s), L.ptr(U), L.ptr(V),
+                                        ctypes.byref(it), ctypes.byref(mp))
+    if rc in (L.SVB_ENOCONV, L.SVB_ENULLSPACE):
+        raise RuntimeError("convergence failed")  # irlba.jl:73
+    L.check(rc)
+    return SVD(U, s, V.T, it.value, mp.value)
+
+
+def pca_counts_devices(counts_hvg, libsize, nu, scale_factor=1e4, scale_max=np.inf, init=None, tol=1e-5, svtol=None, maxit=1000,
+                       rng=None, work=None):
+    """The fused PCA call on the device group: raw counts of the HVG columns (host scipy sparse, cells x HVGs) + the library
+    sizes of the full matrix -> (SVD, stored centre mu). The scaled matrix is never materialised on any GPU."""
+    A = _host_csc(counts_hvg, False)
+    m, n = A.shape
+    nu = int(nu)
+    m_b = nu + 7 if work is None else int(work)
+    if svtol is None:
+        svtol = tol
+    if init is None:
+        rng = np.random.default_rng() if rng is None else rng
+        init = rng.standard_normal(n)
+    init = np.ascontiguousarray(init, dtype=np.float64)
+    lib = np.ascontiguousarray(libsize, dtype=np.int64)
+    if lib.shape[0] != m:
+        raise ValueError("libsize must have one entry per cell")
+    colptr = np.ascontiguousarray(A.indptr, dtype=np.int64)
+    rowval = np.ascontiguousarray(A.indices)
+    if rowval.dtype not in (np.int32, np.int64):
+        rowval = rowval.astype(np.int64)
+    rt = L.SVB_I64 if rowval.dtype == np.int64 else L.SVB_I32
+    nz = np.ascontiguousarray(A.data)
+    U = np.zeros((m, nu), order="F")
+    s = np.zeros(nu)
+    V = np.zeros((n, nu), order="F")
+    mu = np.zeros(n)
+    it, mp = ctypes.c_int64(), ctypes.c_int64()
+    rc = L.load().svb_pca_counts_devices(m, n, L.ptr(colptr), L.ptr(rowval), rt, L.ptr(nz), _DT[nz.dtype], 0, L.ptr(lib),
+                                         float(scale_factor), float(scale_max), nu, m_b, int(maxit), float(tol), float(svtol),
+                                         L.ptr(init), L.ptr(mu), L.ptr(s), L.ptr(U), L.ptr(V), ctypes.byref(it), ctypes.byref(mp))
+    if rc in (L.SVB_ENOCONV, L.SVB_ENULLSPACE):
+        raise RuntimeError("convergence failed")
+    L.check(rc)
+    return SVD(U, s, V.T, it.value, mp.value), mu
 
 
 def gram(A):

@@ -16,6 +16,7 @@ struct NcclApi {
     void *handle = nullptr;
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -37,6 +38,7 @@ static NcclApi &nccl() {
     };
     api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
     api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+    api.CommInitAll = (decltype(api.CommInitAll))sym("ncclCommInitAll");
     api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
     api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
     api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
@@ -56,6 +58,20 @@ void comm_allreduce_dev(double *dbuf, int64_t n) {
     if (p2p_allreduce(dbuf, n)) return;  // small message: one-shot kernel over NVLink peer memory
     KTimer kt(SVB_K_COMM, 8.0 * n, 1);
     SVB_NCCL(nccl().AllReduce(dbuf, dbuf, (size_t)n, ncclFloat64, ncclSum, (ncclComm_t)C.nccl_comm, C.stream));
+}
+
+// one process, N GPUs (multi.cu): the communicators of all devices in one call, no unique id to pass around
+void comm_init_all(int ndev, const int *devs, void **comms_out) {
+    std::vector<ncclComm_t> comms((size_t)ndev);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    SVB_NCCL(nccl().CommInitAll(comms.data(), ndev, devs));
+    cudaSetDevice(cur);
+    for (int i = 0; i < ndev; ++i) comms_out[i] = comms[(size_t)i];
+}
+
+void comm_destroy_one(void *comm) {
+    if (comm) nccl().CommDestroy((ncclComm_t)comm);
 }
 
 }  // namespace svb

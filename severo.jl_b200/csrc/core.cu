@@ -11,10 +11,12 @@ namespace svb {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string &msg) { g_last_error = msg; }
 
+static thread_local Context *tl_ctx = nullptr;
 Context &ctx() {
-    static Context c;
-    return c;
+    static Context primary;
+    return tl_ctx ? *tl_ctx : primary;
 }
+void set_thread_context(Context *c) { tl_ctx = c; }
 
 void require_init() {
     if (!ctx().initialised)
@@ -38,9 +40,10 @@ struct BlockCache {
     size_t cached_bytes = 0;
     bool use_pool = getenv("SVB_ALLOC") != nullptr && std::string(getenv("SVB_ALLOC")) == "pool";
 };
-BlockCache &cache() {
-    static BlockCache c;
-    return c;
+BlockCache &cache() {  // one cache per context: blocks belong to that context's device and stream
+    Context &C = ctx();
+    if (!C.alloc_cache) C.alloc_cache = new BlockCache();
+    return *static_cast<BlockCache *>(C.alloc_cache);
 }
 size_t size_class(size_t bytes) {
     if (bytes <= 512) return 512;

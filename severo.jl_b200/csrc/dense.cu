@@ -17,7 +17,12 @@ struct Scratch {
     unsigned int *counters = nullptr;
     size_t ncounters = 0;
 };
-static Scratch g_scr;
+static Scratch &scr_of_ctx() {
+    Context &C = ctx();
+    if (!C.dense_scratch) C.dense_scratch = new Scratch();
+    return *static_cast<Scratch *>(C.dense_scratch);
+}
+#define g_scr (scr_of_ctx())
 
 static void scratch_reserve(size_t ndoubles, size_t ncounters) {
     cudaStream_t st = ctx().stream;

@@ -770,14 +770,15 @@ struct AdjGeom {
 // tile has its own partial row); inside a tile warp k streams the k-th slice of the tile's chunks.
 // LAZY: lane-private partial sums, cross-lane reduction only in iterations where a segment ends (pays when the segments
 // are longer than a warp iteration: the 1024-cell tiles); otherwise a segmented scan every iteration + a carry register.
-template <int BLOCK, int MINB, bool LAZY>
+template <int BLOCK, int MINB, bool LAZY, int NS>
 __global__ void __launch_bounds__(BLOCK, MINB)
 adj_stream_kernel(const int64_t *__restrict__ gptr, const uint4 *__restrict__ code, const uint8_t *__restrict__ meta,
                   const double *__restrict__ tlevA, int log2L, int log2R, int64_t m, int64_t n, int64_t ntiles,
                   const double *__restrict__ w, const double *__restrict__ inv, double *__restrict__ partial,
                   const int32_t *__restrict__ slices, unsigned int *__restrict__ counters, AdjGeom G) {
     extern __shared__ double smem[];
-    __shared__ long long cur_tile;
+    __shared__ long long cur_tile, nxt_tile;  // tiles are taken from the counter ONE AHEAD: the next tile's level table is
+                                              // prefetched into L2 while this one is streamed (the fill then hits L2)
     double *red = smem;     // 32
     double *T = smem + 32;  // level table (levels 1..nlr in nrep bank-shifted replicas), T[pad] = 0, then R entries of w (exceptions)
     const int64_t R = (int64_t)1 << log2R;
@@ -787,12 +788,21 @@ adj_stream_kernel(const int64_t *__restrict__ gptr, const uint4 *__restrict__ co
     const unsigned lt = (1u << lane) - 1u;
     const unsigned padc = (unsigned)G.pad * 0x10001u;
     const uint4 padq = make_uint4(padc, padc, padc, padc);
+    bool first = true;
     for (;;) {
         __syncthreads();  // everybody is done with the previous tile's table (and has read cur_tile)
-        if (threadIdx.x == 0) cur_tile = (long long)atomicAdd(&counters[0], 1u);
+        if (threadIdx.x == 0) {
+            cur_tile = first ? (long long)atomicAdd(&counters[0], 1u) : nxt_tile;
+            nxt_tile = (long long)atomicAdd(&counters[0], 1u);
+        }
+        first = false;
         __syncthreads();
         const int64_t t = cur_tile;
         if (t >= ntiles) break;
+        if (nxt_tile < ntiles) {
+            const char *nx = reinterpret_cast<const char *>(tlevA + (nxt_tile << (log2R + log2L)));
+            for (int k = threadIdx.x * 128; k < RL * 8; k += BLOCK * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + k));
+        }
         const int64_t row0 = t << log2R;
         const double *tl = tlevA + (row0 << log2L);  // this tile's level-major block
         // table fill: a thread owns a cell — w_i once, then its L table entries (all loads independent, coalesced per level)
@@ -827,19 +837,22 @@ adj_stream_kernel(const int64_t *__restrict__ gptr, const uint4 *__restrict__ co
         const uint4 *pc = code + cbase + lane;
         const uint8_t *pm = meta + cbase + lane;
         int rel = lane;
-        // stages in flight: 3 for the one-CTA-per-SM kernel (56 registers), 2 for the three-CTAs-per-SM one (40-register cap)
-        constexpr int NS = LAZY ? 3 : 2;
-        uint4 q0, q1, q2 = padq;
-        unsigned m0, m1, m2 = 0u;
+        // NS stages in flight: 3 or 4 for the one-CTA-per-SM kernel (64-register budget), 2 for the three-CTAs-per-SM one (40)
+        uint4 q0, q1, q2 = padq, q3 = padq;
+        unsigned m0, m1, m2 = 0u, m3 = 0u;
         {
-            const bool ok0 = rel >= lo && rel < hi, ok1 = rel + 32 < hi, ok2 = NS == 3 && rel + 64 < hi;
+            const bool ok0 = rel >= lo && rel < hi, ok1 = rel + 32 < hi, ok2 = NS >= 3 && rel + 64 < hi, ok3 = NS >= 4 && rel + 96 < hi;
             q0 = ok0 ? ld_stream16(pc) : padq;
             m0 = ok0 ? (unsigned)__ldg(pm) : 0u;
             q1 = ok1 ? ld_stream16(pc + 32) : padq;
             m1 = ok1 ? (unsigned)__ldg(pm + 32) : 0u;
-            if (NS == 3) {
+            if (NS >= 3) {
                 q2 = ok2 ? ld_stream16(pc + 64) : padq;
                 m2 = ok2 ? (unsigned)__ldg(pm + 64) : 0u;
+            }
+            if (NS >= 4) {
+                q3 = ok3 ? ld_stream16(pc + 96) : padq;
+                m3 = ok3 ? (unsigned)__ldg(pm + 96) : 0u;
             }
             pc += 32 * NS;
             pm += 32 * NS;
@@ -900,9 +913,13 @@ adj_stream_kernel(const int64_t *__restrict__ gptr, const uint4 *__restrict__ co
             SVB_ADJ_STEP(q0, m0)
             if (rel - lane >= hi) break;
             SVB_ADJ_STEP(q1, m1)
-            if (NS == 3) {
+            if (NS >= 3) {
                 if (rel - lane >= hi) break;
                 SVB_ADJ_STEP(q2, m2)
+            }
+            if (NS >= 4) {
+                if (rel - lane >= hi) break;
+                SVB_ADJ_STEP(q3, m3)
             }
         }
 #undef SVB_ADJ_STEP
@@ -976,7 +993,9 @@ void fact_adj_stage1(svb_operator_s *op, const double *dx) {
     const size_t smem = (32 + (size_t)f->a_tabsize) * sizeof(double);
     const int block = adj_block_of(f);
     const AdjGeom G{f->a_nlr, f->a_nrep, f->a_strideA, f->a_levstride, f->a_baseB, f->a_pad, f->a_wbase};
-    auto k = (block == 1024) ? adj_stream_kernel<1024, 1, true> : adj_stream_kernel<512, 3, false>;
+    static const int stages = getenv("SVB_ADJ_STAGES") ? atoi(getenv("SVB_ADJ_STAGES")) : 3;
+    auto k = (block == 1024) ? (stages >= 4 ? adj_stream_kernel<1024, 1, true, 4> : adj_stream_kernel<1024, 1, true, 3>)
+                             : adj_stream_kernel<512, 3, false, 2>;
     if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (f->adj_grid == 0) f->adj_grid = (int)std::max<int64_t>(1, std::min<int64_t>(fresident_grid(k, smem, block), f->ntiles));
     k<<<(unsigned)f->adj_grid, block, smem, ctx().stream>>>(f->a_gptr, (const uint4 *)f->a_code, f->a_meta, f->tlevA, f->log2L, f->log2R,

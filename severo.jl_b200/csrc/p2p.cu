@@ -24,8 +24,14 @@ struct P2PState {
     Mailbox **peers_dev = nullptr;  // device array of the mapped peer mailboxes (own entry = local pointer)
     unsigned long long epoch = 0;
     unsigned int *counter = nullptr;  // last-block counter for fused producers
+    bool ipc = true;                  // peers mapped through CUDA IPC (one process per GPU); false: plain peer access (one process, N GPUs)
 };
-static P2PState g_p2p;
+static P2PState &p2p_of_ctx() {
+    Context &C = ctx();
+    if (!C.p2p_state) C.p2p_state = new P2PState();
+    return *static_cast<P2PState *>(C.p2p_state);
+}
+#define g_p2p (p2p_of_ctx())
 
 // buf[0..n) <- sum over ranks of buf (in place). One CTA.
 __global__ void __launch_bounds__(1024) p2p_allreduce_kernel(Mailbox *const *__restrict__ peers, Mailbox *__restrict__ mine,
@@ -103,6 +109,10 @@ void p2p_setup(int nranks, int rank) {
     if (env && atoi(env) == 0) return;
     if (nranks < 2 || nranks > P2P_MAX_RANKS) return;
     Context &C = ctx();
+    // recorded first: p2p_teardown() walks peers_host[0..nranks) and must see every handle opened below, also when the
+    // setup bails out half way (a failed cudaIpcOpenMemHandle, ranks that do not agree) — round-1 advice
+    g_p2p.nranks = nranks;
+    g_p2p.rank = rank;
     try {
         SVB_CUDA(cudaMalloc((void **)&g_p2p.mine, sizeof(Mailbox)));  // plain cudaMalloc: pool memory has no legacy IPC handle
         SVB_CUDA(cudaMemsetAsync(g_p2p.mine, 0, sizeof(Mailbox), C.stream));
@@ -148,26 +158,65 @@ void p2p_setup(int nranks, int rank) {
         SVB_CUDA(cudaMemcpyAsync(&agree, da, 8, cudaMemcpyDeviceToHost, C.stream));
         SVB_CUDA(cudaStreamSynchronize(C.stream));
         cudaFree(da);
-        if (agree != (double)nranks) return;  // stay on NCCL
+        if (agree != (double)nranks) {  // stay on NCCL; close what was opened
+            p2p_teardown();
+            return;
+        }
         SVB_CUDA(cudaMalloc((void **)&g_p2p.peers_dev, sizeof(Mailbox *) * P2P_MAX_RANKS));
         SVB_CUDA(cudaMemcpyAsync(g_p2p.peers_dev, g_p2p.peers_host, sizeof(Mailbox *) * P2P_MAX_RANKS, cudaMemcpyHostToDevice, C.stream));
         SVB_CUDA(cudaStreamSynchronize(C.stream));
         SVB_CUDA(cudaMalloc((void **)&g_p2p.counter, 64));
         SVB_CUDA(cudaMemsetAsync(g_p2p.counter, 0, 64, C.stream));
         SVB_CUDA(cudaStreamSynchronize(C.stream));
-        g_p2p.nranks = nranks;
-        g_p2p.rank = rank;
         g_p2p.ready = true;
     } catch (const Error &) {
-        g_p2p.ready = false;  // stay on NCCL
+        p2p_teardown();  // stay on NCCL; nothing stays mapped
+    }
+}
+
+// ---- one process, N GPUs (multi.cu): the workers live in one address space, so a peer's mailbox is reached through plain
+// peer access (cudaDeviceEnablePeerAccess) — no IPC handles, no exchange through NCCL. Phase 1, every worker: allocate.
+Mailbox *p2p_local_alloc() {
+    g_p2p = P2PState();
+    const char *env = getenv("SVB_P2P");
+    if (env && atoi(env) == 0) return nullptr;
+    Context &C = ctx();
+    if (cudaMalloc((void **)&g_p2p.mine, sizeof(Mailbox)) != cudaSuccess) {
+        cudaGetLastError();
+        g_p2p.mine = nullptr;
+        return nullptr;
+    }
+    cudaMemsetAsync(g_p2p.mine, 0, sizeof(Mailbox), C.stream);
+    cudaStreamSynchronize(C.stream);
+    return g_p2p.mine;
+}
+
+// Phase 2 (after every worker finished phase 1 and enabled peer access): the table of all mailboxes.
+void p2p_local_connect(int nranks, int rank, Mailbox *const *all) {
+    if (g_p2p.mine == nullptr) return;
+    Context &C = ctx();
+    g_p2p.ipc = false;
+    g_p2p.nranks = nranks;
+    g_p2p.rank = rank;
+    for (int q = 0; q < nranks; ++q) g_p2p.peers_host[q] = all[q];
+    try {
+        SVB_CUDA(cudaMalloc((void **)&g_p2p.peers_dev, sizeof(Mailbox *) * P2P_MAX_RANKS));
+        SVB_CUDA(cudaMemcpyAsync(g_p2p.peers_dev, g_p2p.peers_host, sizeof(Mailbox *) * P2P_MAX_RANKS, cudaMemcpyHostToDevice, C.stream));
+        SVB_CUDA(cudaMalloc((void **)&g_p2p.counter, 64));
+        SVB_CUDA(cudaMemsetAsync(g_p2p.counter, 0, 64, C.stream));
+        SVB_CUDA(cudaStreamSynchronize(C.stream));
+        g_p2p.ready = true;
+    } catch (const Error &) {
+        p2p_teardown();
     }
 }
 
 void p2p_teardown() {
     if (g_p2p.mine == nullptr) return;
     cudaDeviceSynchronize();
-    for (int q = 0; q < g_p2p.nranks; ++q)
-        if (q != g_p2p.rank && g_p2p.peers_host[q]) cudaIpcCloseMemHandle(g_p2p.peers_host[q]);
+    if (g_p2p.ipc)
+        for (int q = 0; q < g_p2p.nranks; ++q)
+            if (q != g_p2p.rank && g_p2p.peers_host[q]) cudaIpcCloseMemHandle(g_p2p.peers_host[q]);
     if (g_p2p.peers_dev) cudaFree(g_p2p.peers_dev);
     if (g_p2p.counter) cudaFree(g_p2p.counter);
     cudaFree(g_p2p.mine);

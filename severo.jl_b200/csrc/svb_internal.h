@@ -85,8 +85,16 @@ struct Context {
     int nranks = 1;
     int rank = 0;
     void *nccl_comm = nullptr;
+    // per-context state owned by other translation units (opaque here): the block cache of the device allocator (core.cu),
+    // the reduction scratch of the tall-skinny kernels (dense.cu), the peer-mailbox state (p2p.cu)
+    void *alloc_cache = nullptr;
+    void *dense_scratch = nullptr;
+    void *p2p_state = nullptr;
 };
+// The context of the calling thread: the process-wide one (svb_init: one process drives one GPU), or — inside the worker
+// threads of the in-process device group (multi.cu: svb_init_devices, one thread per GPU) — that worker's own.
 Context &ctx();
+void set_thread_context(Context *c);  // nullptr = back to the process-wide context
 void require_init();
 
 // RAII device buffer
@@ -259,6 +267,9 @@ void p2p_setup(int nranks, int rank);
 void p2p_teardown();
 bool p2p_ready();
 bool p2p_allreduce(double *dbuf, int64_t n);  // false => not handled (use NCCL)
+struct Mailbox;
+Mailbox *p2p_local_alloc();                                              // in-process device group: phase 1 (per worker)
+void p2p_local_connect(int nranks, int rank, Mailbox *const *all);       // phase 2 (per worker, after a host barrier)
 int p2p_error();
 // ---- bsvd.cu : device-side SVD of B + convergence test + restart bookkeeping (single CTA)
 struct BsvdStatus {
