@@ -302,20 +302,34 @@ def _call_trend(fn, mu, sd):
     return fn(mu, sd) if nargs >= 2 else fn(mu)
 
 
-def variance_stabilizing_transformation(A, loess_span=0.5, expected_std_fn=None):
+def variance_stabilizing_transformation(A, loess_span=0.5, expected_std_fn=None, dtype=np.float64):
     """variablefeatures.jl:34-50. The two data sweeps run on the device; the loess fit between them
     is host code (Loess.jl in the reference: third-party and un-pinned). A deterministic
-    parametric ``expected_std_fn(mu)`` may replace the loess for the large synthetic configurations."""
-    mu, sd = mean_std(A)
-    mu = np.asarray(mu, dtype=np.float64)
-    sd = np.asarray(sd, dtype=np.float64)
+    ``expected_std_fn(mu[, sd])`` may replace the loess for the large synthetic configurations.
+    ``dtype`` (variablefeatures.jl:34,37): Float64 (default) or Float32 — the per-gene moments ``mean_std(dtype, A)`` are then
+    the reference's Float32 Welford (device kernel on the Float32 copy of the counts, exact for counts < 2^24) and the
+    trend is fitted in Float32; the clipped variance is accumulated in Float64 as in the reference (``zeros(size(A,2))``),
+    evaluated from the Float32 moments (the reference rounds each ``(x-mu)/std`` to Float32 first: <= 1e-7 relative apart)."""
+    dtype = np.dtype(dtype)
+    if dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+        raise TypeError("dtype must be Float32 or Float64")
+    if dtype == np.float32:
+        P, _, _ = _unwrap(A)
+        if isinstance(P, DeviceMatrix):
+            P = P.to_host()
+        mu, sd = mean_std(sp.csc_matrix(P).astype(np.float32))
+        mu, sd = np.asarray(mu, dtype=np.float32), np.asarray(sd, dtype=np.float32)
+    else:
+        mu, sd = mean_std(A)
+        mu = np.asarray(mu, dtype=np.float64)
+        sd = np.asarray(sd, dtype=np.float64)
     non_const = sd > 0
     expected = sd.copy()
     if expected_std_fn is not None:
         expected[non_const] = _call_trend(expected_std_fn, mu[non_const], sd[non_const])
     else:
         xs, ys = np.log10(mu[non_const]), np.log10(sd[non_const])
-        expected[non_const] = 10.0 ** loess_fit_predict(xs, ys, span=float(loess_span))
+        expected[non_const] = (10.0 ** loess_fit_predict(xs, ys, span=float(dtype.type(loess_span)))).astype(dtype)
     expected = np.where(np.isnan(expected), 0.0, expected)  # nan2zero! variablefeatures.jl:30-32
     return standardized_var_clipped(A, mu, expected)
 
@@ -430,7 +444,7 @@ def _variable_feature_metric(A, method, kw):
 
 def find_variable_features(counts, nfeatures=2000, method="vst", **kw):
     """variablefeatures.jl:128-161: ``:vst`` (default), ``:dispersion``, ``:meanvarplot``, ``:saunders``; ``norm=`` passes a
-    precomputed normalised matrix to the last three (:136-141). Float64 only.
+    precomputed normalised matrix to the last three (:136-141); ``dtype=`` (Float32 | Float64, :128) goes to the :vst moments.
     Returns 0-based gene indices ordered by DEcreasing metric (partialsortperm(..., rev=true), :159)."""
     method = str(method)
     A, names, dimnames = _unwrap(counts)

@@ -33,7 +33,8 @@ __host__ __device__ constexpr int knn_tile_points(int D) { return (KNN_TILE_DOUB
 // P[i*D + c] = X[i + c*ldx] (* 1/|row| for cosine), zero for d <= c < D and for the padding rows n <= i < npad.
 // cn[i] = |row|^2 (Euclidean) or 0 (cosine); +inf for padding rows, so that their key is never below any threshold.
 __global__ void __launch_bounds__(256) knn_pack_kernel(const double *__restrict__ X, int64_t ldx, int64_t n, int64_t npad, int d, int D,
-                                                       int metric, double *__restrict__ P, double *__restrict__ cn) {
+                                                       int metric, double *__restrict__ P, double *__restrict__ cn,
+                                                       int *__restrict__ nonfinite) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npad) return;
     double *row = P + i * D;
@@ -47,6 +48,9 @@ __global__ void __launch_bounds__(256) knn_pack_kernel(const double *__restrict_
         const double v = X[i + (int64_t)c * ldx];
         ss = fma(v, v, ss);
     }
+    // a NaN / Inf coordinate makes every ranking key of the cell NaN: no candidate would ever enter its list (round-1 advice:
+    // the finalize kernel then read P[-1]). Reject the input instead: svb_knn returns SVB_EARG.
+    if (!isfinite(ss)) *nonfinite = 1;
     double scale = 1.0;
     if (metric == SVB_METRIC_COSINE) {
         const double nrm = sqrt(ss);
@@ -278,7 +282,7 @@ __global__ void __launch_bounds__(256) knn_finalize_kernel(const double *__restr
     if (t >= n * k) return;
     const int64_t i = t / k;
     const int r = (int)(t - i * k);
-    const int j = nbr[t];
+    const int j = max(nbr[t], 0);  // (slots are always filled for finite input with k <= n; never index P[-1])
     const double *a = P + i * D, *b = P + (int64_t)j * D;
     double dist;
     if (j == i) {
@@ -366,9 +370,17 @@ void knn_device(const double *Xd, int64_t ldx, int64_t n, int d, int k, int metr
     DevBuf<double> P((size_t)npad * D), cn((size_t)npad), dist((size_t)n * k);
     DevBuf<int> nbr((size_t)n * k);
     DevBuf<int32_t> oidx((size_t)n * k);
-    knn_pack_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, st>>>(Xd, ldx, n, npad, d, D, metric, P.p, cn.p);
+    DevBuf<int> nonfinite(1);
+    SVB_CUDA(cudaMemsetAsync(nonfinite.p, 0, sizeof(int), st));
+    knn_pack_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, st>>>(Xd, ldx, n, npad, d, D, metric, P.p, cn.p, nonfinite.p);
     count_launch();
     SVB_LAUNCH_CHECK();
+    {
+        int bad = 0;
+        SVB_CUDA(cudaMemcpyAsync(&bad, nonfinite.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SVB_CUDA(cudaStreamSynchronize(st));
+        SVB_CHECK(!bad, SVB_EARG, "svb_knn: the coordinates contain NaN or Inf");
+    }
     {
     KTimer kt(SVB_K_VECTOR, 8.0 * (double)npad * D * (double)((n + KNN_THREADS - 1) / KNN_THREADS), 0);  // tile bytes read by all CTAs (L2 mostly)
     if (use_mma) {

@@ -564,6 +564,25 @@ static svb_matrix_s *finish_subset(const svb_matrix_s *a, DevBuf<int64_t> &lens,
 // =================================================================================================
 extern "C" {
 
+// round-1 advice: a malformed matrix arriving through the public ABI must not reach the kernels that index with its rows
+// (atomicAdd(&nfeat[r]) in filter.cu, the binary searches of tile_bounds, ...). One cheap pass over colptr / rowidx after the
+// upload: pointers non-decreasing, rows inside [0, nrow) and strictly ascending inside a column (what SparseMatrixCSC guarantees).
+__global__ void csc_validate_kernel(const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx, int64_t nrow, int64_t ncol,
+                                    int64_t nnz, int *__restrict__ bad) {
+    const int64_t j = blockIdx.x;
+    if (j >= ncol) return;
+    const int64_t b = colptr[j], e = colptr[j + 1];
+    if (b > e || b < 0 || e > nnz) {
+        if (threadIdx.x == 0) atomicOr(bad, 1);
+        return;
+    }
+    for (int64_t k = b + threadIdx.x; k < e; k += blockDim.x) {
+        const int32_t r = rowidx[k];
+        if (r < 0 || (int64_t)r >= nrow) atomicOr(bad, 2);
+        else if (k > b && rowidx[k - 1] >= r) atomicOr(bad, 4);
+    }
+}
+
 int svb_csc_upload(int64_t nrow, int64_t ncol, const int64_t *colptr, const void *rowval, int rowval_type,
                    const void *nzval, int vtype, int index_base, svb_matrix_t *out) {
     SVB_API_BEGIN
@@ -598,10 +617,20 @@ int svb_csc_upload(int64_t nrow, int64_t ncol, const int64_t *colptr, const void
             else
                 SVB_CUDA(cudaMemcpyAsync(a->val, nzval, (size_t)nnz * vtype_size(vtype), cudaMemcpyHostToDevice, st));
         }
-        int over = 0;
+        DevBuf<int> d_bad(1);
+        SVB_CUDA(cudaMemsetAsync(d_bad.p, 0, sizeof(int), st));
+        if (ncol > 0) {
+            csc_validate_kernel<<<(unsigned)ncol, 128, 0, st>>>(a->colptr, a->rowidx, nrow, ncol, nnz, d_bad.p);
+            count_launch();
+        }
+        int over = 0, bad = 0;
         SVB_CUDA(cudaMemcpyAsync(&over, d_over.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SVB_CUDA(cudaMemcpyAsync(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         SVB_CUDA(cudaStreamSynchronize(st));
         SVB_CHECK(!over, SVB_EDIM, "svb_csc_upload: an index or count does not fit in int32");
+        SVB_CHECK(!(bad & 1), SVB_EDIM, "svb_csc_upload: malformed colptr (not non-decreasing / out of range)");
+        SVB_CHECK(!(bad & 2), SVB_EDIM, "svb_csc_upload: a row index lies outside [1, nrow]");
+        SVB_CHECK(!(bad & 4), SVB_EDIM, "svb_csc_upload: row indices must ascend strictly inside every column (SparseMatrixCSC)");
     } catch (...) {
         delete a;
         throw;

@@ -130,3 +130,30 @@ def test_remaining_abi_entry_points(sv):
     assert nl[0] == 1 and nl[1] == 2 and ms[0] > 0 and by[0] > 0 and lib.svb_launch_count() >= 3
     with pytest.raises(sv.SeveroB200Error):
         L.check(lib.svb_mul(C._operator(), b"N", 1.0, None, 0.0, None, 1))
+
+
+def test_malformed_csc_is_refused_at_upload(sv):
+    # round-1 advice: svb_csc_upload validates colptr / rowval (the kernels index with the rows directly)
+    import ctypes
+    L = sv._lib
+    def upload(nrow, ncol, colptr, rowval, base=0):
+        h = ctypes.c_void_p()
+        cp, rv = np.asarray(colptr, dtype=np.int64), np.asarray(rowval, dtype=np.int64)
+        nz = np.ones(max(len(rv), 1))
+        return sv.lib().svb_csc_upload(nrow, ncol, L.ptr(cp), L.ptr(rv), L.SVB_I64, L.ptr(nz), L.SVB_F64, base, ctypes.byref(h)), h
+    rc, h = upload(4, 3, [0, 2, 3, 4], [0, 3, 1, 2])
+    assert rc == 0
+    sv.lib().svb_matrix_free(h)
+    assert upload(4, 3, [0, 2, 3, 4], [0, 4, 1, 2])[0] == L.SVB_EDIM        # row index == nrow
+    assert upload(4, 3, [0, 2, 3, 4], [3, 0, 1, 2])[0] == L.SVB_EDIM        # rows descend inside a column
+    assert upload(4, 3, [0, 2, 2, 4], [0, 0, 1, 2])[0] == L.SVB_EDIM        # duplicate row inside a column
+    assert upload(4, 3, [0, 3, 2, 4], [0, 1, 2, 3])[0] == L.SVB_EDIM        # colptr decreases
+    assert upload(4, 3, [1, 3, 4, 5], [0, 3, 1, 2], base=1)[0] == L.SVB_EDIM  # 1-based arrays with a 0 row
+    assert b"svb_csc_upload" in sv.lib().svb_last_error()
+
+
+def test_knn_rejects_non_finite_coordinates(sv):
+    X = np.random.default_rng(0).standard_normal((300, 5))
+    X[17, 2] = np.nan
+    with pytest.raises(sv.SeveroB200Error):
+        sv.nearest_neighbours(X, 5)

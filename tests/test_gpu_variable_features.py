@@ -40,3 +40,22 @@ def test_selector_keywords_and_errors(sv, orc):
                                orc.variable_feature_metric(X, "saunders", alpha_thresh=0.99), rtol=1e-12, atol=1e-14)
     with pytest.raises(ValueError):
         sv.find_variable_features(X, 10, method="nope")
+
+
+def test_vst_dtype_float32(sv, orc):
+    # variablefeatures.jl:34,37: mean_std(dtype, A) — the Float32 Welford of scaling.jl:18-34 on the counts, bit for bit
+    from conftest import planted_counts
+    X = planted_counts(3000, 500, 5, seed=2)
+    mu32, var32 = orc.mean_var(X, dtype=np.float32)
+    g_mu, g_sd = sv.mean_std(X.astype(np.float32))
+    np.testing.assert_array_equal(g_mu, mu32)
+    np.testing.assert_array_equal(g_sd, np.sqrt(var32))
+    m64 = sv.variance_stabilizing_transformation(X)
+    m32 = sv.variance_stabilizing_transformation(X, dtype=np.float32)
+    assert m32.dtype == np.float64 and m32.shape == m64.shape
+    np.testing.assert_allclose(m32, m64, rtol=2e-4)
+    top64 = set(sv.find_variable_features(X, 100).tolist())
+    top32 = set(sv.find_variable_features(X, 100, dtype=np.float32).tolist())
+    assert len(top64 & top32) >= 97
+    with pytest.raises(TypeError):
+        sv.variance_stabilizing_transformation(X, dtype=np.int32)

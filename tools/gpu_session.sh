@@ -8,6 +8,7 @@
 #   spmv      ncu --set full of the dominant kernels (count-level forward / adjoint stream kernels)
 #   gram      C'C + tssvd timing at C3 and ncu --set full of gram_adj_kernel
 #   knn       kNN timing at 1,306,127 x 10 (exact-width instance against the multiple-of-8 one) and x 50; ncu of knn_kernel
+#   sanitize  compute-sanitizer memcheck + racecheck over tools/sanitize_case.py (every kernel family, tiny sizes)
 #   snn       Jaccard / SNN timing at 1,306,127 x 10, k = 20 (hash and general paths); ncu of snn_enumerate_kernel
 set -u
 cd "$(dirname "$0")/.."
@@ -39,6 +40,11 @@ for stage in "$@"; do
       timeout 600 python tools/snn_check.py 1306127 10 20 > gpurun_out/snn_1306127.log 2>&1; tail -1 gpurun_out/snn_1306127.log
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:snn_enumerate_kernel -c 2 -f -o gpurun_out/snn \
         python tools/snn_check.py 262144 10 20 > gpurun_out/snn_ncu.log 2>&1; ls -la gpurun_out/snn.ncu-rep ;;
+    sanitize)
+      # memcheck (out-of-bounds / misaligned / leaks of device memory) and racecheck (shared-memory hazards) over a small pass
+      # through every kernel family; the logs are the evidence kept under profiles/
+      timeout 1500 compute-sanitizer --tool memcheck --leak-check no --error-exitcode 3 python tools/sanitize_case.py > gpurun_out/sanitize_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/sanitize_memcheck.log
+      timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 3 python tools/sanitize_case.py > gpurun_out/sanitize_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -4 gpurun_out/sanitize_racecheck.log ;;
     *) echo "unknown stage: $stage" ;;
   esac
 done
