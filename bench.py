@@ -518,6 +518,7 @@ def run_b200(args):
             "roofline": roofline, "kernel_classes": classes, "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
             "counts_operator": cinfo, "explicit_operator": explicit,
             "setup_s": {k: round(v, 4) for k, v in winfo["setup"].items()},
+            "pipeline": pipeline_block(winfo["setup"], Z_total / world, z_total / world, cfg["m"] / world, cfg["g"], peak),
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(sv, cfg, steps=1, warmup=0)
@@ -528,6 +529,27 @@ def run_b200(args):
         dist.barrier()
         lib.svb_comm_destroy()
         dist.destroy_process_group()
+    return out
+
+
+def pipeline_block(setup, Z, z, m, g, peak):
+    """The sweeps BEFORE the solve (raw counts -> normalise -> HVG metric -> scale), per rank: wall time of each stage of
+    build_workload (host-synchronised, so the few host steps in between are inside) against SURVEY 8(d)'s algorithmic bytes with
+    THIS build's storage widths (int32 counts, int32 row indices, Float64 values). The order-exact Welford sweeps are serial
+    chains per gene by construction (scaling.jl:18-34): their figure is a latency bound, not a bandwidth one."""
+    stages = {
+        "normalize": (setup.get("normalize_s"), 8 * Z + 8 * Z + 8 * Z + 8 * m,
+                      "row sums (Z*(4+4)) + sf*x/s, log1p (Z*(4+4) read, Z*8 written): two sweeps, bit-exact arithmetic"),
+        "hvg_metric": (setup.get("hvg_metric_s"), 4 * Z + 4 * Z + 40 * g,
+                       "order-exact Welford over the counts (Z*4) + clipped standardised variance (Z*4) + the host trend"),
+        "scale": (setup.get("scale_s"), 12 * z + 8 * z + 16 * z,
+                  "column subset (z*12), order-exact Welford over the normalised HVG columns (z*8), x/sd + clip (z*16)"),
+    }
+    out = {}
+    for k, (sec, nbytes, what) in stages.items():
+        if sec:
+            out[k] = {"ms": round(sec * 1e3, 2), "algorithmic_GB": round(nbytes / 1e9, 2), "GBps": round(nbytes / 1e9 / sec, 1),
+                      "frac_of_hbm_peak": round(nbytes / 1e9 / sec / peak, 4), "what": what}
     return out
 
 

@@ -19,6 +19,11 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
+// LP = lanes per column pair: 32 (a whole warp per pair, one pair per warp) when a round has at most 32 pairs (w <= 64), else 16
+// (two pairs per warp). ncu on the round-1 version (always 16, 15 warps at w = 57: profiles/r04_bsvd.md) shows a pure latency
+// chain — 380 dependent-ish instructions per warp and round at ~9.5 cycles each, issue slots 40 % busy with 4 warps per scheduler:
+// a whole warp per pair halves the trip counts of the dot / rotation loops and doubles the warps that hide each other's latency.
+template <int LP>
 __global__ void __launch_bounds__(1024) bsvd_kernel(int w, int nu, double *__restrict__ B, double *__restrict__ P,
                                                     double *__restrict__ Q, double *__restrict__ sig,
                                                     double *__restrict__ sig_prev, const double *__restrict__ nrm2F,
@@ -60,9 +65,11 @@ __global__ void __launch_bounds__(1024) bsvd_kernel(int w, int nu, double *__res
         }
         __syncthreads();
         for (int r = 0; r < n - 1; ++r) {
-            // one column pair per 16-lane half-warp: all n/2 <= 64 pairs of a round run concurrently
-            for (int pi = 2 * warp + (lane >> 4); pi - (lane >> 4) < n / 2; pi += 2 * nwarps) {
-                const int hl = lane & 15;
+            // one column pair per group of LP lanes: all n/2 pairs of a round run concurrently
+            constexpr int PPW = 32 / LP;  // pairs per warp
+            const int sub = lane / LP;
+            for (int pi = PPW * warp + sub; pi - sub < n / 2; pi += PPW * nwarps) {
+                const int hl = lane % LP;
                 int p, q;
                 if (pi == 0) {
                     p = n - 1;
@@ -76,9 +83,9 @@ __global__ void __launch_bounds__(1024) bsvd_kernel(int w, int nu, double *__res
                 double *gp = G + (live ? p : 0) * ld, *gq = G + (live ? q : 0) * ld;
                 double g = 0.0;
                 if (live)
-                    for (int i = hl; i < w; i += 16) g = fma(gp[i], gq[i], g);
+                    for (int i = hl; i < w; i += LP) g = fma(gp[i], gq[i], g);
 #pragma unroll
-                for (int o = 8; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);  // stays inside the half-warp
+                for (int o = LP / 2; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);  // stays inside the lane group
                 // squared column norms are cached (exact at the start of every sweep, updated by the rotation
                 // formulas in between): one reduction per pair instead of three
                 const double a = live ? nrm[p] : 0.0, b = live ? nrm[q] : 0.0;
@@ -108,7 +115,7 @@ __global__ void __launch_bounds__(1024) bsvd_kernel(int w, int nu, double *__res
                         c = rsqrt(fma(t, t, 1.0));
                     }
                     const double sn = c * t;
-                    __syncwarp(0xffffu << (lane & 16));  // every lane of the half-warp has read nrm[p], nrm[q]
+                    __syncwarp(LP == 32 ? 0xffffffffu : (0xffffu << (lane & 16)));  // every lane of the group has read nrm[p], nrm[q]
                     if (hl == 0) {
                         nrm[p] = fmax(0.0, a - t * g);
                         nrm[q] = fmax(0.0, b + t * g);
@@ -116,7 +123,7 @@ __global__ void __launch_bounds__(1024) bsvd_kernel(int w, int nu, double *__res
                         if (g * g > 1e-16 * (a * b)) coarse = 1;  // a pair still above sqrt(eps)-level coupling
                     }
                     double *vp = V + p * ld, *vq = V + q * ld;
-                    for (int i = hl; i < w; i += 16) {
+                    for (int i = hl; i < w; i += LP) {
                         const double x = gp[i], y = gq[i];
                         gp[i] = c * x - sn * y;
                         gq[i] = sn * x + c * y;
@@ -213,11 +220,18 @@ bool bsvd_supported(int w) { return w <= 256 && bsvd_smem_bytes(w) + 2048 <= ctx
 void bsvd_launch(int w, int nu, double *B, double *P, double *Q, double *sig, double *sig_prev, const double *nrm2F,
                  double *smax_io, double tol, double svtol, int k_in, const int *flag_dev, BsvdStatus *status_dev) {
     const size_t smem = bsvd_smem_bytes(w);
-    if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(bsvd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // one 16-lane half-warp per column pair: ceil(n/4) warps, at most 32
-    int warps = std::min(32, std::max(4, ((w + 1) / 2 + 1) / 2));
+    const int pairs = (w + 1) / 2;
+    static const bool wide = !(getenv("SVB_BSVD_LP") && atoi(getenv("SVB_BSVD_LP")) == 16);
     KTimer kt(SVB_K_VECTOR, 8.0 * 3 * w * w);
-    bsvd_kernel<<<1, warps * 32, smem, ctx().stream>>>(w, nu, B, P, Q, sig, sig_prev, nrm2F, smax_io, tol, svtol, k_in, flag_dev, status_dev);
+    if (pairs <= 32 && wide) {  // a warp per pair
+        if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(bsvd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int warps = std::max(4, pairs);
+        bsvd_kernel<32><<<1, warps * 32, smem, ctx().stream>>>(w, nu, B, P, Q, sig, sig_prev, nrm2F, smax_io, tol, svtol, k_in, flag_dev, status_dev);
+    } else {                    // a half-warp per pair: ceil(pairs/2) warps, at most 32
+        if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(bsvd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int warps = std::min(32, std::max(4, (pairs + 1) / 2));
+        bsvd_kernel<16><<<1, warps * 32, smem, ctx().stream>>>(w, nu, B, P, Q, sig, sig_prev, nrm2F, smax_io, tol, svtol, k_in, flag_dev, status_dev);
+    }
     SVB_LAUNCH_CHECK();
 }
 

@@ -361,6 +361,91 @@ __global__ void __launch_bounds__(DM_THREADS) ts_gemm_dmma_kernel(const double *
     }
 }
 
+// Round 2 (C4 regime: w = 107, k ~ 100 — the product is bound by the fp64 pipe, 2*L*w*k flop): the first DMMA kernel walked K
+// once per group of 4 n-tiles, re-reading its A fragments from L1/L2 up to 4 times, and every 128-row CTA staged the whole
+// of P again (90 KB at C4, 3 x the bytes of its X tile): 0.92 TB/s. Here the CTAs are PERSISTENT (P is staged once per CTA and
+// reused for every row block) and a row block of 32 rows is shared by four warps that split the n-tiles among them, so every
+// warp walks K exactly once with all its accumulators live (NT n-tiles x 4 m-tiles x 2 doubles) and the four warps' identical
+// A loads hit L1. 8 warps per CTA = 2 row groups x 4 column groups.
+constexpr int DP_THREADS = 256;
+template <int NT>
+__global__ void __launch_bounds__(DP_THREADS, (NT <= 4 ? 2 : 1)) ts_gemm_dmma_persistent_kernel(const double *__restrict__ X, int64_t ld, int64_t L, int w,
+                                                                             const double *__restrict__ P, int ldp, int k, int kp8,
+                                                                             int wp4, double *__restrict__ out, int64_t ldo,
+                                                                             const double *__restrict__ colscale) {
+    extern __shared__ double Ps[];  // [wp4][kp8], zero padded
+    for (int idx = threadIdx.x; idx < wp4 * kp8; idx += blockDim.x) {
+        const int l = idx / kp8, c = idx - l * kp8;
+        double v = (l < w && c < k) ? P[l + (int64_t)c * ldp] : 0.0;
+        if (colscale && c < k) v *= colscale[c];
+        Ps[idx] = v;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int rg = warp >> 2, cg = warp & 3;
+    const int ntiles = kp8 >> 3;
+    const int64_t nblk = (L + 63) / 64;
+    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const int64_t r0 = blk * 64 + rg * 32;
+        if (r0 >= L) continue;
+        double acc[4][NT][2];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int i = 0; i < NT; ++i) acc[mt][i][0] = acc[mt][i][1] = 0.0;
+        const double *xrow[4];
+        bool rok[4];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            const int64_t row = r0 + mt * 8 + g;
+            rok[mt] = row < L;
+            xrow[mt] = X + (rok[mt] ? row : 0);
+        }
+#pragma unroll 2
+        for (int l0 = 0; l0 < wp4; l0 += 4) {
+            const int l = l0 + t;
+            const bool lok = l < w;
+            double a[4], b[NT];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) a[mt] = (lok && rok[mt]) ? __ldg(xrow[mt] + (int64_t)l * ld) : 0.0;
+#pragma unroll
+            for (int i = 0; i < NT; ++i) {
+                const int nt = cg + 4 * i;
+                b[i] = (nt < ntiles) ? Ps[l * kp8 + nt * 8 + g] : 0.0;
+            }
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int i = 0; i < NT; ++i) dmma_m8n8k4(acc[mt][i][0], acc[mt][i][1], a[mt], b[i]);
+        }
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            const int64_t row = r0 + mt * 8 + g;
+            if (row < L) {
+#pragma unroll
+                for (int i = 0; i < NT; ++i) {
+                    const int col = (cg + 4 * i) * 8 + 2 * t;
+                    if (col < k) out[row + (int64_t)col * ldo] = acc[mt][i][0];
+                    if (col + 1 < k) out[row + (int64_t)(col + 1) * ldo] = acc[mt][i][1];
+                }
+            }
+        }
+    }
+}
+
+template <int NT>
+static void launch_dmma_persistent(const double *X, int64_t ld, int64_t L, int w, const double *P, int ldp, int k, int kp8, int wp4,
+                                   double *out, int64_t ldo, const double *colscale_dev, size_t smem) {
+    auto kern = ts_gemm_dmma_persistent_kernel<NT>;
+    if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DP_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const int64_t nblk = (L + 63) / 64;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nblk, (int64_t)per_sm * ctx().sm_count));
+    kern<<<grid, DP_THREADS, smem, ctx().stream>>>(X, ld, L, w, P, ldp, k, kp8, wp4, out, ldo, colscale_dev);
+}
+
 void ts_gemm(const double *X, int64_t ld, int64_t L, int w, const double *P, int ldp, int k, double *out, int64_t ldo,
              const double *colscale_dev) {
     if (k <= 0 || L <= 0) return;
@@ -368,6 +453,16 @@ void ts_gemm(const double *X, int64_t ld, int64_t L, int w, const double *P, int
     if (use_dmma) {
         const int kp8 = (k + 7) / 8 * 8, wp4 = (w + 3) / 4 * 4;
         const size_t smem = (size_t)wp4 * kp8 * sizeof(double);
+        static const bool persistent = !(getenv("SVB_DMMA_PERSISTENT") && atoi(getenv("SVB_DMMA_PERSISTENT")) == 0);
+        if (smem <= ctx().smem_optin && persistent && kp8 <= 256) {
+            const int nt = (kp8 / 8 + 3) / 4;  // n-tiles per warp (four column groups)
+            KTimer kt(SVB_K_RESTART, 8.0 * ((double)L * w + (double)L * k));
+            if (nt <= 2) launch_dmma_persistent<2>(X, ld, L, w, P, ldp, k, kp8, wp4, out, ldo, colscale_dev, smem);
+            else if (nt <= 4) launch_dmma_persistent<4>(X, ld, L, w, P, ldp, k, kp8, wp4, out, ldo, colscale_dev, smem);
+            else launch_dmma_persistent<8>(X, ld, L, w, P, ldp, k, kp8, wp4, out, ldo, colscale_dev, smem);
+            SVB_LAUNCH_CHECK();
+            return;
+        }
         if (smem <= ctx().smem_optin) {
             if (smem > 48 * 1024)
                 SVB_CUDA(cudaFuncSetAttribute(ts_gemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
