@@ -30,9 +30,11 @@ using namespace svb;
 
 svb_factored_s::~svb_factored_s() {
     void *ptrs[] = {tlev, tlevA, inv, f_rowptr, f_code, f_meta, a_gptr, a_code, a_meta, a_slices, counters, partial,
-                    fwd_ranges, fwd_rows};
+                    fwd_ranges, fwd_rows, a_estart};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    delete exc;
+    delete excT;
 }
 
 namespace svb {
@@ -466,9 +468,10 @@ __global__ void __launch_bounds__(256) fact_row_hist_kernel(const int64_t *__res
             if (lane >= o) ch += y;
         }
         const int total = __shfl_sync(0xffffffffu, ch, 31);
-        if (total + ne == 0) ch = 1;  // empty row: one all-pad chunk in level 0
+        (void)ne;                     // exception entries live in the side matrix, not in the stream
+        if (total == 0) ch = 1;       // row without coded entries: one all-pad chunk in level 0 (it carries the row end)
         if (lane < L) gend[r * L + lane] = (uint16_t)ch;
-        if (lane == 31) rowchunks[r] = ch + ne;
+        if (lane == 31) rowchunks[r] = ch;
         __syncwarp();
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) rowchunks[m] = 0;
@@ -641,6 +644,21 @@ __device__ __forceinline__ double gather8b(const double *__restrict__ T, const u
     return ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
+// Exception entries of a row (cell-major side matrix), exact value (times sd) x xs[gene]; they run at
+// row ends only.
+__device__ __forceinline__ double fwd_exceptions_lanes(const int64_t *__restrict__ erp, int row, const int32_t *__restrict__ egene,
+                                                    const double *__restrict__ evalr, const double *__restrict__ xs, int lane) {
+    double s = 0.0;  // this lane's share: entries lane, lane + 32, ...
+    for (int64_t k = __ldg(erp + row) + lane, e1 = __ldg(erp + row + 1); k < e1; k += 32) s = fma(__ldg(evalr + k), xs[__ldg(egene + k)], s);
+    return s;
+}
+__device__ __forceinline__ double fwd_exceptions_serial(const int64_t *__restrict__ erp, int row, const int32_t *__restrict__ egene,
+                                                     const double *__restrict__ evalr, const double *__restrict__ xs) {
+    double s = 0.0;
+    for (int64_t k = __ldg(erp + row), e1 = __ldg(erp + row + 1); k < e1; ++k) s = fma(__ldg(evalr + k), xs[__ldg(egene + k)], s);
+    return s;
+}
+
 // forward: y_i = alpha*(sum over the row's chunks of t_i[level] * sum_8 xs[gene] - mu.x) + beta*y_i + csign*(*coef)*cvec_i
 // BO: the codes are byte offsets (n <= 8190). After the ncu pass that showed the issue slots 70 % busy once the bank
 // conflicts were halved, the loop works on 32-bit indices relative to the warp's range and the three pipeline stages
@@ -650,7 +668,8 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 fwd_stream_kernel(const uint4 *__restrict__ code, const uint8_t *__restrict__ meta, const double *__restrict__ tlev, int log2L,
                   const int64_t *__restrict__ wstart, const int64_t *__restrict__ wrow, int64_t n, const double *__restrict__ x,
                   const double *__restrict__ inv, const double *__restrict__ mu, double alpha, double beta, double *__restrict__ y,
-                  const double *__restrict__ coef, double csign, const double *__restrict__ cvec, int nrep, int stride) {
+                  const double *__restrict__ coef, double csign, const double *__restrict__ cvec, int nrep, int stride,
+                  const int64_t *__restrict__ erowptr, const int32_t *__restrict__ egene, const double *__restrict__ evalr) {
     extern __shared__ double smem[];
     double *red = smem;      // 32
     double *xs = smem + 32;  // nrep bank-shifted replicas of {x_j / sd_j, j < n ; 0 (the pad gene)}, `stride` entries apart
@@ -662,8 +681,19 @@ fwd_stream_kernel(const uint4 *__restrict__ code, const uint8_t *__restrict__ me
         part = fma(mu[j], xv, part);
     }
     if ((int)threadIdx.x < nrep) xs[(int64_t)threadIdx.x * stride + n] = 0.0;
-    const double mudot = fblock_sum(part, red);  // its barriers publish xs
-    const double cf = (coef != nullptr) ? csign * (*coef) : 0.0;
+    {
+        // the epilogue constants are needed at row ends only: they live in shared memory (red[0..3]) instead of eight
+        // registers of the stream loop, which runs at the 64-register limit of two 512-thread CTAs per SM
+        const double mudot_ = fblock_sum(part, red);  // its barriers publish xs
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            red[0] = mudot_;
+            red[1] = (coef != nullptr) ? csign * (*coef) : 0.0;
+            red[2] = alpha;
+            red[3] = beta;
+        }
+        __syncthreads();
+    }
 
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
@@ -678,6 +708,7 @@ fwd_stream_kernel(const uint4 *__restrict__ code, const uint8_t *__restrict__ me
     const double *tl = tlev + (rbase << log2L);
     double *yb = y + rbase;
     const double *cvb = cvec ? cvec + rbase : nullptr;
+    const int64_t *erp = erowptr ? erowptr + rbase : nullptr;  // exception entries of this warp's rows (cell-major side matrix)
     const unsigned padc = (unsigned)(BO ? n * 8 : n) * 0x10001u;
     const uint4 padq = make_uint4(padc, padc, padc, padc);
 
@@ -700,7 +731,7 @@ fwd_stream_kernel(const uint4 *__restrict__ code, const uint8_t *__restrict__ me
     unsigned bal0 = __ballot_sync(0xffffffffu, (m0 & 1u) != 0u);
     int row0 = rowrel + __popc(bal0 & lt);
     rowrel += __popc(bal0);
-    double t0 = (rel >= lo && rel < hi && (m0 >> 1) != FEXC) ? __ldg(tl + ((int64_t)row0 << log2L) + (m0 >> 1)) : 0.0;
+    double t0 = (rel >= lo && rel < hi) ? __ldg(tl + ((int64_t)row0 << log2L) + (m0 >> 1)) : 0.0;
     double acc = 0.0;  // this lane's share of the row that is still open (summed across lanes when the row ends)
     // one iteration: QA/MA = current stage (refilled with iteration +FPD once consumed), MB = meta of the next iteration
 #define SVB_FWD_STEP(QA, MA, MB)                                                                                      \
@@ -708,10 +739,8 @@ fwd_stream_kernel(const uint4 *__restrict__ code, const uint8_t *__restrict__ me
         const unsigned bal1 = __ballot_sync(0xffffffffu, ((MB) & 1u) != 0u);                                          \
         const int row1 = rowrel + __popc(bal1 & lt);                                                                  \
         rowrel += __popc(bal1);                                                                                       \
-        const double t1 = (rel + 32 < hi && ((MB) >> 1) != FEXC) ? __ldg(tl + ((int64_t)row1 << log2L) + ((MB) >> 1)) : 0.0; \
-        double v;                                                                                                     \
-        if (((MA) >> 1) == FEXC) v = __hiloint2double((int)(QA).w, (int)(QA).z) * xs[(QA).x];                         \
-        else v = t0 * (BO ? gather8b(xs, (QA)) : gather8(xs, (QA)));                                                  \
+        const double t1 = (rel + 32 < hi) ? __ldg(tl + ((int64_t)row1 << log2L) + ((MB) >> 1)) : 0.0;                 \
+        const double v = t0 * (BO ? gather8b(xs, (QA)) : gather8(xs, (QA)));                                          \
         const unsigned mcur = (MA);                                                                                   \
         if (rel + 32 * FPD < hi) {                                                                                    \
             (QA) = ld_stream16(pc);                                                                                   \
@@ -730,17 +759,22 @@ fwd_stream_kernel(const uint4 *__restrict__ code, const uint8_t *__restrict__ me
             if (nends == 1) { /* the usual case for rows longer than 32 chunks: one butterfly */                      \
                 const int b1 = __ffs(bal0) - 1;                                                                       \
                 r = acc + ((lane <= b1) ? v : 0.0);                                                                   \
+                if (erp != nullptr) /* the row's exception entries (exact values), spread over the 32 lanes */        \
+                    r += fwd_exceptions_lanes(erp, __shfl_sync(0xffffffffu, row0, b1), egene, evalr, xs, lane);       \
                 _Pragma("unroll") for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);           \
             } else { /* several (short) rows: carried sums enter at lane 0, then the segmented scan */                \
                 double tot = acc;                                                                                     \
                 _Pragma("unroll") for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);       \
                 bool head0;                                                                                           \
                 r = seg_scan(v + (lane == 0 ? tot : 0.0), bal0, lane, head0);                                         \
+                if (erp != nullptr && (mcur & 1u)) /* every end lane adds its own row's exceptions */                 \
+                    r += fwd_exceptions_serial(erp, row0, egene, evalr, xs);                                          \
             }                                                                                                         \
             if (mcur & 1u) {                                                                                          \
-                r = alpha * (r - mudot);                                                                              \
-                if (beta != 0.0) r = fma(beta, yb[row0], r);                                                          \
-                if (coef != nullptr) r = fma(cf, cvb[row0], r);                                                       \
+                r = red[2] * (r - red[0]);                                                                            \
+                const double beta_ = red[3];                                                                          \
+                if (beta_ != 0.0) r = fma(beta_, yb[row0], r);                                                        \
+                if (cvb != nullptr) r = fma(red[1], cvb[row0], r);                                                    \
                 yb[row0] = r;                                                                                         \
             }                                                                                                         \
             acc = (lane > 31 - __clz(bal0)) ? v : 0.0; /* the chunks after the last row end open the next row */      \
@@ -760,6 +794,25 @@ fwd_stream_kernel(const uint4 *__restrict__ code, const uint8_t *__restrict__ me
 #undef SVB_FWD_STEP
 }
 
+// sum of the exception entries of segment `seg` = (tile, gene): exact value (times sd) x w of the cell; one lane, serial
+// (the paths where several segments end in one warp iteration; the common single-end path spreads them over the lanes)
+__device__ __forceinline__ double adj_exceptions(const int64_t *__restrict__ estart, const int32_t *__restrict__ erow,
+                                                 const double *__restrict__ eval, int64_t seg, int64_t n, const double *__restrict__ wtile,
+                                                 int row0) {
+    double s = 0.0;
+    for (int64_t k = __ldg(estart + seg), e1 = __ldg(estart + seg + n); k < e1; ++k) s = fma(__ldg(eval + k), wtile[__ldg(erow + k) - row0], s);
+    return s;
+}
+
+__device__ __forceinline__ double adj_exceptions_lanes(const int64_t *__restrict__ estart, const int32_t *__restrict__ erow,
+                                                    const double *__restrict__ eval, int64_t seg, int64_t n, const double *__restrict__ wtile,
+                                                    int row0, int lane) {
+    double s = 0.0;  // this lane's share of the segment's entries
+    for (int64_t k = __ldg(estart + seg) + lane, e1 = __ldg(estart + seg + n); k < e1; k += 32)
+        s = fma(__ldg(eval + k), wtile[__ldg(erow + k) - row0], s);
+    return s;
+}
+
 // physical layout of the adjoint tile table (see the replica assignment above); identity = {0, 1, 0, 0, 0, R*L, R*L + 1}
 struct AdjGeom {
     int nlr, nrep, strideA, levstride, baseB, pad, wbase;
@@ -775,7 +828,8 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 adj_stream_kernel(const int64_t *__restrict__ gptr, const uint4 *__restrict__ code, const uint8_t *__restrict__ meta,
                   const double *__restrict__ tlevA, int log2L, int log2R, int64_t m, int64_t n, int64_t ntiles,
                   const double *__restrict__ w, const double *__restrict__ inv, double *__restrict__ partial,
-                  const int32_t *__restrict__ slices, unsigned int *__restrict__ counters, AdjGeom G) {
+                  const int32_t *__restrict__ slices, unsigned int *__restrict__ counters, AdjGeom G,
+                  const int64_t *__restrict__ estart, const int32_t *__restrict__ erow, const double *__restrict__ eval) {
     extern __shared__ double smem[];
     __shared__ long long cur_tile, nxt_tile;  // tiles are taken from the counter ONE AHEAD: the next tile's level table is
                                               // prefetched into L2 while this one is streamed (the fill then hits L2)
@@ -868,9 +922,7 @@ adj_stream_kernel(const int64_t *__restrict__ gptr, const uint4 *__restrict__ co
         const unsigned bal = __ballot_sync(0xffffffffu, (mcur & 1u) != 0u);                                           \
         const int g = gbase + __popc(bal & lt);                                                                       \
         gbase += __popc(bal);                                                                                         \
-        double v;                                                                                                     \
-        if (mcur & 2u) v = __hiloint2double((int)(QA).w, (int)(QA).z) * T[G.wbase + (QA).x];                          \
-        else v = gather8(T, (QA));                                                                                    \
+        const double v = gather8(T, (QA));                                                                            \
         if (rel + 32 * NS < hi) { /* refill this stage with the chunk of iteration + NS */                            \
             (QA) = ld_stream16(pc);                                                                                   \
             (MA) = (unsigned)__ldg(pm);                                                                               \
@@ -889,22 +941,29 @@ adj_stream_kernel(const int64_t *__restrict__ gptr, const uint4 *__restrict__ co
                 if (nends == 1) {                                                                                     \
                     const int b1 = __ffs(bal) - 1;                                                                    \
                     r = acc + ((lane <= b1) ? v : 0.0);                                                               \
+                    if (estart != nullptr) /* the segment's exception entries (exact values), over the 32 lanes */    \
+                        r += adj_exceptions_lanes(estart, erow, eval, t * n + (gbase - 1), n, T + G.wbase, (int)row0, lane); \
                     _Pragma("unroll") for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);       \
                 } else {                                                                                              \
                     double tot = acc;                                                                                 \
                     _Pragma("unroll") for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);   \
                     bool head0;                                                                                       \
                     r = seg_scan(v + (lane == 0 ? tot : 0.0), bal, lane, head0);                                      \
+                    if (estart != nullptr && (mcur & 1u)) r += adj_exceptions(estart, erow, eval, t * n + g, n, T + G.wbase, (int)row0); \
                 }                                                                                                     \
                 if (mcur & 1u) prow[g] = r * __ldg(inv + g);                                                          \
                 acc = (lane > 31 - __clz(bal)) ? v : 0.0;                                                             \
             }                                                                                                         \
         } else {                                                                                                      \
             bool head0;                                                                                               \
-            v = seg_scan(v, bal, lane, head0);                                                                        \
-            if (head0) v += acc; /* acc = the carried sum of the segment that started in an earlier iteration */      \
-            if (mcur & 1u) prow[g] = v * __ldg(inv + g);                                                              \
-            const double v31 = __shfl_sync(0xffffffffu, v, 31);                                                       \
+            double vs = seg_scan(v, bal, lane, head0);                                                                \
+            if (head0) vs += acc; /* acc = the carried sum of the segment that started in an earlier iteration */     \
+            if (mcur & 1u) {                                                                                          \
+                double r = vs;                                                                                        \
+                if (estart != nullptr) r += adj_exceptions(estart, erow, eval, t * n + g, n, T + G.wbase, (int)row0); \
+                prow[g] = r * __ldg(inv + g);                                                                         \
+            }                                                                                                         \
+            const double v31 = __shfl_sync(0xffffffffu, vs, 31);                                                      \
             acc = (bal >> 31) ? 0.0 : v31;                                                                            \
         }                                                                                                             \
         rel += 32;                                                                                                    \
@@ -966,13 +1025,14 @@ static void launch_fact_fwd(svb_operator_s *op, double alpha, const double *dx, 
     }
     k<<<(unsigned)f->fwd_grid, BLOCK, smem, ctx().stream>>>((const uint4 *)f->f_code, f->f_meta, f->tlev, f->log2L, f->fwd_ranges,
                                                              f->fwd_rows, op->n, dx, f->inv, op->mu, alpha, beta, dy, coef, csign, cvec,
-                                                             f->f_nrep, f->f_stride);
+                                                             f->f_nrep, f->f_stride, f->excT ? f->excT->colptr : nullptr,
+                                                             f->excT ? f->excT->rowidx : nullptr, f->excT ? (const double *)f->excT->val : nullptr);
     SVB_LAUNCH_CHECK();
 }
 
-// adjoint CTA: 512 threads and a 64 KB table (R*L = 8192; three CTAs per SM), or -- SVB_FACT_LOG2R one larger -- 1024
+// adjoint CTA: 384 threads and a 64 KB table (R*L = 8192; three CTAs per SM), or -- SVB_FACT_LOG2R one larger -- 1024
 // threads and a 128 KB table (R*L = 16384; one CTA per SM, segments twice as long)
-static inline int adj_block_of(const svb_factored_s *f) { return (f->log2R + f->log2L >= 14) ? 1024 : 512; }
+static inline int adj_block_of(const svb_factored_s *f) { return (f->log2R + f->log2L >= 14) ? 1024 : 384; }
 
 void fact_fwd(svb_operator_s *op, double alpha, const double *dx, double beta, double *dy, const double *coef, double csign,
               const double *cvec) {
@@ -980,11 +1040,12 @@ void fact_fwd(svb_operator_s *op, double alpha, const double *dx, double beta, d
     // 64 registers per thread (4 x 256 or 2 x 512 threads per SM): 48 registers spill, and the kernel is bound by the
     // shared-memory pipe / issue slots, not by occupancy (measured 5 vs 4 CTAs per SM: within noise)
     if (((size_t)(op->fact->f_nrep - 1) * op->fact->f_stride + (size_t)op->n) * 8 > 24 * 1024) {
-        if (bo) launch_fact_fwd<512, true, 2>(op, alpha, dx, beta, dy, coef, csign, cvec);
-        else launch_fact_fwd<512, false, 2>(op, alpha, dx, beta, dy, coef, csign, cvec);
+        // 448 threads: 2 CTAs per SM leave 72 registers per thread (the loop needs ~70 with the exception side matrix; 64 spills)
+        if (bo) launch_fact_fwd<448, true, 2>(op, alpha, dx, beta, dy, coef, csign, cvec);
+        else launch_fact_fwd<448, false, 2>(op, alpha, dx, beta, dy, coef, csign, cvec);
     } else {
-        if (bo) launch_fact_fwd<256, true, 4>(op, alpha, dx, beta, dy, coef, csign, cvec);
-        else launch_fact_fwd<256, false, 4>(op, alpha, dx, beta, dy, coef, csign, cvec);
+        if (bo) launch_fact_fwd<256, true, 3>(op, alpha, dx, beta, dy, coef, csign, cvec);
+        else launch_fact_fwd<256, false, 3>(op, alpha, dx, beta, dy, coef, csign, cvec);
     }
 }
 
@@ -995,11 +1056,13 @@ void fact_adj_stage1(svb_operator_s *op, const double *dx) {
     const AdjGeom G{f->a_nlr, f->a_nrep, f->a_strideA, f->a_levstride, f->a_baseB, f->a_pad, f->a_wbase};
     static const int stages = getenv("SVB_ADJ_STAGES") ? atoi(getenv("SVB_ADJ_STAGES")) : 3;
     auto k = (block == 1024) ? (stages >= 4 ? adj_stream_kernel<1024, 1, true, 4> : adj_stream_kernel<1024, 1, true, 3>)
-                             : adj_stream_kernel<512, 3, false, 2>;
+                             : adj_stream_kernel<384, 3, false, 2>;  // 3 x 384 threads: 56 registers (512 threads: 40, spills)
     if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (f->adj_grid == 0) f->adj_grid = (int)std::max<int64_t>(1, std::min<int64_t>(fresident_grid(k, smem, block), f->ntiles));
     k<<<(unsigned)f->adj_grid, block, smem, ctx().stream>>>(f->a_gptr, (const uint4 *)f->a_code, f->a_meta, f->tlevA, f->log2L, f->log2R,
-                                                                 op->m, op->n, f->ntiles, dx, f->inv, f->partial, f->a_slices, f->counters, G);
+                                                                 op->m, op->n, f->ntiles, dx, f->inv, f->partial, f->a_slices, f->counters, G,
+                                                                 f->a_estart, f->exc ? f->exc->rowidx : nullptr,
+                                                                 f->exc ? (const double *)f->exc->val : nullptr);
     SVB_LAUNCH_CHECK();
 }
 
@@ -1007,13 +1070,15 @@ void fact_adj_stage1(svb_operator_s *op, const double *dx) {
 // counted), the per-cell tables, the pointers and the vectors
 double fact_fwd_bytes(const svb_operator_s *op) {
     const svb_factored_s *f = op->fact;
-    return 2.125 * (double)f->nnz_main + 17.0 * (double)f->nnz_exc + (double)op->m * (8.0 * f->L + 8.0) + 24.0 * (double)op->n;
+    // exception entries: 12 B each (Float64 value + Int32 gene) + the cell pointers of the side matrix
+    return 2.125 * (double)f->nnz_main + 12.0 * (double)f->nnz_exc + (f->nnz_exc ? 8.0 * op->m : 0.0) +
+           (double)op->m * (8.0 * f->L + 8.0) + 24.0 * (double)op->n;
 }
 double fact_adj_bytes(const svb_operator_s *op) {
     const svb_factored_s *f = op->fact;
     const double nseg = (double)f->ntiles * (double)op->n;
-    return 2.125 * (double)f->nnz_main + 17.0 * (double)f->nnz_exc + (double)op->m * (8.0 * f->L + 8.0) + nseg * (8.0 + 8.0) +
-           24.0 * (double)op->n;
+    return 2.125 * (double)f->nnz_main + 12.0 * (double)f->nnz_exc + (f->nnz_exc ? 8.0 * nseg : 0.0) +
+           (double)op->m * (8.0 * f->L + 8.0) + nseg * (8.0 + 8.0) + 24.0 * (double)op->n;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1225,11 +1290,11 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
     // ---- adjoint layout ----------------------------------------------------------------------------------
     {
         const int64_t nseg = f->ntiles * n;
-        DevBuf<int64_t> startpos((size_t)((f->ntiles + 1) * n + 1)), estart;
+        DevBuf<int64_t> startpos((size_t)((f->ntiles + 1) * n + 1)), estart;  // estart stays empty: no exception chunks
         tile_bounds(a, log2R, f->ntiles, startpos.p);
-        if (e.p) {
-            estart.alloc((size_t)((f->ntiles + 1) * n + 1));
-            tile_bounds(e.p, log2R, f->ntiles, estart.p);
+        if (e.p) {  // the adjoint's view of the exception side matrix: its (tile, gene) segments
+            SVB_CUDA(cudaMalloc((void **)&f->a_estart, (size_t)((f->ntiles + 1) * n + 1) * sizeof(int64_t)));
+            tile_bounds(e.p, log2R, f->ntiles, f->a_estart);
         }
         SVB_CUDA(cudaMalloc((void **)&f->a_gptr, (size_t)(nseg + 1) * sizeof(int64_t)));
         fact_seg_count_kernel<<<fgrid(nseg * 8), 256, 0, st>>>(startpos.p, lvl.p, estart.p, nseg, n, f->a_gptr);
@@ -1241,8 +1306,7 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
         SVB_CUDA(cudaMalloc((void **)&f->a_code, (size_t)std::max<int64_t>(f->a_chunks, 1) * 16));
         SVB_CUDA(cudaMalloc((void **)&f->a_meta, (size_t)std::max<int64_t>(f->a_chunks, 1)));
         fact_seg_fill_kernel<<<fgrid(nseg * 8), 256, 0, st>>>(startpos.p, a->rowidx, lvl.p, nseg, n, log2R, log2L, f->a_gptr, estart.p,
-                                                              e.p ? e.p->rowidx : nullptr, e.p ? (const double *)e.p->val : nullptr,
-                                                              (uint16_t *)f->a_code, f->a_meta);
+                                                              nullptr, nullptr, (uint16_t *)f->a_code, f->a_meta);
         count_launch();
         SVB_LAUNCH_CHECK();
         static const bool stats = getenv("SVB_FACT_STATS") != nullptr;
@@ -1289,8 +1353,7 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
         SVB_CUDA(cudaMalloc((void **)&f->f_meta, (size_t)std::max<int64_t>(f->f_chunks, 1)));
         f->f_cshift = (n <= 8190) ? 3 : 0;  // the codes of the forward stream are byte offsets when they fit in 16 bits
         fact_row_place_kernel<<<gw, 256, (size_t)8 * 2 * L * 16 * sizeof(int), st>>>(rowptr.p, ridx.p, rlvl.p, m, L, (int)n, f->f_cshift, f->f_rowptr, gend.p,
-                                                  e.p ? e.p->colptr : nullptr, e.p ? e.p->rowidx : nullptr,
-                                                  e.p ? (const double *)e.p->val : nullptr, (uint16_t *)f->f_code, f->f_meta);
+                                                  nullptr, nullptr, nullptr, (uint16_t *)f->f_code, f->f_meta);
         count_launch();
         SVB_LAUNCH_CHECK();
         static const bool stats = getenv("SVB_FACT_STATS") != nullptr;
@@ -1302,6 +1365,12 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
     }
 
     tick("forward: grouping + placement");
+    if (e.p) {  // the forward's view: the same entries cell-major (stable device transpose), then both are kept
+        f->excT = matrix_transpose(e.p);
+        f->exc = e.p;
+        e.p = nullptr;
+        tick("exception side matrices");
+    }
     SVB_CUDA(cudaMalloc((void **)&f->partial, (size_t)f->ntiles * (n + 1) * sizeof(double)));
     SVB_CUDA(cudaMalloc((void **)&op->tmp, (size_t)std::max(m, n) * sizeof(double)));
     SVB_CUDA(cudaMalloc((void **)&op->scal, 8 * sizeof(double)));
