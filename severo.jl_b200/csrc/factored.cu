@@ -30,7 +30,7 @@ using namespace svb;
 
 svb_factored_s::~svb_factored_s() {
     void *ptrs[] = {tlev, tlevA, inv, f_rowptr, f_code, f_meta, a_gptr, a_code, a_meta, a_slices, counters, partial,
-                    fwd_ranges, fwd_rows, a_estart};
+                    fwd_ranges, fwd_rows, e_segptr, e_segsum};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     delete exc;
@@ -644,19 +644,51 @@ __device__ __forceinline__ double gather8b(const double *__restrict__ T, const u
     return ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
-// Exception entries of a row (cell-major side matrix), exact value (times sd) x xs[gene]; they run at
-// row ends only.
-__device__ __forceinline__ double fwd_exceptions_lanes(const int64_t *__restrict__ erp, int row, const int32_t *__restrict__ egene,
-                                                    const double *__restrict__ evalr, const double *__restrict__ xs, int lane) {
-    double s = 0.0;  // this lane's share: entries lane, lane + 32, ...
-    for (int64_t k = __ldg(erp + row) + lane, e1 = __ldg(erp + row + 1); k < e1; k += 32) s = fma(__ldg(evalr + k), xs[__ldg(egene + k)], s);
-    return s;
+// Exception entries (count > L, count < 1, clipped by scale_max): NOT in the streams. Round 1 carried each as a 16-byte chunk
+// of its own — 1.3 % of the entries, but 9 % of the lane slots of a warp iteration and a divergent branch in ~95 % of the
+// iterations. Reading them at the row / segment ends inside the stream loop was worse (two dependent global-load latencies in
+// the critical path of every end: 0.55 -> 0.71 ms and 0.63 -> 1.48 ms per product). They are two small side matrices instead:
+// forward: cell-major, one thread per cell adds alpha * sum(value * x_g / sd_g) to y after the stream kernel (this kernel);
+// adjoint: gene-major, summed into the gene's result by the reduce kernel that already adds up the tile partials.
+constexpr int EXS = 4096;  // exception entries per segment of the adjoint's side sum
+__global__ void exc_segcount_kernel(const int64_t *__restrict__ ecolptr, int64_t n, int64_t *__restrict__ segptr) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < n) segptr[g] = (ecolptr[g + 1] - ecolptr[g] + EXS - 1) / EXS;
+    if (g == n) segptr[g] = 0;
 }
-__device__ __forceinline__ double fwd_exceptions_serial(const int64_t *__restrict__ erp, int row, const int32_t *__restrict__ egene,
-                                                     const double *__restrict__ evalr, const double *__restrict__ xs) {
-    double s = 0.0;
-    for (int64_t k = __ldg(erp + row), e1 = __ldg(erp + row + 1); k < e1; ++k) s = fma(__ldg(evalr + k), xs[__ldg(egene + k)], s);
-    return s;
+// one CTA per segment: segsum[s] = sum over the segment's entries of value * w[cell], fixed order (thread-strided partial sums,
+// then the block tree) — deterministic whatever the distribution of the exceptions over the genes
+__global__ void __launch_bounds__(256) adj_exceptions_kernel(const int64_t *__restrict__ ecolptr, const int32_t *__restrict__ erow,
+                                                             const double *__restrict__ eval, const double *__restrict__ w,
+                                                             const int64_t *__restrict__ segptr, int64_t n, double *__restrict__ segsum) {
+    __shared__ double red[32];
+    const int64_t s = blockIdx.x;
+    int64_t lo = 0, hi = n;  // gene of this segment: the last g with segptr[g] <= s
+    while (lo < hi) {
+        const int64_t mid = (lo + hi + 1) >> 1;
+        if (segptr[mid] <= s) lo = mid; else hi = mid - 1;
+    }
+    const int64_t g = lo;
+    const int64_t k0 = ecolptr[g] + (s - segptr[g]) * EXS, k1 = min(k0 + EXS, ecolptr[g + 1]);
+    double p = 0.0;
+    for (int64_t k = k0 + threadIdx.x; k < k1; k += 256) p = fma(__ldg(eval + k), __ldg(w + __ldg(erow + k)), p);
+    const double t = fact_block_sum(p, red);
+    if (threadIdx.x == 0) segsum[s] = t;
+}
+
+__global__ void __launch_bounds__(256) fwd_exceptions_kernel(const int64_t *__restrict__ erowptr, const int32_t *__restrict__ egene,
+                                                             const double *__restrict__ evalr, int64_t m, const double *__restrict__ x,
+                                                             const double *__restrict__ inv, double alpha, double *__restrict__ y) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e0 = erowptr[i], e1 = erowptr[i + 1];
+        if (e0 == e1) continue;
+        double s = 0.0;
+        for (int64_t k = e0; k < e1; ++k) {
+            const int g = __ldg(egene + k);
+            s = fma(__ldg(evalr + k), __ldg(x + g) * __ldg(inv + g), s);  // value*sd times x/sd (same rounding as the table entry xs)
+        }
+        y[i] = fma(alpha, s, y[i]);
+    }
 }
 
 // forward: y_i = alpha*(sum over the row's chunks of t_i[level] * sum_8 xs[gene] - mu.x) + beta*y_i + csign*(*coef)*cvec_i
@@ -668,8 +700,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 fwd_stream_kernel(const uint4 *__restrict__ code, const uint8_t *__restrict__ meta, const double *__restrict__ tlev, int log2L,
                   const int64_t *__restrict__ wstart, const int64_t *__restrict__ wrow, int64_t n, const double *__restrict__ x,
                   const double *__restrict__ inv, const double *__restrict__ mu, double alpha, double beta, double *__restrict__ y,
-                  const double *__restrict__ coef, double csign, const double *__restrict__ cvec, int nrep, int stride,
-                  const int64_t *__restrict__ erowptr, const int32_t *__restrict__ egene, const double *__restrict__ evalr) {
+                  const double *__restrict__ coef, double csign, const double *__restrict__ cvec, int nrep, int stride) {
     extern __shared__ double smem[];
     double *red = smem;      // 32
     double *xs = smem + 32;  // nrep bank-shifted replicas of {x_j / sd_j, j < n ; 0 (the pad gene)}, `stride` entries apart
@@ -708,7 +739,6 @@ fwd_stream_kernel(const uint4 *__restrict__ code, const uint8_t *__restrict__ me
     const double *tl = tlev + (rbase << log2L);
     double *yb = y + rbase;
     const double *cvb = cvec ? cvec + rbase : nullptr;
-    const int64_t *erp = erowptr ? erowptr + rbase : nullptr;  // exception entries of this warp's rows (cell-major side matrix)
     const unsigned padc = (unsigned)(BO ? n * 8 : n) * 0x10001u;
     const uint4 padq = make_uint4(padc, padc, padc, padc);
 
@@ -759,16 +789,12 @@ fwd_stream_kernel(const uint4 *__restrict__ code, const uint8_t *__restrict__ me
             if (nends == 1) { /* the usual case for rows longer than 32 chunks: one butterfly */                      \
                 const int b1 = __ffs(bal0) - 1;                                                                       \
                 r = acc + ((lane <= b1) ? v : 0.0);                                                                   \
-                if (erp != nullptr) /* the row's exception entries (exact values), spread over the 32 lanes */        \
-                    r += fwd_exceptions_lanes(erp, __shfl_sync(0xffffffffu, row0, b1), egene, evalr, xs, lane);       \
                 _Pragma("unroll") for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);           \
             } else { /* several (short) rows: carried sums enter at lane 0, then the segmented scan */                \
                 double tot = acc;                                                                                     \
                 _Pragma("unroll") for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);       \
                 bool head0;                                                                                           \
                 r = seg_scan(v + (lane == 0 ? tot : 0.0), bal0, lane, head0);                                         \
-                if (erp != nullptr && (mcur & 1u)) /* every end lane adds its own row's exceptions */                 \
-                    r += fwd_exceptions_serial(erp, row0, egene, evalr, xs);                                          \
             }                                                                                                         \
             if (mcur & 1u) {                                                                                          \
                 r = red[2] * (r - red[0]);                                                                            \
@@ -794,25 +820,6 @@ fwd_stream_kernel(const uint4 *__restrict__ code, const uint8_t *__restrict__ me
 #undef SVB_FWD_STEP
 }
 
-// sum of the exception entries of segment `seg` = (tile, gene): exact value (times sd) x w of the cell; one lane, serial
-// (the paths where several segments end in one warp iteration; the common single-end path spreads them over the lanes)
-__device__ __forceinline__ double adj_exceptions(const int64_t *__restrict__ estart, const int32_t *__restrict__ erow,
-                                                 const double *__restrict__ eval, int64_t seg, int64_t n, const double *__restrict__ wtile,
-                                                 int row0) {
-    double s = 0.0;
-    for (int64_t k = __ldg(estart + seg), e1 = __ldg(estart + seg + n); k < e1; ++k) s = fma(__ldg(eval + k), wtile[__ldg(erow + k) - row0], s);
-    return s;
-}
-
-__device__ __forceinline__ double adj_exceptions_lanes(const int64_t *__restrict__ estart, const int32_t *__restrict__ erow,
-                                                    const double *__restrict__ eval, int64_t seg, int64_t n, const double *__restrict__ wtile,
-                                                    int row0, int lane) {
-    double s = 0.0;  // this lane's share of the segment's entries
-    for (int64_t k = __ldg(estart + seg) + lane, e1 = __ldg(estart + seg + n); k < e1; k += 32)
-        s = fma(__ldg(eval + k), wtile[__ldg(erow + k) - row0], s);
-    return s;
-}
-
 // physical layout of the adjoint tile table (see the replica assignment above); identity = {0, 1, 0, 0, 0, R*L, R*L + 1}
 struct AdjGeom {
     int nlr, nrep, strideA, levstride, baseB, pad, wbase;
@@ -828,8 +835,7 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 adj_stream_kernel(const int64_t *__restrict__ gptr, const uint4 *__restrict__ code, const uint8_t *__restrict__ meta,
                   const double *__restrict__ tlevA, int log2L, int log2R, int64_t m, int64_t n, int64_t ntiles,
                   const double *__restrict__ w, const double *__restrict__ inv, double *__restrict__ partial,
-                  const int32_t *__restrict__ slices, unsigned int *__restrict__ counters, AdjGeom G,
-                  const int64_t *__restrict__ estart, const int32_t *__restrict__ erow, const double *__restrict__ eval) {
+                  const int32_t *__restrict__ slices, unsigned int *__restrict__ counters, AdjGeom G) {
     extern __shared__ double smem[];
     __shared__ long long cur_tile, nxt_tile;  // tiles are taken from the counter ONE AHEAD: the next tile's level table is
                                               // prefetched into L2 while this one is streamed (the fill then hits L2)
@@ -941,15 +947,12 @@ adj_stream_kernel(const int64_t *__restrict__ gptr, const uint4 *__restrict__ co
                 if (nends == 1) {                                                                                     \
                     const int b1 = __ffs(bal) - 1;                                                                    \
                     r = acc + ((lane <= b1) ? v : 0.0);                                                               \
-                    if (estart != nullptr) /* the segment's exception entries (exact values), over the 32 lanes */    \
-                        r += adj_exceptions_lanes(estart, erow, eval, t * n + (gbase - 1), n, T + G.wbase, (int)row0, lane); \
                     _Pragma("unroll") for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);       \
                 } else {                                                                                              \
                     double tot = acc;                                                                                 \
                     _Pragma("unroll") for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);   \
                     bool head0;                                                                                       \
                     r = seg_scan(v + (lane == 0 ? tot : 0.0), bal, lane, head0);                                      \
-                    if (estart != nullptr && (mcur & 1u)) r += adj_exceptions(estart, erow, eval, t * n + g, n, T + G.wbase, (int)row0); \
                 }                                                                                                     \
                 if (mcur & 1u) prow[g] = r * __ldg(inv + g);                                                          \
                 acc = (lane > 31 - __clz(bal)) ? v : 0.0;                                                             \
@@ -958,11 +961,7 @@ adj_stream_kernel(const int64_t *__restrict__ gptr, const uint4 *__restrict__ co
             bool head0;                                                                                               \
             double vs = seg_scan(v, bal, lane, head0);                                                                \
             if (head0) vs += acc; /* acc = the carried sum of the segment that started in an earlier iteration */     \
-            if (mcur & 1u) {                                                                                          \
-                double r = vs;                                                                                        \
-                if (estart != nullptr) r += adj_exceptions(estart, erow, eval, t * n + g, n, T + G.wbase, (int)row0); \
-                prow[g] = r * __ldg(inv + g);                                                                         \
-            }                                                                                                         \
+            if (mcur & 1u) prow[g] = vs * __ldg(inv + g);                                                             \
             const double v31 = __shfl_sync(0xffffffffu, vs, 31);                                                      \
             acc = (bal >> 31) ? 0.0 : v31;                                                                            \
         }                                                                                                             \
@@ -1025,9 +1024,14 @@ static void launch_fact_fwd(svb_operator_s *op, double alpha, const double *dx, 
     }
     k<<<(unsigned)f->fwd_grid, BLOCK, smem, ctx().stream>>>((const uint4 *)f->f_code, f->f_meta, f->tlev, f->log2L, f->fwd_ranges,
                                                              f->fwd_rows, op->n, dx, f->inv, op->mu, alpha, beta, dy, coef, csign, cvec,
-                                                             f->f_nrep, f->f_stride, f->excT ? f->excT->colptr : nullptr,
-                                                             f->excT ? f->excT->rowidx : nullptr, f->excT ? (const double *)f->excT->val : nullptr);
+                                                             f->f_nrep, f->f_stride);
     SVB_LAUNCH_CHECK();
+    if (f->excT) {
+        fwd_exceptions_kernel<<<fgrid(op->m, 256, 148 * 8), 256, 0, ctx().stream>>>(f->excT->colptr, f->excT->rowidx, (const double *)f->excT->val,
+                                                                                    op->m, dx, f->inv, alpha, dy);
+        count_launch();
+        SVB_LAUNCH_CHECK();
+    }
 }
 
 // adjoint CTA: 384 threads and a 64 KB table (R*L = 8192; three CTAs per SM), or -- SVB_FACT_LOG2R one larger -- 1024
@@ -1040,9 +1044,15 @@ void fact_fwd(svb_operator_s *op, double alpha, const double *dx, double beta, d
     // 64 registers per thread (4 x 256 or 2 x 512 threads per SM): 48 registers spill, and the kernel is bound by the
     // shared-memory pipe / issue slots, not by occupancy (measured 5 vs 4 CTAs per SM: within noise)
     if (((size_t)(op->fact->f_nrep - 1) * op->fact->f_stride + (size_t)op->n) * 8 > 24 * 1024) {
-        // 448 threads: 2 CTAs per SM leave 72 registers per thread (the loop needs ~70 with the exception side matrix; 64 spills)
-        if (bo) launch_fact_fwd<448, true, 2>(op, alpha, dx, beta, dy, coef, csign, cvec);
-        else launch_fact_fwd<448, false, 2>(op, alpha, dx, beta, dy, coef, csign, cvec);
+        // two CTAs per SM: 512 threads (64 registers, 32 warps per SM) or 448 (72 registers, 28 warps); SVB_FWD_BLOCK selects
+        static const int blk = getenv("SVB_FWD_BLOCK") ? atoi(getenv("SVB_FWD_BLOCK")) : 512;
+        if (blk == 448) {
+            if (bo) launch_fact_fwd<448, true, 2>(op, alpha, dx, beta, dy, coef, csign, cvec);
+            else launch_fact_fwd<448, false, 2>(op, alpha, dx, beta, dy, coef, csign, cvec);
+        } else {
+            if (bo) launch_fact_fwd<512, true, 2>(op, alpha, dx, beta, dy, coef, csign, cvec);
+            else launch_fact_fwd<512, false, 2>(op, alpha, dx, beta, dy, coef, csign, cvec);
+        }
     } else {
         if (bo) launch_fact_fwd<256, true, 3>(op, alpha, dx, beta, dy, coef, csign, cvec);
         else launch_fact_fwd<256, false, 3>(op, alpha, dx, beta, dy, coef, csign, cvec);
@@ -1060,10 +1070,14 @@ void fact_adj_stage1(svb_operator_s *op, const double *dx) {
     if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (f->adj_grid == 0) f->adj_grid = (int)std::max<int64_t>(1, std::min<int64_t>(fresident_grid(k, smem, block), f->ntiles));
     k<<<(unsigned)f->adj_grid, block, smem, ctx().stream>>>(f->a_gptr, (const uint4 *)f->a_code, f->a_meta, f->tlevA, f->log2L, f->log2R,
-                                                                 op->m, op->n, f->ntiles, dx, f->inv, f->partial, f->a_slices, f->counters, G,
-                                                                 f->a_estart, f->exc ? f->exc->rowidx : nullptr,
-                                                                 f->exc ? (const double *)f->exc->val : nullptr);
+                                                                 op->m, op->n, f->ntiles, dx, f->inv, f->partial, f->a_slices, f->counters, G);
     SVB_LAUNCH_CHECK();
+    if (f->exc && f->e_nseg > 0) {  // the exception side sums, one CTA per segment of <= 4096 entries (added by the reduce kernel)
+        adj_exceptions_kernel<<<(unsigned)f->e_nseg, 256, 0, ctx().stream>>>(f->exc->colptr, f->exc->rowidx, (const double *)f->exc->val, dx,
+                                                                             f->e_segptr, op->n, f->e_segsum);
+        count_launch();
+        SVB_LAUNCH_CHECK();
+    }
 }
 
 // algorithmic bytes of one product with THIS layout's widths: 2 B per stored entry and 1 B per chunk of 8 (pads are not
@@ -1077,8 +1091,8 @@ double fact_fwd_bytes(const svb_operator_s *op) {
 double fact_adj_bytes(const svb_operator_s *op) {
     const svb_factored_s *f = op->fact;
     const double nseg = (double)f->ntiles * (double)op->n;
-    return 2.125 * (double)f->nnz_main + 12.0 * (double)f->nnz_exc + (f->nnz_exc ? 8.0 * nseg : 0.0) +
-           (double)op->m * (8.0 * f->L + 8.0) + nseg * (8.0 + 8.0) + 24.0 * (double)op->n;
+    return 2.125 * (double)f->nnz_main + 12.0 * (double)f->nnz_exc + (double)op->m * (8.0 * f->L + 8.0) + nseg * (8.0 + 8.0) +
+           24.0 * (double)op->n;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1292,10 +1306,7 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
         const int64_t nseg = f->ntiles * n;
         DevBuf<int64_t> startpos((size_t)((f->ntiles + 1) * n + 1)), estart;  // estart stays empty: no exception chunks
         tile_bounds(a, log2R, f->ntiles, startpos.p);
-        if (e.p) {  // the adjoint's view of the exception side matrix: its (tile, gene) segments
-            SVB_CUDA(cudaMalloc((void **)&f->a_estart, (size_t)((f->ntiles + 1) * n + 1) * sizeof(int64_t)));
-            tile_bounds(e.p, log2R, f->ntiles, f->a_estart);
-        }
+
         SVB_CUDA(cudaMalloc((void **)&f->a_gptr, (size_t)(nseg + 1) * sizeof(int64_t)));
         fact_seg_count_kernel<<<fgrid(nseg * 8), 256, 0, st>>>(startpos.p, lvl.p, estart.p, nseg, n, f->a_gptr);
         count_launch();
@@ -1369,6 +1380,14 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
         f->excT = matrix_transpose(e.p);
         f->exc = e.p;
         e.p = nullptr;
+        SVB_CUDA(cudaMalloc((void **)&f->e_segptr, (size_t)(n + 1) * sizeof(int64_t)));
+        exc_segcount_kernel<<<(unsigned)((n + 256) / 256), 256, 0, st>>>(f->exc->colptr, n, f->e_segptr);
+        count_launch();
+        SVB_LAUNCH_CHECK();
+        exclusive_scan_i64(f->e_segptr, n + 1, st);
+        SVB_CUDA(cudaMemcpyAsync(&f->e_nseg, f->e_segptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        SVB_CUDA(cudaStreamSynchronize(st));
+        SVB_CUDA(cudaMalloc((void **)&f->e_segsum, (size_t)std::max<int64_t>(f->e_nseg, 1) * sizeof(double)));
         tick("exception side matrices");
     }
     SVB_CUDA(cudaMalloc((void **)&f->partial, (size_t)f->ntiles * (n + 1) * sizeof(double)));

@@ -195,7 +195,9 @@ __global__ void __launch_bounds__(32 * ADJR_TY) adj_reduce_kernel(const double *
                                                          const double *__restrict__ mu, double *__restrict__ tmp, int final,
                                                          double alpha, double beta, double *__restrict__ y,
                                                          const double *__restrict__ coef, double csign,
-                                                         const double *__restrict__ cvec, int use_p2p, P2PCtx pc) {
+                                                         const double *__restrict__ cvec, int use_p2p, P2PCtx pc,
+                                                         const int64_t *__restrict__ esegptr, const double *__restrict__ esegsum,
+                                                         const double *__restrict__ einv) {
     __shared__ double sh[ADJR_TY][33];
     __shared__ double shw[ADJR_TY];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -204,6 +206,13 @@ __global__ void __launch_bounds__(32 * ADJR_TY) adj_reduce_kernel(const double *
     for (int64_t t = ty; t < ntiles; t += ADJR_TY) {
         if (g < n) acc += partial[t * (n + 1) + g];
         if (tx == 0) wacc += partial[t * (n + 1) + n];
+    }
+    if (esegptr != nullptr && g < n) {
+        // count-level operator: the gene's exception entries (side matrix; exact value times sd, dotted with w segment by
+        // segment by adj_exceptions_kernel), scaled by 1/sd like the tile partials — fixed order, deterministic
+        double e = 0.0;
+        for (int64_t k = esegptr[g] + ty, e1 = esegptr[g + 1]; k < e1; k += ADJR_TY) e += esegsum[k];
+        acc = fma(e, einv[g], acc);
     }
     sh[ty][tx] = acc;
     if (tx == 0) shw[ty] = wacc;
@@ -439,7 +448,8 @@ void op_apply(svb_operator_s *op, bool trans, double alpha, const double *dx, do
         adj_reduce_kernel<<<(unsigned)((op->n + 31) / 32), 32 * ADJR_TY, 0, st>>>(fc ? fc->partial : op->partial, fc ? fc->ntiles : op->ntiles,
                                                                           op->n, op->mu, op->tmp,
                                                                           multi ? 0 : 1, alpha, beta, dy, coef, csign, cvec,
-                                                                          fused ? 1 : 0, pc);
+                                                                          fused ? 1 : 0, pc, (fc && fc->exc) ? fc->e_segptr : nullptr,
+                                                                          (fc && fc->exc) ? fc->e_segsum : nullptr, fc ? fc->inv : nullptr);
         SVB_LAUNCH_CHECK();
     }
     if (fused) {

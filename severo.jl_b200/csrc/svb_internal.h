@@ -171,9 +171,12 @@ struct svb_factored_s {
     double *partial = nullptr;       // [ntiles*(n+1)]
     int64_t nnz_main = 0, nnz_exc = 0;
     // exception entries (count > L, count < 1, clipped): NOT in the streams (round 2) — two small side matrices with the exact
-    // Float64 value (times sd), read by all the lanes of a warp at the end of the row / (tile, gene) segment they belong to
+    // Float64 value (times sd): the adjoint's reduce kernel and a per-cell kernel after the forward stream add them
     svb_matrix_s *exc = nullptr;     // gene-major (CSC): colptr[n+1], rowidx = cell, val f64 — the adjoint's view
-    int64_t *a_estart = nullptr;     // [(ntiles+1)*n + 1] first entry of column g with cell >= t*R: segment (t, g) = [a_estart[t*n+g], a_estart[(t+1)*n+g])
+    int64_t *e_segptr = nullptr;     // [n+1] the gene-major side matrix cut into segments of at most 4096 entries (balanced work: a few
+                                     // dense genes hold most of the exceptions); e_segsum[e_nseg] = per-segment sums of value*w
+    double *e_segsum = nullptr;
+    int64_t e_nseg = 0;
     svb_matrix_s *excT = nullptr;    // cell-major (CSC of the transpose): colptr[m+1] over cells, rowidx = gene — the forward's view
     // bank-shifted replicas of the gathered tables (round 2): the builder picks, set by set, the replica of every entry so that
     // the 16 gathers of a half-warp fall in 16 different 8-byte banks (bipartite matching at build time, see factored.cu)
