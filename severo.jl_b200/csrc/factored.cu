@@ -39,7 +39,7 @@ svb_factored_s::~svb_factored_s() {
 
 namespace svb {
 
-constexpr int FCH = 8;    // codes per chunk (one 16-byte load)
+constexpr int FCH = 16;   // codes per chunk (one 32-byte load: LDG.256); round 1-2a: 8
 constexpr int FEXC = 63;  // level field of an exception chunk in the forward stream
 
 static inline unsigned fgrid(int64_t n, int threads = 256, int max_blocks = 148 * 16) {
@@ -263,11 +263,11 @@ __device__ __forceinline__ int rr_position(const int *__restrict__ cnt, int rho,
 // the slots are enumerated set by set -- aligned block of 16 chunks, then element e, then chunk
 __device__ __forceinline__ int64_t rr_slot(int64_t g0, int64_t g1, int p) {
     const int w0 = (int)(min(g1, ((g0 >> 4) + 1) << 4) - g0);  // chunks of the group in its first block (1..16)
-    if (p < 8 * w0) return (g0 + p % w0) * FCH + p / w0;
-    const int pp = p - 8 * w0;
-    const int64_t cb = g0 + w0 + ((pp >> 7) << 4);              // every block before the last is full (128 slots)
+    if (p < FCH * w0) return (g0 + p % w0) * FCH + p / w0;
+    const int pp = p - FCH * w0;
+    const int64_t cb = g0 + w0 + ((pp / (16 * FCH)) << 4);      // every block before the last is full (16 chunks x FCH slots)
     const int wb = (int)min((int64_t)16, g1 - cb);
-    const int q = pp & 127;
+    const int q = pp % (16 * FCH);
     return (cb + q % wb) * FCH + q / wb;
 }
 
@@ -283,11 +283,11 @@ __device__ __forceinline__ int64_t rr_slot(int64_t g0, int64_t g1, int p) {
 // The pads of a set share one address and count as ONE entry. Exception chunks are left untouched.
 __global__ void __launch_bounds__(256) fact_assign_kernel(uint16_t *__restrict__ code, const uint8_t *__restrict__ meta,
                                                           int64_t nchunks, AssignGeom G, unsigned long long *__restrict__ stats) {
-    const int64_t nsets = ((nchunks + 15) >> 4) << 3;
+    const int64_t nsets = ((nchunks + 15) >> 4) * FCH;
     unsigned long long mypasses = 0, mysets = 0;
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nsets; s += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t blk = s >> 3;
-        const int e = (int)(s & 7);
+        const int64_t blk = s / FCH;
+        const int e = (int)(s % FCH);
         int v[16];
         unsigned present = 0;
 #pragma unroll
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(256) fact_assign_kernel(uint16_t *__restrict__
             const int64_t ch = (blk << 4) + c;
             if (ch >= nchunks) continue;
             const unsigned mb = meta[ch];
-            if (G.adjoint ? (mb & 2u) != 0u : (mb >> 1) == (unsigned)FEXC) continue;  // exception chunk: another format
+            (void)mb;
             v[c] = code[ch * FCH + e];
             present |= 1u << c;
         }
@@ -323,7 +323,7 @@ static double run_assign(uint16_t *code, const uint8_t *meta, int64_t nchunks, c
     if (nchunks <= 0) return 0.0;
     DevBuf<unsigned long long> d(2);
     SVB_CUDA(cudaMemsetAsync(d.p, 0, 2 * sizeof(unsigned long long), st));
-    const int64_t nsets = ((nchunks + 15) >> 4) << 3;
+    const int64_t nsets = ((nchunks + 15) >> 4) * FCH;
     fact_assign_kernel<<<fgrid(nsets, 256, 148 * 32), 256, 0, st>>>(code, meta, nchunks, G, d.p);
     count_launch();
     SVB_LAUNCH_CHECK();
@@ -349,8 +349,8 @@ __global__ void __launch_bounds__(256) fact_seg_count_kernel(const int64_t *__re
         c += __shfl_xor_sync(submask, c, 4);
         c += __shfl_xor_sync(submask, c, 2);
         c += __shfl_xor_sync(submask, c, 1);
-        const int ne = estart ? (int)(estart[s + ncol] - estart[s]) : 0;  // one chunk per exception
-        if (sl == 0) gptr[s] = max(1, (c + FCH - 1) / FCH + ne);
+        (void)estart;
+        if (sl == 0) gptr[s] = max(1, (c + FCH - 1) / FCH);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) gptr[nseg] = 0;
 }
@@ -378,8 +378,8 @@ __global__ void __launch_bounds__(256) fact_seg_fill_kernel(const int64_t *__res
         const int64_t t = s / ncol;
         const int64_t row0 = t << log2R;
         const int64_t c0 = gptr[s], c1 = gptr[s + 1];
-        const int64_t eb = estart ? estart[s] : 0, ee = estart ? estart[s + ncol] : 0;
-        const int64_t cx = c1 - (ee - eb);  // first exception chunk; the coded chunks are [c0, cx)
+        (void)estart; (void)erow; (void)eval;
+        const int64_t cx = c1;
         cnt[sl] = 0; cnt[sl + 8] = 0; run[sl] = 0; run[sl + 8] = 0;
         for (int64_t p = c0 * FCH + sl; p < cx * FCH; p += 8) code[p] = padcode;
         __syncwarp(submask);
@@ -403,15 +403,7 @@ __global__ void __launch_bounds__(256) fact_seg_fill_kernel(const int64_t *__res
             if (lv && (peers >> sl) == 1u) run[rho] += __popc(peers);  // the last lane of every class updates its counter
             __syncwarp(submask);
         }
-        for (int64_t k = eb + sl; k < ee; k += 8) {  // {i_local, -, value*sd as Float64}
-            uint4 q;
-            q.x = (unsigned)(erow[k] - row0);
-            q.y = 0u;
-            q.z = (unsigned)__double2loint(eval[k]);
-            q.w = (unsigned)__double2hiint(eval[k]);
-            reinterpret_cast<uint4 *>(code)[cx + (k - eb)] = q;
-        }
-        for (int64_t c = c0 + sl; c < c1; c += 8) meta[c] = (uint8_t)((c == c1 - 1) | ((c >= cx) << 1));
+        for (int64_t c = c0 + sl; c < c1; c += 8) meta[c] = (uint8_t)(c == c1 - 1);
         __syncwarp(submask);
     }
 }
@@ -532,33 +524,7 @@ __global__ void __launch_bounds__(256) fact_row_place_kernel(const int64_t *__re
             if (lv && (peers >> lane) == 1u) run[key] += __popc(peers);  // the last lane of every class updates its counter
             __syncwarp();
         }
-        if (ecolptr && coded < total) {  // exception chunks {gene, -, value*sd as Float64}, level field = FEXC, ascending gene
-            int c = coded;
-            for (int64_t k0 = b; k0 < e; k0 += 32) {
-                const int64_t k = k0 + lane;
-                const bool hit = (k < e) && (rlvl[k] == 0);
-                const unsigned bal = __ballot_sync(0xffffffffu, hit);
-                if (hit) {
-                    const int g = ridx[k];
-                    // the value lives in the gene-major exception matrix: find this cell in column g
-                    int64_t lo = ecolptr[g], hi = ecolptr[g + 1];
-                    while (lo < hi) {
-                        const int64_t mid = (lo + hi) >> 1;
-                        if ((int64_t)erow[mid] < r) lo = mid + 1; else hi = mid;
-                    }
-                    const double v = eval[lo];
-                    const int cc = c + __popc(bal & ((1u << lane) - 1u));
-                    uint4 q;
-                    q.x = (unsigned)g;
-                    q.y = 0u;
-                    q.z = (unsigned)__double2loint(v);
-                    q.w = (unsigned)__double2hiint(v);
-                    reinterpret_cast<uint4 *>(code)[cbase + cc] = q;
-                    meta[cbase + cc] = (uint8_t)((FEXC << 1) | (cc == total - 1));
-                }
-                c += __popc(bal);
-            }
-        }
+        (void)ecolptr; (void)erow; (void)eval;
         __syncwarp();
     }
 }
@@ -610,6 +576,17 @@ __device__ __forceinline__ double gather8(const double *__restrict__ T, const ui
     return ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
+// one chunk = 16 codes = 32 bytes, fetched with ONE 256-bit load (LDG.E.256 on sm_100)
+struct __align__(32) Chunk {
+    uint4 lo, hi;
+};
+__device__ __forceinline__ Chunk ld_chunk(const Chunk *p) {  // streamed once: do not keep it in L1
+    Chunk c;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(c.lo.x), "=r"(c.lo.y), "=r"(c.lo.z), "=r"(c.lo.w), "=r"(c.hi.x), "=r"(c.hi.y), "=r"(c.hi.z), "=r"(c.hi.w)
+                 : "l"(p));
+    return c;
+}
 __device__ __forceinline__ uint4 ld_stream16(const uint4 *p) {  // streamed once: do not keep it in L1
     uint4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
@@ -676,18 +653,33 @@ __global__ void __launch_bounds__(256) adj_exceptions_kernel(const int64_t *__re
     if (threadIdx.x == 0) segsum[s] = t;
 }
 
+// y_i += alpha * sum over the cell's exception entries of value * (x_g / sd_g). A block owns 256 consecutive cells: their
+// entries are one contiguous range of the cell-major side matrix, loaded coalesced and turned into products in shared memory
+// (2048 at a time); every thread then adds up its own cell's products in order. (First version: a serial loop per thread
+// over its cell's entries straight from global memory — 74 us at C3 for 124 MB; uncoalesced.)
+constexpr int FXT = 2048;
 __global__ void __launch_bounds__(256) fwd_exceptions_kernel(const int64_t *__restrict__ erowptr, const int32_t *__restrict__ egene,
                                                              const double *__restrict__ evalr, int64_t m, const double *__restrict__ x,
                                                              const double *__restrict__ inv, double alpha, double *__restrict__ y) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t e0 = erowptr[i], e1 = erowptr[i + 1];
-        if (e0 == e1) continue;
+    __shared__ double prod[FXT];
+    for (int64_t c0 = (int64_t)blockIdx.x * 256; c0 < m; c0 += (int64_t)gridDim.x * 256) {
+        const int64_t c1 = min(c0 + 256, m);
+        const int64_t ebeg = erowptr[c0], eend = erowptr[c1];
+        if (ebeg == eend) continue;  // block-uniform
+        const int64_t i = c0 + threadIdx.x;
+        const int64_t a = i < m ? erowptr[i] : eend, b = i < m ? erowptr[i + 1] : eend;
         double s = 0.0;
-        for (int64_t k = e0; k < e1; ++k) {
-            const int g = __ldg(egene + k);
-            s = fma(__ldg(evalr + k), __ldg(x + g) * __ldg(inv + g), s);  // value*sd times x/sd (same rounding as the table entry xs)
+        for (int64_t base = ebeg; base < eend; base += FXT) {
+            const int nb = (int)min((int64_t)FXT, eend - base);
+            for (int k = threadIdx.x; k < nb; k += 256) {
+                const int g = __ldg(egene + base + k);
+                prod[k] = __ldg(evalr + base + k) * (__ldg(x + g) * __ldg(inv + g));  // value*sd times x/sd (the table entry xs)
+            }
+            __syncthreads();
+            for (int64_t k = max(a, base), ke = min(b, base + nb); k < ke; ++k) s += prod[k - base];
+            __syncthreads();
         }
-        y[i] = fma(alpha, s, y[i]);
+        if (b > a) y[i] = fma(alpha, s, y[i]);
     }
 }
 
@@ -697,7 +689,7 @@ __global__ void __launch_bounds__(256) fwd_exceptions_kernel(const int64_t *__re
 // are unrolled by hand (no register rotation): ~200 -> ~150 instructions per 32 chunks.
 template <int BLOCK, bool BO, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
-fwd_stream_kernel(const uint4 *__restrict__ code, const uint8_t *__restrict__ meta, const double *__restrict__ tlev, int log2L,
+fwd_stream_kernel(const Chunk *__restrict__ code, const uint8_t *__restrict__ meta, const double *__restrict__ tlev, int log2L,
                   const int64_t *__restrict__ wstart, const int64_t *__restrict__ wrow, int64_t n, const double *__restrict__ x,
                   const double *__restrict__ inv, const double *__restrict__ mu, double alpha, double beta, double *__restrict__ y,
                   const double *__restrict__ coef, double csign, const double *__restrict__ cvec, int nrep, int stride) {
@@ -734,28 +726,29 @@ fwd_stream_kernel(const uint4 *__restrict__ code, const uint8_t *__restrict__ me
     const int64_t cbase = cbeg & ~(int64_t)31;
     const int lo = (int)(cbeg - cbase), hi = (int)(cend - cbase);  // this warp's chunks, relative to cbase
     const int64_t rbase = __ldg(wrow + gw);
-    const uint4 *pc = code + cbase + lane;
+    const Chunk *pc = code + cbase + lane;
     const uint8_t *pm = meta + cbase + lane;
     const double *tl = tlev + (rbase << log2L);
     double *yb = y + rbase;
     const double *cvb = cvec ? cvec + rbase : nullptr;
     const unsigned padc = (unsigned)(BO ? n * 8 : n) * 0x10001u;
-    const uint4 padq = make_uint4(padc, padc, padc, padc);
+    Chunk padq;
+    padq.lo = make_uint4(padc, padc, padc, padc);
+    padq.hi = padq.lo;
 
     int rel = lane;   // this lane's chunk of the current iteration, relative to cbase
     int rowrel = 0;   // row (relative to rbase) of the first chunk of the next iteration to be decoded
-    uint4 q0, q1, q2;
-    unsigned m0, m1, m2;
+    constexpr int NSF = 2;  // stages in flight: 2 x 32 bytes per lane (round 1: 3 x 16)
+    Chunk q0, q1;
+    unsigned m0, m1;
     {
-        const bool ok0 = rel >= lo && rel < hi, ok1 = rel + 32 < hi, ok2 = rel + 64 < hi;
-        q0 = ok0 ? ld_stream16(pc) : padq;
+        const bool ok0 = rel >= lo && rel < hi, ok1 = rel + 32 < hi;
+        q0 = ok0 ? ld_chunk(pc) : padq;
         m0 = ok0 ? (unsigned)__ldg(pm) : 0u;
-        q1 = ok1 ? ld_stream16(pc + 32) : padq;
+        q1 = ok1 ? ld_chunk(pc + 32) : padq;
         m1 = ok1 ? (unsigned)__ldg(pm + 32) : 0u;
-        q2 = ok2 ? ld_stream16(pc + 64) : padq;
-        m2 = ok2 ? (unsigned)__ldg(pm + 64) : 0u;
-        pc += 96;
-        pm += 96;
+        pc += 32 * NSF;
+        pm += 32 * NSF;
     }
     // decode iteration 0 and fetch its table entries
     unsigned bal0 = __ballot_sync(0xffffffffu, (m0 & 1u) != 0u);
@@ -770,10 +763,10 @@ fwd_stream_kernel(const uint4 *__restrict__ code, const uint8_t *__restrict__ me
         const int row1 = rowrel + __popc(bal1 & lt);                                                                  \
         rowrel += __popc(bal1);                                                                                       \
         const double t1 = (rel + 32 < hi) ? __ldg(tl + ((int64_t)row1 << log2L) + ((MB) >> 1)) : 0.0;                 \
-        const double v = t0 * (BO ? gather8b(xs, (QA)) : gather8(xs, (QA)));                                          \
+        const double v = t0 * (BO ? (gather8b(xs, (QA).lo) + gather8b(xs, (QA).hi)) : (gather8(xs, (QA).lo) + gather8(xs, (QA).hi))); \
         const unsigned mcur = (MA);                                                                                   \
-        if (rel + 32 * FPD < hi) {                                                                                    \
-            (QA) = ld_stream16(pc);                                                                                   \
+        if (rel + 32 * NSF < hi) {                                                                                    \
+            (QA) = ld_chunk(pc);                                                                                      \
             (MA) = (unsigned)__ldg(pm);                                                                               \
         } else {                                                                                                      \
             (QA) = padq;                                                                                              \
@@ -813,9 +806,7 @@ fwd_stream_kernel(const uint4 *__restrict__ code, const uint8_t *__restrict__ me
     while (rel - lane < hi) {
         SVB_FWD_STEP(q0, m0, m1)
         if (rel - lane >= hi) break;
-        SVB_FWD_STEP(q1, m1, m2)
-        if (rel - lane >= hi) break;
-        SVB_FWD_STEP(q2, m2, m0)
+        SVB_FWD_STEP(q1, m1, m0)
     }
 #undef SVB_FWD_STEP
 }
@@ -832,7 +823,7 @@ struct AdjGeom {
 // are longer than a warp iteration: the 1024-cell tiles); otherwise a segmented scan every iteration + a carry register.
 template <int BLOCK, int MINB, bool LAZY, int NS>
 __global__ void __launch_bounds__(BLOCK, MINB)
-adj_stream_kernel(const int64_t *__restrict__ gptr, const uint4 *__restrict__ code, const uint8_t *__restrict__ meta,
+adj_stream_kernel(const int64_t *__restrict__ gptr, const Chunk *__restrict__ code, const uint8_t *__restrict__ meta,
                   const double *__restrict__ tlevA, int log2L, int log2R, int64_t m, int64_t n, int64_t ntiles,
                   const double *__restrict__ w, const double *__restrict__ inv, double *__restrict__ partial,
                   const int32_t *__restrict__ slices, unsigned int *__restrict__ counters, AdjGeom G) {
@@ -847,7 +838,9 @@ adj_stream_kernel(const int64_t *__restrict__ gptr, const uint4 *__restrict__ co
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     const unsigned padc = (unsigned)G.pad * 0x10001u;
-    const uint4 padq = make_uint4(padc, padc, padc, padc);
+    Chunk padq;
+    padq.lo = make_uint4(padc, padc, padc, padc);
+    padq.hi = padq.lo;
     bool first = true;
     for (;;) {
         __syncthreads();  // everybody is done with the previous tile's table (and has read cur_tile)
@@ -894,24 +887,24 @@ adj_stream_kernel(const int64_t *__restrict__ gptr, const uint4 *__restrict__ co
         // iteration (profiles/r04_spmv.md)
         const int64_t cbase = cbeg & ~(int64_t)31;
         const int lo = (int)(cbeg - cbase), hi = (int)(cend - cbase);
-        const uint4 *pc = code + cbase + lane;
+        const Chunk *pc = code + cbase + lane;
         const uint8_t *pm = meta + cbase + lane;
         int rel = lane;
         // NS stages in flight: 3 or 4 for the one-CTA-per-SM kernel (64-register budget), 2 for the three-CTAs-per-SM one (40)
-        uint4 q0, q1, q2 = padq, q3 = padq;
+        Chunk q0, q1, q2 = padq, q3 = padq;
         unsigned m0, m1, m2 = 0u, m3 = 0u;
         {
             const bool ok0 = rel >= lo && rel < hi, ok1 = rel + 32 < hi, ok2 = NS >= 3 && rel + 64 < hi, ok3 = NS >= 4 && rel + 96 < hi;
-            q0 = ok0 ? ld_stream16(pc) : padq;
+            q0 = ok0 ? ld_chunk(pc) : padq;
             m0 = ok0 ? (unsigned)__ldg(pm) : 0u;
-            q1 = ok1 ? ld_stream16(pc + 32) : padq;
+            q1 = ok1 ? ld_chunk(pc + 32) : padq;
             m1 = ok1 ? (unsigned)__ldg(pm + 32) : 0u;
             if (NS >= 3) {
-                q2 = ok2 ? ld_stream16(pc + 64) : padq;
+                q2 = ok2 ? ld_chunk(pc + 64) : padq;
                 m2 = ok2 ? (unsigned)__ldg(pm + 64) : 0u;
             }
             if (NS >= 4) {
-                q3 = ok3 ? ld_stream16(pc + 96) : padq;
+                q3 = ok3 ? ld_chunk(pc + 96) : padq;
                 m3 = ok3 ? (unsigned)__ldg(pm + 96) : 0u;
             }
             pc += 32 * NS;
@@ -928,9 +921,9 @@ adj_stream_kernel(const int64_t *__restrict__ gptr, const uint4 *__restrict__ co
         const unsigned bal = __ballot_sync(0xffffffffu, (mcur & 1u) != 0u);                                           \
         const int g = gbase + __popc(bal & lt);                                                                       \
         gbase += __popc(bal);                                                                                         \
-        const double v = gather8(T, (QA));                                                                            \
+        const double v = gather8(T, (QA).lo) + gather8(T, (QA).hi);                                                   \
         if (rel + 32 * NS < hi) { /* refill this stage with the chunk of iteration + NS */                            \
-            (QA) = ld_stream16(pc);                                                                                   \
+            (QA) = ld_chunk(pc);                                                                                      \
             (MA) = (unsigned)__ldg(pm);                                                                               \
         } else {                                                                                                      \
             (QA) = padq;                                                                                              \
@@ -1012,7 +1005,7 @@ static void launch_fact_fwd(svb_operator_s *op, double alpha, const double *dx, 
     if (f->fwd_grid == 0) {
         // one resident wave; fewer warps when the matrix is small (at least ~8 iterations of 32 chunks per warp)
         int grid = fresident_grid(k, smem, BLOCK);
-        const int64_t want = std::max<int64_t>(1, f->f_chunks / (256 * (BLOCK / 32)));
+        const int64_t want = std::max<int64_t>(1, f->f_chunks / (128 * (BLOCK / 32)));
         grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid, want));
         const int NW = grid * (BLOCK / 32);
         SVB_CUDA(cudaMalloc((void **)&f->fwd_ranges, (size_t)(NW + 1) * sizeof(int64_t)));
@@ -1022,7 +1015,7 @@ static void launch_fact_fwd(svb_operator_s *op, double alpha, const double *dx, 
         SVB_LAUNCH_CHECK();
         f->fwd_grid = grid;
     }
-    k<<<(unsigned)f->fwd_grid, BLOCK, smem, ctx().stream>>>((const uint4 *)f->f_code, f->f_meta, f->tlev, f->log2L, f->fwd_ranges,
+    k<<<(unsigned)f->fwd_grid, BLOCK, smem, ctx().stream>>>((const Chunk *)f->f_code, f->f_meta, f->tlev, f->log2L, f->fwd_ranges,
                                                              f->fwd_rows, op->n, dx, f->inv, op->mu, alpha, beta, dy, coef, csign, cvec,
                                                              f->f_nrep, f->f_stride);
     SVB_LAUNCH_CHECK();
@@ -1064,12 +1057,12 @@ void fact_adj_stage1(svb_operator_s *op, const double *dx) {
     const size_t smem = (32 + (size_t)f->a_tabsize) * sizeof(double);
     const int block = adj_block_of(f);
     const AdjGeom G{f->a_nlr, f->a_nrep, f->a_strideA, f->a_levstride, f->a_baseB, f->a_pad, f->a_wbase};
-    static const int stages = getenv("SVB_ADJ_STAGES") ? atoi(getenv("SVB_ADJ_STAGES")) : 3;
-    auto k = (block == 1024) ? (stages >= 4 ? adj_stream_kernel<1024, 1, true, 4> : adj_stream_kernel<1024, 1, true, 3>)
+    static const int stages = getenv("SVB_ADJ_STAGES") ? atoi(getenv("SVB_ADJ_STAGES")) : 2;
+    auto k = (block == 1024) ? (stages >= 3 ? adj_stream_kernel<1024, 1, true, 3> : adj_stream_kernel<1024, 1, true, 2>)
                              : adj_stream_kernel<384, 3, false, 2>;  // 3 x 384 threads: 56 registers (512 threads: 40, spills)
     if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (f->adj_grid == 0) f->adj_grid = (int)std::max<int64_t>(1, std::min<int64_t>(fresident_grid(k, smem, block), f->ntiles));
-    k<<<(unsigned)f->adj_grid, block, smem, ctx().stream>>>(f->a_gptr, (const uint4 *)f->a_code, f->a_meta, f->tlevA, f->log2L, f->log2R,
+    k<<<(unsigned)f->adj_grid, block, smem, ctx().stream>>>(f->a_gptr, (const Chunk *)f->a_code, f->a_meta, f->tlevA, f->log2L, f->log2R,
                                                                  op->m, op->n, f->ntiles, dx, f->inv, f->partial, f->a_slices, f->counters, G);
     SVB_LAUNCH_CHECK();
     if (f->exc && f->e_nseg > 0) {  // the exception side sums, one CTA per segment of <= 4096 entries (added by the reduce kernel)
@@ -1085,13 +1078,13 @@ void fact_adj_stage1(svb_operator_s *op, const double *dx) {
 double fact_fwd_bytes(const svb_operator_s *op) {
     const svb_factored_s *f = op->fact;
     // exception entries: 12 B each (Float64 value + Int32 gene) + the cell pointers of the side matrix
-    return 2.125 * (double)f->nnz_main + 12.0 * (double)f->nnz_exc + (f->nnz_exc ? 8.0 * op->m : 0.0) +
+    return (2.0 + 1.0 / FCH) * (double)f->nnz_main + 12.0 * (double)f->nnz_exc + (f->nnz_exc ? 8.0 * op->m : 0.0) +
            (double)op->m * (8.0 * f->L + 8.0) + 24.0 * (double)op->n;
 }
 double fact_adj_bytes(const svb_operator_s *op) {
     const svb_factored_s *f = op->fact;
     const double nseg = (double)f->ntiles * (double)op->n;
-    return 2.125 * (double)f->nnz_main + 12.0 * (double)f->nnz_exc + (double)op->m * (8.0 * f->L + 8.0) + nseg * (8.0 + 8.0) +
+    return (2.0 + 1.0 / FCH) * (double)f->nnz_main + 12.0 * (double)f->nnz_exc + (double)op->m * (8.0 * f->L + 8.0) + nseg * (8.0 + 8.0) +
            24.0 * (double)op->n;
 }
 
@@ -1314,7 +1307,7 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
         exclusive_scan_i64(f->a_gptr, nseg + 1, st);
         SVB_CUDA(cudaMemcpyAsync(&f->a_chunks, f->a_gptr + nseg, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
         SVB_CUDA(cudaStreamSynchronize(st));
-        SVB_CUDA(cudaMalloc((void **)&f->a_code, (size_t)std::max<int64_t>(f->a_chunks, 1) * 16));
+        SVB_CUDA(cudaMalloc((void **)&f->a_code, (size_t)std::max<int64_t>(f->a_chunks, 1) * FCH * 2));
         SVB_CUDA(cudaMalloc((void **)&f->a_meta, (size_t)std::max<int64_t>(f->a_chunks, 1)));
         fact_seg_fill_kernel<<<fgrid(nseg * 8), 256, 0, st>>>(startpos.p, a->rowidx, lvl.p, nseg, n, log2R, log2L, f->a_gptr, estart.p,
                                                               nullptr, nullptr, (uint16_t *)f->a_code, f->a_meta);
@@ -1360,7 +1353,7 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
         exclusive_scan_i64(f->f_rowptr, m + 1, st);
         SVB_CUDA(cudaMemcpyAsync(&f->f_chunks, f->f_rowptr + m, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
         SVB_CUDA(cudaStreamSynchronize(st));
-        SVB_CUDA(cudaMalloc((void **)&f->f_code, (size_t)std::max<int64_t>(f->f_chunks, 1) * 16));
+        SVB_CUDA(cudaMalloc((void **)&f->f_code, (size_t)std::max<int64_t>(f->f_chunks, 1) * FCH * 2));
         SVB_CUDA(cudaMalloc((void **)&f->f_meta, (size_t)std::max<int64_t>(f->f_chunks, 1)));
         f->f_cshift = (n <= 8190) ? 3 : 0;  // the codes of the forward stream are byte offsets when they fit in 16 bits
         fact_row_place_kernel<<<gw, 256, (size_t)8 * 2 * L * 16 * sizeof(int), st>>>(rowptr.p, ridx.p, rlvl.p, m, L, (int)n, f->f_cshift, f->f_rowptr, gend.p,
@@ -1454,7 +1447,7 @@ int svb_operator_counts_stream(svb_operator_t op, int adjoint, uint16_t *code, u
     const svb_factored_s *f = op->fact;
     const int64_t nch = adjoint ? f->a_chunks : f->f_chunks;
     cudaStream_t st = ctx().stream;
-    if (code) SVB_CUDA(cudaMemcpyAsync(code, adjoint ? f->a_code : f->f_code, (size_t)nch * 16, cudaMemcpyDeviceToHost, st));
+    if (code) SVB_CUDA(cudaMemcpyAsync(code, adjoint ? f->a_code : f->f_code, (size_t)nch * FCH * 2, cudaMemcpyDeviceToHost, st));
     if (meta) SVB_CUDA(cudaMemcpyAsync(meta, adjoint ? f->a_meta : f->f_meta, (size_t)nch, cudaMemcpyDeviceToHost, st));
     SVB_CUDA(cudaStreamSynchronize(st));
     SVB_API_END

@@ -17,10 +17,10 @@ C = sv.scale_features_counts(X, scale_factor=1e4, scale_max=10.0, features=hvf, 
 info = C.info()
 print(info)
 nch = info["adj_chunks"]
-code = np.zeros(nch * 8, dtype=np.uint16)
+code = np.zeros(nch * 16, dtype=np.uint16)
 meta = np.zeros(nch, dtype=np.uint8)
 sv._lib.check(sv.lib().svb_operator_counts_stream(C._op, 1, sv._lib.ptr(code), sv._lib.ptr(meta)))
-code = code.reshape(nch, 8).astype(np.int64)
+code = code.reshape(nch, 16).astype(np.int64)
 R, L = info["tile_cells"], info["levels"]
 RL = R * L
 exc = (meta & 2) != 0
