@@ -194,7 +194,7 @@ def test_counts_operator_replica_tables(sv, orc, monkeypatch, levels, log2r, wan
     assert info["tile_cells"] == 1 << log2r and info["levels"] == levels
     assert info["fwd_replicas"] == 4 and (info["adj_replicated_levels"], info["adj_replicas"]) == want
     assert 1.0 <= info["fwd_passes_per_set"] < 1.3
-    assert 1.0 <= info["adj_passes_per_set"] < (1.25 if want[1] >= 3 else 1.6)
+    assert 1.0 <= info["adj_passes_per_set"] < 1.6   # (a 9,000-cell matrix: short segments, sets shared by several of them; 1.10-1.17 at C3)
     _check_products(C, So, np.random.default_rng(5))
     init = np.random.default_rng(6).standard_normal(400)
     G = sv.irlba(C, 8, init=init, tol=1e-9)
