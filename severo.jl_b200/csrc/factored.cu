@@ -408,8 +408,11 @@ __global__ void __launch_bounds__(256) fact_seg_fill_kernel(const int64_t *__res
     }
 }
 
-// adjoint: gene boundaries that cut every tile into K slices of equal chunk count (one slice per warp of the CTA)
-__global__ void fact_slices_kernel(const int64_t *__restrict__ gptr, int64_t ntiles, int64_t n, int K, int32_t *__restrict__ slices) {
+// adjoint: gene boundaries that cut every tile into K slices (one per warp of the CTA) of equal WORK. A warp iteration streams
+// 32 chunks in ~120 instructions, the end of a (tile, gene) segment costs ~50 more (reduction across the lanes + store), i.e.
+// as much as ~12 chunks: slices of equal chunk count made the warps that own the sparse genes (many short segments) arrive
+// late at the tile barrier (9 % of the kernel's stall samples, profiles/r04_spmv.md). Work(g) = chunks before gene g + alpha * g.
+__global__ void fact_slices_kernel(const int64_t *__restrict__ gptr, int64_t ntiles, int64_t n, int K, int alpha, int32_t *__restrict__ slices) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ntiles * (K + 1)) return;
     const int64_t t = i / (K + 1);
@@ -420,11 +423,12 @@ __global__ void fact_slices_kernel(const int64_t *__restrict__ gptr, int64_t nti
     if (k == 0) g = 0;
     else if (k == K) g = n;
     else {
-        const int64_t target = c0 + (int64_t)(((__int128)(c1 - c0) * k) / K);
+        const int64_t total = (c1 - c0) + (int64_t)alpha * n;
+        const int64_t target = (int64_t)(((__int128)total * k) / K);
         int64_t lo = 0, hi = n;
         while (lo < hi) {
             const int64_t mid = (lo + hi) >> 1;
-            if (gp[mid] < target) lo = mid + 1; else hi = mid;
+            if ((gp[mid] - c0) + (int64_t)alpha * mid < target) lo = mid + 1; else hi = mid;
         }
         g = lo;
     }
@@ -866,14 +870,24 @@ adj_stream_kernel(const int64_t *__restrict__ gptr, const Chunk *__restrict__ co
             const double wv = (row < m) ? __ldg(w + row) : 0.0;
             T[G.wbase + il] = wv;
             part += wv;
-#pragma unroll 4
-            for (int l = 0; l < Lv; ++l) {
-                const double v = __ldg(tl + (l << log2R) + il) * wv;  // tlevA is zero beyond the last cell
-                if (l < G.nlr) {
-                    double *dst = T + l * G.levstride + il;
-                    for (int r = 0; r < G.nrep; ++r) dst[r * G.strideA] = v;
-                } else {
-                    T[G.baseB + ((l - G.nlr) << log2R) + il] = v;
+            // ALL the loads of a batch of 16 levels first, then the products and the stores: ncu on the first version (unroll
+            // 4) showed four serial L2 round trips per tile here — 12 % of the kernel's stall samples on its four DMULs
+            for (int l0 = 0; l0 < Lv; l0 += 16) {
+                double tv[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) tv[j] = (l0 + j < Lv) ? __ldg(tl + ((l0 + j) << log2R) + il) : 0.0;  // zero beyond the last cell
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int l = l0 + j;
+                    if (l < Lv) {
+                        const double v = tv[j] * wv;
+                        if (l < G.nlr) {
+                            double *dst = T + l * G.levstride + il;
+                            for (int r = 0; r < G.nrep; ++r) dst[r * G.strideA] = v;
+                        } else {
+                            T[G.baseB + ((l - G.nlr) << log2R) + il] = v;
+                        }
+                    }
                 }
             }
         }
@@ -1038,7 +1052,7 @@ void fact_fwd(svb_operator_s *op, double alpha, const double *dx, double beta, d
     // shared-memory pipe / issue slots, not by occupancy (measured 5 vs 4 CTAs per SM: within noise)
     if (((size_t)(op->fact->f_nrep - 1) * op->fact->f_stride + (size_t)op->n) * 8 > 24 * 1024) {
         // two CTAs per SM: 512 threads (64 registers, 32 warps per SM) or 448 (72 registers, 28 warps); SVB_FWD_BLOCK selects
-        static const int blk = getenv("SVB_FWD_BLOCK") ? atoi(getenv("SVB_FWD_BLOCK")) : 512;
+        static const int blk = getenv("SVB_FWD_BLOCK") ? atoi(getenv("SVB_FWD_BLOCK")) : 448;
         if (blk == 448) {
             if (bo) launch_fact_fwd<448, true, 2>(op, alpha, dx, beta, dy, coef, csign, cvec);
             else launch_fact_fwd<448, false, 2>(op, alpha, dx, beta, dy, coef, csign, cvec);
@@ -1320,7 +1334,8 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
         }
         const int K = adj_block_of(f) / 32;
         SVB_CUDA(cudaMalloc((void **)&f->a_slices, (size_t)f->ntiles * (K + 1) * sizeof(int32_t)));
-        fact_slices_kernel<<<(unsigned)((f->ntiles * (K + 1) + 255) / 256), 256, 0, st>>>(f->a_gptr, f->ntiles, n, K, f->a_slices);
+        static const int slice_alpha = getenv("SVB_ADJ_SLICE_ALPHA") ? atoi(getenv("SVB_ADJ_SLICE_ALPHA")) : 8;
+        fact_slices_kernel<<<(unsigned)((f->ntiles * (K + 1) + 255) / 256), 256, 0, st>>>(f->a_gptr, f->ntiles, n, K, slice_alpha, f->a_slices);
         SVB_CUDA(cudaMalloc((void **)&f->counters, 2 * sizeof(unsigned int)));
         SVB_CUDA(cudaMemsetAsync(f->counters, 0, 2 * sizeof(unsigned int), st));
         count_launch();
