@@ -1043,7 +1043,16 @@ static void launch_fact_fwd(svb_operator_s *op, double alpha, const double *dx, 
 
 // adjoint CTA: 384 threads and a 64 KB table (R*L = 8192; three CTAs per SM), or -- SVB_FACT_LOG2R one larger -- 1024
 // threads and a 128 KB table (R*L = 16384; one CTA per SM, segments twice as long)
-static inline int adj_block_of(const svb_factored_s *f) { return (f->log2R + f->log2L >= 14) ? 1024 : 384; }
+// SVB_ADJ_TWO=1 (experiment): tiles of R*L = 8192 entries WITH replica tables (94.5 KB), two 512-thread CTAs per SM — one CTA
+// fills its table while the other streams
+static inline bool adj_two_mode() {
+    static const bool two = getenv("SVB_ADJ_TWO") && atoi(getenv("SVB_ADJ_TWO")) != 0;
+    return two;
+}
+static inline int adj_block_of(const svb_factored_s *f) {
+    if (f->log2R + f->log2L >= 14) return 1024;
+    return (adj_two_mode() && f->a_nrep > 1) ? 512 : 384;
+}
 
 void fact_fwd(svb_operator_s *op, double alpha, const double *dx, double beta, double *dy, const double *coef, double csign,
               const double *cvec) {
@@ -1072,8 +1081,10 @@ void fact_adj_stage1(svb_operator_s *op, const double *dx) {
     const int block = adj_block_of(f);
     const AdjGeom G{f->a_nlr, f->a_nrep, f->a_strideA, f->a_levstride, f->a_baseB, f->a_pad, f->a_wbase};
     static const int stages = getenv("SVB_ADJ_STAGES") ? atoi(getenv("SVB_ADJ_STAGES")) : 2;
+    static const bool lazy2 = getenv("SVB_ADJ_LAZY") && atoi(getenv("SVB_ADJ_LAZY")) != 0;
     auto k = (block == 1024) ? (stages >= 3 ? adj_stream_kernel<1024, 1, true, 3> : adj_stream_kernel<1024, 1, true, 2>)
-                             : adj_stream_kernel<384, 3, false, 2>;  // 3 x 384 threads: 56 registers (512 threads: 40, spills)
+             : (block == 512) ? (lazy2 ? adj_stream_kernel<512, 2, true, 2> : adj_stream_kernel<512, 2, false, 2>)
+                              : adj_stream_kernel<384, 3, false, 2>;  // 3 x 384 threads: 56 registers (512 threads: 40, spills)
     if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (f->adj_grid == 0) f->adj_grid = (int)std::max<int64_t>(1, std::min<int64_t>(fresident_grid(k, smem, block), f->ntiles));
     k<<<(unsigned)f->adj_grid, block, smem, ctx().stream>>>(f->a_gptr, (const Chunk *)f->a_code, f->a_meta, f->tlevA, f->log2L, f->log2R,
@@ -1211,10 +1222,11 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
             f->a_pad = f->a_baseB + RL - (nlr << log2R);
             f->a_wbase = f->a_pad + 1;
             f->a_tabsize = f->a_wbase + (int)f->R;
-            return (size_t)(32 + f->a_tabsize) * sizeof(double) <= C.smem_optin && f->a_tabsize <= 65535;
+            const size_t budget = (log2R + log2L >= 14) ? (size_t)C.smem_optin : (size_t)112 * 1024;  // two CTAs per SM below 16384 entries
+            return (size_t)(32 + f->a_tabsize) * sizeof(double) <= budget && f->a_tabsize <= 65535;
         };
         bool done = false;
-        if (replicas && log2R + log2L >= 14 && log2R >= 4)
+        if (replicas && (log2R + log2L >= 14 || (adj_two_mode() && log2R + log2L == 13)) && log2R >= 4)
             for (int i = 0; i < 6 && !done; ++i)
                 if (cand[i][0] <= L) done = set_geom(cand[i][0], cand[i][1]);
         if (!done) set_geom(0, 1);
