@@ -419,25 +419,24 @@ def run_b200(args):
             def e2e_step(exact_moments=True):
                 t0 = time.perf_counter()
                 h = ctypes.c_void_p()
-                L.check(lib.svb_csc_upload(m_local, n, L.ptr(colptr), L.ptr(rowval), L.SVB_I64, L.ptr(nzval), vcode, 1,
-                                           ctypes.byref(h)))
-                t1 = t1b = time.perf_counter()
                 o = ctypes.c_void_p()
-                if use_counts:
-                    if exact_moments and world == 1:
-                        # the API default (scale_features_counts(moments="exact")): the reference's sequential Welford over the
-                        # log-normalised HVG columns (scaling.jl:18-34), bit-identical stored centre
-                        y = ctypes.c_void_p()
-                        L.check(lib.svb_normalize_libsize(h, L.ptr(lib_h), L.NORM_LOGNORMALIZE, 1e4, L.SVB_F64, ctypes.byref(y)))
-                        L.check(lib.svb_mean_var(y, L.ptr(mean_h), L.ptr(var_h)))
-                        lib.svb_matrix_free(y)
-                        t1b = time.perf_counter()
-                        L.check(lib.svb_operator_create_counts(h, L.ptr(lib_h), 1e4, L.ptr(mean_h), L.ptr(var_h), SCALE_MAX, 0,
-                                                               L.ptr(mu_out), ctypes.byref(o)))
-                    else:
-                        L.check(lib.svb_operator_create_counts(h, L.ptr(lib_h), 1e4, None, None, SCALE_MAX, 0, L.ptr(mu_out), ctypes.byref(o)))
+                if use_counts and exact_moments and world == 1:
+                    # the API default (moments = "exact": the reference's sequential Welford over the log-normalised HVG columns,
+                    # scaling.jl:18-34, bit-identical stored centre) through the pipelined entry point: densest genes first, their
+                    # Welford chains run on side streams while the rest of the matrix is still crossing PCIe
+                    L.check(lib.svb_csc_upload_lognorm_moments(m_local, n, L.ptr(colptr), L.ptr(rowval), L.SVB_I64, L.ptr(nzval), 1,
+                                                               L.ptr(lib_h), 1e4, L.ptr(mean_h), L.ptr(var_h), ctypes.byref(h)))
+                    t1 = t1b = time.perf_counter()
+                    L.check(lib.svb_operator_create_counts(h, L.ptr(lib_h), 1e4, L.ptr(mean_h), L.ptr(var_h), SCALE_MAX, 0,
+                                                           L.ptr(mu_out), ctypes.byref(o)))
                 else:
-                    L.check(lib.svb_operator_create_ex(h, L.ptr(mu_c), 0, L.SVB_F32 if args.storage == "f32" else 0, ctypes.byref(o)))
+                    L.check(lib.svb_csc_upload(m_local, n, L.ptr(colptr), L.ptr(rowval), L.SVB_I64, L.ptr(nzval), vcode, 1,
+                                               ctypes.byref(h)))
+                    t1 = t1b = time.perf_counter()
+                    if use_counts:
+                        L.check(lib.svb_operator_create_counts(h, L.ptr(lib_h), 1e4, None, None, SCALE_MAX, 0, L.ptr(mu_out), ctypes.byref(o)))
+                    else:
+                        L.check(lib.svb_operator_create_ex(h, L.ptr(mu_c), 0, L.SVB_F32 if args.storage == "f32" else 0, ctypes.byref(o)))
                 lib.svb_matrix_free(h)
                 t2 = time.perf_counter()
                 it_, mp_ = ctypes.c_int64(), ctypes.c_int64()
@@ -484,7 +483,8 @@ def run_b200(args):
             if use_counts:
                 h2d = 8 * (n + 1) + 12 * z + 8 * m_local + 8 * n  # colptr + rowval(i64) + counts(i32) + library sizes + init
                 what = ("pinned-host SparseMatrixCSC{Int32,Int64} of the HVG counts + library sizes -> upload, "
-                        + ("log-normalise + order-exact Welford moments (scaling.jl:18-34; the API default), " if exact else
+                        + ("with the order-exact Welford moments of the log-normalised columns (scaling.jl:18-34; the API default) "
+                           "running on side streams during the upload (svb_csc_upload_lognorm_moments), " if exact else
                            "two-pass all-rank moments, ") + "count-level operator build, solve, U/s/V download")
             else:
                 h2d = 8 * (n + 1) + 16 * z + 8 * n + 8 * n  # colptr + rowval + nzval + mu + init

@@ -125,6 +125,15 @@ int svb_pca_counts_devices(int64_t m, int64_t n, const int64_t *colptr, const vo
 int svb_csc_upload(int64_t nrow, int64_t ncol, const int64_t *colptr, const void *rowval,
                    int rowval_type, const void *nzval, int vtype, int index_base,
                    svb_matrix_t *out);
+/* The e2e form of "upload the HVG counts, then scale_features' moments" (normalize.jl:27,36 + scaling.jl:18-34 on Y[:, hvf]): the
+ * SparseMatrixCSC{Int32,Int64|Int32} of the HVG counts is uploaded column group by column group, DENSEST GENES FIRST, and the
+ * order-exact Welford chains of the groups that have arrived (a serial chain per gene: ~0.14 us per stored value, 0.15 s for the
+ * densest gene of a 1.3 M-cell matrix) run on side streams while the rest of the matrix is still crossing PCIe. mean / var [ncol]
+ * are bit-identical to svb_normalize_libsize + svb_mean_var; out = the device matrix of the counts (as svb_csc_upload). */
+int svb_csc_upload_lognorm_moments(int64_t nrow, int64_t ncol, const int64_t *colptr, const void *rowval,
+                                   int rowval_type, const int32_t *counts, int index_base,
+                                   const int64_t *libsize, double scale_factor, double *mean, double *var,
+                                   svb_matrix_t *out);
 int svb_matrix_free(svb_matrix_t a);
 int svb_matrix_info(svb_matrix_t a, int64_t *nrow, int64_t *ncol, int64_t *nnz, int *vtype);
 /* Download. Any of colptr/rowval/nzval may be NULL. Indices are written as int64 with index_base. */

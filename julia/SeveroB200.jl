@@ -244,6 +244,17 @@ function counts_operator(counts_hvg::SparseMatrixCSC{<:Integer}, libsize::Vector
     DeviceOperator(h[]), mu
 end
 
+# upload of the HVG counts + the order-exact moments of their log-normalised values, pipelined (densest genes first; the Welford
+# chains run on side streams during the upload): (DeviceMatrix, mean, var), bit-identical to normalize -> mean_var
+function upload_lognorm_moments(counts_hvg::SparseMatrixCSC{Int32,Int64}, libsize::Vector{Int64}; scale_factor::Real=1e4)
+    n = size(counts_hvg, 2)
+    mean = zeros(n); var = zeros(n); h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:svb_csc_upload_lognorm_moments, libsvb), Cint,
+        (Int64, Int64, Ptr{Int64}, Ptr{Cvoid}, Cint, Ptr{Int32}, Cint, Ptr{Int64}, Float64, Ptr{Float64}, Ptr{Float64}, Ref{Ptr{Cvoid}}),
+        size(counts_hvg, 1), n, counts_hvg.colptr, counts_hvg.rowval, SVB_I64, counts_hvg.nzval, 1, libsize, scale_factor, mean, var, h))
+    DeviceMatrix(h[]), mean, var
+end
+
 # embedding(counts; ...) in one call: pca of the scaled HVG matrix straight from the counts
 function pca_counts(counts::SparseMatrixCSC{<:Integer}, hvf::AbstractVector{<:Integer}, npcs::Integer;
                     scale_factor::Real=1e4, scale_max::Real=Inf, moments::Symbol=:exact, tol=1e-5, init=nothing)

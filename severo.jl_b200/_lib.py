@@ -61,6 +61,8 @@ SIGNATURES = {
                                        c_int64, c_int64, c_int64, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p, _p64, _p64]),
     "svb_csc_upload": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, _ph]),
+    "svb_csc_upload_lognorm_moments": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_double,
+                                               c_void_p, c_void_p, _ph]),
     "svb_matrix_free": (c_int, [_h]),
     "svb_matrix_info": (c_int, [_h, _p64, _p64, _p64, _pint]),
     "svb_matrix_download": (c_int, [_h, c_void_p, c_void_p, c_void_p, c_int, c_int]),

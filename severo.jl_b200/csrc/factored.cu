@@ -849,8 +849,16 @@ adj_stream_kernel(const int64_t *__restrict__ gptr, const Chunk *__restrict__ co
     for (;;) {
         __syncthreads();  // everybody is done with the previous tile's table (and has read cur_tile)
         if (threadIdx.x == 0) {
-            cur_tile = first ? (long long)atomicAdd(&counters[0], 1u) : nxt_tile;
-            nxt_tile = (long long)atomicAdd(&counters[0], 1u);
+            // look-ahead only when every CTA has several tiles to go through: with few tiles per CTA (cells sharded over 8
+            // GPUs: 319 tiles for 444 CTAs) reserving a second tile hoards work — half the CTAs would run two tiles in a row
+            // while the others exit (measured: 0.15 -> 0.28 ms per product at 8 GPUs)
+            if (ntiles >= 4 * (int64_t)gridDim.x) {
+                cur_tile = first ? (long long)atomicAdd(&counters[0], 1u) : nxt_tile;
+                nxt_tile = (long long)atomicAdd(&counters[0], 1u);
+            } else {
+                cur_tile = (long long)atomicAdd(&counters[0], 1u);
+                nxt_tile = ntiles;
+            }
         }
         first = false;
         __syncthreads();

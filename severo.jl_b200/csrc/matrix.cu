@@ -564,6 +564,8 @@ static svb_matrix_s *finish_subset(const svb_matrix_s *a, DevBuf<int64_t> &lens,
 // =================================================================================================
 extern "C" {
 
+}  // extern "C"
+
 // round-1 advice: a malformed matrix arriving through the public ABI must not reach the kernels that index with its rows
 // (atomicAdd(&nfeat[r]) in filter.cu, the binary searches of tile_bounds, ...). One cheap pass over colptr / rowidx after the
 // upload: pointers non-decreasing, rows inside [0, nrow) and strictly ascending inside a column (what SparseMatrixCSC guarantees).
@@ -582,6 +584,25 @@ __global__ void csc_validate_kernel(const int64_t *__restrict__ colptr, const in
         else if (k > b && rowidx[k - 1] >= r) atomicOr(bad, 4);
     }
 }
+
+namespace svb {
+void csc_validate(const svb_matrix_s *a, const char *who) {
+    cudaStream_t st = ctx().stream;
+    if (a->ncol <= 0) return;
+    DevBuf<int> d_bad(1);
+    SVB_CUDA(cudaMemsetAsync(d_bad.p, 0, sizeof(int), st));
+    csc_validate_kernel<<<(unsigned)a->ncol, 128, 0, st>>>(a->colptr, a->rowidx, a->nrow, a->ncol, a->nnz, d_bad.p);
+    count_launch();
+    int bad = 0;
+    SVB_CUDA(cudaMemcpyAsync(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SVB_CUDA(cudaStreamSynchronize(st));
+    SVB_CHECK(!(bad & 1), SVB_EDIM, std::string(who) + ": malformed colptr (not non-decreasing / out of range)");
+    SVB_CHECK(!(bad & 2), SVB_EDIM, std::string(who) + ": a row index lies outside [1, nrow]");
+    SVB_CHECK(!(bad & 4), SVB_EDIM, std::string(who) + ": row indices must ascend strictly inside every column (SparseMatrixCSC)");
+}
+}  // namespace svb
+
+extern "C" {
 
 int svb_csc_upload(int64_t nrow, int64_t ncol, const int64_t *colptr, const void *rowval, int rowval_type,
                    const void *nzval, int vtype, int index_base, svb_matrix_t *out) {
@@ -617,20 +638,11 @@ int svb_csc_upload(int64_t nrow, int64_t ncol, const int64_t *colptr, const void
             else
                 SVB_CUDA(cudaMemcpyAsync(a->val, nzval, (size_t)nnz * vtype_size(vtype), cudaMemcpyHostToDevice, st));
         }
-        DevBuf<int> d_bad(1);
-        SVB_CUDA(cudaMemsetAsync(d_bad.p, 0, sizeof(int), st));
-        if (ncol > 0) {
-            csc_validate_kernel<<<(unsigned)ncol, 128, 0, st>>>(a->colptr, a->rowidx, nrow, ncol, nnz, d_bad.p);
-            count_launch();
-        }
-        int over = 0, bad = 0;
+        int over = 0;
         SVB_CUDA(cudaMemcpyAsync(&over, d_over.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-        SVB_CUDA(cudaMemcpyAsync(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         SVB_CUDA(cudaStreamSynchronize(st));
         SVB_CHECK(!over, SVB_EDIM, "svb_csc_upload: an index or count does not fit in int32");
-        SVB_CHECK(!(bad & 1), SVB_EDIM, "svb_csc_upload: malformed colptr (not non-decreasing / out of range)");
-        SVB_CHECK(!(bad & 2), SVB_EDIM, "svb_csc_upload: a row index lies outside [1, nrow]");
-        SVB_CHECK(!(bad & 4), SVB_EDIM, "svb_csc_upload: row indices must ascend strictly inside every column (SparseMatrixCSC)");
+        svb::csc_validate(a, "svb_csc_upload");
     } catch (...) {
         delete a;
         throw;

@@ -338,9 +338,150 @@ static void mean_var_device(const svb_matrix_s *a, double *d_mu, double *d_var) 
     SVB_CUDA(cudaStreamSynchronize(st));
 }
 
+// ---- upload + order-exact moments, pipelined (svb_csc_upload_lognorm_moments) ---------------------------------------------
+// Y[k] = log1p((sf * c_k) / s[row_k]) for the entries of the listed columns only (the arithmetic of libnorm_kernel<double>)
+__global__ void __launch_bounds__(256) lognorm_cols_kernel(const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowidx,
+                                                           const int32_t *__restrict__ val, const int32_t *__restrict__ cols,
+                                                           const long long *__restrict__ s, double sf, double *__restrict__ Y) {
+    const int64_t c = cols[blockIdx.x];
+    const int64_t b = colptr[c], e = colptr[c + 1];
+    for (int64_t k = b + (int64_t)blockIdx.y * blockDim.x + threadIdx.x; k < e; k += (int64_t)gridDim.y * blockDim.x) {
+        const double t = __dmul_rn(sf, (double)val[k]);
+        Y[k] = log1p(__ddiv_rn(t, (double)s[rowidx[k]]));
+    }
+}
+
+// rowidx of the listed columns from their staged host indices (Int64 or Int32, any base)
+template <typename TH>
+__global__ void __launch_bounds__(256) convert_cols_kernel(const int64_t *__restrict__ colptr, const int32_t *__restrict__ cols,
+                                                           const int64_t *__restrict__ soff, const TH *__restrict__ stage, int64_t base,
+                                                           int32_t *__restrict__ rowidx, int *__restrict__ overflow) {
+    const int64_t c = cols[blockIdx.x];
+    const int64_t b = colptr[c], len = colptr[c + 1] - b;
+    const TH *src = stage + soff[blockIdx.x];
+    for (int64_t k = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; k < len; k += (int64_t)gridDim.y * blockDim.x) {
+        const int64_t v = (int64_t)src[k] - base;
+        if (v > 2147483647LL || v < 0) *overflow = 1;
+        rowidx[b + k] = (int32_t)v;
+    }
+}
+
+template <typename TH>
+static void upload_moments_pipeline(svb_matrix_s *a, const int64_t *h_colptr, const TH *h_rowval, const int32_t *h_counts, int base,
+                                    const long long *d_lib, double sf, double *h_mean, double *h_var) {
+    Context &C = ctx();
+    cudaStream_t st = C.stream;
+    const int64_t n = a->ncol, nnz = a->nnz;
+    // columns by decreasing length: the longest Welford chains start first and run while the rest crosses PCIe
+    std::vector<int32_t> ord((size_t)n);
+    std::iota(ord.begin(), ord.end(), 0);
+    std::stable_sort(ord.begin(), ord.end(), [&](int32_t x, int32_t y) { return h_colptr[x + 1] - h_colptr[x] > h_colptr[y + 1] - h_colptr[y]; });
+    constexpr int GW = 64;
+    const int ng = (int)((n + GW - 1) / GW);
+    std::vector<int64_t> soff((size_t)n);
+    int64_t emax = 1;
+    for (int g = 0; g < ng; ++g) {
+        int64_t off = 0;
+        for (int64_t i = (int64_t)g * GW; i < std::min<int64_t>(n, (int64_t)(g + 1) * GW); ++i) {
+            soff[(size_t)i] = off;
+            off += h_colptr[ord[(size_t)i] + 1] - h_colptr[ord[(size_t)i]];
+        }
+        emax = std::max(emax, off);
+    }
+    DevBuf<int32_t> d_cols((size_t)std::max<int64_t>(n, 1));
+    DevBuf<int64_t> d_soff((size_t)std::max<int64_t>(n, 1));
+    DevBuf<TH> stage0((size_t)emax), stage1((size_t)emax);
+    DevBuf<double> Y((size_t)std::max<int64_t>(nnz, 1)), d_mean((size_t)std::max<int64_t>(n, 1)), d_var((size_t)std::max<int64_t>(n, 1));
+    DevBuf<int> d_over(1);
+    SVB_CUDA(cudaMemsetAsync(d_over.p, 0, sizeof(int), st));
+    SVB_CUDA(cudaMemcpyAsync(d_cols.p, ord.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    SVB_CUDA(cudaMemcpyAsync(d_soff.p, soff.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    SVB_CUDA(cudaStreamSynchronize(st));  // colptr (uploaded by the caller on st), the lists and the flag are in place
+    struct Streams {
+        cudaStream_t copy = nullptr;
+        std::vector<cudaStream_t> wf;
+        std::vector<cudaEvent_t> ev;
+        ~Streams() {
+            for (auto s_ : wf) if (s_) cudaStreamDestroy(s_);
+            for (auto e_ : ev) if (e_) cudaEventDestroy(e_);
+            if (copy) cudaStreamDestroy(copy);
+        }
+    } S;
+    SVB_CUDA(cudaStreamCreateWithFlags(&S.copy, cudaStreamNonBlocking));
+    const int nwf = std::min(ng, 16);
+    S.wf.assign((size_t)nwf, nullptr);
+    for (auto &s_ : S.wf) SVB_CUDA(cudaStreamCreateWithFlags(&s_, cudaStreamNonBlocking));
+    S.ev.assign((size_t)ng, nullptr);
+    for (auto &e_ : S.ev) SVB_CUDA(cudaEventCreateWithFlags(&e_, cudaEventDisableTiming));
+    for (int g = 0; g < ng; ++g) {
+        const int64_t i0 = (int64_t)g * GW, i1 = std::min<int64_t>(n, i0 + GW);
+        const int ncg = (int)(i1 - i0);
+        TH *stage = (g & 1) ? stage1.p : stage0.p;  // reused every other group: the convert kernel of group g-2 precedes on S.copy
+        for (int64_t i = i0; i < i1; ++i) {
+            const int64_t c = ord[(size_t)i], b = h_colptr[c] - base, len = h_colptr[c + 1] - h_colptr[c];
+            if (len == 0) continue;
+            SVB_CUDA(cudaMemcpyAsync(stage + soff[(size_t)i], h_rowval + b, (size_t)len * sizeof(TH), cudaMemcpyHostToDevice, S.copy));
+            SVB_CUDA(cudaMemcpyAsync((int32_t *)a->val + b, h_counts + b, (size_t)len * 4, cudaMemcpyHostToDevice, S.copy));
+        }
+        dim3 grid((unsigned)ncg, 8);
+        convert_cols_kernel<TH><<<grid, 256, 0, S.copy>>>(a->colptr, d_cols.p + i0, d_soff.p + i0, stage, base, a->rowidx, d_over.p);
+        SVB_CUDA(cudaEventRecord(S.ev[(size_t)g], S.copy));
+        cudaStream_t sw = S.wf[(size_t)(g % nwf)];
+        SVB_CUDA(cudaStreamWaitEvent(sw, S.ev[(size_t)g], 0));
+        lognorm_cols_kernel<<<grid, 256, 0, sw>>>(a->colptr, a->rowidx, (const int32_t *)a->val, d_cols.p + i0, d_lib, sf, Y.p);
+        welford_kernel<double, double><<<(unsigned)((ncg + 63) / 64), 64, 0, sw>>>(a->colptr, Y.p, d_cols.p + i0, ncg, a->nrow, d_mean.p, d_var.p);
+        count_launch(3);
+        SVB_LAUNCH_CHECK();
+    }
+    SVB_CUDA(cudaStreamSynchronize(S.copy));
+    for (auto s_ : S.wf) SVB_CUDA(cudaStreamSynchronize(s_));
+    int over = 0;
+    SVB_CUDA(cudaMemcpyAsync(&over, d_over.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SVB_CUDA(cudaMemcpyAsync(h_mean, d_mean.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    SVB_CUDA(cudaMemcpyAsync(h_var, d_var.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    SVB_CUDA(cudaStreamSynchronize(st));
+    SVB_CHECK(!over, SVB_EDIM, "svb_csc_upload_lognorm_moments: a row index does not fit in int32 / lies below the base");
+}
+
 }  // namespace svb
 
 extern "C" {
+
+int svb_csc_upload_lognorm_moments(int64_t nrow, int64_t ncol, const int64_t *colptr, const void *rowval, int rowval_type,
+                                   const int32_t *counts, int index_base, const int64_t *libsize, double scale_factor, double *mean,
+                                   double *var, svb_matrix_t *out) {
+    SVB_API_BEGIN
+    require_init();
+    SVB_CHECK(out && colptr && libsize && mean && var, SVB_EARG, "svb_csc_upload_lognorm_moments: null argument");
+    SVB_CHECK(nrow >= 1 && ncol >= 1 && nrow < 2147483647LL, SVB_EDIM, "svb_csc_upload_lognorm_moments: bad dimensions");
+    SVB_CHECK(index_base == 0 || index_base == 1, SVB_EARG, "index_base must be 0 or 1");
+    SVB_CHECK(rowval_type == SVB_I32 || rowval_type == SVB_I64, SVB_EARG, "rowval_type must be I32 or I64");
+    const int64_t nnz = colptr[ncol] - index_base;
+    SVB_CHECK(nnz >= 0 && colptr[0] == index_base, SVB_EDIM, "svb_csc_upload_lognorm_moments: malformed colptr");
+    for (int64_t j = 0; j < ncol; ++j) SVB_CHECK(colptr[j + 1] >= colptr[j], SVB_EDIM, "svb_csc_upload_lognorm_moments: malformed colptr");
+    SVB_CHECK(nnz == 0 || (rowval && counts), SVB_EARG, "svb_csc_upload_lognorm_moments: null rowval / counts");
+    SVB_CHECK(scale_factor > 0.0, SVB_EARG, "svb_csc_upload_lognorm_moments: scale_factor must be positive");
+    cudaStream_t st = ctx().stream;
+    svb_matrix_s *a = matrix_alloc(nrow, ncol, nnz, SVB_I32);
+    try {
+        std::vector<int64_t> cp((size_t)ncol + 1);
+        for (int64_t j = 0; j <= ncol; ++j) cp[(size_t)j] = colptr[j] - index_base;
+        SVB_CUDA(cudaMemcpyAsync(a->colptr, cp.data(), cp.size() * 8, cudaMemcpyHostToDevice, st));
+        DevBuf<long long> d_lib((size_t)nrow);
+        SVB_CUDA(cudaMemcpyAsync(d_lib.p, libsize, (size_t)nrow * 8, cudaMemcpyHostToDevice, st));
+        SVB_CUDA(cudaStreamSynchronize(st));
+        if (rowval_type == SVB_I64)
+            upload_moments_pipeline<int64_t>(a, colptr, (const int64_t *)rowval, counts, index_base, d_lib.p, scale_factor, mean, var);
+        else
+            upload_moments_pipeline<int32_t>(a, colptr, (const int32_t *)rowval, counts, index_base, d_lib.p, scale_factor, mean, var);
+        csc_validate(a, "svb_csc_upload_lognorm_moments");
+    } catch (...) {
+        delete a;
+        throw;
+    }
+    *out = a;
+    SVB_API_END
+}
 
 int svb_row_sums(svb_matrix_t a, int64_t *s) {
     SVB_API_BEGIN

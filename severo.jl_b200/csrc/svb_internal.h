@@ -236,6 +236,7 @@ void exclusive_scan_i64(int64_t *d_inout, int64_t n, cudaStream_t st);  // in pl
 // ---- matrix.cu
 svb_matrix_s *matrix_alloc(int64_t nrow, int64_t ncol, int64_t nnz, int vtype);
 size_t vtype_size(int vtype);
+void csc_validate(const svb_matrix_s *a, const char *who);  // rows in range and strictly ascending inside every column (throws SVB_EDIM)
 // ---- operator / spmv
 void op_apply(svb_operator_s *op, bool trans, double alpha, const double *dx, double beta, double *dy,
               const double *axpy_coef_dev = nullptr, double axpy_sign = 0.0, const double *axpy_vec = nullptr);

@@ -157,3 +157,46 @@ def test_knn_rejects_non_finite_coordinates(sv):
     X[17, 2] = np.nan
     with pytest.raises(sv.SeveroB200Error):
         sv.nearest_neighbours(X, 5)
+
+
+def test_pipelined_upload_moments_bit_identical(sv, orc):
+    # svb_csc_upload_lognorm_moments (densest genes first, Welford chains on side streams during the upload) == the plain
+    # sequence svb_csc_upload -> svb_normalize_libsize -> svb_mean_var, bit for bit; matrix identical; Julia-style arrays
+    import ctypes
+    from conftest import planted_counts
+    L = sv._lib
+    X = planted_counts(5000, 700, 6, seed=4, mean_nnz=90)
+    hv = np.arange(0, 700, 3)
+    chv = sp.csc_matrix(X[:, hv])
+    m, n = chv.shape
+    libsize = np.asarray(X.sum(axis=1)).ravel().astype(np.int64)
+    colptr = chv.indptr.astype(np.int64) + 1
+    rowval = chv.indices.astype(np.int64) + 1
+    counts = chv.data.astype(np.int32)
+    mean, var = np.zeros(n), np.zeros(n)
+    h = ctypes.c_void_p()
+    L.check(sv.lib().svb_csc_upload_lognorm_moments(m, n, L.ptr(colptr), L.ptr(rowval), L.SVB_I64, L.ptr(counts), 1, L.ptr(libsize), 1e4,
+                                                    L.ptr(mean), L.ptr(var), ctypes.byref(h)))
+    d = sv.DeviceMatrix(h)
+    assert (d.to_host() != chv).nnz == 0
+    Yo = orc.normalize_cells(X, "lognorm" if False else "lognormalize", 1e4)[:, hv]
+    Yg = sv.normalize_cells(X, method="lognormalize", scale_factor=1e4)      # device log1p (the oracle's glibc log1p differs by <= 1 ulp)
+    mu_ref, var_ref = sv.mean_var(sp.csc_matrix(Yg[:, hv]))
+    np.testing.assert_array_equal(mean, mu_ref)
+    np.testing.assert_array_equal(var, var_ref)
+    np.testing.assert_allclose(mean, orc.mean_var(sp.csc_matrix(Yo))[0], rtol=1e-13)
+    # 32-bit 0-based indices take the same path
+    h2 = ctypes.c_void_p()
+    m2, v2 = np.zeros(n), np.zeros(n)
+    L.check(sv.lib().svb_csc_upload_lognorm_moments(m, n, L.ptr(chv.indptr.astype(np.int64)), L.ptr(chv.indices.astype(np.int32)), L.SVB_I32,
+                                                    L.ptr(counts), 0, L.ptr(libsize), 1e4, L.ptr(m2), L.ptr(v2), ctypes.byref(h2)))
+    np.testing.assert_array_equal(m2, mean)
+    sv.lib().svb_matrix_free(h2)
+    # malformed input is refused
+    bad = rowval.copy()
+    bad[3] = m + 5
+    h3 = ctypes.c_void_p()
+    rc = sv.lib().svb_csc_upload_lognorm_moments(m, n, L.ptr(colptr), L.ptr(bad), L.SVB_I64, L.ptr(counts), 1, L.ptr(libsize), 1e4,
+                                                 L.ptr(mean), L.ptr(var), ctypes.byref(h3))
+    assert rc == L.SVB_EDIM
+    d.free()
