@@ -281,11 +281,17 @@ __device__ __forceinline__ int64_t rr_slot(int64_t g0, int64_t g1, int p) {
 // kernels are unchanged apart from a larger table. Host simulation on the C3 matrix (tools/studies/bank_sim.py): forward,
 // 4 replicas of xs (64 KB): 1.91 -> 1.10 passes per set; adjoint, 4 replicas of levels 1-2 only (176 KB table): 1.55 -> 1.10.
 // The pads of a set share one address and count as ONE entry. Exception chunks are left untouched.
+// Two kernels: the FAST one (greedy, registers only) handles most sets and appends the rest to a list; the FULL one runs the
+// augmenting-path matching (local arrays) on that list only. (One kernel doing both kept its 16-entry arrays in local memory
+// for every set: 55 + 75 ms of a 195 ms operator build at C3.)
+template <bool FULL, int EFFORT>
 __global__ void __launch_bounds__(256) fact_assign_kernel(uint16_t *__restrict__ code, const uint8_t *__restrict__ meta,
-                                                          int64_t nchunks, AssignGeom G, unsigned long long *__restrict__ stats) {
-    const int64_t nsets = ((nchunks + 15) >> 4) * FCH;
+                                                          int64_t nchunks, AssignGeom G, unsigned long long *__restrict__ stats,
+                                                          unsigned int *__restrict__ hard_list, unsigned int hard_n, bool commit_all) {
+    const int64_t nsets = FULL ? (int64_t)hard_n : ((nchunks + 15) >> 4) * FCH;
     unsigned long long mypasses = 0, mysets = 0;
-    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < nsets; s += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t si = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; si < nsets; si += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = FULL ? (int64_t)hard_list[si] : si;
         const int64_t blk = s / FCH;
         const int e = (int)(s % FCH);
         int v[16];
@@ -294,14 +300,28 @@ __global__ void __launch_bounds__(256) fact_assign_kernel(uint16_t *__restrict__
         for (int c = 0; c < 16; ++c) {
             v[c] = 0;
             const int64_t ch = (blk << 4) + c;
-            if (ch >= nchunks) continue;
-            const unsigned mb = meta[ch];
-            (void)mb;
-            v[c] = code[ch * FCH + e];
-            present |= 1u << c;
+            if (ch < nchunks) {
+                v[c] = code[ch * FCH + e];
+                present |= 1u << c;
+            }
         }
         if (!present) continue;
-        mypasses += (unsigned long long)assign_set(G, v, present);
+        int p;
+        if (FULL) {
+            p = assign_set_full(G, v, present);
+        } else {
+            p = assign_set_fast(G, v, present, commit_all, EFFORT);
+            if (p < 0) {  // one atomic per warp (the counter lives behind the list)
+                const unsigned act = __activemask();
+                const int leader = __ffs((int)act) - 1, lane = threadIdx.x & 31;
+                unsigned int at = 0;
+                if (lane == leader) at = atomicAdd(&hard_list[nsets], (unsigned int)__popc(act));
+                at = __shfl_sync(act, at, leader);
+                hard_list[at + __popc(act & ((1u << lane) - 1u))] = (unsigned int)s;
+                continue;
+            }
+        }
+        mypasses += (unsigned long long)p;
         mysets += 1;
 #pragma unroll
         for (int c = 0; c < 16; ++c)
@@ -318,14 +338,51 @@ __global__ void __launch_bounds__(256) fact_assign_kernel(uint16_t *__restrict__
     }
 }
 
-// passes per set of a stream WITHOUT touching it (statistics of the placement: the "before" figure / streams without replicas)
+// Default: the sets the greedy pass leaves with a bank conflict (about half of them at C3) go through the augmenting-path
+// matching (C3: 4 + 10 ms per stream, passes per set 1.49 / 1.55 -> 1.10 / 1.17, 9.6 ms off one IRLBA solve).
+// SVB_FACT_MATCH=greedy0 | greedy1 | greedy keeps the greedy pass alone (its steps up to 3 / 2+3 / all; assign.cuh) for an
+// operator that is used for a handful of products only.
+static bool fact_full_matching() {
+    static const bool full = !getenv("SVB_FACT_MATCH") || !strcmp(getenv("SVB_FACT_MATCH"), "full");
+    return full;
+}
+
+static int fact_greedy_effort() {  // SVB_FACT_MATCH=greedy0 / greedy1: the greedy pass without its steps 4 / 2+4 (assign.cuh)
+    static const int e = !getenv("SVB_FACT_MATCH") ? 2 : !strcmp(getenv("SVB_FACT_MATCH"), "greedy0") ? 0 : !strcmp(getenv("SVB_FACT_MATCH"), "greedy1") ? 1 : 2;
+    return e;
+}
+
+// rewrites the stream with the chosen replicas; returns the average passes per set
 static double run_assign(uint16_t *code, const uint8_t *meta, int64_t nchunks, const AssignGeom &G, cudaStream_t st) {
     if (nchunks <= 0) return 0.0;
-    DevBuf<unsigned long long> d(2);
-    SVB_CUDA(cudaMemsetAsync(d.p, 0, 2 * sizeof(unsigned long long), st));
+    const bool full = fact_full_matching();
     const int64_t nsets = ((nchunks + 15) >> 4) * FCH;
-    fact_assign_kernel<<<fgrid(nsets, 256, 148 * 32), 256, 0, st>>>(code, meta, nchunks, G, d.p);
-    count_launch();
+    SVB_CHECK(nsets < 4000000000ll, SVB_EDIM, "count-level operator: stream too long for the replica assignment");
+    DevBuf<unsigned long long> d(2);
+    DevBuf<unsigned int> hard(full ? (size_t)nsets + 1 : 1);
+    SVB_CUDA(cudaMemsetAsync(d.p, 0, 2 * sizeof(unsigned long long), st));
+    if (full) SVB_CUDA(cudaMemsetAsync(hard.p + nsets, 0, sizeof(unsigned int), st));
+    const bool timing = getenv("SVB_FACT_TIMING") != nullptr;
+    auto now = [&]() { cudaStreamSynchronize(st); return std::chrono::steady_clock::now(); };
+    auto t0 = timing ? now() : std::chrono::steady_clock::time_point();
+    const int effort = full ? 0 : fact_greedy_effort();
+    const int g1 = fgrid(nsets, 256, 148 * 32);
+    if (effort == 0) fact_assign_kernel<false, 0><<<g1, 256, 0, st>>>(code, meta, nchunks, G, d.p, hard.p, 0u, !full);
+    else if (effort == 1) fact_assign_kernel<false, 1><<<g1, 256, 0, st>>>(code, meta, nchunks, G, d.p, hard.p, 0u, !full);
+    else fact_assign_kernel<false, 2><<<g1, 256, 0, st>>>(code, meta, nchunks, G, d.p, hard.p, 0u, !full);
+    unsigned int nhard = 0;
+    if (full) {
+        SVB_CUDA(cudaMemcpyAsync(&nhard, hard.p + nsets, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        SVB_CUDA(cudaStreamSynchronize(st));
+    }
+    auto t1 = timing ? now() : t0;
+    if (nhard) fact_assign_kernel<true, 0><<<fgrid(nhard, 256, 148 * 32), 256, 0, st>>>(code, meta, nchunks, G, d.p, hard.p, nhard, false);
+    if (timing) {
+        auto t2 = now();
+        fprintf(stderr, "[svb counts build]     assignment: %lld sets, greedy %.3f ms, %u sets to the matching %.3f ms\n", (long long)nsets,
+                std::chrono::duration<double, std::milli>(t1 - t0).count(), nhard, std::chrono::duration<double, std::milli>(t2 - t1).count());
+    }
+    count_launch(2);
     SVB_LAUNCH_CHECK();
     unsigned long long h[2];
     SVB_CUDA(cudaMemcpyAsync(h, d.p, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -1347,10 +1404,12 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
                                                               nullptr, nullptr, (uint16_t *)f->a_code, f->a_meta);
         count_launch();
         SVB_LAUNCH_CHECK();
+        tick("  adjoint: segments + placement");
         static const bool stats = getenv("SVB_FACT_STATS") != nullptr;
         if (f->a_nrep > 1 || stats) {
             const AssignGeom G{1, f->a_nrep, f->a_strideA ? f->a_strideA : 5, 1 << (log2R + log2L), log2R, f->a_nlr, f->a_baseB, f->a_pad, f->a_levstride};
             f->a_passes = run_assign((uint16_t *)f->a_code, f->a_meta, f->a_chunks, G, st);
+            tick("  adjoint: replica assignment");
         }
         const int K = adj_block_of(f) / 32;
         SVB_CUDA(cudaMalloc((void **)&f->a_slices, (size_t)f->ntiles * (K + 1) * sizeof(int32_t)));
@@ -1395,10 +1454,12 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
                                                   nullptr, nullptr, nullptr, (uint16_t *)f->f_code, f->f_meta);
         count_launch();
         SVB_LAUNCH_CHECK();
+        tick("  forward: placement");
         static const bool stats = getenv("SVB_FACT_STATS") != nullptr;
         if (f->f_cshift == 3 && (f->f_nrep > 1 || stats)) {
             const AssignGeom G{0, f->f_nrep, f->f_stride, (int)n, 0, 0, 0, 0, 0};
             f->f_passes = run_assign((uint16_t *)f->f_code, f->f_meta, f->f_chunks, G, st);
+            tick("  forward: replica assignment");
         }
         SVB_CUDA(cudaStreamSynchronize(st));
     }
