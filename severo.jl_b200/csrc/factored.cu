@@ -69,7 +69,7 @@ __global__ void fact_prepare_kernel(const double *__restrict__ mean, const doubl
 // written twice: cell-major tlev[i*L + l] (forward: one row's table is contiguous) and, per adjoint tile, level-major
 // tlevA[tile*R*L + l*R + i_local] (the shared-memory table of the adjoint is level-major so that the bank of an entry is
 // its CELL, not its level: 63 % of the entries have count 1 and would otherwise all hit the same bank)
-__global__ void fact_tlev_kernel(const long long *__restrict__ s, int64_t m, int log2L, int log2R, double sf,
+__global__ void fact_tlev_kernel(const long long *__restrict__ s, int64_t m, int log2L, int log2R, int64_t rc, double sf,
                                  double *__restrict__ tlev, double *__restrict__ tlevA) {
     const int64_t total = m << log2L;
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
@@ -79,7 +79,7 @@ __global__ void fact_tlev_kernel(const long long *__restrict__ s, int64_t m, int
         double v = 0.0;
         if (si > 0) v = log1p(__ddiv_rn(__dmul_rn(sf, (double)(l + 1)), (double)si));
         tlev[k] = v;
-        const int64_t t = i >> log2R, il = i & (((int64_t)1 << log2R) - 1);
+        const int64_t t = i / rc, il = i - t * rc;  // rc cells per tile, in a table with room for 1 << log2R
         tlevA[(t << (log2R + log2L)) + ((int64_t)l << log2R) + il] = v;
     }
 }
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(256) fact_seg_count_kernel(const int64_t *__re
 // and the per-chunk flag "last chunk of its segment"
 __global__ void __launch_bounds__(256) fact_seg_fill_kernel(const int64_t *__restrict__ startpos, const int32_t *__restrict__ rowidx,
                                                             const uint8_t *__restrict__ lvl, int64_t nseg, int64_t ncol,
-                                                            int log2R, int log2L, const int64_t *__restrict__ gptr,
+                                                            int log2R, int64_t rc, int log2L, const int64_t *__restrict__ gptr,
                                                             const int64_t *__restrict__ estart, const int32_t *__restrict__ erow,
                                                             const double *__restrict__ eval, uint16_t *__restrict__ code,
                                                             uint8_t *__restrict__ meta) {
@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(256) fact_seg_fill_kernel(const int64_t *__res
     for (int64_t s = sub; s < nseg; s += nsub) {
         const int64_t b = startpos[s], e = startpos[s + ncol];
         const int64_t t = s / ncol;
-        const int64_t row0 = t << log2R;
+        const int64_t row0 = t * rc;
         const int64_t c0 = gptr[s], c1 = gptr[s + 1];
         (void)estart; (void)erow; (void)eval;
         const int64_t cx = c1;
@@ -875,6 +875,7 @@ fwd_stream_kernel(const Chunk *__restrict__ code, const uint8_t *__restrict__ me
 // physical layout of the adjoint tile table (see the replica assignment above); identity = {0, 1, 0, 0, 0, R*L, R*L + 1}
 struct AdjGeom {
     int nlr, nrep, strideA, levstride, baseB, pad, wbase;
+    int rc;  // cells per tile (<= R = 1 << log2R, a multiple of 16: the bank of an entry stays cell mod 16)
 };
 
 // adjoint, stage 1: partial[t][g] = (1/sd_g) * sum over the chunks of segment (t,g) of sum_8 T[code], T[l*R+i] = t_i[l]*w_i;
@@ -925,12 +926,12 @@ adj_stream_kernel(const int64_t *__restrict__ gptr, const Chunk *__restrict__ co
             const char *nx = reinterpret_cast<const char *>(tlevA + (nxt_tile << (log2R + log2L)));
             for (int k = threadIdx.x * 128; k < RL * 8; k += BLOCK * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + k));
         }
-        const int64_t row0 = t << log2R;
-        const double *tl = tlevA + (row0 << log2L);  // this tile's level-major block
+        const int64_t row0 = t * G.rc;
+        const double *tl = tlevA + (t << (log2R + log2L));  // this tile's level-major block
         // table fill: a thread owns a cell — w_i once, then its L table entries (all loads independent, coalesced per level)
         double part = 0.0;
         const int Lv = 1 << log2L;
-        for (int il = threadIdx.x; il < (int)R; il += BLOCK) {
+        for (int il = threadIdx.x; il < G.rc; il += BLOCK) {
             const int64_t row = row0 + il;
             const double wv = (row < m) ? __ldg(w + row) : 0.0;
             T[G.wbase + il] = wv;
@@ -1144,7 +1145,7 @@ void fact_adj_stage1(svb_operator_s *op, const double *dx) {
     svb_factored_s *f = op->fact;
     const size_t smem = (32 + (size_t)f->a_tabsize) * sizeof(double);
     const int block = adj_block_of(f);
-    const AdjGeom G{f->a_nlr, f->a_nrep, f->a_strideA, f->a_levstride, f->a_baseB, f->a_pad, f->a_wbase};
+    const AdjGeom G{f->a_nlr, f->a_nrep, f->a_strideA, f->a_levstride, f->a_baseB, f->a_pad, f->a_wbase, (int)f->Rc};
     static const int stages = getenv("SVB_ADJ_STAGES") ? atoi(getenv("SVB_ADJ_STAGES")) : 2;
     static const bool lazy2 = getenv("SVB_ADJ_LAZY") && atoi(getenv("SVB_ADJ_LAZY")) != 0;
     auto k = (block == 1024) ? (stages >= 3 ? adj_stream_kernel<1024, 1, true, 3> : adj_stream_kernel<1024, 1, true, 2>)
@@ -1254,16 +1255,27 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
     while ((1 << log2L) < L) ++log2L;
     f->L = L;
     f->log2L = log2L;
-    // cells per adjoint tile: R*L = 16384 table entries (128 KB, one 1024-thread CTA per SM; measured 0.67 vs 0.76 ms per
-    // product at C3) when there are at least 8 tiles per SM, else R*L = 8192 (64 KB, three 512-thread CTAs per SM: with
-    // fewer tiles than that the coarser tiles quantise badly over the SMs); small inputs get one small tile
-    int log2R = (m >= (int64_t)8 * C.sm_count * (16384 >> log2L)) ? 14 - log2L : 13 - log2L;
+    // Adjoint tiles. The shared-memory table has room for R*L entries: 16384 (128 KB + replicas, one 1024-thread CTA per SM;
+    // measured 0.67 vs 0.76 ms per product at C3) from 256 cells per SM on, else 8192 (64 KB, three 384-thread CTAs per SM);
+    // small inputs get one small tile. A tile holds Rc <= R cells, chosen so that the tiles fill WHOLE rounds of the grid:
+    // k = ceil(m / (R * SMs)) rounds of Rc = m / (k * SMs) cells (rounded up to 16: the bank of an entry stays cell mod 16).
+    // With Rc = R a shard of 163,266 cells (C3 on 8 GPUs) was 160 tiles on 148 SMs: two rounds for the work of 1.08.
+    const bool big = m >= (int64_t)256 * C.sm_count;
+    int log2R = big ? 14 - log2L : 13 - log2L;
     const char *envr = getenv("SVB_FACT_LOG2R");
     if (envr) log2R = std::max(5, std::min(atoi(envr), 14 - log2L));
     while (log2R > 5 && (1ll << (log2R - 1)) >= m) --log2R;
     f->log2R = log2R;
     f->R = 1ll << log2R;
-    f->ntiles = std::max<int64_t>(1, (m + f->R - 1) / f->R);
+    f->Rc = f->R;
+    static const bool whole_rounds = !(getenv("SVB_FACT_ROUNDS") && atoi(getenv("SVB_FACT_ROUNDS")) == 0);
+    if (whole_rounds && big && log2R + log2L >= 14 && log2R >= 6) {
+        const int64_t slots = C.sm_count;
+        const int64_t k = (m + f->R * slots - 1) / (f->R * slots);
+        const int64_t rc = ((m + k * slots - 1) / (k * slots) + 15) & ~(int64_t)15;
+        f->Rc = std::max<int64_t>(16, std::min<int64_t>(rc, f->R));
+    }
+    f->ntiles = std::max<int64_t>(1, (m + f->Rc - 1) / f->Rc);
     // ---- bank-shifted replicas of the gathered tables (see fact_assign_kernel) ------------------------------------------
     static const bool replicas = !(getenv("SVB_FACT_REPLICAS") && atoi(getenv("SVB_FACT_REPLICAS")) == 0);
     {
@@ -1306,7 +1318,7 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
     SVB_CUDA(cudaMalloc((void **)&f->tlev, (size_t)std::max<int64_t>(m << log2L, 1) * sizeof(double)));
     SVB_CUDA(cudaMalloc((void **)&f->tlevA, (size_t)(f->ntiles << (log2R + log2L)) * sizeof(double)));
     SVB_CUDA(cudaMemsetAsync(f->tlevA, 0, (size_t)(f->ntiles << (log2R + log2L)) * sizeof(double), st));
-    fact_tlev_kernel<<<fgrid(m << log2L), 256, 0, st>>>(d_lib.p, m, log2L, log2R, sf, f->tlev, f->tlevA);
+    fact_tlev_kernel<<<fgrid(m << log2L), 256, 0, st>>>(d_lib.p, m, log2L, log2R, f->Rc, sf, f->tlev, f->tlevA);
     count_launch();
     SVB_LAUNCH_CHECK();
 
@@ -1389,7 +1401,7 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
     {
         const int64_t nseg = f->ntiles * n;
         DevBuf<int64_t> startpos((size_t)((f->ntiles + 1) * n + 1)), estart;  // estart stays empty: no exception chunks
-        tile_bounds(a, log2R, f->ntiles, startpos.p);
+        tile_bounds(a, f->Rc, f->ntiles, startpos.p);
 
         SVB_CUDA(cudaMalloc((void **)&f->a_gptr, (size_t)(nseg + 1) * sizeof(int64_t)));
         fact_seg_count_kernel<<<fgrid(nseg * 8), 256, 0, st>>>(startpos.p, lvl.p, estart.p, nseg, n, f->a_gptr);
@@ -1400,7 +1412,7 @@ static void build_factored(svb_operator_s *op, const svb_matrix_s *a, const int6
         SVB_CUDA(cudaStreamSynchronize(st));
         SVB_CUDA(cudaMalloc((void **)&f->a_code, (size_t)std::max<int64_t>(f->a_chunks, 1) * FCH * 2));
         SVB_CUDA(cudaMalloc((void **)&f->a_meta, (size_t)std::max<int64_t>(f->a_chunks, 1)));
-        fact_seg_fill_kernel<<<fgrid(nseg * 8), 256, 0, st>>>(startpos.p, a->rowidx, lvl.p, nseg, n, log2R, log2L, f->a_gptr, estart.p,
+        fact_seg_fill_kernel<<<fgrid(nseg * 8), 256, 0, st>>>(startpos.p, a->rowidx, lvl.p, nseg, n, log2R, f->Rc, log2L, f->a_gptr, estart.p,
                                                               nullptr, nullptr, (uint16_t *)f->a_code, f->a_meta);
         count_launch();
         SVB_LAUNCH_CHECK();
@@ -1528,7 +1540,7 @@ int svb_operator_counts_info(svb_operator_t op, int *levels, int64_t *tile_cells
     SVB_CHECK(op && op->fact, SVB_EARG, "svb_operator_counts_info: not a count-level operator");
     const svb_factored_s *f = op->fact;
     if (levels) *levels = f->L;
-    if (tile_cells) *tile_cells = f->R;
+    if (tile_cells) *tile_cells = f->Rc;
     if (nnz_coded) *nnz_coded = f->nnz_main;
     if (nnz_exception) *nnz_exception = f->nnz_exc;
     if (fwd_chunks) *fwd_chunks = f->f_chunks;

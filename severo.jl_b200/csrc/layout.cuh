@@ -22,7 +22,7 @@ template <typename V, typename IdxT>
 void csr_from_tilecsc(const TileCSC<V> &tc, const svb_matrix_s *a, DevBuf<int64_t> &rowptr, DevBuf<IdxT> &fidx,
                       DevBuf<V> &fval);
 // startpos[t*ncol + j] = first position of column j whose row >= t*2^log2R, t = 0..ntiles (inclusive)
-void tile_bounds(const svb_matrix_s *a, int log2R, int64_t ntiles, int64_t *startpos);
+void tile_bounds(const svb_matrix_s *a, int64_t tile_rows, int64_t ntiles, int64_t *startpos);
 svb_matrix_s *matrix_transpose(const svb_matrix_s *a);
 void launch_strided_copy(const int64_t *src, int64_t stride, int64_t n, int64_t *dst, cudaStream_t st);
 

@@ -99,15 +99,15 @@ static void upload_index(const TH *host, int64_t n, int64_t base, int32_t *dev, 
 // =================================================================================================
 namespace svb {
 
-// startpos[t*ncol + j] = first position in column j whose row >= t*R   (t = 0..ntiles, inclusive)
+// startpos[t*ncol + j] = first position in column j whose row >= t*R   (t = 0..ntiles, inclusive; R = tile_rows)
 __global__ void tile_bounds_kernel(const int64_t *colptr, const int32_t *rowidx, int64_t ncol, int64_t ntiles,
-                                   int log2R, int64_t *startpos) {
+                                   int64_t tile_rows, int64_t *startpos) {
     const int64_t total = (ntiles + 1) * ncol;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < total; i += stride) {
         const int64_t t = i / ncol, j = i - t * ncol;
-        const int64_t target = t << log2R;
+        const int64_t target = t * tile_rows;
         int64_t lo = colptr[j], hi = colptr[j + 1];
         while (lo < hi) {
             const int64_t mid = (lo + hi) >> 1;
@@ -117,8 +117,8 @@ __global__ void tile_bounds_kernel(const int64_t *colptr, const int32_t *rowidx,
     }
 }
 
-void tile_bounds(const svb_matrix_s *a, int log2R, int64_t ntiles, int64_t *startpos) {
-    tile_bounds_kernel<<<grid_for((ntiles + 1) * a->ncol), 256, 0, ctx().stream>>>(a->colptr, a->rowidx, a->ncol, ntiles, log2R, startpos);
+void tile_bounds(const svb_matrix_s *a, int64_t tile_rows, int64_t ntiles, int64_t *startpos) {
+    tile_bounds_kernel<<<grid_for((ntiles + 1) * a->ncol), 256, 0, ctx().stream>>>(a->colptr, a->rowidx, a->ncol, ntiles, tile_rows, startpos);
     count_launch();
     SVB_LAUNCH_CHECK();
 }
@@ -159,7 +159,7 @@ void build_tilecsc(const svb_matrix_s *a, int log2R, TileCSC<VO> &out) {
     out.rloc.alloc((size_t)std::max<int64_t>(a->nnz, 1));
     out.aval.alloc((size_t)std::max<int64_t>(a->nnz, 1));
     DevBuf<int64_t> startpos((size_t)((ntiles + 1) * a->ncol + 1));
-    tile_bounds_kernel<<<grid_for((ntiles + 1) * a->ncol), 256, 0, st>>>(a->colptr, a->rowidx, a->ncol, ntiles, log2R, startpos.p);
+    tile_bounds_kernel<<<grid_for((ntiles + 1) * a->ncol), 256, 0, st>>>(a->colptr, a->rowidx, a->ncol, ntiles, (int64_t)1 << log2R, startpos.p);
     tile_counts_kernel<<<grid_for(ntiles * a->ncol), 256, 0, st>>>(startpos.p, a->ncol, ntiles, out.gptr.p);
     count_launch(2);
     SVB_LAUNCH_CHECK();

@@ -153,6 +153,7 @@ struct svb_operator_s;
 struct svb_factored_s {
     int L = 0, log2L = 0;            // count levels 1..L are coded; everything else is an exception chunk (exact Float64 value)
     int log2R = 0;                   // cells per adjoint tile (R*L table entries in shared memory)
+    int64_t Rc = 0;                  // cells a tile actually holds (<= R, a multiple of 16; whole rounds of the grid)
     int64_t R = 0, ntiles = 0;
     double *tlev = nullptr;          // [m*L] t_i[l] = log1p(sf*(l+1)/s_i), cell-major (forward)
     double *tlevA = nullptr;         // [ntiles*R*L] the same, level-major inside every adjoint tile

@@ -166,6 +166,8 @@ def test_counts_operator_properties_at_scale(sv):
     info = C.info()
     assert info["nnz_coded"] + info["nnz_exception"] == S.A.nnz
     assert info["nnz_exception"] <= 0.02 * S.A.nnz
+    # adjoint tiles fill whole rounds of the grid: 200,000 cells = 2 rounds of <= 1024-cell tiles, a multiple of 16 cells each
+    assert info["tile_cells"] % 16 == 0 and 512 < info["tile_cells"] < 1024
     rng = np.random.default_rng(0)
     x, w = rng.standard_normal(2000), rng.standard_normal(200_000)
     Sx, Stw = C @ x, C.T @ w
