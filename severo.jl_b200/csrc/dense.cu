@@ -5,6 +5,7 @@
 // last-block pass in a fixed order, so every result is run-to-run deterministic.
 #include "svb_internal.h"
 #include "p2p.cuh"
+#include <cooperative_groups.h>
 
 #include <algorithm>
 
@@ -546,6 +547,117 @@ void vec_normalize(const double *x, int64_t L, const double *nrm2_dev, double *y
     KTimer kt(SVB_K_VECTOR, 16.0 * L);
     normalize_kernel<<<(unsigned)nrb, 256, 0, ctx().stream>>>(x, L, nrm2_dev, y, norm_out, flag_dev, eps, consume_nrm ? 1 : 0,
                                                               consume_nrm ? *consume_nrm : P2PCtx{});
+    SVB_LAUNCH_CHECK();
+}
+
+// ---- gene-side Gram-Schmidt step in ONE launch -------------------------------------------------------------------------
+// The gene-side vectors (length n = 2,000 HVGs) live whole on every rank; one Lanczos step there was three launches of
+// latency-bound kernels (coefficients V'f: 10 us, update f -= V h + |f|^2: 19 us on 4 CTAs, normalise: 5 us — ncu launch list of
+// a C3 shard, profiles/r04_scaling.md), i.e. 34 us for 1.8 MB that sit in L2. Here a thread-block CLUSTER of 8 CTAs owns n/8
+// rows each and exchanges its partial coefficients and partial |f|^2 through distributed shared memory: every CTA adds the
+// eight partials in rank order (same bits in every CTA, run to run), two cluster barriers instead of two kernel boundaries.
+namespace cg = cooperative_groups;
+constexpr int VS_CL = 8, VS_T = 256, VS_MAXW = 256, VS_MAXROWS = 1024;
+
+__global__ void __cluster_dims__(VS_CL, 1, 1) __launch_bounds__(VS_T)
+vside_cgs_kernel(const double *__restrict__ V, int64_t n, int j, double *__restrict__ f, double *__restrict__ nrm2,
+                 double *__restrict__ out, double *__restrict__ slot, int *__restrict__ flag, double eps) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank(), t = threadIdx.x;
+    __shared__ double fs[VS_MAXROWS];
+    __shared__ double ph[VS_CL][VS_MAXW];  // partial coefficients of every CTA of the cluster (written by their owners)
+    __shared__ double h[VS_MAXW];
+    __shared__ double red[4][64];
+    __shared__ double pss[VS_CL];
+    __shared__ double wred[VS_T / 32];
+    const int64_t per = (n + VS_CL - 1) / VS_CL;
+    const int64_t r0 = std::min<int64_t>(n, rank * per);
+    const int nr = (int)(std::min<int64_t>(n, r0 + per) - r0);
+    for (int i = t; i < nr; i += VS_T) fs[i] = f[r0 + i];
+    __syncthreads();
+    // coefficients: thread = (column c of a group of 64, quarter q of this CTA's rows); a thread walks DOWN its column
+    const int cl = t & 63, q = t >> 6;
+    const int qrows = (nr + 3) / 4, qa = std::min(nr, q * qrows), qb = std::min(nr, qa + qrows);
+    for (int c0 = 0; c0 < j; c0 += 64) {
+        const int c = c0 + cl;
+        double a0 = 0.0, a1 = 0.0;
+        if (c < j) {
+            const double *col = V + (int64_t)c * n + r0;
+            int i = qa;
+            for (; i + 1 < qb; i += 2) {
+                a0 = fma(col[i], fs[i], a0);
+                a1 = fma(col[i + 1], fs[i + 1], a1);
+            }
+            if (i < qb) a0 = fma(col[i], fs[i], a0);
+        }
+        red[q][cl] = a0 + a1;
+        __syncthreads();
+        if (q == 0 && c < j) {
+            const double sum = (red[0][cl] + red[1][cl]) + (red[2][cl] + red[3][cl]);
+            for (int p = 0; p < VS_CL; ++p) *cluster.map_shared_rank(&ph[rank][c], p) = sum;
+        }
+        __syncthreads();
+    }
+    cluster.sync();
+    for (int c = t; c < j; c += VS_T) {
+        double sum = 0.0;
+#pragma unroll
+        for (int p = 0; p < VS_CL; ++p) sum += ph[p][c];
+        h[c] = sum;
+    }
+    __syncthreads();
+    // update of this CTA's rows, |f|^2
+    double ss = 0.0;
+    for (int i = t; i < nr; i += VS_T) {
+        const double *row = V + r0 + i;
+        double a0 = 0.0, a1 = 0.0;
+        int c = 0;
+        for (; c + 1 < j; c += 2) {
+            a0 = fma(row[(int64_t)c * n], h[c], a0);
+            a1 = fma(row[(int64_t)(c + 1) * n], h[c + 1], a1);
+        }
+        if (c < j) a0 = fma(row[(int64_t)c * n], h[c], a0);
+        const double v = fs[i] - (a0 + a1);
+        fs[i] = v;
+        ss = fma(v, v, ss);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((t & 31) == 0) wred[t >> 5] = ss;
+    __syncthreads();
+    if (t == 0) {
+        double sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < VS_T / 32; ++k) sum += wred[k];
+        for (int p = 0; p < VS_CL; ++p) *cluster.map_shared_rank(&pss[rank], p) = sum;
+    }
+    cluster.sync();
+    double tot = 0.0;
+#pragma unroll
+    for (int p = 0; p < VS_CL; ++p) tot += pss[p];
+    const double nrm = sqrt(tot), inv = 1.0 / nrm;
+    for (int i = t; i < nr; i += VS_T) {
+        f[r0 + i] = fs[i];
+        if (out) out[r0 + i] = fs[i] * inv;
+    }
+    if (rank == 0 && t == 0) {
+        *nrm2 = tot;
+        if (out) {
+            if (slot) *slot = nrm;
+            if (flag && !(nrm >= eps)) *flag = 1;
+        }
+    }
+}
+
+bool vside_cgs_supported(int64_t n, int j) {
+    static const bool on = !(getenv("SVB_VSIDE_FUSED") && atoi(getenv("SVB_VSIDE_FUSED")) == 0);
+    return on && j >= 1 && j <= VS_MAXW && n >= 1 && n <= (int64_t)VS_CL * VS_MAXROWS;
+}
+
+// f <- f - V[:, :j] (V[:, :j]' f); *nrm2 = |f|^2; out (if given) = f/|f|, *slot = |f|, *flag = 1 when |f| < eps
+void vside_cgs(const double *V, int64_t n, int j, double *f, double *nrm2, double *out, double *slot, int *flag, double eps) {
+    KTimer kt(SVB_K_REORTH, 8.0 * (2.0 * (double)n * j + 4.0 * n));
+    vside_cgs_kernel<<<VS_CL, VS_T, 0, ctx().stream>>>(V, n, j, f, nrm2, out, slot, flag, eps);
     SVB_LAUNCH_CHECK();
 }
 

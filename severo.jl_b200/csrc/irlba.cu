@@ -202,9 +202,12 @@ static void irlba_run(svb_operator_s *op, int64_t nu_, int64_t work_, int64_t ma
             // F = S'*W_j - s*V_j ; orthogonalise against V[:, :j+1]
             op_apply(op, true, 1.0, S.Wc(j), 0.0, S.F.p, Bdiag(j), -1.0, S.Vc(j));
             S.mprod++;
-            S.orthog(S.V.p, n, j + 1, S.F.p, S.nrm2F(), false);
+            // (gene side: whole on every rank — one cluster launch does coefficients, update, norm and the next basis vector)
+            const bool vfused = !S.careful && vside_cgs_supported(n, j + 1);
+            if (vfused) vside_cgs(S.V.p, n, j + 1, S.F.p, S.nrm2F(), j + 1 < w ? S.Vc(j + 1) : nullptr, j + 1 < w ? Bsup(j) : nullptr, S.flag.p, EPS23);
+            else S.orthog(S.V.p, n, j + 1, S.F.p, S.nrm2F(), false);
             if (j + 1 < w) {
-                S.finish(S.V.p, n, j + 1, S.F.p, S.nrm2F(), S.Vc(j + 1), Bsup(j), false, nullptr);
+                if (!vfused) S.finish(S.V.p, n, j + 1, S.F.p, S.nrm2F(), S.Vc(j + 1), Bsup(j), false, nullptr);
                 // W_{j+1} = S*V_{j+1} - r*W_j ; orthogonalise against W[:, :j+1]
                 op_apply(op, false, 1.0, S.Vc(j + 1), 0.0, S.Wc(j + 1), Bsup(j), -1.0, S.Wc(j));
                 S.mprod++;

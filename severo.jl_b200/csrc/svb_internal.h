@@ -266,6 +266,8 @@ void ts_gemm(const double *X, int64_t ld, int64_t L, int w, const double *P, int
              int64_t ldo, const double *colscale_dev);
 void vec_sumsq(const double *x, int64_t L, double *out);            // out = sum x^2 (device scalar)
 // y = x * (1/sqrt(*nrm2)) ; also writes sqrt(*nrm2) to *norm_out (device) and flags breakdown
+bool vside_cgs_supported(int64_t n, int j);
+void vside_cgs(const double *V, int64_t n, int j, double *f, double *nrm2, double *out, double *slot, int *flag, double eps);
 void vec_normalize(const double *x, int64_t L, const double *nrm2_dev, double *y, double *norm_out,
                    int *flag_dev, double eps, const P2PCtx *consume_nrm = nullptr);
 void vec_copy(const double *x, int64_t L, double *y);
