@@ -378,9 +378,11 @@ def run_b200(args):
         classes = class_profile(sv, lib, op, nu, init)
         roofline = roofline_of(classes, peak, peak_src, "counts" if use_counts else None, args.config, world)
         if use_counts:
-            roofline["note"] = ("count-level operator: 2.125 B per nonzero in HBM; ncu (profiles/r02_kernels.md) shows the kernel "
-                                "bound by the shared-memory gather pipe (L1TEX 75-89 %, issue slots 61-63 % busy, DRAM ~35 %), not by "
-                                "HBM; the explicit operator of the same matrix (explicit_operator) is the HBM-bound one")
+            roofline["note"] = ("count-level operator: 2.06 B per coded nonzero + 12 B per exception entry in HBM; ncu "
+                                "(profiles/r04_spmv.md) shows the stream kernels bound by the shared-memory gather pipe (one 8-byte "
+                                "gather per nonzero: L1TEX 90 % busy in the forward kernel, 72 % in the adjoint, DRAM 62 % / 46 % "
+                                "of the ncu peak), not by HBM; the explicit operator of the same matrix (explicit_operator) is "
+                                "the HBM-bound one. spmv_adj = stream kernel + exception side sums + reduce kernel")
         parity = parity_checks(sv, lib, op, nu, init, args.config, world, s_host, m_local, n)
         explicit = None
         if use_counts:

@@ -574,7 +574,7 @@ vside_cgs_kernel(const double *__restrict__ V, int64_t n, int j, double *__restr
     const int64_t r0 = std::min<int64_t>(n, rank * per);
     const int nr = (int)(std::min<int64_t>(n, r0 + per) - r0);
     for (int i = t; i < nr; i += VS_T) fs[i] = f[r0 + i];
-    __syncthreads();
+    cluster.sync();  // (also: every CTA of the cluster is running before anybody stores into its shared memory)
     // coefficients: thread = (column c of a group of 64, quarter q of this CTA's rows); a thread walks DOWN its column
     const int cl = t & 63, q = t >> 6;
     const int qrows = (nr + 3) / 4, qa = std::min(nr, q * qrows), qb = std::min(nr, qa + qrows);
