@@ -6,6 +6,7 @@
 // Arithmetic that must be bit-identical to Julia uses the _rn intrinsics so nvcc cannot contract
 // a*b+c into an FMA (Julia does not).
 #include "svb_internal.h"
+#include <chrono>
 
 #include <algorithm>
 #include <cmath>
@@ -73,18 +74,30 @@ template <> __device__ __forceinline__ float div_rn<float>(float a, float b) { r
 // this is the correctly rounded quotient (Markstein); checked against `/` on 6.4e8 random + adversarial pairs
 // (see DESIGN.md). The dependent chain per element is 5 fp64 ops instead of a ~40-instruction software divide.
 // Zero / huge / tiny deltas take the plain IEEE divide so signed zeros, infinities and subnormals stay exact.
-__device__ __forceinline__ void welford_step_f64(double v, long long count, double y, double &mu, double &s) {
+// (kept out of line: inlined, the compiler evaluates the ~15-instruction divide for EVERY element and selects afterwards —
+// ncu on the dense-gene case: 63 instructions per element on a single warp that issues one every ~3 cycles)
+__device__ __noinline__ double welford_slow_div(double delta, double c) { return __ddiv_rn(delta, c); }
+
+__device__ __forceinline__ void welford_step_f64(double v, double c, double y, double &mu, double &s) {
     const double delta = __dsub_rn(v, mu);
-    const double ad = fabs(delta);
-    double q;
-    if (ad > 1e-290 && ad < 1e290) {
-        const double c = (double)count;
-        const double q0 = __dmul_rn(delta, y);
-        const double r = __fma_rn(-c, q0, delta);
-        q = __fma_rn(r, y, q0);
-    } else {
-        q = __ddiv_rn(delta, (double)count);
-    }
+    const double q0 = __dmul_rn(delta, y);
+    const double r = __fma_rn(-c, q0, delta);
+    double q = __fma_rn(r, y, q0);
+    // fast path for 2^-962 <= |delta| < 2^963 (biased exponent 61..1985), tested on the exponent bits with integer instructions
+    const unsigned be = ((unsigned)__double2hiint(delta) >> 20) & 0x7ffu;
+    if (__builtin_expect(be - 61u > 1924u, 0)) q = welford_slow_div(delta, c);
+    mu = __dadd_rn(mu, q);
+    s = __dadd_rn(s, __dmul_rn(delta, __dsub_rn(v, mu)));
+}
+
+// the same step with the fast quotient only; `bad` collects the range test (the caller redoes the steps exactly if it is set)
+__device__ __forceinline__ void welford_step_fast(double v, double c, double y, double &mu, double &s, unsigned &bad) {
+    const double delta = __dsub_rn(v, mu);
+    const double q0 = __dmul_rn(delta, y);
+    const double r = __fma_rn(-c, q0, delta);
+    const double q = __fma_rn(r, y, q0);
+    const unsigned be = ((unsigned)__double2hiint(delta) >> 20) & 0x7ffu;
+    bad |= (unsigned)(be - 61u > 1924u);
     mu = __dadd_rn(mu, q);
     s = __dadd_rn(s, __dmul_rn(delta, __dsub_rn(v, mu)));
 }
@@ -95,6 +108,8 @@ __device__ __forceinline__ void welford_step_f64(double v, long long count, doub
 // 1/c^4 < 1 ulp for c >= 2^14; the third step is the Markstein correction that rounds correctly) — verified equal
 // to RN(1/c) for every c in [16385, 6e7] on the CPU. Below 2^14 the exact reciprocal is used.
 template <typename T> struct WelfordStep {
+    __device__ __forceinline__ bool can4(long long) const { return false; }
+    __device__ __forceinline__ void run4(T, T, T, T, long long, T &, T &) {}
     __device__ __forceinline__ void run(T v, long long count, T &mu, T &s) {
         const T delta = sub_rn<T>(v, mu);
         mu = add_rn<T>(mu, div_rn<T>(delta, (T)count));
@@ -117,7 +132,43 @@ template <> struct WelfordStep<double> {
             y = __drcp_rn(c);
             valid = true;
         }
-        welford_step_f64(v, count, y, mu, s);
+        welford_step_f64(v, c, y, mu, s);
+    }
+    // FOUR steps at once: the reciprocals of count+1 .. count+4 each by three Newton steps started at y = RN(1/count) —
+    // four independent chains next to the data chain instead of one 6-FMA chain in front of every step (the dependent path
+    // per element goes from 11 fp64 operations to 5: sub, mul, 2 fma, add). Equal to RN(1/d) for every count >= 16384 and
+    // d < 2^32, jumps up to 8: tools/studies/recip_check.c (exhaustive).
+    __device__ __forceinline__ bool can4(long long count) const { return valid && count >= 16384; }
+    __device__ __forceinline__ void run4(double v0, double v1, double v2, double v3, long long count, double &mu, double &s) {
+        const double c = (double)count;
+        const double c1 = c + 1.0, c2 = c + 2.0, c3 = c + 3.0, c4 = c + 4.0;
+        double y1 = y, y2 = y, y3 = y, y4 = y;
+#pragma unroll
+        for (int it = 0; it < 3; ++it) {
+            const double e1 = __fma_rn(-c1, y1, 1.0), e2 = __fma_rn(-c2, y2, 1.0), e3 = __fma_rn(-c3, y3, 1.0), e4 = __fma_rn(-c4, y4, 1.0);
+            y1 = __fma_rn(y1, e1, y1);
+            y2 = __fma_rn(y2, e2, y2);
+            y3 = __fma_rn(y3, e3, y3);
+            y4 = __fma_rn(y4, e4, y4);
+        }
+        // the four steps WITHOUT a branch between them (the s-updates of one step then overlap the mean chain of the next: a
+        // single warp issues in order, and a branch per element kept the compiler from interleaving them — 80 ns per element);
+        // the range test of the fast quotient is accumulated and, if any step failed it (rare), the four are redone exactly
+        const double mu0 = mu, s0 = s;
+        unsigned bad = 0;
+        welford_step_fast(v0, c1, y1, mu, s, bad);
+        welford_step_fast(v1, c2, y2, mu, s, bad);
+        welford_step_fast(v2, c3, y3, mu, s, bad);
+        welford_step_fast(v3, c4, y4, mu, s, bad);
+        if (__builtin_expect(bad != 0u, 0)) {
+            mu = mu0;
+            s = s0;
+            welford_step_f64(v0, c1, y1, mu, s);
+            welford_step_f64(v1, c2, y2, mu, s);
+            welford_step_f64(v2, c3, y3, mu, s);
+            welford_step_f64(v3, c4, y4, mu, s);
+        }
+        y = y4;
     }
 };
 
@@ -168,7 +219,12 @@ __device__ __forceinline__ void welford_warp_stream(const VI *__restrict__ val, 
         __syncwarp();
         const int64_t rem = len - base;
         const int cnt = rem >= 32 ? 32 : (rem > 0 ? (int)rem : 0);
-        for (int i = 0; i < cnt; ++i) {
+        int i = 0;
+        for (; i + 4 <= cnt && step.can4(count); i += 4) {
+            step.run4((T)buf[b][lane][i], (T)buf[b][lane][i + 1], (T)buf[b][lane][i + 2], (T)buf[b][lane][i + 3], count, mu, s);
+            count += 4;
+        }
+        for (; i < cnt; ++i) {
             count += 1;
             step.run((T)buf[b][lane][i], count, mu, s);
         }
@@ -398,25 +454,34 @@ static void upload_moments_pipeline(svb_matrix_s *a, const int64_t *h_colptr, co
     SVB_CUDA(cudaMemcpyAsync(d_soff.p, soff.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
     SVB_CUDA(cudaStreamSynchronize(st));  // colptr (uploaded by the caller on st), the lists and the flag are in place
     struct Streams {
-        cudaStream_t copy = nullptr;
+        cudaStream_t copy = nullptr, conv = nullptr;
         std::vector<cudaStream_t> wf;
-        std::vector<cudaEvent_t> ev;
+        std::vector<cudaEvent_t> ev, evc;
         ~Streams() {
             for (auto s_ : wf) if (s_) cudaStreamDestroy(s_);
             for (auto e_ : ev) if (e_) cudaEventDestroy(e_);
+            for (auto e_ : evc) if (e_) cudaEventDestroy(e_);
+            if (conv) cudaStreamDestroy(conv);
             if (copy) cudaStreamDestroy(copy);
         }
     } S;
     SVB_CUDA(cudaStreamCreateWithFlags(&S.copy, cudaStreamNonBlocking));
+    SVB_CUDA(cudaStreamCreateWithFlags(&S.conv, cudaStreamNonBlocking));  // the row-index conversion: NOT on the copy stream (the copy engine idled behind it: 32 x 0.3 ms)
     const int nwf = std::min(ng, 16);
     S.wf.assign((size_t)nwf, nullptr);
     for (auto &s_ : S.wf) SVB_CUDA(cudaStreamCreateWithFlags(&s_, cudaStreamNonBlocking));
     S.ev.assign((size_t)ng, nullptr);
     for (auto &e_ : S.ev) SVB_CUDA(cudaEventCreateWithFlags(&e_, cudaEventDisableTiming));
+    S.evc.assign((size_t)ng, nullptr);
+    for (auto &e_ : S.evc) SVB_CUDA(cudaEventCreateWithFlags(&e_, cudaEventDisableTiming));
+    const bool dbg = getenv("SVB_DEBUG_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
     for (int g = 0; g < ng; ++g) {
         const int64_t i0 = (int64_t)g * GW, i1 = std::min<int64_t>(n, i0 + GW);
         const int ncg = (int)(i1 - i0);
-        TH *stage = (g & 1) ? stage1.p : stage0.p;  // reused every other group: the convert kernel of group g-2 precedes on S.copy
+        TH *stage = (g & 1) ? stage1.p : stage0.p;  // reused every other group: after the conversion of group g-2
+        if (g >= 2) SVB_CUDA(cudaStreamWaitEvent(S.copy, S.evc[(size_t)(g - 2)], 0));
         for (int64_t i = i0; i < i1; ++i) {
             const int64_t c = ord[(size_t)i], b = h_colptr[c] - base, len = h_colptr[c + 1] - h_colptr[c];
             if (len == 0) continue;
@@ -424,17 +489,25 @@ static void upload_moments_pipeline(svb_matrix_s *a, const int64_t *h_colptr, co
             SVB_CUDA(cudaMemcpyAsync((int32_t *)a->val + b, h_counts + b, (size_t)len * 4, cudaMemcpyHostToDevice, S.copy));
         }
         dim3 grid((unsigned)ncg, 8);
-        convert_cols_kernel<TH><<<grid, 256, 0, S.copy>>>(a->colptr, d_cols.p + i0, d_soff.p + i0, stage, base, a->rowidx, d_over.p);
         SVB_CUDA(cudaEventRecord(S.ev[(size_t)g], S.copy));
+        SVB_CUDA(cudaStreamWaitEvent(S.conv, S.ev[(size_t)g], 0));
+        convert_cols_kernel<TH><<<grid, 256, 0, S.conv>>>(a->colptr, d_cols.p + i0, d_soff.p + i0, stage, base, a->rowidx, d_over.p);
+        SVB_CUDA(cudaEventRecord(S.evc[(size_t)g], S.conv));
         cudaStream_t sw = S.wf[(size_t)(g % nwf)];
-        SVB_CUDA(cudaStreamWaitEvent(sw, S.ev[(size_t)g], 0));
+        SVB_CUDA(cudaStreamWaitEvent(sw, S.evc[(size_t)g], 0));
         lognorm_cols_kernel<<<grid, 256, 0, sw>>>(a->colptr, a->rowidx, (const int32_t *)a->val, d_cols.p + i0, d_lib, sf, Y.p);
         welford_kernel<double, double><<<(unsigned)((ncg + 63) / 64), 64, 0, sw>>>(a->colptr, Y.p, d_cols.p + i0, ncg, a->nrow, d_mean.p, d_var.p);
         count_launch(3);
         SVB_LAUNCH_CHECK();
     }
+    const double t_issued = now();
     SVB_CUDA(cudaStreamSynchronize(S.copy));
+    SVB_CUDA(cudaStreamSynchronize(S.conv));
+    const double t_copied = now();
     for (auto s_ : S.wf) SVB_CUDA(cudaStreamSynchronize(s_));
+    if (dbg)
+        fprintf(stderr, "[svb upload+moments] %d groups: issued %.1f ms, copies + row conversion done %.1f ms, moments done %.1f ms\n", ng,
+                (t_issued - t_begin) * 1e3, (t_copied - t_begin) * 1e3, (now() - t_begin) * 1e3);
     int over = 0;
     SVB_CUDA(cudaMemcpyAsync(&over, d_over.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     SVB_CUDA(cudaMemcpyAsync(h_mean, d_mean.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
