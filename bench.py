@@ -350,6 +350,25 @@ def run_b200(args):
             for _ in range(warmup):
                 r, it, mp, info = solve_device(sv, opx, nu, init)
                 lib.svb_result_free(r)
+            # extra UNTIMED settle steps (reported as `settle_steps`): a freshly booted box showed sporadic 0.129-0.156 s
+            # solves on identical kernels (118 ms of kernel time) in the first seconds of a process; keep warming up until two
+            # consecutive solves agree within 1.5 % (at most 8 more), every rank the same number of times
+            settle, prev = 0, None
+            while settle < 8:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                r, it, mp, info = solve_device(sv, opx, nu, init)
+                torch.cuda.synchronize()
+                dt = torch.tensor([time.perf_counter() - t0], device="cuda")
+                lib.svb_result_free(r)
+                if world > 1:
+                    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+                dt = float(dt.item())
+                settle += 1
+                if prev is not None and abs(dt - prev) <= 0.015 * prev:
+                    break
+                prev = dt
+            timed_solves.settle = settle
             barrier()
             lib.svb_launch_count_reset()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -373,6 +392,7 @@ def run_b200(args):
         # ---- device-resident timing --------------------------------------------------------------
         sampler = ClockSampler(local) if rank == 0 else None
         ms_per_step, launches, s_host, (it, mp, info) = timed_solves(op, args.warmup, args.steps)
+        settle_steps = timed_solves.settle
         clocks = sampler.stop() if sampler else None
         peak, peak_src = measured_peak_gbs()
         classes = class_profile(sv, lib, op, nu, init)
@@ -517,7 +537,7 @@ def run_b200(args):
                     z_total * (2.2 if use_counts else 10) / 1e9 / world, cfg["m"] * (cfg["nu"] + 7) * 8 / 1e9 / world)},
             "solve": {"restarts": it, "matvecs": mp, "info": info, "sigma_1": float(s_host[0]), "sigma_nu": float(s_host[-1])},
             "parity": parity,
-            "roofline": roofline, "kernel_classes": classes, "gpu_launches": launches, "clocks": clocks, "e2e": e2e,
+            "roofline": roofline, "kernel_classes": classes, "gpu_launches": launches, "settle_steps": settle_steps, "clocks": clocks, "e2e": e2e,
             "counts_operator": cinfo, "explicit_operator": explicit,
             "setup_s": {k: round(v, 4) for k, v in winfo["setup"].items()},
             "pipeline": pipeline_block(winfo["setup"], Z_total / world, z_total / world, cfg["m"] / world, cfg["g"], peak),
