@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(DM_THREADS) ts_gemm_dmma_kernel(const double *
 // warp walks K exactly once with all its accumulators live (NT n-tiles x 4 m-tiles x 2 doubles) and the four warps' identical
 // A loads hit L1. 8 warps per CTA = 2 row groups x 4 column groups.
 constexpr int DP_THREADS = 256;
-template <int NT>
+template <int NT, int CG>
 __global__ void __launch_bounds__(DP_THREADS, (NT <= 4 ? 2 : 1)) ts_gemm_dmma_persistent_kernel(const double *__restrict__ X, int64_t ld, int64_t L, int w,
                                                                              const double *__restrict__ P, int ldp, int k, int kp8,
                                                                              int wp4, double *__restrict__ out, int64_t ldo,
@@ -384,11 +384,13 @@ __global__ void __launch_bounds__(DP_THREADS, (NT <= 4 ? 2 : 1)) ts_gemm_dmma_pe
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int rg = warp >> 2, cg = warp & 3;
+    // CG column groups share a row block of 32 rows (their identical A loads hit L1), 8 / CG row groups per CTA
+    constexpr int RG = 8 / CG, ROWS = RG * 32;
+    const int rg = warp / CG, cg = warp % CG;
     const int ntiles = kp8 >> 3;
-    const int64_t nblk = (L + 63) / 64;
+    const int64_t nblk = (L + ROWS - 1) / ROWS;
     for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-        const int64_t r0 = blk * 64 + rg * 32;
+        const int64_t r0 = blk * ROWS + rg * 32;
         if (r0 >= L) continue;
         double acc[4][NT][2];
 #pragma unroll
@@ -403,7 +405,9 @@ __global__ void __launch_bounds__(DP_THREADS, (NT <= 4 ? 2 : 1)) ts_gemm_dmma_pe
             rok[mt] = row < L;
             xrow[mt] = X + (rok[mt] ? row : 0);
         }
-#pragma unroll 2
+        // five k-steps in flight: 20 loads of 256 B per warp (with two the restart product ran at 1.9 TB/s — too few bytes in
+        // flight per SM for HBM)
+#pragma unroll 5
         for (int l0 = 0; l0 < wp4; l0 += 4) {
             const int l = l0 + t;
             const bool lok = l < w;
@@ -412,7 +416,7 @@ __global__ void __launch_bounds__(DP_THREADS, (NT <= 4 ? 2 : 1)) ts_gemm_dmma_pe
             for (int mt = 0; mt < 4; ++mt) a[mt] = (lok && rok[mt]) ? __ldg(xrow[mt] + (int64_t)l * ld) : 0.0;
 #pragma unroll
             for (int i = 0; i < NT; ++i) {
-                const int nt = cg + 4 * i;
+                const int nt = cg + CG * i;
                 b[i] = (nt < ntiles) ? Ps[l * kp8 + nt * 8 + g] : 0.0;
             }
 #pragma unroll
@@ -426,7 +430,7 @@ __global__ void __launch_bounds__(DP_THREADS, (NT <= 4 ? 2 : 1)) ts_gemm_dmma_pe
             if (row < L) {
 #pragma unroll
                 for (int i = 0; i < NT; ++i) {
-                    const int col = (cg + 4 * i) * 8 + 2 * t;
+                    const int col = (cg + CG * i) * 8 + 2 * t;
                     if (col < k) out[row + (int64_t)col * ldo] = acc[mt][i][0];
                     if (col + 1 < k) out[row + (int64_t)(col + 1) * ldo] = acc[mt][i][1];
                 }
@@ -435,14 +439,14 @@ __global__ void __launch_bounds__(DP_THREADS, (NT <= 4 ? 2 : 1)) ts_gemm_dmma_pe
     }
 }
 
-template <int NT>
+template <int NT, int CG>
 static void launch_dmma_persistent(const double *X, int64_t ld, int64_t L, int w, const double *P, int ldp, int k, int kp8, int wp4,
                                    double *out, int64_t ldo, const double *colscale_dev, size_t smem) {
-    auto kern = ts_gemm_dmma_persistent_kernel<NT>;
+    auto kern = ts_gemm_dmma_persistent_kernel<NT, CG>;
     if (smem > 48 * 1024) SVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DP_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-    const int64_t nblk = (L + 63) / 64;
+    const int64_t nblk = (L + (8 / CG) * 32 - 1) / ((8 / CG) * 32);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(nblk, (int64_t)per_sm * ctx().sm_count));
     kern<<<grid, DP_THREADS, smem, ctx().stream>>>(X, ld, L, w, P, ldp, k, kp8, wp4, out, ldo, colscale_dev);
 }
@@ -456,11 +460,19 @@ void ts_gemm(const double *X, int64_t ld, int64_t L, int w, const double *P, int
         const size_t smem = (size_t)wp4 * kp8 * sizeof(double);
         static const bool persistent = !(getenv("SVB_DMMA_PERSISTENT") && atoi(getenv("SVB_DMMA_PERSISTENT")) == 0);
         if (smem <= ctx().smem_optin && persistent && kp8 <= 256) {
-            const int nt = (kp8 / 8 + 3) / 4;  // n-tiles per warp (four column groups)
+            const int ntl = kp8 / 8;
+            static const int cg_env = getenv("SVB_DMMA_CG") ? atoi(getenv("SVB_DMMA_CG")) : 0;
             KTimer kt(SVB_K_RESTART, 8.0 * ((double)L * w + (double)L * k));
-            if (nt <= 2) launch_dmma_persistent<2>(X, ld, L, w, P, ldp, k, kp8, wp4, out, ldo, colscale_dev, smem);
-            else if (nt <= 4) launch_dmma_persistent<4>(X, ld, L, w, P, ldp, k, kp8, wp4, out, ldo, colscale_dev, smem);
-            else launch_dmma_persistent<8>(X, ld, L, w, P, ldp, k, kp8, wp4, out, ldo, colscale_dev, smem);
+            // n-tiles per warp: two column groups (half the redundant A loads) while a warp's accumulators fit (<= 4 tiles)
+            if (ntl <= 8 && cg_env != 4) {
+                if (ntl <= 4) launch_dmma_persistent<2, 2>(X, ld, L, w, P, ldp, k, kp8, wp4, out, ldo, colscale_dev, smem);
+                else launch_dmma_persistent<4, 2>(X, ld, L, w, P, ldp, k, kp8, wp4, out, ldo, colscale_dev, smem);
+            } else {
+                const int nt = (ntl + 3) / 4;  // four column groups
+                if (nt <= 2) launch_dmma_persistent<2, 4>(X, ld, L, w, P, ldp, k, kp8, wp4, out, ldo, colscale_dev, smem);
+                else if (nt <= 4) launch_dmma_persistent<4, 4>(X, ld, L, w, P, ldp, k, kp8, wp4, out, ldo, colscale_dev, smem);
+                else launch_dmma_persistent<8, 4>(X, ld, L, w, P, ldp, k, kp8, wp4, out, ldo, colscale_dev, smem);
+            }
             SVB_LAUNCH_CHECK();
             return;
         }
