@@ -6,8 +6,10 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdint.h>
-int main(void) {
-    const int64_t lo = 16384, hi = (int64_t)1 << 32; /* ~25 s on 16 threads */
+#include <stdlib.h>
+int main(int argc, char **argv) {
+    /* default: every count below 2^32 (~25 s on 16 threads); argv[1] = log2 of the upper bound */
+    const int64_t lo = 16384, hi = (int64_t)1 << (argc > 1 ? atoi(argv[1]) : 32);
     int64_t bad = 0;
 #pragma omp parallel for reduction(+ : bad) schedule(static)
     for (int64_t c = lo; c < hi; ++c) {
