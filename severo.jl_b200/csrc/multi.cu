@@ -123,9 +123,9 @@ static void shard_bounds(int64_t m, int n, std::vector<int64_t> &b) {
 // the rows [lo, hi) of a host CSC (ascending rows inside a column) as a CSC of its own: 0-based int32 rows, values copied as they are
 template <typename IdxT>
 static void cut_rows(int64_t ncol, const int64_t *colptr, const IdxT *rowval, const char *nzval, size_t vsize, int base, int64_t lo,
-                     int64_t hi, std::vector<int64_t> &cp, std::vector<int32_t> &rv, std::vector<char> &nz) {
+                     int64_t hi, std::vector<int64_t> &cp, std::vector<int32_t> &rv, std::vector<char> &nz, std::vector<int64_t> &first) {
     cp.assign((size_t)ncol + 1, 0);
-    std::vector<int64_t> first((size_t)ncol);
+    first.assign((size_t)ncol, 0);
     for (int64_t j = 0; j < ncol; ++j) {
         const IdxT *b = rowval + (colptr[j] - base), *e = rowval + (colptr[j + 1] - base);
         const IdxT *p0 = std::lower_bound(b, e, (IdxT)(lo + base)), *p1 = std::lower_bound(p0, e, (IdxT)(hi + base));
@@ -153,19 +153,61 @@ struct ShardedCSC {
     int vtype, index_base;
 };
 
+// The piece of every column that worker r took: [first[j], first[j] + count[j]) of the caller's arrays
+struct ShardPieces {
+    std::vector<int64_t> first, count;
+};
+
 // upload worker r's cells; returns the device matrix (owned by the caller, to be freed on the same worker)
-static svb_matrix_t upload_shard(const ShardedCSC &A, int64_t lo, int64_t hi) {
+static svb_matrix_t upload_shard(const ShardedCSC &A, int64_t lo, int64_t hi, ShardPieces &pieces) {
     std::vector<int64_t> cp;
     std::vector<int32_t> rv;
     std::vector<char> nz;
     const size_t vs = host_vsize(A.vtype);
     if (A.rowval_type == SVB_I64)
-        cut_rows<int64_t>(A.n, A.colptr, (const int64_t *)A.rowval, (const char *)A.nzval, vs, A.index_base, lo, hi, cp, rv, nz);
+        cut_rows<int64_t>(A.n, A.colptr, (const int64_t *)A.rowval, (const char *)A.nzval, vs, A.index_base, lo, hi, cp, rv, nz, pieces.first);
     else
-        cut_rows<int32_t>(A.n, A.colptr, (const int32_t *)A.rowval, (const char *)A.nzval, vs, A.index_base, lo, hi, cp, rv, nz);
+        cut_rows<int32_t>(A.n, A.colptr, (const int32_t *)A.rowval, (const char *)A.nzval, vs, A.index_base, lo, hi, cp, rv, nz, pieces.first);
+    pieces.count.resize((size_t)A.n);
+    for (int64_t j = 0; j < A.n; ++j) pieces.count[(size_t)j] = cp[(size_t)j + 1] - cp[(size_t)j];
     svb_matrix_t h = nullptr;
-    wcheck(svb_csc_upload(hi - lo, A.n, cp.data(), rv.data(), SVB_I32, nz.data(), A.vtype, 0, &h));
+    wcheck(svb_csc_upload(hi - lo, A.n, cp.data(), rv.data(), SVB_I32, nz.data(), A.vtype, 0, &h));  // validates the shard on the device
     return h;
+}
+
+// Phase 1 of the multi-device entry points: every worker cuts and uploads its cells — NO collective in here, so a malformed
+// input fails on its worker and run_all reports it after all workers have returned (an error raised between two collectives
+// would leave the peers waiting). The cut is a binary search per column and shard, which is only right when the rows ascend
+// inside every column: each shard is validated on the device (ascending, in range), and here the pieces of a column must tile
+// it exactly — together that IS "rows ascend strictly in the whole column". On failure the uploaded shards are released.
+static void upload_all_shards(Group *G, const ShardedCSC &A, const std::vector<int64_t> &bounds, std::vector<svb_matrix_t> &mats,
+                              const char *who) {
+    const int N = (int)G->w.size();
+    std::vector<ShardPieces> pieces((size_t)N);
+    mats.assign((size_t)N, nullptr);
+    auto release = [&] {
+        try {
+            run_all(G, [&](int r) {
+                if (mats[(size_t)r]) svb_matrix_free(mats[(size_t)r]);
+                mats[(size_t)r] = nullptr;
+            });
+        } catch (...) {
+        }
+    };
+    try {
+        run_all(G, [&](int r) { mats[(size_t)r] = upload_shard(A, bounds[(size_t)r], bounds[(size_t)r + 1], pieces[(size_t)r]); });
+        for (int64_t j = 0; j < A.n; ++j) {
+            int64_t at = A.colptr[j] - A.index_base;
+            for (int r = 0; r < N; ++r) {
+                SVB_CHECK(pieces[(size_t)r].first[(size_t)j] == at, SVB_EDIM, std::string(who) + ": row indices must ascend inside every column");
+                at += pieces[(size_t)r].count[(size_t)j];
+            }
+            SVB_CHECK(at == A.colptr[j + 1] - A.index_base, SVB_EDIM, std::string(who) + ": row indices must ascend inside every column and lie in [0, m)");
+        }
+    } catch (...) {
+        release();
+        throw;
+    }
 }
 
 static void check_csc_args(const ShardedCSC &A, const char *who) {
@@ -356,11 +398,13 @@ int svb_irlba_csc_devices(int64_t m, int64_t n, const int64_t *colptr, const voi
         std::vector<int64_t> bounds;
         shard_bounds(m, N, bounds);
         std::vector<svb_operator_t> ops((size_t)N, nullptr);
+        std::vector<svb_matrix_t> mats;
+        upload_all_shards(G, A, bounds, mats, "svb_irlba_csc_devices");
         try {
             run_all(G, [&](int r) {
-                svb_matrix_t a = upload_shard(A, bounds[(size_t)r], bounds[(size_t)r + 1]);
-                const int rc = svb_operator_create(a, mu, 0, &ops[(size_t)r]);
-                svb_matrix_free(a);
+                const int rc = svb_operator_create(mats[(size_t)r], mu, 0, &ops[(size_t)r]);
+                svb_matrix_free(mats[(size_t)r]);
+                mats[(size_t)r] = nullptr;
                 wcheck(rc);
             });
             solve_and_collect(G, bounds, ops, m, n, nu, m_b, maxit, tol, svtol, init, s, U, V, iter, mprod, &info);
@@ -394,14 +438,16 @@ int svb_pca_counts_devices(int64_t m, int64_t n, const int64_t *colptr, const vo
         shard_bounds(m, N, bounds);
         std::vector<svb_operator_t> ops((size_t)N, nullptr);
         std::vector<double> mu0((size_t)n);
+        std::vector<svb_matrix_t> mats;
+        upload_all_shards(G, A, bounds, mats, "svb_pca_counts_devices");
         try {
             run_all(G, [&](int r) {
-                const int64_t lo = bounds[(size_t)r], hi = bounds[(size_t)r + 1];
-                svb_matrix_t a = upload_shard(A, lo, hi);
+                const int64_t lo = bounds[(size_t)r];
                 // moments = NULL: two parallel passes over the cells of ALL workers inside the build (allreduced)
-                const int rc = svb_operator_create_counts(a, libsize + lo, scale_factor, nullptr, nullptr, scale_max, 0,
+                const int rc = svb_operator_create_counts(mats[(size_t)r], libsize + lo, scale_factor, nullptr, nullptr, scale_max, 0,
                                                           r == 0 ? mu0.data() : nullptr, &ops[(size_t)r]);
-                svb_matrix_free(a);
+                svb_matrix_free(mats[(size_t)r]);
+                mats[(size_t)r] = nullptr;
                 wcheck(rc);
             });
             if (mu_out) memcpy(mu_out, mu0.data(), (size_t)n * 8);

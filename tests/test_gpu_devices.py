@@ -76,3 +76,38 @@ def test_devices_errors_and_single_gpu_context_coexist(sv, orc, group):
     b = sv.irlba(X, 5, init=np.ones(120), tol=1e-9)                           # svb_init context, device 0
     np.testing.assert_allclose(a.S, b.S, rtol=1e-9)
     np.testing.assert_allclose(a.S, np.linalg.svd(X.toarray(), compute_uv=False)[:5], rtol=1e-8)
+
+
+def test_devices_refuse_malformed_csc_and_stay_usable(sv, group):
+    """The library cuts the caller's columns by binary search, which is only right for ascending rows: unsorted or out-of-range
+    row indices must come back as SVB_EDIM from the phase that has no collective in it (no worker left waiting), and the
+    group must solve the next, well-formed matrix."""
+    import ctypes
+    L = sv._lib
+    m, n, nu = 6000, 60, 4
+    X = sp.random(m, n, 0.05, random_state=2, format="csc")
+    X.sort_indices()
+    colptr = X.indptr.astype(np.int64)
+    data = np.ascontiguousarray(X.data)
+    init = np.ones(n)
+
+    def call(rowval):
+        U = np.zeros((m, nu), order="F"); s = np.zeros(nu); V = np.zeros((n, nu), order="F")
+        it, mp = ctypes.c_int64(), ctypes.c_int64()
+        return L.lib().svb_irlba_csc_devices(m, n, L.ptr(colptr), L.ptr(rowval), L.SVB_I64, L.ptr(data), L.SVB_F64, 0, None, nu, nu + 7,
+                                             1000, 1e-9, 1e-9, L.ptr(init), L.ptr(s), L.ptr(U), L.ptr(V), ctypes.byref(it), ctypes.byref(mp)), s
+
+    good = X.indices.astype(np.int64)
+    j = int(np.argmax(np.diff(colptr)))                       # the longest column
+    b, e = int(colptr[j]), int(colptr[j + 1])
+    swapped = good.copy()
+    swapped[b], swapped[e - 1] = good[e - 1], good[b]         # first and last row of the column exchanged: not ascending
+    rc, _ = call(swapped)
+    assert rc == L.SVB_EDIM
+    beyond = good.copy()
+    beyond[e - 1] = m + 5                                     # a row index outside [0, m)
+    rc, _ = call(beyond)
+    assert rc == L.SVB_EDIM
+    rc, s = call(good)
+    assert rc == 0
+    np.testing.assert_allclose(s, np.linalg.svd(X.toarray(), compute_uv=False)[:nu], rtol=1e-8)
