@@ -36,3 +36,33 @@ def test_reference_arm_small_configuration():
     # the same call again gives the same matrix: the generator twin is deterministic
     C2, info2 = bench.reference_problem(cfg)
     assert info2["z"] == info["z"] and info2["Z"] == info["Z"]
+
+
+def test_reference_arm_never_loads_the_product(tmp_path):
+    """`bench.py --impl reference` on the reference's own CPU-runnable configuration (C1): one JSON line with impl = reference,
+    and neither the product package nor libsevero_b200.so in the process afterwards."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, json\n"
+        "sys.argv = ['bench.py', '--impl', 'reference', '--config', 'C1', '--steps', '1', '--warmup', '0']\n"
+        "import bench\n"
+        "lines = []\n"
+        "bench.emit = lines.append\n"
+        "bench.main()\n"
+        "line = lines[-1]\n"
+        "maps = open('/proc/self/maps').read()\n"
+        "print(json.dumps({'impl': line.get('impl'), 'value': line.get('value'), 'metric': line.get('metric'),\n"
+        "                  'kind': line.get('cpu_baseline', {}).get('kind'),\n"
+        "                  'product_module': any(k.startswith('severo_jl_b200') or k.startswith('severo.jl_b200') for k in sys.modules),\n"
+        "                  'product_so': 'libsevero_b200' in maps}))\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    # (bench.main() points fd 1 at stderr to keep the real stdout for its one line: the summary arrives on either stream)
+    out = json.loads([ln for ln in (r.stdout + r.stderr).splitlines() if ln.startswith('{"impl"')][-1])
+    assert out["impl"] == "reference" and out["kind"] == "port" and out["value"] > 0
+    assert out["metric"] == bench.METRIC
+    assert not out["product_module"] and not out["product_so"]
