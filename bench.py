@@ -767,6 +767,17 @@ def run_reference(args):
                                how="measured single-thread costs of one forward product (stdlib scatter order), one adjoint "
                                    "product and one CGS pass, weighted by this solve's operation counts (average basis 0.6 w); "
                                    "an estimate — a full single-thread solve does not fit the run")}
+    # probe for the real reference at run time and record the fact (it has never been present: the image has no Julia)
+    import shutil
+    import subprocess
+    julia = shutil.which("julia")
+    severo_loads = None
+    if julia:
+        try:
+            severo_loads = subprocess.run([julia, "-e", "using Severo"], capture_output=True, timeout=120).returncode == 0
+        except Exception:
+            severo_loads = False
+    probe = {"julia": julia, "severo_jl_loads": severo_loads}
     out = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "s", "n_gpus": world, "steps": steps,
            "warmup": warmup, "steps_requested": args.steps, "warmup_requested": args.warmup,
            "ms_per_step": round(t * 1e3, 2), "higher_is_better": False,
@@ -776,7 +787,10 @@ def run_reference(args):
            "parity": {"sigma_max_rel_diff_vs_committed_gpu_n1": dsig},
            "cpu_baseline": base, "setup_s": pinfo["setup_s"],
            "e2e": {"value": base["value"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "note": "Julia and libcell are absent from the image; this arm times the oracle port of the reference algorithm on all "
+           "reference_probe": probe,
+           "note": ("Julia and libcell are absent from the image" if not severo_loads else
+                    "Julia and Severo.jl ARE present on this box (see reference_probe), but") +
+                   "; this arm times the oracle port of the reference algorithm on all "
                    "host threads on the full configuration. Its input comes from the host twin of the generator "
                    "(oracle/csrc/synth_twin.c, bit-identical to the device generator: tests/test_gpu_synth_twin.py); the "
                    "product library is not loaded"}
