@@ -225,16 +225,21 @@ end
 # :fast lets the library compute them in two parallel passes (a few ulp away; spans all ranks of a communicator).
 function counts_operator(counts_hvg::SparseMatrixCSC{<:Integer}, libsize::Vector{Int64};
                          scale_factor::Real=1e4, scale_max::Real=Inf, moments::Symbol=:exact, levels::Integer=0)
-    d = upload(counts_hvg)
     n = size(counts_hvg, 2)
     mean = var = Ptr{Float64}(C_NULL)
-    if moments == :exact
+    if moments == :exact && counts_hvg isa SparseMatrixCSC{Int32,Int64}
+        # the pipelined entry point: the order-exact moments are computed while the matrix crosses PCIe (bit-identical)
+        d, mean, var = upload_lognorm_moments(counts_hvg, libsize; scale_factor)
+    elseif moments == :exact
+        d = upload(counts_hvg)
         y = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:svb_normalize_libsize, libsvb), Cint, (Ptr{Cvoid}, Ptr{Int64}, Cint, Float64, Cint, Ref{Ptr{Cvoid}}),
             d, libsize, 0, scale_factor, 3, y))
         mean, var = zeros(n), zeros(n)
         check(ccall((:svb_mean_var, libsvb), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), y[], mean, var))
         ccall((:svb_matrix_free, libsvb), Cint, (Ptr{Cvoid},), y[])
+    else
+        d = upload(counts_hvg)
     end
     mu = zeros(n)                                    # receives mean/std, the stored centre (scaling.jl:207)
     h = Ref{Ptr{Cvoid}}(C_NULL)
